@@ -1,0 +1,107 @@
+// HOST-CHECK build of the kernels' per-frame code (g++ -DFSD_HOSTCHECK, a warp of ONE lane).
+//
+// Test infrastructure for `pytest -m "not gpu"`: it lets the CPU-only container exercise the
+// control flow and numerics of sort.cuh / match.cuh / spline.cuh / path.cuh against the golden
+// vectors before any GPU time is spent.  It is NOT a product path: the package never loads this
+// library (ft_fsd_path_planning_b200/_lib.py loads libfsdplan.so only and raises without CUDA).
+#define FSD_HOSTCHECK 1
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "frame.cuh"
+
+using namespace fsd;
+
+extern "C" int fsd_hostcheck_initial_path(const fsd_params *params, double *out) {
+  DevParams P = make_dev_params(*params);
+  PathSmem *S = new PathSmem();
+  unsigned st = initial_path_frame(*S, P, out);
+  delete S;
+  return (int)st;
+}
+
+extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const double *xy, const uint8_t *type,
+                                  const int32_t *offsets, const double *pos, const double *dir,
+                                  const int16_t *force_P, const double *prev, double *out_path, int16_t *left_idx,
+                                  int16_t *right_idx, int16_t *n_wv, double *left_wv, double *right_wv, int16_t *l2r,
+                                  int16_t *r2l, int16_t *grid, int16_t *sort_dbg, uint32_t *status) {
+  DevParams P = make_dev_params(*params);
+  SortSmem *S = new SortSmem();
+  MatchSmem *M = new MatchSmem();
+  PathSmem *Q = new PathSmem();
+  double initial[FSD_HORIZON * 4];
+  if (!prev) {
+    initial_path_frame(*Q, P, initial);
+    prev = initial;
+  }
+  StageOut O = {left_idx, right_idx, sort_dbg, n_wv, left_wv, right_wv, l2r, r2l, status};
+  for (int b = 0; b < n_frames; ++b) {
+    int lo = offsets[b], n = offsets[b + 1] - lo;
+    unsigned st = 0;
+    if (n > FSD_MAX_CONES) {
+      n = FSD_MAX_CONES;
+      st |= FSD_ST_OVERFLOW;
+    }
+    FramePose F = {pos[2 * b], pos[2 * b + 1], dir[2 * b], dir[2 * b + 1]};
+    load_frame_plain(*S, xy + 2 * (size_t)lo, type + lo, n);
+    st |= sort_frame(*S, n, F, P, sort_dbg + 8 * (size_t)b);
+    store_sort(*S, b, O);
+    st |= match_from_sort(*S, *M, F, P);
+    store_match(*M, b, O);
+    status[b] = st;
+    path_from_tensors(*Q, b, O, F, force_P ? force_P[b] : 0, prev, P, out_path, nullptr, grid);
+  }
+  delete S;
+  delete M;
+  delete Q;
+  return 0;
+}
+
+extern "C" int fsd_hostcheck_params_default(fsd_params *p) {
+  std::memset(p, 0, sizeof(*p));
+  p->max_n_neighbors = 5;
+  p->max_length = 12;
+  p->max_dist = 6.5;
+  p->max_dist_to_first = 6.0;
+  p->threshold_directional_angle = 40.0 * PI / 180.0;
+  p->threshold_absolute_angle = 65.0 * PI / 180.0;
+  p->car_size = 2.1;
+  p->max_dfs_pops = 1 << 16;
+  p->min_track_width = 3.0;
+  p->max_search_range = 5.0;
+  p->max_search_angle = 50.0 * PI / 180.0;
+  p->smoothing = 0.2;
+  p->predict_every = 0.1;
+  p->maximal_distance_for_valid_path = 5.0;
+  p->mpc_path_length = 20.0;
+  p->refit_smoothing = 0.01;
+  return 0;
+}
+
+// the spline fit alone, for the comparison with scipy.interpolate.splprep
+extern "C" int fsd_hostcheck_fit(const double *pts, int m, double s, double *t, int *n, double *c, int *k) {
+  PathSmem *Q = new PathSmem();
+  if (m > PCAP) {
+    delete Q;
+    return 10;
+  }
+  for (int i = 0; i < m; ++i) {
+    Q->pts[i].x = pts[2 * i];
+    Q->pts[i].y = pts[2 * i + 1];
+  }
+  chord_params(Q->pts, m, Q->u);
+  unsigned st = 0;
+  int ier = fit_curve(Q->W, Q->pts, Q->u, m, s, &st);
+  if (ier != 10) {
+    *n = Q->W.n;
+    *k = Q->W.k;
+    for (int i = 0; i < Q->W.n; ++i) t[i] = Q->W.t[i];
+    for (int i = 0; i < Q->W.n - Q->W.k - 1; ++i) {
+      c[2 * i] = Q->W.c[i][0];
+      c[2 * i + 1] = Q->W.c[i][1];
+    }
+  }
+  delete Q;
+  return ier;
+}

@@ -1,0 +1,124 @@
+// Warp-cooperative primitives, written once for two builds:
+//
+//   * device build (nvcc, sm_100a): one warp plans one frame; FSD_LANES == 32; the primitives are
+//     shuffles / ballots / __syncwarp.
+//   * host-check build (g++, -DFSD_HOSTCHECK): FSD_LANES == 1; every primitive degenerates to the
+//     identity.  It exists only so that `pytest -m "not gpu"` can exercise the kernels' control
+//     flow and numerics on the CPU (tests/test_hostcheck.py).  It is never loaded by the product
+//     package; the product has no CPU path.
+//
+// Coding discipline that makes both builds correct from one source:
+//   - data-parallel loops are lane-strided:   for (int i = fsd_lane(); i < n; i += FSD_LANES)
+//   - values produced by one lane for all lanes travel through per-warp shared memory followed
+//     by wsync(); reductions go through wsum / wargmin / ... which return the result to ALL lanes;
+//   - serial sections are guarded by `if (fsd_lane() == 0)` and followed by wsync().
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(FSD_HOSTCHECK)
+#define FSD_DEVICE_BUILD 1
+#define FSD_DEV __device__ __forceinline__
+#define FSD_DEVFN __device__
+#else
+#define FSD_DEV static inline
+#define FSD_DEVFN static
+#endif
+
+namespace fsd {
+
+struct d2 {
+  double x, y;
+};
+
+#ifdef FSD_DEVICE_BUILD
+
+constexpr int FSD_LANES = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+FSD_DEV int fsd_lane() { return (int)(threadIdx.x & 31u); }
+FSD_DEV void wsync() { __syncwarp(); }
+
+FSD_DEV double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+FSD_DEV int wsum_i(int v) { return __reduce_add_sync(FULL, v); }
+FSD_DEV int wmin_i(int v) { return __reduce_min_sync(FULL, v); }
+FSD_DEV int wmax_i(int v) { return __reduce_max_sync(FULL, v); }
+FSD_DEV double wmin_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+FSD_DEV unsigned wballot(bool p) { return __ballot_sync(FULL, p); }
+FSD_DEV bool wany(bool p) { return __any_sync(FULL, p); }
+// argmin with ties -> smallest index; lanes with idx < 0 do not take part
+FSD_DEV void wargmin(double &v, int &idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(FULL, v, o);
+    int oi = __shfl_xor_sync(FULL, idx, o);
+    bool take = (oi >= 0) && (idx < 0 || ov < v || (ov == v && oi < idx));
+    if (take) {
+      v = ov;
+      idx = oi;
+    }
+  }
+}
+// inclusive prefix sum across the lanes
+FSD_DEV double wscan_incl(double v) {
+  int lane = fsd_lane();
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// value of the last lane
+FSD_DEV double wlast(double v) { return __shfl_sync(FULL, v, 31); }
+
+#else  // host-check build: a warp of one lane
+
+constexpr int FSD_LANES = 1;
+
+FSD_DEV int fsd_lane() { return 0; }
+FSD_DEV void wsync() {}
+FSD_DEV double wsum(double v) { return v; }
+FSD_DEV int wsum_i(int v) { return v; }
+FSD_DEV int wmin_i(int v) { return v; }
+FSD_DEV int wmax_i(int v) { return v; }
+FSD_DEV double wmin_d(double v) { return v; }
+FSD_DEV unsigned wballot(bool p) { return p ? 1u : 0u; }
+FSD_DEV bool wany(bool p) { return p; }
+FSD_DEV void wargmin(double &, int &) {}
+FSD_DEV double wscan_incl(double v) { return v; }
+FSD_DEV double wlast(double v) { return v; }
+
+#endif
+
+constexpr double PI = 3.14159265358979323846;
+
+FSD_DEV double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
+
+// (a1 - a2 + 3 pi) mod 2 pi - pi with Python's modulo
+// (reference: fsd_path_planning/utils/math_utils.py:663-676)
+FSD_DEV double angle_difference(double a1, double a2) {
+  double v = fmod(a1 - a2 + 3.0 * PI, 2.0 * PI);
+  if (v < 0.0) v += 2.0 * PI;
+  return v - PI;
+}
+
+// cosine of the angle between two vectors, clipped like vec_angle_between
+// (fsd_path_planning/utils/math_utils.py:70-100); comparisons `angle < a` become `cos > cos(a)`
+FSD_DEV double cos_between(double ax, double ay, double bx, double by) {
+  double c = (ax * bx + ay * by) / (sqrt(ax * ax + ay * ay) * sqrt(bx * bx + by * by));
+  if (c < -1.0) c = -1.0;  // NaN (zero-length vector) stays NaN: every comparison is then false,
+  if (c > 1.0) c = 1.0;    // as with the reference's arccos(NaN)
+  return c;
+}
+
+}  // namespace fsd

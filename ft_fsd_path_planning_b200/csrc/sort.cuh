@@ -1,0 +1,796 @@
+// Cone sorting for ONE frame by ONE warp (S1-S8 of SURVEY.md section 8a).
+//
+// Behaviour follows the reference's TraceSorter
+//   fsd_path_planning/sorting_cones/trace_sorter/core_trace_sorter.py:148-465   (seeds, per-side driver)
+//   .../adjacency_matrix.py:60-128, common.py:36-67                             (k-NN graph, reachability)
+//   .../end_configurations.py:108-520                                           (exhaustive search + filter)
+//   .../cost_function.py, cone_distance_cost.py, nearby_cone_search.py          (7-term cost)
+//   .../combine_traces.py:21-275                                                (left/right conflict)
+// but is laid out for a warp: the O(N^2) distance/k-NN step and all O(N) masks are lane-strided,
+// the per-pop admissibility test runs one candidate neighbour per lane, the sparse serial
+// decisions run on lane 0.  Pure sign / threshold tests on angles are evaluated on cosines and
+// cross products instead of atan2/acos (same predicate, no trigonometry); angles that enter sums
+// or are compared against each other keep atan2.
+#pragma once
+
+#include "lane.cuh"
+#include "plan_types.cuh"
+
+namespace fsd {
+
+constexpr int MAX_LEAVES = 64;
+constexpr int STACK_CAP = 64;  // depth <= 12, <= 5 pushes per level
+
+struct SortSmem {
+  d2 xy[FSD_MAX_CONES];
+  double dist[FSD_MAX_CONES];
+  double costs[MAX_LEAVES];
+  int16_t leaves[MAX_LEAVES][FSD_MAX_SORTED];
+  int16_t best[2][FSD_MAX_SORTED];
+  int16_t attempt[16];
+  int16_t idxs[FSD_MAX_CONES];   // cone indices used by any configuration (cost term)
+  int16_t close[FSD_MAX_CONES];  // nearby cones (cost term)
+  int32_t n_good[MAX_LEAVES], n_bad[MAX_LEAVES];
+  int32_t nbest[2];
+  int32_t scratch[8];
+  uint8_t type[FSD_MAX_CONES];
+  uint8_t knn[2][FSD_MAX_CONES][5];
+  uint8_t kcnt[2][FSD_MAX_CONES];
+  uint8_t nbr[2][FSD_MAX_CONES][5];
+  uint8_t deg[2][FSD_MAX_CONES];
+  uint8_t flag[FSD_MAX_CONES];  // seed mask / in-configuration mask
+  uint8_t flag2[FSD_MAX_CONES];
+  uint8_t stack_node[STACK_CAP], stack_pos[STACK_CAP];
+  uint8_t can[8];
+};
+
+// ---- k-NN graph: adjacency_matrix.py:60-110 ------------------------------------------------
+// Both sides in one sweep: the LEFT graph ignores yellow cones, the RIGHT graph ignores blue.
+
+FSD_DEV void top5_insert(double (&d)[5], int (&id)[5], double v, int j) {
+  if (!(v < d[4])) return;
+  d[4] = v;
+  id[4] = j;
+#pragma unroll
+  for (int q = 4; q > 0; --q) {
+    if (d[q] < d[q - 1]) {
+      double td = d[q];
+      d[q] = d[q - 1];
+      d[q - 1] = td;
+      int ti = id[q];
+      id[q] = id[q - 1];
+      id[q - 1] = ti;
+    }
+  }
+}
+
+FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
+  const double inf = INFINITY;
+  int k = n - 1 < P.max_n_neighbors ? n - 1 : P.max_n_neighbors;
+  if (k > 5) k = 5;
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+    double dl[5] = {inf, inf, inf, inf, inf}, dr[5] = {inf, inf, inf, inf, inf};
+    int il[5] = {0, 0, 0, 0, 0}, ir[5] = {0, 0, 0, 0, 0};
+    const double xi = S.xy[i].x, yi = S.xy[i].y;
+    const int ti = S.type[i];
+    const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
+    for (int j = 0; j < n; ++j) {
+      double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
+      double dd = ddx * ddx + ddy * ddy;
+      // edges longer than max_dist are removed after the k-NN selection (:102-107): a longer edge
+      // can never displace a shorter one, so it is dropped before the selection
+      if (dd > P.max_dist2 || j == i) continue;
+      int tj = S.type[j];
+      if (li && tj != FSD_CONE_RIGHT) top5_insert(dl, il, dd, j);
+      if (ri && tj != FSD_CONE_LEFT) top5_insert(dr, ir, dd, j);
+    }
+    int cl = 0, cr = 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      if (q < k && dl[q] < inf) {
+        S.knn[0][i][q] = (uint8_t)il[q];
+        cl = q + 1;
+      }
+      if (q < k && dr[q] < inf) {
+        S.knn[1][i][q] = (uint8_t)ir[q];
+        cr = q + 1;
+      }
+    }
+    S.kcnt[0][i] = (uint8_t)cl;
+    S.kcnt[1][i] = (uint8_t)cr;
+  }
+  wsync();
+  // keep edges present in both directions (:110); neighbour lists in ascending index order, the
+  // order np.where gives the CSR lists of end_configurations.py:28-71
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      int cnt = 0;
+      int tmp[5];
+      for (int q = 0; q < S.kcnt[s][i]; ++q) {
+        int j = S.knn[s][i][q];
+        bool back = false;
+        for (int r = 0; r < S.kcnt[s][j]; ++r) back |= S.knn[s][j][r] == i;
+        if (back) {
+          int p = cnt++;
+          while (p > 0 && tmp[p - 1] > j) {
+            tmp[p] = tmp[p - 1];
+            --p;
+          }
+          tmp[p] = j;
+        }
+      }
+      for (int q = 0; q < cnt; ++q) S.nbr[s][i][q] = (uint8_t)tmp[q];
+      S.deg[s][i] = (uint8_t)cnt;
+    }
+  }
+  wsync();
+}
+
+// ---- seeds: core_trace_sorter.py:344-465 ----------------------------------------------------
+
+FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int *fk) {
+  const int opp = side == FSD_CONE_LEFT ? FSD_CONE_RIGHT : FSD_CONE_LEFT;
+  const double dn = sqrt(F.dx * F.dx + F.dy * F.dy);
+  const double c = F.dx / dn, s = F.dy / dn;  // rotation by -yaw
+  const double major = P.max_dist_to_first * 1.5, minor = P.max_dist_to_first / 1.5;
+  const double cos_max = cos(PI - PI / 5.0), cos_min = cos(PI / 10.0);
+  double bv = 0.0;
+  int bi = -1;
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+    double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
+    double rx = px * c + py * s, ry = -px * s + py * c;
+    double r = sqrt(rx * rx + ry * ry);
+    S.dist[i] = r;
+    bool in_ellipse = (rx * rx / (major * major) + ry * ry / (minor * minor)) < 1.0;
+    // sign(bearing) == +-1, pi/10 < |bearing| < 4pi/5  (:395-399), on the cosine of the bearing
+    bool side_ok = side == FSD_CONE_LEFT ? ry > 0.0 : ry < 0.0;
+    double cb = rx / r;
+    bool ang_ok = cb > cos_max && cb < cos_min;
+    int t = S.type[i];
+    bool valid = in_ellipse && ((side_ok && ang_ok) || t == side) && t != opp;
+    S.flag[i] = valid ? 1 : 0;
+    S.flag2[i] = rx > 0.0 ? 1 : 0;  // in front of the car: |angle to heading| < pi/2 (:433)
+    if (valid && (bi < 0 || r < bv)) {
+      bv = r;
+      bi = i;
+    }
+  }
+  wargmin(bv, bi);
+  wsync();
+  if (bi < 0 || bv > P.max_dist_to_first) return 0;
+  int i1 = bi;
+  bv = 0.0;
+  bi = -1;
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+    if (!S.flag[i] || S.flag2[i] || i == i1) continue;
+    double r = S.dist[i];
+    if (bi < 0 || r < bv) {
+      bv = r;
+      bi = i;
+    }
+  }
+  wargmin(bv, bi);
+  wsync();
+  if (bi < 0 || bv > P.max_dist_to_first) {
+    fk[0] = i1;
+    return 1;
+  }
+  int i2 = bi;
+  double ex = S.xy[i1].x - S.xy[i2].x, ey = S.xy[i1].y - S.xy[i2].y;
+  // angle(c1 - c2, heading) > angle(c2 - c1, heading)  <=>  (c1 - c2) . heading < 0  (:450-457)
+  if (ex * F.dx + ey * F.dy < 0.0) {
+    int t = i1;
+    i1 = i2;
+    i2 = t;
+  }
+  double d = sqrt(ex * ex + ey * ey);
+  if (d > P.max_dist * 1.1 || d < 1.4) {
+    fk[0] = i1;
+    return 1;
+  }
+  fk[0] = i2;
+  fk[1] = i1;
+  return 2;
+}
+
+// ---- reachability: common.py:36-67; only min(#reachable, max_length) is used ----------------
+
+FSD_DEVFN int reachable_count(SortSmem &S, int n, int sidx, int start, int cap) {
+  if (fsd_lane() == 0) {
+    // flag2 doubles as the visited mask, idxs as the queue
+    for (int i = 0; i < n; ++i) S.flag2[i] = 0;
+    int head = 0, tail = 0;
+    S.idxs[tail++] = (int16_t)start;
+    S.flag2[start] = 1;
+    while (head < tail && tail < cap) {
+      int node = S.idxs[head++];
+      for (int q = 0; q < S.deg[sidx][node]; ++q) {
+        int j = S.nbr[sidx][node][q];
+        if (!S.flag2[j]) {
+          S.flag2[j] = 1;
+          S.idxs[tail++] = (int16_t)j;
+        }
+      }
+    }
+    S.scratch[0] = tail < cap ? tail : cap;
+  }
+  wsync();
+  int r = S.scratch[0];
+  wsync();
+  return r;
+}
+
+// ---- admissibility of one candidate: end_configurations.py:108-278 --------------------------
+
+FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, double b0x, double b0y, double b1x,
+                                double b1y) {
+  // lines_segments_intersect_indicator, line_segment_intersection.py:136-200
+  const double eps = 1e-6;
+  double lax = a0y - a1y, lay = a1x - a0x, laz = a0x * a1y - a0y * a1x;
+  double lbx = b0y - b1y, lby = b1x - b0x, lbz = b0x * b1y - b0y * b1x;
+  double ix = lay * lbz - laz * lby;
+  double iy = laz * lbx - lax * lbz;
+  double iz = lax * lby - lay * lbx;
+  if (fabs(iz) < eps) {
+    // parallel case :34-72 (`difference[0] < epsilon` has no abs in the reference)
+    double ddx = a1x - a0x, ddy = a1y - a0y;
+    bool overlap;
+    double slope;
+    if (ddx < eps) {
+      overlap = fabs(a0x - b0x) < eps;
+      slope = INFINITY;
+    } else {
+      slope = ddy / ddx;
+      overlap = fabs((a0y - slope * a0x) - (b0y - slope * b0x)) < eps;
+    }
+    if (!overlap) return false;
+    bool use_y = slope > 1.0;
+    double a0 = use_y ? a0y : a0x, a1 = use_y ? a1y : a1x, b0 = use_y ? b0y : b0x, b1 = use_y ? b1y : b1x;
+    double left_end, right_start;
+    if (a0 < b0) {
+      left_end = a1;
+      right_start = fmin(b0, b1);
+    } else {
+      left_end = b1;
+      right_start = fmin(a0, a1);
+    }
+    return left_end >= right_start;
+  }
+  double x = ix / iz, y = iy / iz;
+  return (fmin(a0x, a1x) - eps <= x && x <= fmax(a0x, a1x) + eps) &&
+         (fmin(b0x, b1x) - eps <= x && x <= fmax(b0x, b1x) + eps) &&
+         (fmin(a0y, a1y) - eps <= y && y <= fmax(a0y, a1y) + eps) &&
+         (fmin(b0y, b1y) - eps <= y && y <= fmax(b0y, b1y) + eps);
+}
+
+FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int sidx, int pos, int i,
+                            const DevParams &P) {
+  const int last = S.attempt[pos];
+  const uint8_t *nb = S.nbr[sidx][last];
+  const int nnb = S.deg[sidx][last];
+  const int cand = nb[i];
+  for (int q = 0; q <= pos; ++q)
+    if (S.attempt[q] == cand) return false;  // already in the attempt (:126)
+  const double lx = S.xy[last].x, ly = S.xy[last].y;
+  const double cx = S.xy[cand].x, cy = S.xy[cand].y;
+  const double bx = cx - lx, by = cy - ly;  // last -> candidate
+  double ax = 0.0, ay = 0.0;                // previous -> last
+  if (pos >= 1) {
+    const int prev = S.attempt[pos - 1];
+    ax = lx - S.xy[prev].x;
+    ay = ly - S.xy[prev].y;
+    // ellipse around `last`, major axis 6 m along (last - previous), minor 3 m (:281-300)
+    double an = sqrt(ax * ax + ay * ay);
+    double rx = (bx * ax + by * ay) / an, ry = (by * ax - bx * ay) / an;
+    if (!((rx * rx / 36.0 + ry * ry / 9.0) < 1.0)) return false;
+  } else {
+    // second cone of the attempt must lie on the expected side of the car, 5 deg tolerance (:260-278)
+    double vx = cx - F.px, vy = cy - F.py;
+    double cross = F.dx * vy - F.dy * vx;
+    bool expected = side == FSD_CONE_LEFT ? cross > 0.0 : cross < 0.0;
+    bool tolerance = cos_between(F.dx, F.dy, vx, vy) > P.cos_5deg;
+    if (!(expected || tolerance)) return false;
+  }
+  // another neighbour of `last` lying between `last` and the candidate (:226-257)
+  for (int q = 0; q < nnb; ++q) {
+    int o = nb[q];
+    if (o == cand) continue;
+    double v1x = lx - S.xy[o].x, v1y = ly - S.xy[o].y;
+    double v2x = cx - S.xy[o].x, v2y = cy - S.xy[o].y;
+    double d1 = v1x * v1x + v1y * v1y, d2 = v2x * v2x + v2y * v2y;
+    if (sqrt(d2) < 6.0 && sqrt(d1) < 6.0 && cos_between(v1x, v1y, v2x, v2y) < P.cos_150deg) return false;
+  }
+  if (pos >= 1) {
+    double angle_1 = atan2(ay, ax), angle_2 = atan2(by, bx);
+    double difference = angle_difference(angle_2, angle_1);
+    double len = sqrt(bx * bx + by * by);
+    bool ok;
+    if (fabs(difference) > P.thr_abs)
+      ok = false;
+    else if (side == FSD_CONE_LEFT)
+      ok = difference < P.thr_dir || len < 4.0;
+    else
+      ok = difference > -P.thr_dir || len < 4.0;
+    if (pos >= 2) {
+      const int prev = S.attempt[pos - 1], pp = S.attempt[pos - 2];
+      double angle_3 = atan2(S.xy[prev].y - S.xy[pp].y, S.xy[prev].x - S.xy[pp].x);
+      double difference_2 = angle_difference(angle_1, angle_3);
+      if (sgn(difference) != sgn(difference_2) && fabs(difference - difference_2) > 1.3) ok = false;
+    }
+    if (!ok) return false;
+  }
+  if (pos == 1) {
+    // angle(heading, candidate - first) < pi/2 (:207-211)
+    const int first = S.attempt[0];
+    if (!(cos_between(F.dx, F.dy, cx - S.xy[first].x, cy - S.xy[first].y) > 0.0)) return false;
+  }
+  // the new edge must not cross the car (:213-221)
+  double dn = sqrt(F.dx * F.dx + F.dy * F.dy);
+  double ux = F.dx / dn, uy = F.dy / dn;
+  double csx = F.px - ux * P.car_size / 2.0, csy = F.py - uy * P.car_size / 2.0;
+  double cex = F.px + ux * P.car_size, cey = F.py + uy * P.car_size;
+  return !segments_intersect(lx, ly, cx, cy, csx, csy, cex, cey);
+}
+
+// ---- exhaustive search: end_configurations.py:320-431 ----------------------------------------
+// returns the number of raw leaves in S.leaves (rows padded with -1 up to FSD_MAX_SORTED)
+
+FSD_DEVFN int find_leaves(SortSmem &S, const FramePose &F, int side, int sidx, const int *fk, int nfk, int L,
+                          const DevParams &P, int *pops_out, unsigned *status) {
+  const int lane = fsd_lane();
+  int sp = 0, n_leaves = 0, pops = 0;
+  if (lane == 0) {
+    for (int q = 0; q < 16; ++q) S.attempt[q] = -1;
+    if (nfk > 1) {
+      S.attempt[0] = (int16_t)fk[0];
+      S.stack_node[0] = (uint8_t)fk[1];
+      S.stack_pos[0] = 1;
+    } else {
+      S.stack_node[0] = (uint8_t)fk[0];
+      S.stack_pos[0] = 0;
+    }
+  }
+  wsync();
+  while (sp >= 0) {
+    if (++pops > P.max_dfs_pops) {
+      *status |= FSD_ST_OVERFLOW;
+      break;
+    }
+    const int node = S.stack_node[sp], pos = S.stack_pos[sp];
+    --sp;
+    wsync();
+    if (lane == 0) {
+      S.attempt[pos] = (int16_t)node;
+      for (int q = pos + 1; q < L; ++q) S.attempt[q] = -1;
+    }
+    wsync();
+    const int nnb = S.deg[sidx][node];
+    for (int i = lane; i < nnb; i += FSD_LANES) S.can[i] = can_be_added(S, F, side, sidx, pos, i, P) ? 1 : 0;
+    wsync();
+    int n_ok = 0;
+    for (int i = 0; i < nnb; ++i) n_ok += S.can[i];
+    if (pos < L - 1 && n_ok > 0) {
+      if (lane == 0) {
+        int w = sp;
+        for (int i = 0; i < nnb; ++i)
+          if (S.can[i] && w + 1 < STACK_CAP) {
+            ++w;
+            S.stack_node[w] = S.nbr[sidx][node][i];
+            S.stack_pos[w] = (uint8_t)(pos + 1);
+          }
+      }
+      sp += n_ok;
+      if (sp >= STACK_CAP) {
+        sp = STACK_CAP - 1;
+        *status |= FSD_ST_OVERFLOW;
+      }
+    } else {
+      if (n_leaves < MAX_LEAVES) {
+        if (lane == 0)
+          for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[n_leaves][q] = q < L ? S.attempt[q] : (int16_t)-1;
+        ++n_leaves;
+      } else {
+        *status |= FSD_ST_OVERFLOW;
+      }
+    }
+    wsync();
+  }
+  *pops_out = pops;
+  return n_leaves;
+}
+
+// ---- post-filter: end_configurations.py:484-518 (lane 0; a handful of rows) -------------------
+
+FSD_DEV int row_len(const int16_t *row) {
+  int n = 0;
+  for (int q = 0; q < FSD_MAX_SORTED; ++q) n += row[q] != -1;
+  return n;
+}
+
+FSD_DEV int row_cmp(const int16_t *a, const int16_t *b) {
+  for (int q = 0; q < FSD_MAX_SORTED; ++q)
+    if (a[q] != b[q]) return a[q] < b[q] ? -1 : 1;
+  return 0;
+}
+
+FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, int nfk) {
+  if (fsd_lane() == 0) {
+    int kept = 0;
+    for (int r = 0; r < n_leaves; ++r) {
+      int16_t *row = S.leaves[r];
+      int len = row_len(row);
+      if (len <= 2) continue;
+      bool ok = true;
+      if (nfk > 1)
+        for (int q = 0; q < nfk; ++q) ok &= row[q] == fk[q];
+      if (!ok) continue;
+      // a trailing cone that does not have the side's colour is dropped (:492-500)
+      if (S.type[row[len - 1]] != side) {
+        row[len - 1] = -1;
+        --len;
+      }
+      if (len < 3) continue;
+      // np.unique(axis=0): sorted insertion, duplicates skipped
+      int p = kept;
+      bool dup = false;
+      int16_t tmp[FSD_MAX_SORTED];
+      for (int q = 0; q < FSD_MAX_SORTED; ++q) tmp[q] = row[q];
+      while (p > 0) {
+        int c = row_cmp(S.leaves[p - 1], tmp);
+        if (c == 0) dup = true;
+        if (c <= 0) break;
+        --p;
+      }
+      if (dup) continue;
+      for (int m = kept; m > p; --m)
+        for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[m][q] = S.leaves[m - 1][q];
+      for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[p][q] = tmp[q];
+      ++kept;
+    }
+    // rows that are a strict prefix of another row are removed (:509-515)
+    int out = 0;
+    for (int j = 0; j < kept; ++j) {
+      int covered = 0;
+      for (int i = 0; i < kept; ++i) {
+        bool all = true;
+        for (int q = 0; q < FSD_MAX_SORTED; ++q) all &= (S.leaves[i][q] == S.leaves[j][q]) || (S.leaves[j][q] == -1);
+        covered += all;
+      }
+      S.flag2[j] = covered > 1 ? 1 : 0;
+    }
+    for (int j = 0; j < kept; ++j)
+      if (!S.flag2[j]) {
+        if (out != j)
+          for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[out][q] = S.leaves[j][q];
+        ++out;
+      }
+    S.scratch[0] = out;
+  }
+  wsync();
+  int c = S.scratch[0];
+  wsync();
+  return c;
+}
+
+// NOTE on the unique step above: rows kept so far are sorted; the incoming row may alias a slot
+// that is about to be overwritten (r >= kept always holds, and slots < kept are only shifted up to
+// index kept <= r), so it is copied to `tmp` first.
+
+// ---- cost: cost_function.py:213-304 -------------------------------------------------------------
+
+FSD_DEV void search_dir(const SortSmem &S, int a, int b, int side, double &ox, double &oy) {
+  // normal of the track direction, +90 deg for RIGHT / -90 deg for LEFT (match_directions.py:7-20)
+  double tx = S.xy[b].x - S.xy[a].x, ty = S.xy[b].y - S.xy[a].y;
+  double rx = side == FSD_CONE_RIGHT ? -ty : ty, ry = side == FSD_CONE_RIGHT ? tx : -tx;
+  double nrm = sqrt(rx * rx + ry * ry);
+  ox = rx / nrm;
+  oy = ry / nrm;
+}
+
+// lane-strided stream compaction of the indices i < n with flag[i] != 0 (ascending order)
+FSD_DEVFN int compact_flags(const uint8_t *flag, int n, int16_t *out) {
+  int count = 0;
+  const int lane = fsd_lane();
+  for (int base = 0; base < n; base += FSD_LANES) {
+    int i = base + lane;
+    bool p = i < n && flag[i];
+    unsigned m = wballot(p);
+    if (p) out[count + FSD_POPC(m & ((1u << lane) - 1u))] = (int16_t)i;
+    count += FSD_POPC(m);
+  }
+  wsync();
+  return count;
+}
+
+FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
+  // nearby_cone_search.py:212-297, search distance 6 m, search angle 120 deg
+  const int lane = fsd_lane();
+  const double range2 = 36.0;
+  for (int i = lane; i < n; i += FSD_LANES) S.flag[i] = 0;
+  wsync();
+  if (lane == 0)
+    for (int r = 0; r < C; ++r)
+      for (int q = 0; q < FSD_MAX_SORTED; ++q)
+        if (S.leaves[r][q] != -1) S.flag[S.leaves[r][q]] = 1;
+  wsync();
+  int nidx = compact_flags(S.flag, n, S.idxs);
+  // cones within 6 m of any configuration cone (:97-103)
+  for (int j = lane; j < n; j += FSD_LANES) {
+    bool near = false;
+    for (int q = 0; q < nidx && !near; ++q) {
+      int i = S.idxs[q];
+      if (i == j) continue;
+      double ddx = S.xy[i].x - S.xy[j].x, ddy = S.xy[i].y - S.xy[j].y;
+      near = ddx * ddx + ddy * ddy < range2;
+    }
+    S.flag2[j] = near ? 1 : 0;
+  }
+  wsync();
+  // `close` first holds all nearby cones, then loses the entries hit by the reference's
+  // sorted_set_diff (:88-94): mask[searchsorted(all, idxs)] = False, no membership test
+  int nall = compact_flags(S.flag2, n, S.close);
+  for (int j = lane; j < n; j += FSD_LANES) S.flag2[j] = 0;
+  wsync();
+  for (int q = lane; q < nidx; q += FSD_LANES) {
+    int v = S.idxs[q], lo = 0, hi = nall;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (S.close[mid] < v)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo < nall) S.flag2[S.close[lo]] = 1;  // removed
+  }
+  wsync();
+  for (int r = 0; r < C; ++r) {
+    const int16_t *c = S.leaves[r];
+    int len = row_len(c);
+    int good = 0, bad = 0;
+    for (int j = 0; j < len; ++j) {
+      double sx, sy;
+      if (j == 0)
+        search_dir(S, c[0], c[1], side, sx, sy);
+      else if (j == len - 1)
+        search_dir(S, c[j - 1], c[j], side, sx, sy);
+      else
+        search_dir(S, c[j - 1], c[j + 1], side, sx, sy);
+      const int cj = c[j];
+      const double x0 = S.xy[cj].x, y0 = S.xy[cj].y;
+      // other = close (minus removed) ++ configuration cones of OTHER configurations
+      for (int q = lane; q < nall + nidx; q += FSD_LANES) {
+        int o;
+        if (q < nall) {
+          o = S.close[q];
+          if (S.flag2[o]) continue;
+        } else {
+          o = S.idxs[q - nall];
+          bool member = false;
+          for (int w = 0; w < len; ++w) member |= c[w] == o;
+          if (member) continue;
+        }
+        if (o == cj) continue;
+        double vx = S.xy[o].x - x0, vy = S.xy[o].y - y0;
+        if (!(vx * vx + vy * vy < range2)) continue;
+        double cb = cos_between(vx, vy, sx, sy);
+        good += cb > 0.5;   // angle to the search direction < 60 deg
+        bad += -cb > 0.5;   // angle to the opposite direction < 60 deg
+      }
+    }
+    good = wsum_i(good);
+    bad = wsum_i(bad);
+    if (lane == 0) {
+      S.n_good[r] = good;
+      S.n_bad[r] = bad;
+    }
+  }
+  wsync();
+}
+
+FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const FramePose &F) {
+  if (C == 1) return 0;
+  cones_on_either_side(S, n, C, side);
+  const double w[7] = {1000.0, 200.0, 5000.0, 1000.0, 0.0, 1000.0, 1000.0};
+  const double wsum_ = 9200.0;
+  int mn = 0;
+  for (int r = 0; r < C; ++r) {
+    int d = S.n_good[r] - S.n_bad[r];
+    if (r == 0 || d < mn) mn = d;
+  }
+  for (int r = fsd_lane(); r < C; r += FSD_LANES) {
+    const int16_t *c = S.leaves[r];
+    const int len = row_len(c);
+    double px[FSD_MAX_SORTED], py[FSD_MAX_SORTED];
+    for (int q = 0; q < len; ++q) {
+      px[q] = S.xy[c[q]].x;
+      py[q] = S.xy[c[q]].y;
+    }
+    // angle cost (:41-79): mean of (pi - theta)/pi over interior angles, times (1 + #{theta < 40 deg})
+    double asum = 0.0;
+    int under = 0;
+    for (int q = 0; q + 2 < len; ++q) {
+      double th = acos(cos_between(px[q + 1] - px[q + 2], py[q + 1] - py[q + 2], px[q + 1] - px[q], py[q + 1] - py[q]));
+      asum += (PI - th) / PI;
+      under += th < 40.0 * PI / 180.0;
+    }
+    double angle_cost = asum / (double)(len - 2) * (double)(under + 1);
+    // residual distance (cone_distance_cost.py:14-32)
+    double resid = 0.0;
+    for (int q = 0; q + 1 < len; ++q) {
+      double ddx = px[q + 1] - px[q], ddy = py[q + 1] - py[q];
+      double d = sqrt(ddx * ddx + ddy * ddy) - 3.0;
+      resid += d > 0.0 ? d : 0.0;
+    }
+    double ncones = 1.0 / (double)len;
+    double init_dir = acos(cos_between(px[1] - px[0], py[1] - py[0], F.dx, F.dy));
+    double either = 1.0 / (double)(S.n_good[r] - S.n_bad[r] + (mn < 0 ? -mn : mn) + 1);
+    // wrong direction (:149-188)
+    double wrong = 0.0;
+    if (len != 3) {
+      double unwanted = side == FSD_CONE_LEFT ? 1.0 : -1.0, sum = 0.0;
+      double prev = atan2(py[1] - py[0], px[1] - px[0]);
+      for (int q = 1; q + 1 < len; ++q) {
+        double cur = atan2(py[q + 1] - py[q], px[q + 1] - px[q]);
+        double d = angle_difference(prev, cur);
+        if (sgn(d) == unwanted && fabs(d) > 40.0 * PI / 180.0) sum += d;
+        prev = cur;
+      }
+      wrong = fabs(sum);
+    }
+    double terms[7] = {angle_cost, resid, ncones, init_dir, 0.0, either, wrong};
+    double total = 0.0;
+    for (int q = 0; q < 7; ++q) total += terms[q] * (w[q] / wsum_);
+    S.costs[r] = total;
+  }
+  wsync();
+  int arg = 0;
+  for (int r = 1; r < C; ++r)
+    if (S.costs[r] < S.costs[arg]) arg = r;
+  wsync();
+  return arg;
+}
+
+// ---- one side: core_trace_sorter.py:252-327 -----------------------------------------------------
+
+FSD_DEVFN int sort_one_side(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int16_t *dbg,
+                            unsigned *status) {
+  const int sidx = side == FSD_CONE_LEFT ? 0 : 1;
+  int fk[2] = {-1, -1};
+  int len = 0, n_cfg = 0, pops = 0;
+  int nfk = n < 3 ? 0 : select_first_k(S, n, F, side, P, fk);
+  if (nfk > 0) {
+    int R = reachable_count(S, n, sidx, fk[0], P.max_length);
+    int L = R < P.max_length ? R : P.max_length;  // find_configs_and_scores.py:76
+    if (L >= 3) {
+      int n_leaves = find_leaves(S, F, side, sidx, fk, nfk, L, P, &pops, status);
+      n_cfg = post_filter(S, n_leaves, side, fk, nfk);
+      if (n_cfg > 0) {
+        int arg = best_configuration(S, n, n_cfg, side, F);
+        len = row_len(S.leaves[arg]);
+        if (fsd_lane() == 0)
+          for (int q = 0; q < FSD_MAX_SORTED; ++q) S.best[sidx][q] = S.leaves[arg][q];
+        wsync();
+      }
+    }
+  }
+  if (dbg && fsd_lane() == 0) {
+    dbg[2 * sidx] = (int16_t)fk[0];
+    dbg[2 * sidx + 1] = (int16_t)(nfk > 1 ? fk[1] : -1);
+    dbg[4 + sidx] = (int16_t)n_cfg;
+    dbg[6 + sidx] = (int16_t)(pops > 32767 ? 32767 : pops);
+  }
+  return len;
+}
+
+// ---- left/right conflict: combine_traces.py:115-257 (lane 0) --------------------------------------
+
+FSD_DEV double angle_change_at(const SortSmem &S, const int16_t *cfg, int p) {
+  int a = cfg[p - 1], b = cfg[p], c = cfg[p + 1];
+  double an = atan2(S.xy[c].y - S.xy[b].y, S.xy[c].x - S.xy[b].x);
+  double ap = atan2(S.xy[a].y - S.xy[b].y, S.xy[a].x - S.xy[b].x);
+  return angle_difference(an, ap);
+}
+
+FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
+  const int16_t *left = S.best[0], *right = S.best[1];
+  int li = -1, ri = -1;
+  for (int a = 0; a < nl && li < 0; ++a)
+    for (int b = 0; b < nr; ++b)
+      if (left[a] == right[b]) {
+        li = a;
+        break;
+      }
+  if (li < 0) return;
+  for (int b = 0; b < nr && ri < 0; ++b)
+    for (int a = 0; a < nl; ++a)
+      if (left[a] == right[b]) {
+        ri = b;
+        break;
+      }
+  int ls = -1, rs = -1;
+  bool have = false;
+  if (li > 0 && ri > 0) {
+    int pl = left[li - 1], pr = right[ri - 1], ic = left[li];
+    double dlx = S.xy[ic].x - S.xy[pl].x, dly = S.xy[ic].y - S.xy[pl].y;
+    double drx = S.xy[ic].x - S.xy[pr].x, dry = S.xy[ic].y - S.xy[pr].y;
+    bool l_low = sqrt(dlx * dlx + dly * dly) < 3.0, r_low = sqrt(drx * drx + dry * dry) < 3.0;
+    if ((l_low || r_low) && !(l_low && r_low)) {
+      have = true;
+      if (l_low) {
+        ls = nl;
+        rs = ri;
+      } else {
+        ls = li;
+        rs = nr;
+      }
+    }
+  }
+  if (!have && left[li] == right[ri] && li >= 1 && li <= nl - 2 && ri >= 1 && ri <= nr - 2) {
+    double al = angle_change_at(S, left, li), ar = angle_change_at(S, right, ri);
+    double sl = sgn(al), sr = sgn(ar);
+    int ndiff = nl > nr ? nl - nr : nr - nl;
+    bool prefer_left;
+    bool both = false;
+    if (sl == sr)
+      prefer_left = sl == 1.0;
+    else if (ndiff > 2)
+      prefer_left = nl > nr;
+    else if (fabs(fabs(al) - fabs(ar)) > 5.0 * PI / 180.0)
+      prefer_left = fabs(al) > fabs(ar);
+    else {
+      both = true;
+      prefer_left = false;
+    }
+    if (both) {
+      ls = li;
+      rs = ri;
+    } else if (prefer_left) {
+      ls = nl;
+      rs = ri;
+    } else {
+      ls = li;
+      rs = nr;
+    }
+  } else if (!have) {
+    bool l_end = li == nl - 1, r_end = ri == nr - 1;
+    if (l_end && r_end) {
+      ls = nl - 1;
+      rs = nr - 1;
+    } else if (l_end) {
+      rs = nr;
+      ls = li;
+    } else if (r_end) {
+      ls = nl;
+      rs = ri;
+    } else {
+      ls = li;
+      rs = ri;
+    }
+  }
+  nl = ls;
+  nr = rs;
+}
+
+// ---- whole frame: TraceSorter.sort_left_right, core_trace_sorter.py:148-216 -----------------------
+// S.xy / S.type must hold the frame's n cones.  On return S.best[0..1] / S.nbest hold the sort indices.
+
+FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg) {
+  unsigned status = 0;
+  if (n >= 3) build_knn(S, n, P);
+  int nl = sort_one_side(S, n, F, FSD_CONE_LEFT, P, dbg, &status);
+  int nr = sort_one_side(S, n, F, FSD_CONE_RIGHT, P, dbg, &status);
+  if (nl == 0) status |= FSD_ST_NO_LEFT;
+  if (nr == 0) status |= FSD_ST_NO_RIGHT;
+  if (nl > 0 && nr > 0) combine_sides(S, nl, nr);
+  if (fsd_lane() == 0) {
+    for (int q = nl; q < FSD_MAX_SORTED; ++q) S.best[0][q] = -1;
+    for (int q = nr; q < FSD_MAX_SORTED; ++q) S.best[1][q] = -1;
+    S.nbest[0] = nl;
+    S.nbest[1] = nr;
+  }
+  wsync();
+  return status;
+}
+
+}  // namespace fsd

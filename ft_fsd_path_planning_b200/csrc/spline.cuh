@@ -1,0 +1,489 @@
+// Smoothing-spline curve fit (the reference's scipy.interpolate.splprep / splev call sites,
+// fsd_path_planning/utils/spline_fit.py:46-128) for ONE frame by ONE warp.
+//
+// Same fit as Dierckx' FITPACK parcur/fppara (knot strategy, smoothing-parameter iteration and
+// acceptance tests follow SURVEY.md Appendix A step by step), but the linear algebra is laid out
+// for a warp instead of FITPACK's row-by-row Givens sweep over the m data points:
+//
+//   * least-squares spline for a knot set:   N = B^T B  (banded, half-bandwidth k),  r = B^T x,
+//     assembled lane-parallel over the data points, one knot interval at a time (all points of an
+//     interval touch the same (k+1)^2 block), then ONE banded Cholesky N = G^T G of the tiny
+//     (n-k-1)^2 system.  G equals FITPACK's triangular factor (positive diagonal), so
+//     p0 = nk1 / sum(diag G) and every later decision see the same numbers up to rounding;
+//   * smoothing step F(p) = s:   (N + D^T D / p^2) c = r  with D the discontinuity-jump matrix
+//     (fpdisc), again one banded Cholesky per p, and a lane-parallel residual sweep for F(p).
+//
+// Conditioning measured on the reference's call sites: cond(G) <= 12, cond([G; D/p]) <= 22, so
+// the normal equations lose nothing at fp64 (knot vectors identical to scipy's, coefficients to
+// 4e-13 on 260 call-site fits; tests/test_hostcheck.py and tests/test_gpu_parity.py repeat this).
+#pragma once
+
+#include "lane.cuh"
+#include "plan_types.cuh"
+
+namespace fsd {
+
+constexpr int NCAP = 40;  // knots handled per fit (the reference's own data stays below 20)
+constexpr int BW = 5;     // k + 2 for cubic splines
+
+struct SplineWork {
+  double t[NCAP];
+  double N[NCAP][BW];
+  double G[NCAP][BW];
+  double DtD[NCAP][BW];
+  double bd[NCAP][BW];
+  double rhs[NCAP][2];
+  double z[NCAP][2];
+  double c[NCAP][2];
+  double fpint[NCAP];
+  int32_t nrdata[NCAP];
+  int32_t start[NCAP + 1];
+  int32_t n, k;   // result: knot count, degree
+  double max_u;   // last parameter value of the fitted data
+};
+
+// B-spline basis values of degree k at x for the knot interval t[l] <= x < t[l+1] (0-based l)
+FSD_DEV void bspl(const double *t, int k, double x, int l, double *h) {
+  double hh[4];
+  h[0] = 1.0;
+  for (int j = 1; j <= k; ++j) {
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+    for (int i = 1; i <= j; ++i) {
+      double tl = t[l + i], tr = t[l + i - j];
+      if (tl == tr) {
+        h[i] = 0.0;
+      } else {
+        double f = hh[i - 1] / (tl - tr);
+        h[i - 1] += f * (tl - x);
+        h[i] = f * (x - tr);
+      }
+    }
+  }
+}
+
+FSD_DEV void spline_point(const SplineWork &W, double x, double &ox, double &oy) {
+  // splev with ext=0: the end polynomial pieces extrapolate
+  const int k = W.k, nk1 = W.n - k - 1;
+  int l = k;
+  while (l < nk1 - 1 && x >= W.t[l + 1]) ++l;
+  double h[4];
+  bspl(W.t, k, x, l, h);
+  double sx = 0.0, sy = 0.0;
+  for (int j = 0; j <= k; ++j) {
+    sx += W.c[l - k + j][0] * h[j];
+    sy += W.c[l - k + j][1] * h[j];
+  }
+  ox = sx;
+  oy = sy;
+}
+
+// banded Cholesky (upper, in place in M), forward and back substitution; lane 0 only.
+// returns false on a non-positive pivot.
+FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2]) {
+  for (int i = 0; i < nk1; ++i) {
+    for (int d = 0; d < kb; ++d) {
+      int j = i + d;
+      if (j >= nk1) break;
+      double s = M[i][d];
+      int p0 = j - kb + 1;
+      if (p0 < 0) p0 = 0;
+      for (int p = p0; p < i; ++p) s -= M[p][i - p] * M[p][j - p];
+      if (d == 0) {
+        if (!(s > 0.0)) return false;
+        M[i][0] = sqrt(s);
+      } else {
+        M[i][d] = s / M[i][0];
+      }
+    }
+  }
+  for (int i = 0; i < nk1; ++i) {
+    double s0 = rhs[i][0], s1 = rhs[i][1];
+    int p0 = i - kb + 1;
+    if (p0 < 0) p0 = 0;
+    for (int p = p0; p < i; ++p) {
+      double g = M[p][i - p];
+      s0 -= g * z[p][0];
+      s1 -= g * z[p][1];
+    }
+    z[i][0] = s0 / M[i][0];
+    z[i][1] = s1 / M[i][0];
+  }
+  for (int i = nk1 - 1; i >= 0; --i) {
+    double s0 = z[i][0], s1 = z[i][1];
+    int l1 = nk1 - 1 - i;
+    if (l1 > kb - 1) l1 = kb - 1;
+    for (int l = 1; l <= l1; ++l) {
+      double g = M[i][l];
+      s0 -= g * c[i + l][0];
+      s1 -= g * c[i + l][1];
+    }
+    c[i][0] = s0 / M[i][0];
+    c[i][1] = s1 / M[i][0];
+  }
+  return true;
+}
+
+// first data index of every knot interval: start[ii] = first i with u[i] >= t[k + ii]
+FSD_DEVFN void interval_starts(SplineWork &W, const double *u, int m, int n, int k) {
+  const int nrint = n - 2 * k - 1;
+  for (int ii = fsd_lane(); ii <= nrint; ii += FSD_LANES) {
+    int v;
+    if (ii == 0)
+      v = 0;
+    else if (ii == nrint)
+      v = m;
+    else {
+      double tk = W.t[k + ii];
+      int lo = 0, hi = m;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (u[mid] < tk)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      v = lo;
+    }
+    W.start[ii] = v;
+  }
+  wsync();
+}
+
+// N = B^T B and r = B^T x for the current knots (k == 3 uses all 4 x 4 entries; lower degrees fewer)
+FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, int n, int k) {
+  const int lane = fsd_lane();
+  const int nk1 = n - k - 1, nrint = n - 2 * k - 1, k1 = k + 1;
+  for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.N[0][0])[i] = 0.0;
+  for (int i = lane; i < nk1 * 2; i += FSD_LANES) (&W.rhs[0][0])[i] = 0.0;
+  wsync();
+  for (int ii = 0; ii < nrint; ++ii) {
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double rx[4] = {0, 0, 0, 0}, ry[4] = {0, 0, 0, 0};
+    const int lo = W.start[ii], hi = W.start[ii + 1];
+    for (int i = lo + lane; i < hi; i += FSD_LANES) {
+      double h[4] = {0, 0, 0, 0};
+      bspl(W.t, k, u[i], k + ii, h);
+      const double x = pts[i].x, y = pts[i].y;
+      int e = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = a; b < 4; ++b) acc[e++] += h[a] * h[b];
+        rx[a] += h[a] * x;
+        ry[a] += h[a] * y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 10; ++e) acc[e] = wsum(acc[e]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      rx[a] = wsum(rx[a]);
+      ry[a] = wsum(ry[a]);
+    }
+    if (lane == 0) {
+      int e = 0;
+      for (int a = 0; a < 4; ++a) {
+        for (int b = a; b < 4; ++b) {
+          if (b < k1) W.N[ii + a][b - a] += acc[e];
+          ++e;
+        }
+        if (a < k1) {
+          W.rhs[ii + a][0] += rx[a];
+          W.rhs[ii + a][1] += ry[a];
+        }
+      }
+    }
+    wsync();
+  }
+}
+
+// squared residuals: fp (returned) and, when `per_interval`, fpint[] with FITPACK's half/half split
+// of a data point that coincides with a knot (fppara's residual walk)
+FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n, int k, bool per_interval) {
+  const int lane = fsd_lane();
+  const int nrint = n - 2 * k - 1;
+  double fp = 0.0;
+  for (int ii = 0; ii < nrint; ++ii) {
+    const int lo = W.start[ii], hi = W.start[ii + 1];
+    const int last = ii < nrint - 1 ? hi : hi - 1;  // the next interval's first point is shared
+    double part = 0.0, full = 0.0;
+    for (int i = lo + lane; i <= last; i += FSD_LANES) {
+      const int li = i >= hi ? ii + 1 : ii;
+      double h[4] = {0, 0, 0, 0};
+      bspl(W.t, k, u[i], k + li, h);
+      double sx = 0.0, sy = 0.0;
+      for (int j = 0; j <= k; ++j) {
+        sx += W.c[li + j][0] * h[j];
+        sy += W.c[li + j][1] * h[j];
+      }
+      double ex = sx - pts[i].x, ey = sy - pts[i].y;
+      double term = ex * ex + ey * ey;
+      double wgt = ((i == lo && ii > 0) || i >= hi) ? 0.5 : 1.0;
+      part += wgt * term;
+      if (i < hi) full += term;
+    }
+    part = wsum(part);
+    full = wsum(full);
+    fp += full;
+    if (per_interval && lane == 0) W.fpint[ii] = part;
+  }
+  wsync();
+  return fp;
+}
+
+// fpknot: split the interval with the largest residual at its middle data point (lane 0)
+FSD_DEV void add_knot(SplineWork &W, const double *u, int n, int nrint) {
+  const int k = (n - nrint - 1) / 2;
+  double fpmax = 0.0;
+  int jbegin = 1, number = 1, maxpt = 0, maxbeg = 1;
+  for (int j = 1; j <= nrint; ++j) {
+    int jpoint = W.nrdata[j - 1];
+    if (!(fpmax >= W.fpint[j - 1] || jpoint == 0)) {
+      fpmax = W.fpint[j - 1];
+      number = j;
+      maxpt = jpoint;
+      maxbeg = jbegin;
+    }
+    jbegin += jpoint + 1;
+  }
+  const int ihalf = maxpt / 2 + 1, nrx = maxbeg + ihalf, next = number + 1;
+  for (int j = nrint; j >= next; --j) {
+    W.fpint[j] = W.fpint[j - 1];
+    W.nrdata[j] = W.nrdata[j - 1];
+    W.t[j + k] = W.t[j + k - 1];
+  }
+  W.nrdata[number - 1] = ihalf - 1;
+  W.nrdata[next - 1] = maxpt - ihalf;
+  const double am = maxpt > 0 ? (double)maxpt : 1.0;
+  W.fpint[number - 1] = fpmax * (double)W.nrdata[number - 1] / am;
+  W.fpint[next - 1] = fpmax * (double)W.nrdata[next - 1] / am;
+  W.t[next + k - 1] = u[nrx - 1];
+}
+
+// discontinuity jumps of the k-th derivative at the interior knots (fpdisc), rows lane-strided
+FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
+  const int k1 = k + 1, k2 = k + 2, nk1 = n - k1, nrint = nk1 - k;
+  const double fac = (double)nrint / (W.t[nk1] - W.t[k]);
+  for (int l = k2 + fsd_lane(); l <= nk1; l += FSD_LANES) {  // 1-based row index of FITPACK
+    const int lmk = l - k1;
+    double h[10];
+    for (int j = 1; j <= k1; ++j) {
+      h[j - 1] = W.t[l - 1] - W.t[l + j - k2 - 1];
+      h[j + k1 - 1] = W.t[l - 1] - W.t[l + j - 1];
+    }
+    int lp = lmk;
+    for (int j = 1; j <= k2; ++j) {
+      int jk = j;
+      double prod = h[j - 1];
+      for (int i = 1; i <= k; ++i) {
+        ++jk;
+        prod = prod * h[jk - 1] * fac;
+      }
+      W.bd[lmk - 1][j - 1] = (W.t[lp + k1 - 1] - W.t[lp - 1]) / prod;
+      ++lp;
+    }
+  }
+  wsync();
+}
+
+// The fit.  pts/u: m data points and their (strictly increasing) parameters.  Result in W.t, W.c,
+// W.n, W.k, W.max_u.  Returns FITPACK's ier (10 = invalid input, the reference's ValueError).
+FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, double s, unsigned *status) {
+  const int lane = fsd_lane();
+  const int k = m - 1 < 1 ? 1 : (m - 1 > 3 ? 3 : m - 1);
+  const int k1 = k + 1, k2 = k + 2, nmin = 2 * k1;
+  int nest = m + 2 * k;
+  const int nmax = m + k1;
+  if (m < 2) return 10;
+  // u strictly increasing (parcur's input check)
+  int bad = 0;
+  for (int i = 1 + lane; i < m; i += FSD_LANES) bad |= !(u[i - 1] < u[i]);
+  if (wany(bad != 0)) return 10;
+  const double tol = 1e-3, acc = tol * s;
+  const double ub = u[0], ue = u[m - 1];
+  bool capped = false;
+  if (nest > NCAP) {
+    nest = NCAP;
+    capped = true;
+  }
+  int n = nmin, nplus = 0, ier = 0, nk1 = 0;
+  double fp = 0.0, fpold = 0.0, fp0 = 0.0, fpms = 0.0;
+  if (lane == 0) W.nrdata[0] = m - 2;
+  W.k = k;
+  W.max_u = ue;
+  bool done = false, part2 = false;
+  for (int iter = 1; iter <= m; ++iter) {
+    if (n == nmin) ier = -2;
+    int nrint = n - nmin + 1;
+    nk1 = n - k1;
+    if (lane == 0)
+      for (int j = 0; j < k1; ++j) {
+        W.t[j] = ub;
+        W.t[n - 1 - j] = ue;
+      }
+    wsync();
+    interval_starts(W, u, m, n, k);
+    assemble_normal(W, pts, u, n, k);
+    if (lane == 0) {
+      for (int i = 0; i < nk1; ++i)
+        for (int d = 0; d < BW; ++d) W.G[i][d] = W.N[i][d];
+      bool ok = chol_solve(W.G, nk1, k1, W.rhs, W.z, W.c);
+      W.start[NCAP] = ok ? 1 : 0;
+    }
+    wsync();
+    if (!W.start[NCAP]) {
+      *status |= FSD_ST_UNSUPPORTED;
+      return 10;
+    }
+    fp = residuals(W, pts, u, n, k, true);
+    if (ier == -2) fp0 = fp;
+    if (lane == 0) {
+      W.fpint[n - 1] = fp0;
+      W.fpint[n - 2] = fpold;
+      W.nrdata[n - 1] = nplus;
+    }
+    fpms = fp - s;
+    if (fabs(fpms) < acc) {
+      done = true;
+      break;
+    }
+    if (fpms < 0.0) {
+      part2 = true;
+      break;
+    }
+    if (n == nmax) {
+      ier = -1;
+      done = true;
+      break;
+    }
+    if (n == nest) {
+      ier = 1;
+      if (capped) *status |= FSD_ST_OVERFLOW;
+      done = true;
+      break;
+    }
+    if (ier == 0) {
+      int npl1 = nplus * 2;
+      double rn = (double)nplus;
+      if (fpold - fp > acc) npl1 = (int)(rn * fpms / (fpold - fp));
+      int mx = npl1 > nplus / 2 ? npl1 : nplus / 2;
+      if (mx < 1) mx = 1;
+      nplus = nplus * 2 < mx ? nplus * 2 : mx;
+    } else {
+      nplus = 1;
+      ier = 0;
+    }
+    fpold = fp;
+    wsync();
+    for (int l = 1; l <= nplus; ++l) {
+      if (lane == 0) add_knot(W, u, n, nrint);
+      ++n;
+      ++nrint;
+      if (n == nmax) {
+        // every data abscissa becomes a knot (interpolating curve); k is odd whenever interior knots exist
+        if (lane == 0) {
+          const int k3 = k / 2;
+          int i = k2, j = k3 + 2;
+          for (int l2 = 0; l2 < m - k1; ++l2) {
+            W.t[i - 1] = (k3 * 2 != k) ? u[j - 1] : (u[j - 1] + u[j - 2]) * 0.5;
+            ++i;
+            ++j;
+          }
+        }
+        break;
+      }
+      if (n == nest) break;
+    }
+    wsync();
+  }
+  (void)done;
+  if (part2 && ier != -2) {
+    // smoothing parameter p with F(p) = s
+    disc_jumps(W, n, k);
+    const int n8 = n - nmin;
+    if (lane == 0) {
+      for (int i = 0; i < nk1; ++i)
+        for (int d = 0; d < BW; ++d) W.DtD[i][d] = 0.0;
+      for (int r = 0; r < n8; ++r)
+        for (int a = 0; a < k2 && r + a < nk1; ++a)
+          for (int b = a; b < k2 && r + b < nk1; ++b) W.DtD[r + a][b - a] += W.bd[r][a] * W.bd[r][b];
+    }
+    wsync();
+    double p1 = 0.0, f1 = fp0 - s, p3 = -1.0, f3 = fpms, p = 0.0;
+    for (int i = 0; i < nk1; ++i) p += W.G[i][0];
+    p = (double)nk1 / p;
+    wsync();
+    int ich1 = 0, ich3 = 0;
+    const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
+    for (int iter = 1; iter <= 20; ++iter) {
+      const double pinv2 = (1.0 / p) * (1.0 / p);
+      for (int i = lane; i < nk1 * BW; i += FSD_LANES)
+        (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
+      wsync();
+      if (lane == 0) W.start[NCAP] = chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c) ? 1 : 0;
+      wsync();
+      if (!W.start[NCAP]) {
+        *status |= FSD_ST_UNSUPPORTED;
+        return 10;
+      }
+      fp = residuals(W, pts, u, n, k, false);
+      fpms = fp - s;
+      if (fabs(fpms) < acc) {
+        ier = 0;
+        break;
+      }
+      if (iter == 20) {
+        ier = 3;
+        break;
+      }
+      const double p2 = p, f2 = fpms;
+      if (ich3 == 0) {
+        if (!((f2 - f3) > acc)) {
+          p3 = p2;
+          f3 = f2;
+          p = p * con4;
+          if (p <= p1) p = p1 * con9 + p2 * con1;
+          continue;
+        }
+        if (f2 < 0.0) ich3 = 1;
+      }
+      if (ich1 == 0) {
+        if (!((f1 - f2) > acc)) {
+          p1 = p2;
+          f1 = f2;
+          p = p / con4;
+          if (p3 < 0.0) continue;
+          if (p >= p3) p = p2 * con1 + p3 * con9;
+          continue;
+        }
+        if (f2 > 0.0) ich1 = 1;
+      }
+      if (f2 >= f1 || f2 <= f3) {
+        ier = 2;
+        break;
+      }
+      // fprati: rational interpolation through (p1,f1), (p2,f2), (p3,f3)
+      double pn;
+      if (p3 > 0.0) {
+        double h1 = f1 * (f2 - f3), h2 = f2 * (f3 - f1), h3 = f3 * (f1 - f2);
+        pn = -(p1 * p2 * h3 + p2 * p3 * h1 + p3 * p1 * h2) / (p1 * h1 + p2 * h2 + p3 * h3);
+      } else {
+        pn = (p1 * (f1 - f3) * f2 - p2 * (f2 - f3) * f1) / ((f1 - f2) * f3);
+      }
+      if (f2 < 0.0) {
+        p3 = p2;
+        f3 = f2;
+      } else {
+        p1 = p2;
+        f1 = f2;
+      }
+      p = pn;
+    }
+  }
+  if (lane == 0) W.n = n;
+  wsync();
+  return ier;
+}
+
+}  // namespace fsd

@@ -1,0 +1,165 @@
+/*
+ * libfsdplan.so -- C-ABI of the B200-native batched cone-track path planner.
+ *
+ * Drop-in boundary for the reference's per-frame planner
+ *   PathPlanner.calculate_path_in_global_frame            fsd_path_planning/full_pipeline/full_pipeline.py:84-207
+ * i.e. its three stage calls
+ *   ConeSorting.run_cone_sorting                          fsd_path_planning/sorting_cones/core_cone_sorting.py:117-136
+ *   ConeMatching.run_cone_matching                        fsd_path_planning/cone_matching/core_cone_matching.py:87-124
+ *   CalculatePath.run_path_calculation                    fsd_path_planning/calculate_path/core_calculate_path.py:514-575
+ * executed for a whole batch of independent frames ("fresh PathPlanner per frame") per call.
+ * The reference has no FFI layer of its own (it is pure Python); INTEGRATION.md shows the ctypes
+ * binding a maintainer adds to route PathPlanner through this library.
+ *
+ * Conventions
+ *   - every pointer except `params`, `inter` (the struct itself) is a DEVICE pointer; the caller
+ *     owns all buffers (e.g. torch tensors); the library never allocates or frees caller memory,
+ *     keeps no pointer after return and is asynchronous on `stream`;
+ *   - return value 0 = launched; negative = argument / launch error (fsd_strerror); per-frame soft
+ *     failures are reported in out_status bits, never as errors;
+ *   - packed frame batch: frame b owns cones offsets[b] .. offsets[b+1]-1; at most
+ *     FSD_MAX_CONES cones per frame (more -> FSD_ST_OVERFLOW, frame planned on the first 256);
+ *   - sort indices index the frame's own cone list (reference: flatten_cones_by_type_array,
+ *     fsd_path_planning/sorting_cones/trace_sorter/core_trace_sorter.py:37-54);
+ *   - no CPU fallback exists: without a CUDA device every entry point returns FSD_ERR_NO_DEVICE.
+ */
+#ifndef FSDPLAN_H
+#define FSDPLAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSD_ABI_VERSION 1
+
+#define FSD_MAX_CONES 256 /* cones per frame */
+#define FSD_MAX_SORTED 12 /* max_length, fsd_path_planning/config.py:37 */
+#define FSD_MAX_WV 32     /* cones per side after virtual-cone insertion (12 real + 12 virtual, rounded up) */
+#define FSD_HORIZON 40    /* mpc_prediction_horizon, fsd_path_planning/config.py:58 */
+
+/* ConeTypes, fsd_path_planning/utils/cone_types.py:10-19 */
+#define FSD_CONE_UNKNOWN 0
+#define FSD_CONE_RIGHT 1 /* yellow */
+#define FSD_CONE_LEFT 2  /* blue */
+#define FSD_CONE_ORANGE_SMALL 3
+#define FSD_CONE_ORANGE_BIG 4
+
+/* MissionTypes, fsd_path_planning/utils/mission_types.py:11-25 (trackdrive/autocross share one path) */
+#define FSD_MISSION_AUTOCROSS 3
+#define FSD_MISSION_TRACKDRIVE 4
+
+/* out_status bits */
+#define FSD_ST_NO_LEFT (1u << 0)      /* no left configuration (NoPathError / no start cone) */
+#define FSD_ST_NO_RIGHT (1u << 1)
+#define FSD_ST_FEW_CONES (1u << 2)    /* both sides < 3 cones: previous path used as centre line  (core_calculate_path.py:531-536) */
+#define FSD_ST_FEW_MATCHES (1u << 3)  /* < 2 centre points: previous path                          (:201-203) */
+#define FSD_ST_FIT1_FAILED (1u << 4)  /* first fit invalid (ValueError): previous path re-fitted   (:214-221) */
+#define FSD_ST_PATH_TOO_FAR (1u << 5) /* path > 5 m from the car: previous path                    (:232-237) */
+#define FSD_ST_MPC_FAILED (1u << 6)   /* tail raised ValueError: redone with the previous path     (:561-570) */
+#define FSD_ST_TIE_P (1u << 7)        /* size of the last evaluation grid decided by the tie rule */
+#define FSD_ST_OVERFLOW (1u << 8)     /* a static bound was exceeded (cones, DFS leaves, knots, path points) */
+#define FSD_ST_REF_RAISES (1u << 9)   /* the reference raises an exception on this input; output = previous path */
+#define FSD_ST_UNSUPPORTED (1u << 10) /* reference takes a latent-bug path that is not reproduced; output = previous path */
+
+#define FSD_OK 0
+#define FSD_ERR_ARG (-1)
+#define FSD_ERR_WORKSPACE (-2)
+#define FSD_ERR_LAUNCH (-3)
+#define FSD_ERR_NO_DEVICE (-4)
+#define FSD_ERR_MISSION (-5)
+
+/* Every tunable of the path, default-initialised to the reference's values by fsd_params_default. */
+typedef struct fsd_params {
+  /* cone sorting: fsd_path_planning/config.py:33-41 and inline constants of trace_sorter/ */
+  int32_t max_n_neighbors;             /* 5 */
+  int32_t max_length;                  /* 12 */
+  double max_dist;                     /* 6.5 m */
+  double max_dist_to_first;            /* 6.0 m */
+  double threshold_directional_angle;  /* 40 deg, rad */
+  double threshold_absolute_angle;     /* 65 deg, rad */
+  double car_size;                     /* 2.1 m, find_configs_and_scores.py:93 */
+  int32_t max_dfs_pops;                /* guard for the exhaustive search (the reference has none) */
+  int32_t reserved0;
+  /* cone matching: config.py:124-129, core_cone_matching.py:101-102 */
+  double min_track_width;   /* 3 m */
+  double max_search_range;  /* 5 m (major radius = 1.5 x) */
+  double max_search_angle;  /* 50 deg, rad */
+  /* path calculation: config.py:48, 55-59 */
+  double smoothing;                        /* 0.2 */
+  double predict_every;                    /* 0.1 m */
+  double maximal_distance_for_valid_path;  /* 5 m */
+  double mpc_path_length;                  /* 20 m */
+  double refit_smoothing;                  /* 0.01, path_parameterization.py:157-159 */
+} fsd_params;
+
+/* Optional per-frame intermediates (device pointers, each nullable).  When a pointer is NULL the
+ * library keeps that tensor in `workspace`. */
+typedef struct fsd_intermediate {
+  double *path_f64;   /* [B][40][4] u, x, y, curvature in fp64 (out_path is the fp32 copy) */
+  int16_t *n_wv;      /* [B][2]   cones per side after matching: left, right */
+  double *left_wv;    /* [B][FSD_MAX_WV][2] left cones with virtual cones */
+  double *right_wv;   /* [B][FSD_MAX_WV][2] */
+  int16_t *l2r;       /* [B][FSD_MAX_WV] match index into right_wv or -1; entries >= n are -2 */
+  int16_t *r2l;       /* [B][FSD_MAX_WV] */
+  int16_t *grid;      /* [B][2]   P (size of the last evaluation grid), points entering the last re-fit */
+  int16_t *sort_dbg;  /* [B][8]   first_k left[2], right[2], n_configs[2], dfs pops[2] */
+} fsd_intermediate;
+
+int fsd_abi_version(void);
+const char *fsd_strerror(int code);
+int fsd_params_default(fsd_params *params);
+
+/* bytes of scratch needed by the batch entry points below for B frames */
+size_t fsd_workspace_bytes(int n_frames, int total_cones);
+
+/* The constant initial path of a fresh planner (core_calculate_path.py:103-107), computed on the
+ * device with the path kernels; out_prev_path: device, [40][4] fp64. */
+int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stream);
+
+/*
+ * Full planner: sort -> match -> path for n_frames independent frames.
+ *   cones_xy [total][2], pos [B][2], dir [B][2] : fp32 (fsd_plan_batch) or fp64 (fsd_plan_batch_f64)
+ *   out_path      [B][40][4] fp32  (u, x, y, curvature)
+ *   out_left_idx  [B][12] int16, -1 padded;  out_right_idx likewise  (the "sort indices")
+ *   inter         nullable
+ *   force_P       nullable, [B]; > 0 forces the size of the last evaluation grid (parity mode)
+ *   prev_path     nullable; fp64 [40][4] (prev_path_stride = 0, shared) or per frame
+ *                 (prev_path_stride = 160); NULL = the initial path of a fresh planner
+ *   out_status    [B] uint32
+ */
+int fsd_plan_batch(const fsd_params *params, int mission, int n_frames, const float *cones_xy,
+                   const uint8_t *cones_type, const int32_t *offsets, const float *pos, const float *dir,
+                   float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                   const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+int fsd_plan_batch_f64(const fsd_params *params, int mission, int n_frames, const double *cones_xy,
+                       const uint8_t *cones_type, const int32_t *offsets, const double *pos, const double *dir,
+                       float *out_path, int16_t *out_left_idx, int16_t *out_right_idx,
+                       const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
+                       int prev_path_stride, uint32_t *out_status, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* Stage entry points (same conventions).  fsd_sort_batch: ConeSorting only. */
+int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy, const uint8_t *cones_type,
+                   const int32_t *offsets, const float *pos, const float *dir, int16_t *out_left_idx,
+                   int16_t *out_right_idx, int16_t *sort_dbg, uint32_t *out_status, void *stream);
+
+/* fsd_match_batch: ConeMatching on given sort indices; writes n_wv, left_wv, right_wv, l2r, r2l of `inter`
+ * (all five must be non-NULL). */
+int fsd_match_batch(const fsd_params *params, int n_frames, const float *cones_xy, const int32_t *offsets,
+                    const float *pos, const float *dir, const int16_t *left_idx, const int16_t *right_idx,
+                    const fsd_intermediate *inter, uint32_t *out_status, void *stream);
+
+/* fsd_path_batch: CalculatePath on given matching results (n_wv, left_wv, right_wv, l2r, r2l of `inter`). */
+int fsd_path_batch(const fsd_params *params, int n_frames, const double *pos, const double *dir,
+                   const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSDPLAN_H */

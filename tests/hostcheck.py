@@ -1,0 +1,118 @@
+"""ctypes binding of the HOST-CHECK build of the kernels' per-frame code (tests only).
+
+`libfsdplan_hostcheck.so` is ft_fsd_path_planning_b200/csrc/hostcheck.cpp: the same sort / match /
+spline / path sources the CUDA kernels are compiled from, built by g++ with a warp of one lane.
+It exists so that the CPU-only test tier can check the kernels' logic; the product never loads it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CSRC = os.path.join(_ROOT, "ft_fsd_path_planning_b200", "csrc")
+_LIB = os.path.join(_CSRC, "libfsdplan_hostcheck.so")
+MAX_SORTED, MAX_WV, HORIZON = 12, 32, 40
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("max_n_neighbors", C.c_int32), ("max_length", C.c_int32), ("max_dist", C.c_double),
+        ("max_dist_to_first", C.c_double), ("threshold_directional_angle", C.c_double),
+        ("threshold_absolute_angle", C.c_double), ("car_size", C.c_double), ("max_dfs_pops", C.c_int32),
+        ("reserved0", C.c_int32), ("min_track_width", C.c_double), ("max_search_range", C.c_double),
+        ("max_search_angle", C.c_double), ("smoothing", C.c_double), ("predict_every", C.c_double),
+        ("maximal_distance_for_valid_path", C.c_double), ("mpc_path_length", C.c_double),
+        ("refit_smoothing", C.c_double),
+    ]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".cpp"))]
+    srcs.append(os.path.join(_ROOT, "include", "fsdplan.h"))
+    stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    if stale:
+        subprocess.check_call(
+            ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
+             "-o", _LIB, os.path.join(_CSRC, "hostcheck.cpp")])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().fsd_hostcheck_params_default(C.byref(p))
+    return p
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def initial_path() -> np.ndarray:
+    out = np.zeros((HORIZON, 4))
+    p = default_params()
+    lib().fsd_hostcheck_initial_path(C.byref(p), _p(out, C.c_double))
+    return out
+
+
+def plan_batch(batch, force_P=None, prev=None):
+    xy = np.ascontiguousarray(batch.cones_xy, dtype=np.float64)
+    ty = np.ascontiguousarray(batch.cones_type, dtype=np.uint8)
+    off = np.ascontiguousarray(batch.offsets, dtype=np.int32)
+    pos = np.ascontiguousarray(batch.pos, dtype=np.float64)
+    dr = np.ascontiguousarray(batch.dir, dtype=np.float64)
+    B = len(off) - 1
+    out = {
+        "path": np.zeros((B, HORIZON, 4)),
+        "left_idx": np.zeros((B, MAX_SORTED), np.int16), "right_idx": np.zeros((B, MAX_SORTED), np.int16),
+        "n_wv": np.zeros((B, 2), np.int16),
+        "left_wv": np.zeros((B, MAX_WV, 2)), "right_wv": np.zeros((B, MAX_WV, 2)),
+        "l2r": np.zeros((B, MAX_WV), np.int16), "r2l": np.zeros((B, MAX_WV), np.int16),
+        "grid": np.zeros((B, 2), np.int16), "sort_dbg": np.zeros((B, 8), np.int16),
+        "status": np.zeros(B, np.uint32),
+    }
+    fp = None
+    if force_P is not None:
+        fpa = np.ascontiguousarray(force_P, dtype=np.int16)
+        fp = _p(fpa, C.c_int16)
+    pv = None
+    if prev is not None:
+        pva = np.ascontiguousarray(prev, dtype=np.float64)
+        pv = _p(pva, C.c_double)
+    p = default_params()
+    i16 = C.c_int16
+    lib().fsd_hostcheck_plan(
+        C.byref(p), B, _p(xy, C.c_double), _p(ty, C.c_uint8), _p(off, C.c_int32), _p(pos, C.c_double),
+        _p(dr, C.c_double), fp, pv, _p(out["path"], C.c_double), _p(out["left_idx"], i16),
+        _p(out["right_idx"], i16), _p(out["n_wv"], i16), _p(out["left_wv"], C.c_double),
+        _p(out["right_wv"], C.c_double), _p(out["l2r"], i16), _p(out["r2l"], i16), _p(out["grid"], i16),
+        _p(out["sort_dbg"], i16), _p(out["status"], C.c_uint32))
+    return out
+
+
+def fit(points: np.ndarray, s: float):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    m = len(pts)
+    t = np.zeros(64)
+    c = np.zeros(128)
+    n = C.c_int(0)
+    k = C.c_int(0)
+    ier = lib().fsd_hostcheck_fit(_p(pts, C.c_double), m, float(s), _p(t, C.c_double), C.byref(n),
+                                  _p(c, C.c_double), C.byref(k))
+    nn, kk = n.value, k.value
+    cc = c[: 2 * (nn - kk - 1)].reshape(-1, 2)
+    return t[:nn].copy(), cc[:, 0].copy(), cc[:, 1].copy(), kk, ier
