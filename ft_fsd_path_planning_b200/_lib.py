@@ -1,0 +1,104 @@
+"""ctypes binding of libfsdplan.so (include/fsdplan.h).  There is no CPU path: loading fails loudly when the
+CUDA library has not been built, and every entry point returns FSD_ERR_NO_DEVICE without a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libfsdplan.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "fsdplan.h")
+
+MAX_CONES, MAX_SORTED, MAX_WV, HORIZON = 256, 12, 32, 40
+MISSION_AUTOCROSS, MISSION_TRACKDRIVE = 3, 4
+
+STATUS_BITS = {
+    "NO_LEFT": 1 << 0, "NO_RIGHT": 1 << 1, "FEW_CONES": 1 << 2, "FEW_MATCHES": 1 << 3,
+    "FIT1_FAILED": 1 << 4, "PATH_TOO_FAR": 1 << 5, "MPC_FAILED": 1 << 6, "TIE_P": 1 << 7,
+    "OVERFLOW": 1 << 8, "REF_RAISES": 1 << 9, "UNSUPPORTED": 1 << 10,
+}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class Params(C.Structure):
+    """struct fsd_params"""
+    _fields_ = [
+        ("max_n_neighbors", C.c_int32), ("max_length", C.c_int32), ("max_dist", C.c_double),
+        ("max_dist_to_first", C.c_double), ("threshold_directional_angle", C.c_double),
+        ("threshold_absolute_angle", C.c_double), ("car_size", C.c_double), ("max_dfs_pops", C.c_int32),
+        ("reserved0", C.c_int32), ("min_track_width", C.c_double), ("max_search_range", C.c_double),
+        ("max_search_angle", C.c_double), ("smoothing", C.c_double), ("predict_every", C.c_double),
+        ("maximal_distance_for_valid_path", C.c_double), ("mpc_path_length", C.c_double),
+        ("refit_smoothing", C.c_double),
+    ]
+
+
+class Intermediate(C.Structure):
+    """struct fsd_intermediate (device pointers)"""
+    _fields_ = [(n, C.c_void_p) for n in
+                ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg")]
+
+
+def sources():
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    return files + [INCLUDE]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/kernels.cu for sm_100a into csrc/libfsdplan.so (in-tree, so it travels with the repo)."""
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in sources())
+    if stale:
+        cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "kernels.cu")]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                "g.build()').  ft_fsd_path_planning_b200 has no CPU implementation.")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.fsd_abi_version.restype = C.c_int
+        L.fsd_strerror.restype = C.c_char_p
+        L.fsd_strerror.argtypes = [C.c_int]
+        L.fsd_params_default.argtypes = [C.POINTER(Params)]
+        L.fsd_workspace_bytes.restype = sz
+        L.fsd_workspace_bytes.argtypes = [i32, i32]
+        L.fsd_initial_path.argtypes = [C.POINTER(Params), vp, vp]
+        plan_args = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Intermediate), vp, vp, i32,
+                     vp, vp, sz, vp]
+        L.fsd_plan_batch.argtypes = plan_args
+        L.fsd_plan_batch_f64.argtypes = plan_args
+        L.fsd_sort_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.fsd_match_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, C.POINTER(Intermediate), vp, vp]
+        L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp, vp]
+        if L.fsd_abi_version() != 1:
+            raise RuntimeError("libfsdplan.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise RuntimeError(f"libfsdplan: {lib().fsd_strerror(code).decode()} ({code})")
+
+
+def default_params() -> Params:
+    p = Params()
+    check(lib().fsd_params_default(C.byref(p)))
+    return p

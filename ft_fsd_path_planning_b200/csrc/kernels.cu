@@ -1,0 +1,514 @@
+// libfsdplan.so: CUDA kernels (sm_100a) and the C-ABI of include/fsdplan.h.
+//
+// Execution model: ONE WARP PLANS ONE FRAME.  Every kernel is launched with 32-thread CTAs (one warp, its
+// frame state in that CTA's shared memory) and a grid of  min(B, #SM x resident CTAs per SM)  CTAs that
+// stride over the frame batch, so the grid is an exact multiple of the SM count whenever B allows.
+//
+//   sort_match_kernel   S1-S8 + M1-M6.  The frame's cone coordinates are staged global -> shared with a
+//                       TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx, SASS: UBLKCP) and widened to
+//                       fp64 in shared memory; the k-NN cost matrix never leaves registers/shared memory.
+//   path_kernel         P1-P4: three smoothing-spline fits, extension, curvature, 40 samples.
+//   initial_path_kernel the constant path of a fresh planner, one warp.
+//
+// Per-frame algorithms live in sort.cuh / match.cuh / spline.cuh / path.cuh (see frame.cuh).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+
+#include "frame.cuh"
+
+using namespace fsd;
+
+namespace {
+
+// ---- TMA bulk copy helpers (raw PTX) ------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// shared-memory image of one sort/match CTA
+struct SortCta {
+  SortSmem S;
+  MatchSmem M;
+  alignas(16) float raw[2 * (FSD_MAX_CONES + 2)];  // fp32 staging area of the bulk copy
+  alignas(8) uint64_t mbar;
+};
+
+// Stage the frame's coordinates into S.xy (fp64).  The 16-byte aligned interior of the frame's slice goes
+// through the TMA bulk copy; a leading / trailing cone that is not 16-byte aligned (fp32 input, odd offset)
+// is loaded directly.
+template <typename T>
+__device__ void stage_frame(SortCta &C, const T *xy, const uint8_t *type, int n, uint32_t &phase) {
+  const int lane = fsd_lane();
+  SortSmem &S = C.S;
+  for (int i = lane; i < n; i += 32) S.type[i] = type[i];
+  if constexpr (sizeof(T) == 8) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(xy) & 15u) == 0;
+    if (aligned && n > 0) {
+      if (lane == 0) {
+        mbar_expect_tx(&C.mbar, (uint32_t)n * 16u);
+        bulk_g2s(S.xy, xy, (uint32_t)n * 16u, &C.mbar);
+      }
+      mbar_wait(&C.mbar, phase);
+      phase ^= 1u;
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        S.xy[i].x = (double)xy[2 * i];
+        S.xy[i].y = (double)xy[2 * i + 1];
+      }
+    }
+  } else {
+    // fp32: cone i lives at byte 8 i of the slice
+    const int head = (int)((reinterpret_cast<uintptr_t>(xy) >> 3) & 1u);  // 1 -> first cone is not 16 B aligned
+    const int h = head < n ? head : n;
+    const int interior = ((n - h) / 2) * 2;
+    float *store = C.raw + 2 * head;  // keeps the interior 16 B aligned in shared memory
+    if (interior > 0) {
+      if (lane == 0) {
+        mbar_expect_tx(&C.mbar, (uint32_t)interior * 8u);
+        bulk_g2s(store + 2 * h, xy + 2 * h, (uint32_t)interior * 8u, &C.mbar);
+      }
+    }
+    // leading / trailing cones outside the aligned interior
+    if (lane == 0 && h == 1) {
+      S.xy[0].x = (double)xy[0];
+      S.xy[0].y = (double)xy[1];
+    }
+    if (lane == 1 && h + interior < n) {
+      const int i = n - 1;
+      S.xy[i].x = (double)xy[2 * i];
+      S.xy[i].y = (double)xy[2 * i + 1];
+    }
+    if (interior > 0) {
+      mbar_wait(&C.mbar, phase);
+      phase ^= 1u;
+      for (int i = h + lane; i < h + interior; i += 32) {
+        S.xy[i].x = (double)store[2 * i];
+        S.xy[i].y = (double)store[2 * i + 1];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) sort_match_kernel(DevParams P, int n_frames, const T *cones_xy,
+                                                        const uint8_t *cones_type, const int32_t *offsets,
+                                                        const T *pos, const T *dir, StageOut O, int do_match) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortCta &C = *reinterpret_cast<SortCta *>(smem_raw);
+  if (fsd_lane() == 0) mbar_init(&C.mbar, 1);
+  __syncwarp();
+  uint32_t phase = 0;
+  for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
+    const int lo = offsets[b];
+    int n = offsets[b + 1] - lo;
+    unsigned st = 0;
+    if (n > FSD_MAX_CONES) {
+      n = FSD_MAX_CONES;
+      st |= FSD_ST_OVERFLOW;
+    }
+    if (n < 0) n = 0;
+    const FramePose F = {(double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]};
+    stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
+    st |= sort_frame(C.S, n, F, P, O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr);
+    store_sort(C.S, b, O);
+    if (do_match) {
+      st |= match_from_sort(C.S, C.M, F, P);
+      store_match(C.M, b, O);
+    }
+    if (fsd_lane() == 0) O.status[b] = st;
+    __syncwarp();
+  }
+}
+
+// matching on given sort indices (stage entry point fsd_match_batch)
+template <typename T>
+__global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, const T *cones_xy,
+                                                   const int32_t *offsets, const T *pos, const T *dir,
+                                                   const int16_t *left_idx, const int16_t *right_idx, StageOut O) {
+  __shared__ MatchSmem M;
+  for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
+    const T *xy = cones_xy + 2 * (size_t)offsets[b];
+    const FramePose F = {(double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]};
+    int nl = 0, nr = 0;
+    for (int q = 0; q < FSD_MAX_SORTED; ++q) {
+      nl += left_idx[(size_t)b * FSD_MAX_SORTED + q] >= 0;
+      nr += right_idx[(size_t)b * FSD_MAX_SORTED + q] >= 0;
+    }
+    for (int q = fsd_lane(); q < 2 * FSD_MAX_SORTED; q += 32) {
+      const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
+      const int idx = (s == 0 ? left_idx : right_idx)[(size_t)b * FSD_MAX_SORTED + j];
+      if (idx >= 0) {
+        M.side[s][j].x = (double)xy[2 * idx];
+        M.side[s][j].y = (double)xy[2 * idx + 1];
+      }
+    }
+    if (fsd_lane() == 0) {
+      M.nside[0] = nl;
+      M.nside[1] = nr;
+    }
+    __syncwarp();
+    unsigned st = match_frame(M, F, P);
+    store_match(M, b, O);
+    if (fsd_lane() == 0) O.status[b] = st;
+    __syncwarp();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O,
+                                                  const int16_t *force_P, const double *prev, int prev_stride,
+                                                  double *out_f64, float *out_f32, int16_t *grid_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
+  for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
+    const FramePose F = {(double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]};
+    path_from_tensors(S, b, O, F, force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out_f64, out_f32,
+                      grid_out);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
+  initial_path_frame(S, P, out);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+
+constexpr int MAX_DEVICES = 64;
+__device__ double g_initial_path[FSD_HORIZON * 4];  // cache of the default-parameter initial path
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int sort_ctas = 0, path_ctas = 0;  // resident CTAs per SM
+  bool initial_ready = false;
+  double key[3] = {0, 0, 0};
+};
+DeviceInfo g_dev[MAX_DEVICES];
+std::mutex g_mutex;
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int device_info(DeviceInfo **out) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) {
+    cudaGetLastError();
+    return FSD_ERR_NO_DEVICE;
+  }
+  DeviceInfo &D = g_dev[dev];
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (D.sm_count == 0) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return FSD_ERR_NO_DEVICE;
+    }
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float>, 32, sizeof(SortCta));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, 32, sizeof(PathSmem));
+    D.sort_ctas = a > 0 ? a : 1;
+    D.path_ctas = b > 0 ? b : 1;
+    D.sm_count = prop.multiProcessorCount;
+  }
+  *out = &D;
+  return FSD_OK;
+}
+
+int grid_for(int n_frames, int sm_count, int ctas_per_sm) {
+  long cap = (long)sm_count * ctas_per_sm;
+  return (int)(n_frames < cap ? n_frames : cap);
+}
+
+struct Carve {
+  unsigned char *base;
+  size_t used, cap;
+  template <typename T>
+  T *take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    T *p = reinterpret_cast<T *>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+size_t workspace_bytes(int n_frames) {
+  const size_t B = (size_t)(n_frames > 0 ? n_frames : 0);
+  size_t total = 0;
+  total += align_up(B * FSD_HORIZON * 4 * sizeof(double), 256);         // path_f64
+  total += align_up(B * 2 * sizeof(int16_t), 256);                      // n_wv
+  total += 2 * align_up(B * FSD_MAX_WV * 2 * sizeof(double), 256);      // left_wv, right_wv
+  total += 2 * align_up(B * FSD_MAX_WV * sizeof(int16_t), 256);         // l2r, r2l
+  total += align_up(B * 2 * sizeof(int16_t), 256);                      // grid
+  total += align_up(FSD_HORIZON * 4 * sizeof(double), 256);             // initial path (non-default params)
+  return total;
+}
+
+// resolve every intermediate tensor to user memory or workspace
+int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t workspace_bytes_given,
+            fsd_intermediate *out, double **initial_slot) {
+  fsd_intermediate r;
+  std::memset(&r, 0, sizeof(r));
+  if (inter) r = *inter;
+  if (!workspace || workspace_bytes_given < workspace_bytes(n_frames)) return FSD_ERR_WORKSPACE;
+  Carve cv = {static_cast<unsigned char *>(workspace), 0, workspace_bytes_given};
+  const size_t B = (size_t)n_frames;
+  double *w_path = cv.take<double>(B * FSD_HORIZON * 4);
+  int16_t *w_nwv = cv.take<int16_t>(B * 2);
+  double *w_lwv = cv.take<double>(B * FSD_MAX_WV * 2);
+  double *w_rwv = cv.take<double>(B * FSD_MAX_WV * 2);
+  int16_t *w_l2r = cv.take<int16_t>(B * FSD_MAX_WV);
+  int16_t *w_r2l = cv.take<int16_t>(B * FSD_MAX_WV);
+  int16_t *w_grid = cv.take<int16_t>(B * 2);
+  double *w_init = cv.take<double>(FSD_HORIZON * 4);
+  if (!r.path_f64) r.path_f64 = w_path;
+  if (!r.n_wv) r.n_wv = w_nwv;
+  if (!r.left_wv) r.left_wv = w_lwv;
+  if (!r.right_wv) r.right_wv = w_rwv;
+  if (!r.l2r) r.l2r = w_l2r;
+  if (!r.r2l) r.r2l = w_r2l;
+  if (!r.grid) r.grid = w_grid;
+  if (initial_slot) *initial_slot = w_init;
+  *out = r;
+  return FSD_OK;
+}
+
+int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? FSD_OK : FSD_ERR_LAUNCH;
+}
+
+// the previous path used when the caller passes none: the initial path of a fresh planner
+int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &D, double *scratch,
+                      cudaStream_t stream, const double **prev) {
+  const double key[3] = {params->smoothing, params->predict_every, params->refit_smoothing};
+  double *cached = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void **>(&cached), g_initial_path) != cudaSuccess) {
+    cudaGetLastError();
+    return FSD_ERR_LAUNCH;
+  }
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (!D.initial_ready) {
+    initial_path_kernel<<<1, 32, sizeof(PathSmem), stream>>>(P, cached);
+    if (check_launch() != FSD_OK) return FSD_ERR_LAUNCH;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return FSD_ERR_LAUNCH;  // once per device
+    D.initial_ready = true;
+    std::memcpy(D.key, key, sizeof(key));
+  }
+  if (std::memcmp(D.key, key, sizeof(key)) == 0) {
+    *prev = cached;
+    return FSD_OK;
+  }
+  initial_path_kernel<<<1, 32, sizeof(PathSmem), stream>>>(P, scratch);  // non-default spline parameters
+  *prev = scratch;
+  return check_launch();
+}
+
+template <typename T>
+int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T *cones_xy, const uint8_t *cones_type,
+                    const int32_t *offsets, const T *pos, const T *dir, float *out_path, int16_t *out_left_idx,
+                    int16_t *out_right_idx, const fsd_intermediate *inter, const int16_t *force_P,
+                    const double *prev_path, int prev_path_stride, uint32_t *out_status, void *workspace,
+                    size_t workspace_bytes_given, void *stream_v) {
+  if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status) return FSD_ERR_ARG;
+  if (mission != FSD_MISSION_AUTOCROSS && mission != FSD_MISSION_TRACKDRIVE) return FSD_ERR_MISSION;
+  if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  if (!cones_xy || !cones_type) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  fsd_intermediate R;
+  double *init_slot = nullptr;
+  rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot);
+  if (rc != FSD_OK) return rc;
+  const DevParams P = make_dev_params(*params);
+  const double *prev = prev_path;
+  int stride = prev_path_stride;
+  if (!prev) {
+    rc = default_prev_path(params, P, *D, init_slot, stream, &prev);
+    if (rc != FSD_OK) return rc;
+    stride = 0;
+  }
+  StageOut O = {out_left_idx,  out_right_idx, inter ? inter->sort_dbg : nullptr, R.n_wv, R.left_wv, R.right_wv, R.l2r,
+                R.r2l,         out_status};
+  sort_match_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), 32, sizeof(SortCta), stream>>>(
+      P, n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1);
+  rc = check_launch();
+  if (rc != FSD_OK) return rc;
+  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), 32, sizeof(PathSmem), stream>>>(
+      P, n_frames, pos, dir, O, force_P, prev, stride, R.path_f64, out_path, R.grid);
+  return check_launch();
+}
+
+}  // namespace
+
+// ---- C-ABI ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int fsd_abi_version(void) { return FSD_ABI_VERSION; }
+
+const char *fsd_strerror(int code) {
+  switch (code) {
+    case FSD_OK: return "ok";
+    case FSD_ERR_ARG: return "invalid argument";
+    case FSD_ERR_WORKSPACE: return "workspace missing or smaller than fsd_workspace_bytes()";
+    case FSD_ERR_LAUNCH: return "CUDA launch failed";
+    case FSD_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case FSD_ERR_MISSION: return "mission not handled by the batched planner (trackdrive / autocross only)";
+    default: return "unknown error";
+  }
+}
+
+int fsd_params_default(fsd_params *p) {
+  if (!p) return FSD_ERR_ARG;
+  std::memset(p, 0, sizeof(*p));
+  p->max_n_neighbors = 5;
+  p->max_length = 12;
+  p->max_dist = 6.5;
+  p->max_dist_to_first = 6.0;
+  p->threshold_directional_angle = 40.0 * PI / 180.0;
+  p->threshold_absolute_angle = 65.0 * PI / 180.0;
+  p->car_size = 2.1;
+  p->max_dfs_pops = 1 << 16;
+  p->min_track_width = 3.0;
+  p->max_search_range = 5.0;
+  p->max_search_angle = 50.0 * PI / 180.0;
+  p->smoothing = 0.2;
+  p->predict_every = 0.1;
+  p->maximal_distance_for_valid_path = 5.0;
+  p->mpc_path_length = 20.0;
+  p->refit_smoothing = 0.01;
+  return FSD_OK;
+}
+
+size_t fsd_workspace_bytes(int n_frames, int total_cones) {
+  (void)total_cones;
+  return workspace_bytes(n_frames);
+}
+
+int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stream) {
+  if (!params || !out_prev_path) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  initial_path_kernel<<<1, 32, sizeof(PathSmem), static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params),
+                                                                                      out_prev_path);
+  return check_launch();
+}
+
+int fsd_plan_batch(const fsd_params *params, int mission, int n_frames, const float *cones_xy,
+                   const uint8_t *cones_type, const int32_t *offsets, const float *pos, const float *dir,
+                   float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                   const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                   void *workspace, size_t workspace_bytes_given, void *stream) {
+  return plan_batch_impl<float>(params, mission, n_frames, cones_xy, cones_type, offsets, pos, dir, out_path,
+                                out_left_idx, out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status,
+                                workspace, workspace_bytes_given, stream);
+}
+
+int fsd_plan_batch_f64(const fsd_params *params, int mission, int n_frames, const double *cones_xy,
+                       const uint8_t *cones_type, const int32_t *offsets, const double *pos, const double *dir,
+                       float *out_path, int16_t *out_left_idx, int16_t *out_right_idx,
+                       const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
+                       int prev_path_stride, uint32_t *out_status, void *workspace, size_t workspace_bytes_given,
+                       void *stream) {
+  return plan_batch_impl<double>(params, mission, n_frames, cones_xy, cones_type, offsets, pos, dir, out_path,
+                                 out_left_idx, out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status,
+                                 workspace, workspace_bytes_given, stream);
+}
+
+int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy, const uint8_t *cones_type,
+                   const int32_t *offsets, const float *pos, const float *dir, int16_t *out_left_idx,
+                   int16_t *out_right_idx, int16_t *sort_dbg, uint32_t *out_status, void *stream) {
+  if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status || !out_left_idx || !out_right_idx)
+    return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  if (!cones_xy || !cones_type) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  StageOut O = {out_left_idx, out_right_idx, sort_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, out_status};
+  sort_match_kernel<float><<<grid_for(n_frames, D->sm_count, D->sort_ctas), 32, sizeof(SortCta),
+                             static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
+                                                                  cones_type, offsets, pos, dir, O, 0);
+  return check_launch();
+}
+
+int fsd_match_batch(const fsd_params *params, int n_frames, const float *cones_xy, const int32_t *offsets,
+                    const float *pos, const float *dir, const int16_t *left_idx, const int16_t *right_idx,
+                    const fsd_intermediate *inter, uint32_t *out_status, void *stream) {
+  if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status || !left_idx || !right_idx || !inter)
+    return FSD_ERR_ARG;
+  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  if (!cones_xy) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  StageOut O = {nullptr,        nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
+                inter->l2r,     inter->r2l, out_status};
+  match_kernel<float><<<grid_for(n_frames, D->sm_count, 16), 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      make_dev_params(*params), n_frames, cones_xy, offsets, pos, dir, left_idx, right_idx, O);
+  return check_launch();
+}
+
+int fsd_path_batch(const fsd_params *params, int n_frames, const double *pos, const double *dir,
+                   const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *stream_v) {
+  if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
+  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l || !inter->path_f64)
+    return FSD_ERR_ARG;
+  if (!prev_path || (prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4)) return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (cudaMemsetAsync(out_status, 0, sizeof(uint32_t) * (size_t)n_frames, stream) != cudaSuccess) return FSD_ERR_LAUNCH;
+  StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
+                inter->l2r, inter->r2l, out_status};
+  path_kernel<double><<<grid_for(n_frames, D->sm_count, D->path_ctas), 32, sizeof(PathSmem), stream>>>(
+      make_dev_params(*params), n_frames, pos, dir, O, force_P, prev_path, prev_path_stride, inter->path_f64, out_path,
+      inter->grid);
+  return check_launch();
+}
+
+}  // extern "C"

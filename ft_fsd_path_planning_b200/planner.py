@@ -1,0 +1,254 @@
+"""Host side of the batched planner: torch tensors as device buffers, libfsdplan.so through ctypes.
+
+`BatchPlanner` is the batched entry point (thousands of independent frames per call, "fresh planner per
+frame" semantics).  `PathPlanner` mirrors the reference's facade
+(fsd_path_planning/full_pipeline/full_pipeline.py:53-217): same constructor, same
+`calculate_path_in_global_frame` signature / return values / ValueError, same statefulness
+(the previous path feeds the fallbacks of the next call, core_calculate_path.py:103-110, 561-573).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .enums import ConeTypes, MissionTypes
+from .synth import FrameBatch, pack_frames
+
+HORIZON, MAX_SORTED, MAX_WV = _lib.HORIZON, _lib.MAX_SORTED, _lib.MAX_WV
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class PlanResult:
+    """Device tensors produced by one batched call."""
+
+    path: torch.Tensor  # [B, 40, 4] float32: u, x, y, curvature
+    left_idx: torch.Tensor  # [B, 12] int16, -1 padded (indices into the frame's cone list)
+    right_idx: torch.Tensor  # [B, 12] int16
+    status: torch.Tensor  # [B] int32 bit field (see _lib.STATUS_BITS)
+    path_f64: Optional[torch.Tensor] = None  # [B, 40, 4] float64
+    n_wv: Optional[torch.Tensor] = None  # [B, 2] int16
+    left_wv: Optional[torch.Tensor] = None  # [B, 32, 2] float64
+    right_wv: Optional[torch.Tensor] = None
+    l2r: Optional[torch.Tensor] = None  # [B, 32] int16
+    r2l: Optional[torch.Tensor] = None
+    grid: Optional[torch.Tensor] = None  # [B, 2] int16: P, points entering the last re-fit
+    sort_dbg: Optional[torch.Tensor] = None  # [B, 8] int16
+
+
+class BatchPlanner:
+    """Plans batches of independent frames on one GPU.
+
+    Buffers (outputs, intermediates, workspace) are torch tensors owned by this object and re-used
+    across calls with the same batch size; the C library only sees raw pointers and the stream.
+    """
+
+    def __init__(self, device: Union[str, torch.device, int] = "cuda", mission: int = _lib.MISSION_TRACKDRIVE):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ft_fsd_path_planning_b200 needs a CUDA device: the planner has no CPU implementation")
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchPlanner runs on CUDA devices only")
+        self.lib = _lib.lib()
+        self.params = _lib.default_params()
+        self.mission = int(mission)
+        self._bufs = {}
+
+    # -- buffers -------------------------------------------------------------------------------------------
+    def _buffers(self, B: int, intermediates: bool):
+        key = (B, intermediates)
+        if key not in self._bufs:
+            dev = self.device
+            bufs = {
+                "path": torch.empty((B, HORIZON, 4), dtype=torch.float32, device=dev),
+                "left_idx": torch.empty((B, MAX_SORTED), dtype=torch.int16, device=dev),
+                "right_idx": torch.empty((B, MAX_SORTED), dtype=torch.int16, device=dev),
+                "status": torch.empty((B,), dtype=torch.int32, device=dev),
+                "workspace": torch.empty((int(self.lib.fsd_workspace_bytes(B, 0)),), dtype=torch.uint8, device=dev),
+            }
+            if intermediates:
+                bufs.update({
+                    "path_f64": torch.empty((B, HORIZON, 4), dtype=torch.float64, device=dev),
+                    "n_wv": torch.empty((B, 2), dtype=torch.int16, device=dev),
+                    "left_wv": torch.empty((B, MAX_WV, 2), dtype=torch.float64, device=dev),
+                    "right_wv": torch.empty((B, MAX_WV, 2), dtype=torch.float64, device=dev),
+                    "l2r": torch.empty((B, MAX_WV), dtype=torch.int16, device=dev),
+                    "r2l": torch.empty((B, MAX_WV), dtype=torch.int16, device=dev),
+                    "grid": torch.empty((B, 2), dtype=torch.int16, device=dev),
+                    "sort_dbg": torch.empty((B, 8), dtype=torch.int16, device=dev),
+                })
+            self._bufs = {key: bufs}  # keep one shape resident
+        return self._bufs[key]
+
+    # -- the batched call ------------------------------------------------------------------------------------
+    def plan(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
+             direction: torch.Tensor, *, force_P: Optional[torch.Tensor] = None,
+             prev_path: Optional[torch.Tensor] = None, intermediates: bool = False) -> PlanResult:
+        """cones_xy [total, 2] float32|float64, cones_type [total] uint8, offsets [B+1] int32, pos/direction [B, 2]
+        (same dtype as cones_xy); all on this planner's device.  Asynchronous on the current stream."""
+        B = offsets.numel() - 1
+        f64 = cones_xy.dtype == torch.float64
+        for t, dt in ((cones_xy, None), (cones_type, torch.uint8), (offsets, torch.int32), (pos, cones_xy.dtype),
+                      (direction, cones_xy.dtype)):
+            if t.device != self.device or not t.is_contiguous() or (dt is not None and t.dtype != dt):
+                raise ValueError("inputs must be contiguous tensors of the documented dtype on the planner's device")
+        if cones_xy.dtype not in (torch.float32, torch.float64):
+            raise ValueError("cones_xy must be float32 or float64")
+        bufs = self._buffers(B, intermediates)
+        inter = None
+        if intermediates:
+            inter = _lib.Intermediate(*[bufs[n].data_ptr() for n in
+                                        ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg")])
+        stride = 0
+        if prev_path is not None:
+            if prev_path.dtype != torch.float64 or not prev_path.is_contiguous() or prev_path.device != self.device:
+                raise ValueError("prev_path must be a contiguous float64 tensor on the planner's device")
+            stride = 0 if prev_path.numel() == HORIZON * 4 else HORIZON * 4
+            if stride and prev_path.numel() != B * HORIZON * 4:
+                raise ValueError("prev_path must be [40, 4] or [B, 40, 4]")
+        if force_P is not None and (force_P.dtype != torch.int16 or force_P.numel() != B):
+            raise ValueError("force_P must be int16 [B]")
+        fn = self.lib.fsd_plan_batch_f64 if f64 else self.lib.fsd_plan_batch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = fn(C.byref(self.params), self.mission, B, cones_xy.data_ptr(), cones_type.data_ptr(),
+                    offsets.data_ptr(), pos.data_ptr(), direction.data_ptr(), bufs["path"].data_ptr(),
+                    bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
+                    C.byref(inter) if inter is not None else None, _ptr(force_P), _ptr(prev_path), stride,
+                    bufs["status"].data_ptr(), bufs["workspace"].data_ptr(), bufs["workspace"].numel(), stream)
+        _lib.check(rc)
+        res = PlanResult(bufs["path"], bufs["left_idx"], bufs["right_idx"], bufs["status"])
+        if intermediates:
+            for n in ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg"):
+                setattr(res, n, bufs[n])
+        return res
+
+    def plan_host(self, batch: FrameBatch, *, force_P: Optional[np.ndarray] = None,
+                  prev_path: Optional[np.ndarray] = None, intermediates: bool = False) -> PlanResult:
+        """Convenience: host FrameBatch in, device PlanResult out (copies on the current stream)."""
+        dev = self.device
+        dt = torch.float64 if batch.cones_xy.dtype == np.float64 else torch.float32
+        xy = torch.from_numpy(np.ascontiguousarray(batch.cones_xy)).to(dev, dt)
+        ty = torch.from_numpy(np.ascontiguousarray(batch.cones_type, dtype=np.uint8)).to(dev)
+        off = torch.from_numpy(np.ascontiguousarray(batch.offsets, dtype=np.int32)).to(dev)
+        pos = torch.from_numpy(np.ascontiguousarray(batch.pos)).to(dev, dt)
+        dr = torch.from_numpy(np.ascontiguousarray(batch.dir)).to(dev, dt)
+        fp = None if force_P is None else torch.from_numpy(np.ascontiguousarray(force_P, dtype=np.int16)).to(dev)
+        pv = None if prev_path is None else torch.from_numpy(np.ascontiguousarray(prev_path, dtype=np.float64)).to(dev)
+        if xy.numel() == 0:
+            xy = torch.zeros((1, 2), dtype=dt, device=dev)
+            ty = torch.zeros((1,), dtype=torch.uint8, device=dev)
+        return self.plan(xy, ty, off, pos, dr, force_P=fp, prev_path=pv, intermediates=intermediates)
+
+    def initial_path(self) -> torch.Tensor:
+        """The constant path of a fresh planner (core_calculate_path.py:103-107), computed on the device."""
+        out = torch.empty((HORIZON, 4), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fsd_initial_path(C.byref(self.params), out.data_ptr(),
+                                                 torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+
+@dataclass
+class RelocalizationInformation:
+    """fsd_path_planning/relocalization/relocalization_information.py:13-35"""
+
+    translation: np.ndarray
+    rotation: float
+
+
+class PathPlanner:
+    """Drop-in for fsd_path_planning.PathPlanner on the trackdrive / autocross path."""
+
+    def __init__(self, mission: MissionTypes, experimental_performance_improvements: bool = False,
+                 device: Union[str, torch.device, int] = "cuda") -> None:
+        self.mission = MissionTypes(mission)
+        if self.mission in (MissionTypes.skidpad, MissionTypes.acceleration, MissionTypes.ebs_test):
+            raise NotImplementedError(
+                f"mission {self.mission.name} needs relocalization, which is outside the batched hot path "
+                "(SURVEY.md section 8f); use trackdrive / autocross")
+        # the experimental sorting cache of the reference changes results and is not reproduced
+        self.experimental_performance_improvements = experimental_performance_improvements
+        self._planner = BatchPlanner(device, mission=_lib.MISSION_TRACKDRIVE)
+        self.global_path = None
+        self._prev_path: Optional[torch.Tensor] = None  # previous_paths[-1] of the reference
+
+    @staticmethod
+    def _convert_direction_to_array(direction: Any) -> np.ndarray:
+        direction = np.squeeze(np.array(direction))
+        if direction.shape == (2,):
+            return direction.astype(np.float64)
+        if direction.shape in [(1,), ()]:
+            yaw = float(np.asarray(direction).reshape(-1)[0])
+            return np.array([np.cos(yaw), np.sin(yaw)])
+        raise ValueError("direction must be a float or a 2 element array")
+
+    def set_global_path(self, global_path):
+        self.global_path = global_path
+
+    @property
+    def relocalization_info(self) -> Optional[RelocalizationInformation]:
+        return None
+
+    def calculate_path_in_global_frame(
+        self,
+        cones: List[np.ndarray],
+        vehicle_position: np.ndarray,
+        vehicle_direction: Union[np.ndarray, float],
+        return_intermediate_results: bool = False,
+    ):
+        """Same contract as the reference: returns a (40, 4) float64 array [u, x, y, curvature], or the
+        7-tuple (path, sorted_left, sorted_right, left_with_virtual, right_with_virtual, l2r, r2l)."""
+        direction = self._convert_direction_to_array(vehicle_direction)
+        if self.global_path is not None:
+            raise NotImplementedError("global-path tracking belongs to the skidpad mission")
+        batch = pack_frames([(cones, np.asarray(vehicle_position, dtype=np.float64).reshape(2), direction)],
+                            dtype=np.float64)
+        if self._prev_path is None:
+            self._prev_path = self._planner.initial_path()
+        res = self._plan_with_prev(batch)
+        path = res.path_f64[0].clone()
+        self._prev_path = path
+        out_path = path.cpu().numpy()
+        if not return_intermediate_results:
+            return out_path
+        xy = batch.cones_xy
+        li = res.left_idx[0].cpu().numpy()
+        ri = res.right_idx[0].cpu().numpy()
+        n_wv = res.n_wv[0].cpu().numpy()
+        nl, nr = int(n_wv[0]), int(n_wv[1])
+        return (
+            out_path,
+            xy[li[li >= 0]],
+            xy[ri[ri >= 0]],
+            res.left_wv[0, :nl].cpu().numpy(),
+            res.right_wv[0, :nr].cpu().numpy(),
+            res.l2r[0, :nl].cpu().numpy().astype(np.int64),
+            res.r2l[0, :nr].cpu().numpy().astype(np.int64),
+        )
+
+    def _plan_with_prev(self, batch: FrameBatch) -> PlanResult:
+        dev = self._planner.device
+        xy = torch.from_numpy(batch.cones_xy).to(dev)
+        ty = torch.from_numpy(batch.cones_type).to(dev)
+        if xy.numel() == 0:
+            xy = torch.zeros((1, 2), dtype=torch.float64, device=dev)
+            ty = torch.zeros((1,), dtype=torch.uint8, device=dev)
+        return self._planner.plan(xy, ty, torch.from_numpy(batch.offsets).to(dev), torch.from_numpy(batch.pos).to(dev),
+                                  torch.from_numpy(batch.dir).to(dev), prev_path=self._prev_path, intermediates=True)
+
+    def calculate_paths_batched(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor,
+                                positions: torch.Tensor, directions: torch.Tensor, *,
+                                return_intermediate: bool = False) -> PlanResult:
+        """Batched entry point next to the single-frame one: torch CUDA tensors in, PlanResult out; every frame
+        is planned by a fresh planner (no state is read or written)."""
+        return self._planner.plan(cones_xy, cones_type, offsets, positions, directions,
+                                  intermediates=return_intermediate)
