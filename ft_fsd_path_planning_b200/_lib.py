@@ -86,7 +86,10 @@ def lib():
         L.fsd_plan_batch_f64.argtypes = plan_args
         L.fsd_sort_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.fsd_match_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, C.POINTER(Intermediate), vp, vp]
-        L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp, vp]
+        L.fsd_sort_match_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp,
+                                           C.POINTER(Intermediate), vp, vp]
+        L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp,
+                                     vp]
         if L.fsd_abi_version() != 1:
             raise RuntimeError("libfsdplan.so ABI version mismatch")
         _lib = L

@@ -334,8 +334,54 @@ int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &
     *prev = cached;
     return FSD_OK;
   }
-  initial_path_kernel<<<1, 32, sizeof(PathSmem), stream>>>(P, scratch);  // non-default spline parameters
+  if (!scratch) return FSD_ERR_ARG;  // non-default spline parameters: the caller must pass prev_path
+  initial_path_kernel<<<1, 32, sizeof(PathSmem), stream>>>(P, scratch);
   *prev = scratch;
+  return check_launch();
+}
+
+template <typename T>
+int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, const uint8_t *cones_type,
+                    const int32_t *offsets, const T *pos, const T *dir, int16_t *out_left_idx, int16_t *out_right_idx,
+                    const fsd_intermediate *inter, uint32_t *out_status, cudaStream_t stream) {
+  if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
+  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  if (!cones_xy || !cones_type) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  StageOut O = {out_left_idx, out_right_idx, inter->sort_dbg, inter->n_wv, inter->left_wv, inter->right_wv,
+                inter->l2r,   inter->r2l,    out_status};
+  sort_match_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), 32, sizeof(SortCta), stream>>>(
+      make_dev_params(*params), n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1);
+  return check_launch();
+}
+
+template <typename T>
+int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
+              const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
+              float *out_path, uint32_t *out_status, cudaStream_t stream) {
+  if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
+  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l || !inter->path_f64)
+    return FSD_ERR_ARG;
+  if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  const DevParams P = make_dev_params(*params);
+  const double *prev = prev_path;
+  int stride = prev_path_stride;
+  if (!prev) {
+    rc = default_prev_path(params, P, *D, init_scratch, stream, &prev);
+    if (rc != FSD_OK) return rc;
+    stride = 0;
+  }
+  StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
+                inter->l2r, inter->r2l, out_status};
+  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), 32, sizeof(PathSmem), stream>>>(
+      P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid);
   return check_launch();
 }
 
@@ -347,34 +393,17 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                     size_t workspace_bytes_given, void *stream_v) {
   if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status) return FSD_ERR_ARG;
   if (mission != FSD_MISSION_AUTOCROSS && mission != FSD_MISSION_TRACKDRIVE) return FSD_ERR_MISSION;
-  if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
   if (n_frames == 0) return FSD_OK;
-  if (!cones_xy || !cones_type) return FSD_ERR_ARG;
-  DeviceInfo *D = nullptr;
-  int rc = device_info(&D);
-  if (rc != FSD_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   fsd_intermediate R;
   double *init_slot = nullptr;
-  rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot);
+  int rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot);
   if (rc != FSD_OK) return rc;
-  const DevParams P = make_dev_params(*params);
-  const double *prev = prev_path;
-  int stride = prev_path_stride;
-  if (!prev) {
-    rc = default_prev_path(params, P, *D, init_slot, stream, &prev);
-    if (rc != FSD_OK) return rc;
-    stride = 0;
-  }
-  StageOut O = {out_left_idx,  out_right_idx, inter ? inter->sort_dbg : nullptr, R.n_wv, R.left_wv, R.right_wv, R.l2r,
-                R.r2l,         out_status};
-  sort_match_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), 32, sizeof(SortCta), stream>>>(
-      P, n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1);
-  rc = check_launch();
+  rc = sort_match_impl<T>(params, n_frames, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
+                          out_status, stream);
   if (rc != FSD_OK) return rc;
-  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), 32, sizeof(PathSmem), stream>>>(
-      P, n_frames, pos, dir, O, force_P, prev, stride, R.path_f64, out_path, R.grid);
-  return check_launch();
+  return path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev_path, prev_path_stride, init_slot, out_path,
+                      out_status, stream);
 }
 
 }  // namespace
@@ -490,25 +519,29 @@ int fsd_match_batch(const fsd_params *params, int n_frames, const float *cones_x
   return check_launch();
 }
 
-int fsd_path_batch(const fsd_params *params, int n_frames, const double *pos, const double *dir,
+int fsd_sort_match_batch(const fsd_params *params, int n_frames, int coords_f64, const void *cones_xy,
+                         const uint8_t *cones_type, const int32_t *offsets, const void *pos, const void *dir,
+                         int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                         uint32_t *out_status, void *stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (coords_f64)
+    return sort_match_impl<double>(params, n_frames, static_cast<const double *>(cones_xy), cones_type, offsets,
+                                   static_cast<const double *>(pos), static_cast<const double *>(dir), out_left_idx,
+                                   out_right_idx, inter, out_status, st);
+  return sort_match_impl<float>(params, n_frames, static_cast<const float *>(cones_xy), cones_type, offsets,
+                                static_cast<const float *>(pos), static_cast<const float *>(dir), out_left_idx,
+                                out_right_idx, inter, out_status, st);
+}
+
+int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                    const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
-                   int prev_path_stride, float *out_path, uint32_t *out_status, void *stream_v) {
-  if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
-  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l || !inter->path_f64)
-    return FSD_ERR_ARG;
-  if (!prev_path || (prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4)) return FSD_ERR_ARG;
-  if (n_frames == 0) return FSD_OK;
-  DeviceInfo *D = nullptr;
-  int rc = device_info(&D);
-  if (rc != FSD_OK) return rc;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (cudaMemsetAsync(out_status, 0, sizeof(uint32_t) * (size_t)n_frames, stream) != cudaSuccess) return FSD_ERR_LAUNCH;
-  StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
-                inter->l2r, inter->r2l, out_status};
-  path_kernel<double><<<grid_for(n_frames, D->sm_count, D->path_ctas), 32, sizeof(PathSmem), stream>>>(
-      make_dev_params(*params), n_frames, pos, dir, O, force_P, prev_path, prev_path_stride, inter->path_f64, out_path,
-      inter->grid);
-  return check_launch();
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (coords_f64)
+    return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
+                             force_P, prev_path, prev_path_stride, nullptr, out_path, out_status, st);
+  return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
+                          force_P, prev_path, prev_path_stride, nullptr, out_path, out_status, st);
 }
 
 }  // extern "C"

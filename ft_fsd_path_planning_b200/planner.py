@@ -61,6 +61,20 @@ class BatchPlanner:
         self.params = _lib.default_params()
         self.mission = int(mission)
         self._bufs = {}
+        self._prev0: Optional[torch.Tensor] = None
+        self.kernel_events: list = []
+
+    def _default_prev(self) -> torch.Tensor:
+        if self._prev0 is None:
+            self._prev0 = self.initial_path()
+        return self._prev0
+
+    def kernel_times_ms(self, clear: bool = True):
+        """[(sort_match_ms, path_ms), ...] for the calls made with kernel_events=True (synchronize first)."""
+        out = [(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) for e in self.kernel_events]
+        if clear:
+            self.kernel_events = []
+        return out
 
     # -- buffers -------------------------------------------------------------------------------------------
     def _buffers(self, B: int, intermediates: bool):
@@ -91,9 +105,14 @@ class BatchPlanner:
     # -- the batched call ------------------------------------------------------------------------------------
     def plan(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
              direction: torch.Tensor, *, force_P: Optional[torch.Tensor] = None,
-             prev_path: Optional[torch.Tensor] = None, intermediates: bool = False) -> PlanResult:
+             prev_path: Optional[torch.Tensor] = None, intermediates: bool = False,
+             kernel_events: bool = False) -> PlanResult:
         """cones_xy [total, 2] float32|float64, cones_type [total] uint8, offsets [B+1] int32, pos/direction [B, 2]
-        (same dtype as cones_xy); all on this planner's device.  Asynchronous on the current stream."""
+        (same dtype as cones_xy); all on this planner's device.  Asynchronous on the current stream.
+
+        kernel_events=True issues the two launches through the stage entry points (fsd_sort_match_batch,
+        fsd_path_batch) with CUDA events around each; the events are kept in `self.kernel_events`
+        (read them with `kernel_times_ms()` after a synchronize)."""
         B = offsets.numel() - 1
         f64 = cones_xy.dtype == torch.float64
         for t, dt in ((cones_xy, None), (cones_type, torch.uint8), (offsets, torch.int32), (pos, cones_xy.dtype),
@@ -102,6 +121,7 @@ class BatchPlanner:
                 raise ValueError("inputs must be contiguous tensors of the documented dtype on the planner's device")
         if cones_xy.dtype not in (torch.float32, torch.float64):
             raise ValueError("cones_xy must be float32 or float64")
+        intermediates = intermediates or kernel_events
         bufs = self._buffers(B, intermediates)
         inter = None
         if intermediates:
@@ -119,11 +139,29 @@ class BatchPlanner:
         fn = self.lib.fsd_plan_batch_f64 if f64 else self.lib.fsd_plan_batch
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            rc = fn(C.byref(self.params), self.mission, B, cones_xy.data_ptr(), cones_type.data_ptr(),
-                    offsets.data_ptr(), pos.data_ptr(), direction.data_ptr(), bufs["path"].data_ptr(),
-                    bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
-                    C.byref(inter) if inter is not None else None, _ptr(force_P), _ptr(prev_path), stride,
-                    bufs["status"].data_ptr(), bufs["workspace"].data_ptr(), bufs["workspace"].numel(), stream)
+            if kernel_events:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                rc = self.lib.fsd_sort_match_batch(
+                    C.byref(self.params), B, int(f64), cones_xy.data_ptr(), cones_type.data_ptr(), offsets.data_ptr(),
+                    pos.data_ptr(), direction.data_ptr(), bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
+                    C.byref(inter), bufs["status"].data_ptr(), stream)
+                _lib.check(rc)
+                ev[1].record()
+                if prev_path is None:
+                    prev_path = self._default_prev()
+                rc = self.lib.fsd_path_batch(
+                    C.byref(self.params), B, int(f64), pos.data_ptr(), direction.data_ptr(), C.byref(inter),
+                    _ptr(force_P), prev_path.data_ptr(), stride, bufs["path"].data_ptr(), bufs["status"].data_ptr(),
+                    stream)
+                ev[2].record()
+                self.kernel_events.append(ev)
+            else:
+                rc = fn(C.byref(self.params), self.mission, B, cones_xy.data_ptr(), cones_type.data_ptr(),
+                        offsets.data_ptr(), pos.data_ptr(), direction.data_ptr(), bufs["path"].data_ptr(),
+                        bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
+                        C.byref(inter) if inter is not None else None, _ptr(force_P), _ptr(prev_path), stride,
+                        bufs["status"].data_ptr(), bufs["workspace"].data_ptr(), bufs["workspace"].numel(), stream)
         _lib.check(rc)
         res = PlanResult(bufs["path"], bufs["left_idx"], bufs["right_idx"], bufs["status"])
         if intermediates:

@@ -154,8 +154,19 @@ int fsd_match_batch(const fsd_params *params, int n_frames, const float *cones_x
                     const float *pos, const float *dir, const int16_t *left_idx, const int16_t *right_idx,
                     const fsd_intermediate *inter, uint32_t *out_status, void *stream);
 
-/* fsd_path_batch: CalculatePath on given matching results (n_wv, left_wv, right_wv, l2r, r2l of `inter`). */
-int fsd_path_batch(const fsd_params *params, int n_frames, const double *pos, const double *dir,
+/* The two launches fsd_plan_batch is made of, callable one by one (e.g. to time each kernel).
+ * coords_f64 != 0: cones_xy / pos / dir are fp64, else fp32.
+ * fsd_sort_match_batch: ConeSorting + ConeMatching.  inter->n_wv, left_wv, right_wv, l2r, r2l must be non-NULL
+ * (sort_dbg optional).  Writes out_status. */
+int fsd_sort_match_batch(const fsd_params *params, int n_frames, int coords_f64, const void *cones_xy,
+                         const uint8_t *cones_type, const int32_t *offsets, const void *pos, const void *dir,
+                         int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                         uint32_t *out_status, void *stream);
+
+/* fsd_path_batch: CalculatePath on given matching results.  inter->n_wv, left_wv, right_wv, l2r, r2l (inputs) and
+ * path_f64 (output) must be non-NULL (grid optional).  Status bits are OR-ed INTO out_status (zero it when the
+ * stage is used on its own).  prev_path NULL = initial path of a fresh planner (default spline parameters only). */
+int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                    const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
                    int prev_path_stride, float *out_path, uint32_t *out_status, void *stream);
 

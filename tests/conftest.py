@@ -1,0 +1,56 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_SETS = ["fsg_color", "fsg_colorless", "fss_color", "fss_colorless", "fixtures", "synth_color",
+               "synth_colorless", "synth_mixed"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+def load_golden(name):
+    """(FrameBatch fp64, dict of golden arrays) of tests/golden/<name>.npz"""
+    from ft_fsd_path_planning_b200.synth import FrameBatch
+
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    batch = FrameBatch(g["cones_xy"], g["cones_type"], g["offsets"], g["pos"], g["dir"])
+    return batch, g
+
+
+@pytest.fixture(scope="session", params=GOLDEN_SETS)
+def golden(request):
+    return (request.param, *load_golden(request.param))
+
+
+def compare_with_golden(name, g, left_idx, right_idx, n_wv, left_wv, right_wv, l2r, r2l, path, status=None,
+                        path_tol=1e-4, check_path=True):
+    """The parity gates of SURVEY.md 8(d): sort indices and matches exact, with-virtual cones 1e-6,
+    path 1e-4 (the caller passes the golden P as force_P, i.e. the P-conditioned gate)."""
+    ok = g["error"] == 0
+    B = len(ok)
+    assert (np.asarray(left_idx)[:, :12] == g["left_idx"]).all(), f"{name}: left sort indices differ"
+    assert (np.asarray(right_idx)[:, :12] == g["right_idx"]).all(), f"{name}: right sort indices differ"
+    n_wv = np.asarray(n_wv)
+    assert (n_wv[ok, 0] == g["n_left_wv"][ok]).all() and (n_wv[ok, 1] == g["n_right_wv"][ok]).all(), name
+    for b in np.where(ok)[0]:
+        nl, nr = int(g["n_left_wv"][b]), int(g["n_right_wv"][b])
+        if nl:
+            assert np.abs(left_wv[b][:nl] - g["left_wv"][b][:nl]).max() <= 1e-6, (name, b)
+        if nr:
+            assert np.abs(right_wv[b][:nr] - g["right_wv"][b][:nr]).max() <= 1e-6, (name, b)
+        assert (np.asarray(l2r[b][:nl]) == g["l2r"][b][:nl]).all(), (name, b)
+        assert (np.asarray(r2l[b][:nr]) == g["r2l"][b][:nr]).all(), (name, b)
+    if check_path:
+        err = np.abs(np.asarray(path, dtype=np.float64) - g["path"]).reshape(B, -1).max(1)
+        bad = np.where(ok & ~(err <= path_tol))[0]
+        assert len(bad) == 0, f"{name}: {len(bad)} frames above {path_tol}: {bad[:8]} err {err[bad[:8]]}"

@@ -111,7 +111,7 @@ def fit(points: np.ndarray, s: float):
     c = np.zeros(128)
     n = C.c_int(0)
     k = C.c_int(0)
-    ier = lib().fsd_hostcheck_fit(_p(pts, C.c_double), m, float(s), _p(t, C.c_double), C.byref(n),
+    ier = lib().fsd_hostcheck_fit(_p(pts, C.c_double), m, C.c_double(float(s)), _p(t, C.c_double), C.byref(n),
                                   _p(c, C.c_double), C.byref(k))
     nn, kk = n.value, k.value
     cc = c[: 2 * (nn - kk - 1)].reshape(-1, 2)

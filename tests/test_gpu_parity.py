@@ -1,0 +1,254 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes -> libfsdplan.so), against the golden
+vectors of the unmodified reference, against the oracle on seeded synthetic batches, and -- at BASELINE.json's
+full sizes -- through size-independent properties (determinism, batch-order and shard independence, rigid-motion
+equivariance).  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle  # the checker, never the thing under test
+from conftest import GOLDEN_SETS, compare_with_golden, load_golden
+from ft_fsd_path_planning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from ft_fsd_path_planning_b200 import BatchPlanner, MissionTypes, PathPlanner, _lib  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def planner():
+    return BatchPlanner("cuda:0")
+
+
+def _np(res):
+    return {k: getattr(res, k).cpu().numpy() for k in
+            ("path", "left_idx", "right_idx", "status", "path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid")}
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_cuda_matches_reference_P_conditioned(planner, name):
+    """Gate (i) of SURVEY 8(d): sort indices / matches exact, path within 1e-4 with the reference's P."""
+    batch, g = load_golden(name)
+    r = _np(planner.plan_host(batch, force_P=g["P"], intermediates=True))
+    compare_with_golden(name, g, r["left_idx"], r["right_idx"], r["n_wv"], r["left_wv"], r["right_wv"], r["l2r"],
+                        r["r2l"], r["path_f64"], path_tol=1e-7)
+    # the fp32 output tensor of the ABI: tolerance of the north star, 1e-4
+    compare_with_golden(name, g, r["left_idx"], r["right_idx"], r["n_wv"], r["left_wv"], r["right_wv"], r["l2r"],
+                        r["r2l"], r["path"], path_tol=1e-4)
+    ok = g["error"] == 0
+    assert (r["grid"][ok, 1] == g["n_trim"][ok]).all()
+    assert not (r["status"].astype(np.uint32) & ((1 << 8) | (1 << 10))).any()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_cuda_tie_normalised(planner, name):
+    """Gate (ii): default evaluation-grid rule vs the reference patched to the same rule; (iii) strict: reported."""
+    batch, g = load_golden(name)
+    r = _np(planner.plan_host(batch, intermediates=True))
+    ok = g["error"] == 0
+    assert (r["grid"][ok, 0] == g["tie_P"][ok]).all()
+    err = np.abs(r["path_f64"] - g["tie_path"]).reshape(len(ok), -1).max(1)
+    assert (err[ok] <= 1e-7).all()
+    strict = np.abs(r["path_f64"] - g["path"]).reshape(len(ok), -1).max(1) <= 1e-4
+    print(f"{name}: strict parity {int(strict[ok].sum())}/{int(ok.sum())} (reference's own P coin flip)")
+
+
+@pytest.mark.parametrize("gen,seed,n", [("color", 11, 2048), ("colorless", 12, 2048), ("mixed", 13, 2048)])
+def test_cuda_f32_batches_match_oracle(planner, gen, seed, n):
+    """fp32 coordinates in HBM (the BASELINE layout); the oracle is fed the same values widened to fp64."""
+    batch = synth.gen_mixed(seed, n) if gen == "mixed" else synth.gen_autocross(seed, n)
+    if gen == "colorless":
+        batch = synth.remove_color_info(batch)
+    ref = oracle.plan_batch(batch.astype(np.float64), threads=8)
+    r = _np(planner.plan_host(batch, force_P=ref["P"].astype(np.int16), intermediates=True))
+    assert (r["left_idx"] == ref["left_idx"]).all() and (r["right_idx"] == ref["right_idx"]).all()
+    assert (r["n_wv"][:, 0] == ref["n_left_wv"]).all() and (r["n_wv"][:, 1] == ref["n_right_wv"]).all()
+    assert (r["l2r"] == ref["l2r"]).all() and (r["r2l"] == ref["r2l"]).all()
+    assert np.abs(r["left_wv"] - ref["left_wv"]).max() <= 1e-9 and np.abs(r["right_wv"] - ref["right_wv"]).max() <= 1e-9
+    assert np.abs(r["path_f64"] - ref["path"]).max() <= 1e-7
+    assert np.abs(r["path"] - ref["path"]).max() <= 1e-4
+    assert ((r["status"].astype(np.uint32) & 0xFFFFFF7F) == (ref["status"] & 0xFFFFFF7F)).all()
+
+
+def test_full_size_properties(planner):
+    """BASELINE config 3 (10 000 colourless frames): properties that need no oracle."""
+    B = 10000
+    batch = synth.remove_color_info(synth.gen_autocross(3, B))
+    a = _np(planner.plan_host(batch, intermediates=True))
+    b = _np(planner.plan_host(batch, intermediates=True))
+    for k in ("path", "left_idx", "right_idx", "status", "path_f64"):
+        assert np.array_equal(a[k], b[k]), f"{k} not deterministic"
+    # shard independence: two halves planned separately equal the full batch (multi-GPU partition)
+    lo = _np(planner.plan_host(batch.slice(0, B // 2), intermediates=True))
+    hi = _np(planner.plan_host(batch.slice(B // 2, B), intermediates=True))
+    assert np.array_equal(np.concatenate([lo["path"], hi["path"]]), a["path"])
+    assert np.array_equal(np.concatenate([lo["left_idx"], hi["left_idx"]]), a["left_idx"])
+    # every frame produced a usable path: u strictly increasing, finite values, |curvature| <= 1
+    assert np.isfinite(a["path"]).all()
+    assert (np.diff(a["path"][:, :, 0], axis=1) > 0).all()
+    assert (np.abs(a["path"][:, :, 3]) <= 1.0 + 1e-6).all()
+    # sort indices: valid, unique within a side, -1 padded at the end only
+    n = np.diff(batch.offsets)
+    for idx in (a["left_idx"], a["right_idx"]):
+        valid = idx >= 0
+        assert (idx[valid] < np.repeat(n, valid.sum(1))).all()
+        assert (np.diff(valid.astype(int), axis=1) <= 0).all()
+        s = np.sort(idx, axis=1)
+        assert ((np.diff(s, axis=1) != 0) | (s[:, 1:] < 0)).all()
+
+
+def test_rigid_motion_equivariance(planner):
+    """Planning a rotated + translated copy of a frame gives the same sort indices and the transformed path."""
+    B = 1024
+    batch = synth.gen_autocross(21, B).astype(np.float64)
+    rng = np.random.default_rng(0)
+    th = rng.uniform(-np.pi, np.pi, B)
+    tr = rng.uniform(-50, 50, (B, 2))
+    c, s = np.cos(th), np.sin(th)
+    frame_of = np.repeat(np.arange(B), np.diff(batch.offsets))
+
+    def move(p, f):
+        return np.stack([c[f] * p[:, 0] - s[f] * p[:, 1], s[f] * p[:, 0] + c[f] * p[:, 1]], 1) + tr[f]
+
+    moved = synth.FrameBatch(move(batch.cones_xy, frame_of), batch.cones_type, batch.offsets,
+                             move(batch.pos, np.arange(B)),
+                             np.stack([c * batch.dir[:, 0] - s * batch.dir[:, 1], s * batch.dir[:, 0] + c * batch.dir[:, 1]], 1))
+    a = _np(planner.plan_host(batch, intermediates=True))
+    force = torch.from_numpy(a["grid"][:, 0].copy())
+    m = _np(planner.plan_host(moved, force_P=a["grid"][:, 0], intermediates=True))
+    same = (a["left_idx"] == m["left_idx"]).all(1) & (a["right_idx"] == m["right_idx"]).all(1)
+    assert same.mean() > 0.999, f"sort indices changed under a rigid motion in {int((~same).sum())} frames"
+    exp_xy = np.stack([c[:, None] * a["path_f64"][:, :, 1] - s[:, None] * a["path_f64"][:, :, 2] + tr[:, None, 0],
+                       s[:, None] * a["path_f64"][:, :, 1] + c[:, None] * a["path_f64"][:, :, 2] + tr[:, None, 1]], -1)
+    # frames whose previous-path fallback fired are tied to the global origin and are not equivariant
+    clean = same & ((a["status"].astype(np.uint32) & 0x7C) == 0) & ((m["status"].astype(np.uint32) & 0x7C) == 0)
+    err = np.abs(m["path_f64"][:, :, 1:3] - exp_xy).reshape(B, -1).max(1)
+    kerr = np.abs(m["path_f64"][:, :, 3] - a["path_f64"][:, :, 3]).max(1)
+    assert clean.mean() > 0.8
+    assert np.percentile(err[clean], 99) < 1e-6 and np.percentile(kerr[clean], 99) < 1e-6
+
+
+def test_stage_entry_points_compose(planner):
+    """fsd_sort_batch -> fsd_match_batch -> fsd_path_batch equals fsd_plan_batch."""
+    lib, dev = planner.lib, planner.device
+    batch = synth.gen_autocross(31, 512)
+    B = batch.n_frames
+    full = _np(planner.plan_host(batch, intermediates=True))
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if dt is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    xy, ty, off, pos, dr = t(batch.cones_xy), t(batch.cones_type), t(batch.offsets), t(batch.pos), t(batch.dir)
+    li = torch.empty((B, 12), dtype=torch.int16, device=dev)
+    ri = torch.empty_like(li)
+    dbg = torch.empty((B, 8), dtype=torch.int16, device=dev)
+    st = torch.empty((B,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    p = planner.params
+    _lib.check(lib.fsd_sort_batch(C.byref(p), B, xy.data_ptr(), ty.data_ptr(), off.data_ptr(), pos.data_ptr(),
+                                  dr.data_ptr(), li.data_ptr(), ri.data_ptr(), dbg.data_ptr(), st.data_ptr(), stream))
+    assert np.array_equal(li.cpu().numpy(), full["left_idx"]) and np.array_equal(ri.cpu().numpy(), full["right_idx"])
+    bufs = {k: torch.empty_like(getattr(planner.plan_host(batch, intermediates=True), k)) for k in
+            ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg")}
+    inter = _lib.Intermediate(*[bufs[k].data_ptr() for k in
+                                ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg")])
+    st2 = torch.empty_like(st)
+    _lib.check(lib.fsd_match_batch(C.byref(p), B, xy.data_ptr(), off.data_ptr(), pos.data_ptr(), dr.data_ptr(),
+                                   li.data_ptr(), ri.data_ptr(), C.byref(inter), st2.data_ptr(), stream))
+    assert np.array_equal(bufs["n_wv"].cpu().numpy(), full["n_wv"])
+    assert np.array_equal(bufs["l2r"].cpu().numpy(), full["l2r"])
+    assert np.array_equal(bufs["left_wv"].cpu().numpy(), full["left_wv"])
+    out = torch.empty((B, 40, 4), dtype=torch.float32, device=dev)
+    st3 = torch.zeros_like(st)
+    prev = planner.initial_path()
+    _lib.check(lib.fsd_path_batch(C.byref(p), B, 0, pos.data_ptr(), dr.data_ptr(), C.byref(inter), None,
+                                  prev.data_ptr(), 0, out.data_ptr(), st3.data_ptr(), stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), full["path"])
+    assert np.array_equal((st.cpu().numpy() | st2.cpu().numpy() | st3.cpu().numpy()), full["status"])
+
+
+def test_kernel_event_mode_equals_single_call(planner):
+    batch = synth.gen_autocross(41, 256)
+    a = _np(planner.plan_host(batch, intermediates=True))
+    dev = planner.device
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    res = planner.plan(t(batch.cones_xy), t(batch.cones_type), t(batch.offsets), t(batch.pos), t(batch.dir),
+                       kernel_events=True)
+    torch.cuda.synchronize()
+    times = planner.kernel_times_ms()
+    assert len(times) == 1 and times[0][0] > 0 and times[0][1] > 0
+    assert np.array_equal(res.path.cpu().numpy(), a["path"]) and np.array_equal(res.status.cpu().numpy(), a["status"])
+
+
+def test_edge_cases(planner):
+    """Empty batch, frames without cones, ragged frames, more than FSD_MAX_CONES cones."""
+    z = np.zeros((0, 2))
+    frames = [([z, z, z, z, z], np.zeros(2), np.array([1.0, 0.0]))]
+    cones, pos, direction = synth.gen_autocross_frame(2, 0)
+    frames.append((cones, pos, direction))
+    frames.append(([z, z, z, z, z], np.ones(2), np.array([0.0, 1.0])))
+    rng = np.random.default_rng(1)
+    big = [rng.uniform(-60, 60, (300, 2)), z, z, z, z]  # 300 cones > FSD_MAX_CONES
+    frames.append((big, np.zeros(2), np.array([1.0, 0.0])))
+    batch = synth.pack_frames(frames)
+    r = _np(planner.plan_host(batch, intermediates=True))
+    ref = oracle.plan_batch(batch.slice(0, 3), force_P=r["grid"][:3, 0])
+    assert np.abs(r["path_f64"][:3] - ref["path"]).max() < 1e-7
+    assert (r["left_idx"][:3] == ref["left_idx"]).all()
+    assert r["status"][0] & _lib.STATUS_BITS["FEW_CONES"] and r["status"][3] & _lib.STATUS_BITS["OVERFLOW"]
+    assert np.isfinite(r["path"]).all()
+    # B = 0
+    empty = synth.pack_frames([])
+    res = planner.plan_host(empty)
+    assert res.path.shape[0] == 0
+
+
+def test_previous_path_input(planner):
+    """Stateful use: a per-frame previous path feeds the fallbacks (core_calculate_path.py:531-536)."""
+    z = np.zeros((0, 2))
+    frames = [([z, z, z, z, z], np.array([1.0, 0.5]), np.array([1.0, 0.1])) for _ in range(3)]
+    batch = synth.pack_frames(frames)
+    init = oracle.initial_path()
+    other = init.copy()
+    other[:, 2] += 0.05 * other[:, 1]  # a slightly different previous path
+    prev = np.stack([init, other, init])
+    r = _np(planner.plan_host(batch, prev_path=prev, intermediates=True))
+    assert np.array_equal(r["path_f64"][0], r["path_f64"][2])
+    assert not np.array_equal(r["path_f64"][0], r["path_f64"][1])
+    lib = oracle.lib()
+    res = oracle.Result()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    xy, ty = np.zeros((1, 2)), np.zeros(1, np.uint8)
+    pos, dr = np.array([1.0, 0.5]), np.array([1.0, 0.1])
+    lib.fsd_oracle_plan_frame(dp(xy), ty.ctypes.data_as(C.POINTER(C.c_ubyte)), 0, dp(pos), dp(dr), int(r["grid"][1, 0]),
+                              dp(np.ascontiguousarray(other)), C.byref(res))
+    assert np.abs(np.ctypeslib.as_array(res.path) - r["path_f64"][1]).max() < 1e-7
+
+
+def test_drop_in_path_planner_sequential():
+    """The facade, called like the reference (one frame after the other, stateful), on the recorded FSG log."""
+    batch, g = load_golden("fsg_color")
+    pp = PathPlanner(MissionTypes.trackdrive)
+    worst = 0.0
+    for b in range(0, 40):
+        cones, pos, direction = batch.frame(b)
+        out = pp.calculate_path_in_global_frame(cones, pos, direction, return_intermediate_results=True)
+        path, sl, sr, lwv, rwv, l2r, r2l = out
+        assert path.shape == (40, 4) and path.dtype == np.float64
+        worst = max(worst, np.abs(path - g["tie_path"][b]).max())
+        nl, nr = int(g["n_left_wv"][b]), int(g["n_right_wv"][b])
+        assert lwv.shape == (nl, 2) and rwv.shape == (nr, 2)
+        assert (l2r == g["l2r"][b][:nl]).all() and (r2l == g["r2l"][b][:nr]).all()
+        li = g["left_idx"][b]
+        assert np.array_equal(sl, batch.cones_xy[batch.offsets[b]:batch.offsets[b + 1]][li[li >= 0]])
+    assert worst < 1e-7
+    yaw = float(np.arctan2(direction[1], direction[0]))
+    p2 = PathPlanner(MissionTypes.trackdrive).calculate_path_in_global_frame(cones, pos, yaw)
+    assert np.abs(p2 - PathPlanner(MissionTypes.trackdrive).calculate_path_in_global_frame(cones, pos, direction / np.linalg.norm(direction))).max() < 1e-6
+    with pytest.raises(ValueError, match="direction must be a float or a 2 element array"):
+        pp.calculate_path_in_global_frame(cones, pos, [1.0, 0.0, 0.0])
+    with pytest.raises(NotImplementedError):
+        PathPlanner(MissionTypes.skidpad)

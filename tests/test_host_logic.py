@@ -1,0 +1,73 @@
+"""Host-side logic: packed frame format, synthetic generator, sharding arithmetic, facade argument handling."""
+import numpy as np
+import pytest
+
+from ft_fsd_path_planning_b200 import synth
+from ft_fsd_path_planning_b200.distributed import shard_bounds
+from ft_fsd_path_planning_b200.enums import ConeTypes, MissionTypes
+
+
+def test_enums_match_reference_values():
+    assert [int(c) for c in ConeTypes] == [0, 1, 2, 3, 4]
+    assert ConeTypes.YELLOW == ConeTypes.RIGHT == 1 and ConeTypes.BLUE == ConeTypes.LEFT == 2
+    assert MissionTypes.trackdrive == 4 and MissionTypes.autocross == 3 and MissionTypes.skidpad == 2
+
+
+def test_generator_is_a_pure_function_of_seed_and_index():
+    a = synth.gen_autocross(2, 8)
+    b = synth.gen_autocross(2, 4, start=4)
+    c = a.slice(4, 8)
+    assert np.array_equal(b.cones_xy, c.cones_xy) and np.array_equal(b.offsets, c.offsets)
+    assert np.array_equal(b.pos, c.pos) and np.array_equal(b.cones_type, c.cones_type)
+    n = np.diff(a.offsets)
+    assert n.min() >= 40 and n.max() <= synth.MAX_CONES_PER_FRAME
+    assert a.cones_xy.dtype == np.float32
+
+
+def test_pack_and_unpack_round_trip():
+    frames = [synth.gen_autocross_frame(3, i) for i in range(5)]
+    batch = synth.pack_frames(frames)
+    for i, (cones, pos, direction) in enumerate(frames):
+        c2, p2, d2 = batch.frame(i)
+        for t in range(5):
+            assert np.array_equal(np.asarray(cones[t]).reshape(-1, 2), c2[t])
+        assert np.array_equal(pos, p2) and np.array_equal(direction, d2)
+    # cones are stored in ConeTypes order inside a frame
+    lo, hi = batch.offsets[0], batch.offsets[1]
+    assert (np.diff(batch.cones_type[lo:hi].astype(int)) >= 0).all()
+
+
+def test_remove_color_and_mixed():
+    b = synth.gen_autocross(5, 6)
+    u = synth.remove_color_info(b)
+    assert (u.cones_type == 0).all() and np.array_equal(u.cones_xy, b.cones_xy)
+    m = synth.gen_mixed(5, 6)
+    assert np.array_equal(np.diff(m.offsets), np.diff(b.offsets))
+    assert (m.slice(1, 2).cones_type == b.slice(1, 2).cones_type).all()  # odd frames keep their colours
+    assert (m.slice(0, 1).cones_type == 0).any()
+
+
+def test_algorithmic_bytes_formula():
+    b = synth.gen_autocross(2, 3)
+    assert b.algorithmic_bytes() == 9 * b.total_cones + 708 * 3
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (65536, 8), (5, 8), (0, 2)])
+def test_shard_bounds_partition(n, world):
+    covered = []
+    for r in range(world):
+        lo, hi = shard_bounds(n, r, world)
+        assert 0 <= lo <= hi <= n
+        covered.extend(range(lo, hi))
+    assert covered == list(range(n))
+
+
+def test_direction_conversion_like_reference():
+    from ft_fsd_path_planning_b200.planner import PathPlanner
+
+    conv = PathPlanner._convert_direction_to_array
+    assert np.allclose(conv(np.pi / 2), [0.0, 1.0])
+    assert np.allclose(conv([0.0, 2.0]), [0.0, 2.0])
+    assert np.allclose(conv(np.array([[0.3]])), [np.cos(0.3), np.sin(0.3)])
+    with pytest.raises(ValueError, match="direction must be a float or a 2 element array"):
+        conv([1.0, 2.0, 3.0])

@@ -1,0 +1,52 @@
+"""The kernels' own per-frame sources (sort.cuh / match.cuh / spline.cuh / path.cuh) compiled for the host with a
+one-lane warp (csrc/hostcheck.cpp) against the golden vectors and scipy's spline fits.  CPU only; this is a check
+of the kernel logic, not a product path."""
+import os
+
+import numpy as np
+
+import hostcheck
+from conftest import GOLDEN_DIR, compare_with_golden
+
+
+def test_kernel_sources_match_reference(golden):
+    name, batch, g = golden
+    h = hostcheck.plan_batch(batch, force_P=g["P"])
+    compare_with_golden(name, g, h["left_idx"], h["right_idx"], h["n_wv"], h["left_wv"], h["right_wv"], h["l2r"],
+                        h["r2l"], h["path"], path_tol=1e-7)
+    ok = g["error"] == 0
+    assert (h["grid"][ok, 1] == g["n_trim"][ok]).all()
+    assert not (h["status"] & ((1 << 8) | (1 << 10))).any(), "overflow / unsupported flagged"
+
+
+def test_kernel_sources_tie_rule(golden):
+    name, batch, g = golden
+    h = hostcheck.plan_batch(batch)
+    ok = g["error"] == 0
+    assert (h["grid"][ok, 0] == g["tie_P"][ok]).all()
+    err = np.abs(h["path"] - g["tie_path"]).reshape(len(ok), -1).max(1)
+    assert (err[ok] <= 1e-7).all(), name
+    assert (h["status"][ok] & (1 << 7)).mean() > 0.9, "run-time grids are ties by construction (SURVEY Q13)"
+
+
+def test_normal_equation_spline_fit_matches_scipy():
+    """Knot vectors identical to scipy.interpolate.splprep, coefficients to 1e-9 (normal equations + Cholesky vs
+    FITPACK's Givens sweep)."""
+    f = np.load(os.path.join(GOLDEN_DIR, "fitpack.npz"))
+    pts, meta = f["points"], f["meta"]
+    worst = 0.0
+    for i, (m, k, s, fp, ier, n, start) in enumerate(meta):
+        m, k, n, start, ier = int(m), int(k), int(n), int(start), int(ier)
+        p = pts[start : start + m]
+        t, cx, cy, kk, ier2 = hostcheck.fit(p, s)
+        assert kk == k and len(t) == n and ier2 == ier, (i, m, s, len(t), n, ier2, ier)
+        assert np.array_equal(t, f["knots"][i][:n]), i
+        nk1 = n - k - 1
+        worst = max(worst, np.abs(cx - f["coefs"][i][0][:nk1]).max(), np.abs(cy - f["coefs"][i][1][:nk1]).max())
+    assert worst < 1e-9, worst
+
+
+def test_initial_path_matches_oracle():
+    import oracle
+
+    assert np.abs(hostcheck.initial_path() - oracle.initial_path()).max() < 1e-9
