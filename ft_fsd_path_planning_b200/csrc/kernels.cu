@@ -125,7 +125,7 @@ __device__ void stage_frame(SortCta &C, const T *xy, const uint8_t *type, int n,
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32) sort_match_kernel(DevParams P, int n_frames, const T *cones_xy,
+__global__ void __launch_bounds__(32, 8) sort_match_kernel(DevParams P, int n_frames, const T *cones_xy,
                                                         const uint8_t *cones_type, const int32_t *offsets,
                                                         const T *pos, const T *dir, StageOut O, int do_match) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, co
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32) path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O,
+__global__ void __launch_bounds__(32, 8) path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O,
                                                   const int16_t *force_P, const double *prev, int prev_stride,
                                                   double *out_f64, float *out_f32, int16_t *grid_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -391,9 +391,10 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                     int16_t *out_right_idx, const fsd_intermediate *inter, const int16_t *force_P,
                     const double *prev_path, int prev_path_stride, uint32_t *out_status, void *workspace,
                     size_t workspace_bytes_given, void *stream_v) {
-  if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status) return FSD_ERR_ARG;
+  if (!params || n_frames < 0) return FSD_ERR_ARG;
   if (mission != FSD_MISSION_AUTOCROSS && mission != FSD_MISSION_TRACKDRIVE) return FSD_ERR_MISSION;
   if (n_frames == 0) return FSD_OK;
+  if (!offsets || !pos || !dir || !out_status) return FSD_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   fsd_intermediate R;
   double *init_slot = nullptr;

@@ -20,7 +20,7 @@
 #if defined(__CUDACC__) && !defined(FSD_HOSTCHECK)
 #define FSD_DEVICE_BUILD 1
 #define FSD_DEV __device__ __forceinline__
-#define FSD_DEVFN __device__
+#define FSD_DEVFN __device__ __noinline__
 #else
 #define FSD_DEV static inline
 #define FSD_DEVFN static
@@ -101,6 +101,12 @@ FSD_DEV double wlast(double v) { return v; }
 #endif
 
 constexpr double PI = 3.14159265358979323846;
+
+// double-precision transcendental functions are large once inlined: one out-of-line copy per kernel
+FSD_DEVFN double fsd_atan2(double y, double x) { return atan2(y, x); }
+FSD_DEVFN double fsd_acos(double x) { return acos(x); }
+FSD_DEVFN double fsd_cos(double x) { return cos(x); }
+FSD_DEVFN double fsd_sin(double x) { return sin(x); }
 
 FSD_DEV double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 

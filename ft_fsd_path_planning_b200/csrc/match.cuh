@@ -63,7 +63,7 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
     return m == 1;
   }
   const double inv_major2 = 1.0 / (P.match_major * P.match_major), inv_minor2 = 1.0 / (P.match_minor * P.match_minor);
-  const double cos_limit = cos(2.0 * P.max_search_angle);
+  const double cos_limit = P.cos_match_limit;
   for (int i = lane; i < n; i += FSD_LANES) {
     const double dxi = S.dirs[i].x, dyi = S.dirs[i].y;
     bool any = false;
@@ -91,7 +91,7 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
 }
 
 // insert_virtual_cones_to_existing :195-261 (lane 0).  Result in S.ex, returns its length.
-FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, const FramePose &F) {
+FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, const FramePose &F, const DevParams &P) {
   int ne, ni;
   if (no > nv) {
     for (int i = 0; i < no; ++i) S.ex[i] = other[i];
@@ -160,7 +160,7 @@ FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, cons
     ++ne;
   }
   // interior points whose polyline angle is below 85 deg are removed, all at once (:252-259)
-  const double cos85 = cos(85.0 * PI / 180.0);
+  const double cos85 = P.cos_85deg;
   bool drop[WV_CAP + 1];
   for (int i = 0; i < ne; ++i) drop[i] = false;
   for (int i = 1; i + 1 < ne; ++i)
@@ -194,7 +194,7 @@ FSD_DEVFN int cones_for_other_side(MatchSmem &S, const d2 *cones, int n, int sid
       for (int i = 0; i < m; ++i) out[i] = other[i];
       no = m;
     } else {
-      no = insert_virtual(S, other, m, nv, F);
+      no = insert_virtual(S, other, m, nv, F, P);
       for (int i = 0; i < no; ++i) out[i] = S.ex[i];
     }
     if (no < 2) {

@@ -315,14 +315,14 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
         d2 p0 = {rel[0].x - cx, rel[0].y - cy}, p1 = {rel[nr / 2].x - cx, rel[nr / 2].y - cy},
            p2 = {rel[nr - 1].x - cx, rel[nr - 1].y - cy};
         const double sg = sgn(orient(p0, p1, p2));
-        const double a0 = atan2(p0.y, p0.x), a1 = a0 + sg * PI;
+        const double a0 = fsd_atan2(p0.y, p0.x), a1 = a0 + sg * PI;
         const double stepa = (a1 - a0) / 49.0;  // np.linspace(a0, a1) has 50 samples; the first is dropped
-        const double r0x = cos(a0) * r_use, r0y = sin(a0) * r_use;
+        const double r0x = fsd_cos(a0) * r_use, r0y = fsd_sin(a0) * r_use;
         wsync();
         for (int i = 1 + lane; i < 50; i += FSD_LANES) {
           double ang = i == 49 ? a1 : (double)i * stepa + a0;
-          path[n + i - 1].x = cos(ang) * r_use - r0x + lastx;
-          path[n + i - 1].y = sin(ang) * r_use - r0y + lasty;
+          path[n + i - 1].x = fsd_cos(ang) * r_use - r0x + lastx;
+          path[n + i - 1].y = fsd_sin(ang) * r_use - r0y + lasty;
         }
         n += 49;
       } else {
@@ -503,10 +503,10 @@ FSD_DEVFN unsigned initial_path_frame(PathSmem &S, const DevParams &P, double *o
   unsigned status = 0;
   // calculate_almost_straight_path: 40 points of a chord, radius 1000 m, angle pi/50, turned by -pi/2
   const double max_angle = PI / 50.0, radius = 1000.0, stp = max_angle / (FSD_HORIZON - 1);
-  const double c = cos(-PI / 2.0), s = sin(-PI / 2.0);
+  const double c = fsd_cos(-PI / 2.0), s = fsd_sin(-PI / 2.0);
   for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
     double a = i == FSD_HORIZON - 1 ? max_angle : (double)i * stp;
-    double px = (cos(a) - 1.0) * radius, py = sin(a) * radius;
+    double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;
     S.centre[i].x = px * c - py * s;
     S.centre[i].y = px * s + py * c;
   }

@@ -13,7 +13,7 @@ struct FramePose {
 struct DevParams {
   int max_n_neighbors, max_length, max_dfs_pops;
   double max_dist, max_dist2, max_dist_to_first, thr_dir, thr_abs, car_size;
-  double cos_5deg, cos_150deg;
+  double cos_5deg, cos_150deg, cos_seed_max, cos_seed_min, cos_match_limit, cos_85deg;
   double min_track_width, match_major, match_minor, max_search_angle;
   double smoothing, predict_every, max_valid_dist, mpc_len, refit_smoothing;
 };
@@ -31,6 +31,10 @@ static inline DevParams make_dev_params(const fsd_params &p) {
   d.car_size = p.car_size;
   d.cos_5deg = cos(5.0 * PI / 180.0);
   d.cos_150deg = cos(150.0 * PI / 180.0);
+  d.cos_seed_max = cos(PI - PI / 5.0);   // |bearing| < 4 pi / 5
+  d.cos_seed_min = cos(PI / 10.0);        // |bearing| > pi / 10
+  d.cos_match_limit = cos(2.0 * p.max_search_angle);
+  d.cos_85deg = cos(85.0 * PI / 180.0);
   d.min_track_width = p.min_track_width;
   d.match_major = p.max_search_range * 1.5;
   d.match_minor = p.min_track_width;

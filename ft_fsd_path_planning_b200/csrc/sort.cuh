@@ -134,7 +134,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
   const double dn = sqrt(F.dx * F.dx + F.dy * F.dy);
   const double c = F.dx / dn, s = F.dy / dn;  // rotation by -yaw
   const double major = P.max_dist_to_first * 1.5, minor = P.max_dist_to_first / 1.5;
-  const double cos_max = cos(PI - PI / 5.0), cos_min = cos(PI / 10.0);
+  const double cos_max = P.cos_seed_max, cos_min = P.cos_seed_min;
   double bv = 0.0;
   int bi = -1;
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
@@ -302,7 +302,7 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
     if (sqrt(d2) < 6.0 && sqrt(d1) < 6.0 && cos_between(v1x, v1y, v2x, v2y) < P.cos_150deg) return false;
   }
   if (pos >= 1) {
-    double angle_1 = atan2(ay, ax), angle_2 = atan2(by, bx);
+    double angle_1 = fsd_atan2(ay, ax), angle_2 = fsd_atan2(by, bx);
     double difference = angle_difference(angle_2, angle_1);
     double len = sqrt(bx * bx + by * by);
     bool ok;
@@ -314,7 +314,7 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
       ok = difference > -P.thr_dir || len < 4.0;
     if (pos >= 2) {
       const int prev = S.attempt[pos - 1], pp = S.attempt[pos - 2];
-      double angle_3 = atan2(S.xy[prev].y - S.xy[pp].y, S.xy[prev].x - S.xy[pp].x);
+      double angle_3 = fsd_atan2(S.xy[prev].y - S.xy[pp].y, S.xy[prev].x - S.xy[pp].x);
       double difference_2 = angle_difference(angle_1, angle_3);
       if (sgn(difference) != sgn(difference_2) && fabs(difference - difference_2) > 1.3) ok = false;
     }
@@ -610,7 +610,7 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
     double asum = 0.0;
     int under = 0;
     for (int q = 0; q + 2 < len; ++q) {
-      double th = acos(cos_between(px[q + 1] - px[q + 2], py[q + 1] - py[q + 2], px[q + 1] - px[q], py[q + 1] - py[q]));
+      double th = fsd_acos(cos_between(px[q + 1] - px[q + 2], py[q + 1] - py[q + 2], px[q + 1] - px[q], py[q + 1] - py[q]));
       asum += (PI - th) / PI;
       under += th < 40.0 * PI / 180.0;
     }
@@ -623,15 +623,15 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
       resid += d > 0.0 ? d : 0.0;
     }
     double ncones = 1.0 / (double)len;
-    double init_dir = acos(cos_between(px[1] - px[0], py[1] - py[0], F.dx, F.dy));
+    double init_dir = fsd_acos(cos_between(px[1] - px[0], py[1] - py[0], F.dx, F.dy));
     double either = 1.0 / (double)(S.n_good[r] - S.n_bad[r] + (mn < 0 ? -mn : mn) + 1);
     // wrong direction (:149-188)
     double wrong = 0.0;
     if (len != 3) {
       double unwanted = side == FSD_CONE_LEFT ? 1.0 : -1.0, sum = 0.0;
-      double prev = atan2(py[1] - py[0], px[1] - px[0]);
+      double prev = fsd_atan2(py[1] - py[0], px[1] - px[0]);
       for (int q = 1; q + 1 < len; ++q) {
-        double cur = atan2(py[q + 1] - py[q], px[q + 1] - px[q]);
+        double cur = fsd_atan2(py[q + 1] - py[q], px[q + 1] - px[q]);
         double d = angle_difference(prev, cur);
         if (sgn(d) == unwanted && fabs(d) > 40.0 * PI / 180.0) sum += d;
         prev = cur;
@@ -687,8 +687,8 @@ FSD_DEVFN int sort_one_side(SortSmem &S, int n, const FramePose &F, int side, co
 
 FSD_DEV double angle_change_at(const SortSmem &S, const int16_t *cfg, int p) {
   int a = cfg[p - 1], b = cfg[p], c = cfg[p + 1];
-  double an = atan2(S.xy[c].y - S.xy[b].y, S.xy[c].x - S.xy[b].x);
-  double ap = atan2(S.xy[a].y - S.xy[b].y, S.xy[a].x - S.xy[b].x);
+  double an = fsd_atan2(S.xy[c].y - S.xy[b].y, S.xy[c].x - S.xy[b].x);
+  double ap = fsd_atan2(S.xy[a].y - S.xy[b].y, S.xy[a].x - S.xy[b].x);
   return angle_difference(an, ap);
 }
 

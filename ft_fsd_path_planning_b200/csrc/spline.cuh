@@ -38,28 +38,61 @@ struct SplineWork {
   double fpint[NCAP];
   int32_t nrdata[NCAP];
   int32_t start[NCAP + 1];
+  double rk[NCAP][6];  // reciprocal knot differences of the B-spline recursion, per knot interval
   int32_t n, k;   // result: knot count, degree
   double max_u;   // last parameter value of the fitted data
 };
 
-// B-spline basis values of degree k at x for the knot interval t[l] <= x < t[l+1] (0-based l)
-FSD_DEV void bspl(const double *t, int k, double x, int l, double *h) {
+// Reciprocal knot differences 1 / (t[l+i] - t[l+i-j]) of the de Boor recursion for every knot interval
+// (0 where the difference vanishes, which reproduces fpbspl's "h(i+1) = 0" branch).  Entry order: (j,i) =
+// (1,1) (2,1) (2,2) (3,1) (3,2) (3,3).  One division per table entry instead of six per evaluated point.
+FSD_DEVFN void knot_reciprocals(SplineWork &W, int n, int k) {
+  const int nrint = n - 2 * k - 1;
+  for (int e = fsd_lane(); e < nrint * 6; e += FSD_LANES) {
+    const int ii = e / 6, q = e % 6;
+    const int j = q == 0 ? 1 : (q < 3 ? 2 : 3);
+    const int i = q == 0 ? 1 : (q < 3 ? q : q - 2);
+    double r = 0.0;
+    if (j <= k) {
+      const int l = k + ii;
+      const double d = W.t[l + i] - W.t[l + i - j];
+      r = d == 0.0 ? 0.0 : 1.0 / d;
+    }
+    W.rk[ii][q] = r;
+  }
+  wsync();
+}
+
+// B-spline basis values of degree k at x for knot interval ii (t[k+ii] <= x < t[k+ii+1]); fully unrolled,
+// division-free, h stays in registers
+template <int K>
+FSD_DEV void bspl_k(const SplineWork &W, double x, int ii, double (&h)[4]) {
+  const int l = K + ii;
+  const double *rk = W.rk[ii];
   double hh[4];
   h[0] = 1.0;
-  for (int j = 1; j <= k; ++j) {
+#pragma unroll
+  for (int j = 1; j <= K; ++j) {
+#pragma unroll
     for (int i = 0; i < j; ++i) hh[i] = h[i];
     h[0] = 0.0;
+#pragma unroll
     for (int i = 1; i <= j; ++i) {
-      double tl = t[l + i], tr = t[l + i - j];
-      if (tl == tr) {
-        h[i] = 0.0;
-      } else {
-        double f = hh[i - 1] / (tl - tr);
-        h[i - 1] += f * (tl - x);
-        h[i] = f * (x - tr);
-      }
+      const double tl = W.t[l + i], tr = W.t[l + i - j];
+      const double f = hh[i - 1] * rk[(j * (j - 1)) / 2 + i - 1];
+      h[i - 1] += f * (tl - x);
+      h[i] = f * (x - tr);
     }
   }
+}
+
+FSD_DEV void bspl(const SplineWork &W, int k, double x, int ii, double (&h)[4]) {
+  if (k == 3)
+    bspl_k<3>(W, x, ii, h);
+  else if (k == 2)
+    bspl_k<2>(W, x, ii, h);
+  else
+    bspl_k<1>(W, x, ii, h);
 }
 
 FSD_DEV void spline_point(const SplineWork &W, double x, double &ox, double &oy) {
@@ -67,13 +100,15 @@ FSD_DEV void spline_point(const SplineWork &W, double x, double &ox, double &oy)
   const int k = W.k, nk1 = W.n - k - 1;
   int l = k;
   while (l < nk1 - 1 && x >= W.t[l + 1]) ++l;
-  double h[4];
-  bspl(W.t, k, x, l, h);
+  double h[4] = {0, 0, 0, 0};
+  bspl(W, k, x, l - k, h);
   double sx = 0.0, sy = 0.0;
-  for (int j = 0; j <= k; ++j) {
-    sx += W.c[l - k + j][0] * h[j];
-    sy += W.c[l - k + j][1] * h[j];
-  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j <= k) {
+      sx += W.c[l - k + j][0] * h[j];
+      sy += W.c[l - k + j][1] * h[j];
+    }
   ox = sx;
   oy = sy;
 }
@@ -81,7 +116,9 @@ FSD_DEV void spline_point(const SplineWork &W, double x, double &ox, double &oy)
 // banded Cholesky (upper, in place in M), forward and back substitution; lane 0 only.
 // returns false on a non-positive pivot.
 FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2]) {
+  // M[i][0] holds the diagonal of G on return (fppara's p0 needs it); rows are scaled with one reciprocal each
   for (int i = 0; i < nk1; ++i) {
+    double rinv = 0.0;
     for (int d = 0; d < kb; ++d) {
       int j = i + d;
       if (j >= nk1) break;
@@ -91,13 +128,14 @@ FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2]
       for (int p = p0; p < i; ++p) s -= M[p][i - p] * M[p][j - p];
       if (d == 0) {
         if (!(s > 0.0)) return false;
-        M[i][0] = sqrt(s);
+        const double g = sqrt(s);
+        M[i][0] = g;
+        rinv = 1.0 / g;
       } else {
-        M[i][d] = s / M[i][0];
+        M[i][d] = s * rinv;
       }
     }
-  }
-  for (int i = 0; i < nk1; ++i) {
+    // forward substitution of row i rides along: z = G^-T rhs
     double s0 = rhs[i][0], s1 = rhs[i][1];
     int p0 = i - kb + 1;
     if (p0 < 0) p0 = 0;
@@ -106,8 +144,8 @@ FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2]
       s0 -= g * z[p][0];
       s1 -= g * z[p][1];
     }
-    z[i][0] = s0 / M[i][0];
-    z[i][1] = s1 / M[i][0];
+    z[i][0] = s0 * rinv;
+    z[i][1] = s1 * rinv;
   }
   for (int i = nk1 - 1; i >= 0; --i) {
     double s0 = z[i][0], s1 = z[i][1];
@@ -118,8 +156,9 @@ FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2]
       s0 -= g * c[i + l][0];
       s1 -= g * c[i + l][1];
     }
-    c[i][0] = s0 / M[i][0];
-    c[i][1] = s1 / M[i][0];
+    const double rinv = 1.0 / M[i][0];
+    c[i][0] = s0 * rinv;
+    c[i][1] = s1 * rinv;
   }
   return true;
 }
@@ -163,7 +202,7 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
     const int lo = W.start[ii], hi = W.start[ii + 1];
     for (int i = lo + lane; i < hi; i += FSD_LANES) {
       double h[4] = {0, 0, 0, 0};
-      bspl(W.t, k, u[i], k + ii, h);
+      bspl(W, k, u[i], ii, h);
       const double x = pts[i].x, y = pts[i].y;
       int e = 0;
 #pragma unroll
@@ -211,12 +250,14 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
     for (int i = lo + lane; i <= last; i += FSD_LANES) {
       const int li = i >= hi ? ii + 1 : ii;
       double h[4] = {0, 0, 0, 0};
-      bspl(W.t, k, u[i], k + li, h);
+      bspl(W, k, u[i], li, h);
       double sx = 0.0, sy = 0.0;
-      for (int j = 0; j <= k; ++j) {
-        sx += W.c[li + j][0] * h[j];
-        sy += W.c[li + j][1] * h[j];
-      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j <= k) {
+          sx += W.c[li + j][0] * h[j];
+          sy += W.c[li + j][1] * h[j];
+        }
       double ex = sx - pts[i].x, ey = sy - pts[i].y;
       double term = ex * ex + ey * ey;
       double wgt = ((i == lo && ii > 0) || i >= hi) ? 0.5 : 1.0;
@@ -324,6 +365,7 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
       }
     wsync();
     interval_starts(W, u, m, n, k);
+    knot_reciprocals(W, n, k);
     assemble_normal(W, pts, u, n, k);
     if (lane == 0) {
       for (int i = 0; i < nk1; ++i)

@@ -57,6 +57,8 @@ class BatchPlanner:
         self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if self.device.type != "cuda":
             raise RuntimeError("BatchPlanner runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = _lib.lib()
         self.params = _lib.default_params()
         self.mission = int(mission)
@@ -115,6 +117,10 @@ class BatchPlanner:
         (read them with `kernel_times_ms()` after a synchronize)."""
         B = offsets.numel() - 1
         f64 = cones_xy.dtype == torch.float64
+        if B == 0:
+            e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=self.device)
+            return PlanResult(e(0, HORIZON, 4), e(0, MAX_SORTED, dt=torch.int16), e(0, MAX_SORTED, dt=torch.int16),
+                              e(0, dt=torch.int32))
         for t, dt in ((cones_xy, None), (cones_type, torch.uint8), (offsets, torch.int32), (pos, cones_xy.dtype),
                       (direction, cones_xy.dtype)):
             if t.device != self.device or not t.is_contiguous() or (dt is not None and t.dtype != dt):
