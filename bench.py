@@ -162,8 +162,9 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
-        step()
+        step(events=True)
     barrier()
+    planner.kernel_times_ms()  # drop the warm-up events
 
     # ---- device-resident throughput: K steps, CUDA events per step, L2 flushed between steps ----------------
     sampler = ClockSampler(local_rank)

@@ -101,7 +101,8 @@ class BatchPlanner:
                     "grid": torch.empty((B, 2), dtype=torch.int16, device=dev),
                     "sort_dbg": torch.empty((B, 8), dtype=torch.int16, device=dev),
                 })
-            self._bufs = {key: bufs}  # keep one shape resident
+            self._bufs = {k: v for k, v in self._bufs.items() if k[0] == B}  # one batch size resident
+            self._bufs[key] = bufs
         return self._bufs[key]
 
     # -- the batched call ------------------------------------------------------------------------------------
