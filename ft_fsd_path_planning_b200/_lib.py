@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libfsdplan.so")
+LIB_PATH = os.environ.get("FSD_LIBFSDPLAN", os.path.join(CSRC, "libfsdplan.so"))  # override: kernel A/B experiments
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "fsdplan.h")
 
 MAX_CONES, MAX_SORTED, MAX_WV, HORIZON = 256, 12, 32, 40
@@ -89,7 +89,7 @@ def lib():
         L.fsd_sort_match_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp,
                                            C.POINTER(Intermediate), vp, vp]
         L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp,
-                                     vp]
+                                     vp, sz, vp]
         if L.fsd_abi_version() != 1:
             raise RuntimeError("libfsdplan.so ABI version mismatch")
         _lib = L

@@ -41,7 +41,10 @@ FSD_DEVFN void store_sort(const SortSmem &S, int b, const StageOut &O) {
 }
 
 // S holds the sorted frame; M is filled from it
-FSD_DEVFN unsigned match_from_sort(const SortSmem &S, MatchSmem &M, const FramePose &F, const DevParams &P) {
+// the sorted cones are read from S.xy into registers first: M overlays the sorting scratch of S
+FSD_DEVFN unsigned match_from_sort(SortSmem &S, const FramePose &F, const DevParams &P) {
+  MatchSmem &M = S.M;
+  wsync();
   for (int q = fsd_lane(); q < 2 * FSD_MAX_SORTED; q += FSD_LANES) {
     const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
     if (j < S.nbest[s]) M.side[s][j] = S.xy[S.best[s][j]];

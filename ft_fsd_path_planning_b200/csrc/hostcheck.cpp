@@ -13,11 +13,23 @@
 
 using namespace fsd;
 
+static PathSmem *new_path_smem() {
+  PathSmem *S = new PathSmem();
+  S->pts = new d2[PCAP];
+  S->u = new double[PCAP];
+  return S;
+}
+static void free_path_smem(PathSmem *S) {
+  delete[] S->pts;
+  delete[] S->u;
+  delete S;
+}
+
 extern "C" int fsd_hostcheck_initial_path(const fsd_params *params, double *out) {
   DevParams P = make_dev_params(*params);
-  PathSmem *S = new PathSmem();
+  PathSmem *S = new_path_smem();
   unsigned st = initial_path_frame(*S, P, out);
-  delete S;
+  free_path_smem(S);
   return (int)st;
 }
 
@@ -28,8 +40,7 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
                                   int16_t *r2l, int16_t *grid, int16_t *sort_dbg, uint32_t *status) {
   DevParams P = make_dev_params(*params);
   SortSmem *S = new SortSmem();
-  MatchSmem *M = new MatchSmem();
-  PathSmem *Q = new PathSmem();
+  PathSmem *Q = new_path_smem();
   double initial[FSD_HORIZON * 4];
   if (!prev) {
     initial_path_frame(*Q, P, initial);
@@ -43,18 +54,17 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
       n = FSD_MAX_CONES;
       st |= FSD_ST_OVERFLOW;
     }
-    FramePose F = {pos[2 * b], pos[2 * b + 1], dir[2 * b], dir[2 * b + 1]};
+    FramePose F = make_pose(pos[2 * b], pos[2 * b + 1], dir[2 * b], dir[2 * b + 1]);
     load_frame_plain(*S, xy + 2 * (size_t)lo, type + lo, n);
     st |= sort_frame(*S, n, F, P, sort_dbg + 8 * (size_t)b);
     store_sort(*S, b, O);
-    st |= match_from_sort(*S, *M, F, P);
-    store_match(*M, b, O);
+    st |= match_from_sort(*S, F, P);
+    store_match(S->M, b, O);
     status[b] = st;
     path_from_tensors(*Q, b, O, F, force_P ? force_P[b] : 0, prev, P, out_path, nullptr, grid);
   }
   delete S;
-  delete M;
-  delete Q;
+  free_path_smem(Q);
   return 0;
 }
 
@@ -81,9 +91,9 @@ extern "C" int fsd_hostcheck_params_default(fsd_params *p) {
 
 // the spline fit alone, for the comparison with scipy.interpolate.splprep
 extern "C" int fsd_hostcheck_fit(const double *pts, int m, double s, double *t, int *n, double *c, int *k) {
-  PathSmem *Q = new PathSmem();
+  PathSmem *Q = new_path_smem();
   if (m > PCAP) {
-    delete Q;
+    free_path_smem(Q);
     return 10;
   }
   for (int i = 0; i < m; ++i) {
@@ -102,6 +112,6 @@ extern "C" int fsd_hostcheck_fit(const double *pts, int m, double s, double *t, 
       c[2 * i + 1] = Q->W.c[i][1];
     }
   }
-  delete Q;
+  free_path_smem(Q);
   return ier;
 }

@@ -23,6 +23,16 @@ using namespace fsd;
 
 namespace {
 
+// Warps (= frames in flight) per CTA.  The warps of a CTA start every frame together (one __syncthreads per
+// frame): frames walk through the same phases at roughly the same time, so the SM's instruction cache serves
+// all of them from one copy of the phase's code (the kernels are instruction-fetch bound).
+#ifndef FSD_WARPS_PER_CTA
+#define FSD_WARPS_PER_CTA 16
+#endif
+constexpr int WPC = FSD_WARPS_PER_CTA;
+constexpr int CTA_THREADS = 32 * WPC;
+constexpr int CTAS_PER_SM = 16 / WPC;
+
 // ---- TMA bulk copy helpers (raw PTX) ------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,11 +71,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 // shared-memory image of one sort/match CTA
 struct SortCta {
-  SortSmem S;
-  MatchSmem M;
-  alignas(16) float raw[2 * (FSD_MAX_CONES + 2)];  // fp32 staging area of the bulk copy
+  SortSmem S;  // includes the fp32 staging area of the bulk copy (S.raw) and the matching state (S.M)
   alignas(8) uint64_t mbar;
 };
+constexpr size_t SORT_CTA_STRIDE = (sizeof(SortCta) + 15) / 16 * 16;
+constexpr size_t PATH_CTA_STRIDE = (sizeof(PathSmem) + 15) / 16 * 16;
 
 // Stage the frame's coordinates into S.xy (fp64).  The 16-byte aligned interior of the frame's slice goes
 // through the TMA bulk copy; a leading / trailing cone that is not 16-byte aligned (fp32 input, odd offset)
@@ -95,7 +105,7 @@ __device__ void stage_frame(SortCta &C, const T *xy, const uint8_t *type, int n,
     const int head = (int)((reinterpret_cast<uintptr_t>(xy) >> 3) & 1u);  // 1 -> first cone is not 16 B aligned
     const int h = head < n ? head : n;
     const int interior = ((n - h) / 2) * 2;
-    float *store = C.raw + 2 * head;  // keeps the interior 16 B aligned in shared memory
+    float *store = S.raw + 2 * head;  // keeps the interior 16 B aligned in shared memory
     if (interior > 0) {
       if (lane == 0) {
         mbar_expect_tx(&C.mbar, (uint32_t)interior * 8u);
@@ -125,15 +135,19 @@ __device__ void stage_frame(SortCta &C, const T *xy, const uint8_t *type, int n,
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32, 8) sort_match_kernel(DevParams P, int n_frames, const T *cones_xy,
-                                                        const uint8_t *cones_type, const int32_t *offsets,
-                                                        const T *pos, const T *dir, StageOut O, int do_match) {
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+    sort_match_kernel(DevParams P, int n_frames, const T *cones_xy, const uint8_t *cones_type, const int32_t *offsets,
+                      const T *pos, const T *dir, StageOut O, int do_match) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortCta &C = *reinterpret_cast<SortCta *>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  SortCta &C = *reinterpret_cast<SortCta *>(smem_raw + (size_t)warp * SORT_CTA_STRIDE);
   if (fsd_lane() == 0) mbar_init(&C.mbar, 1);
   __syncwarp();
   uint32_t phase = 0;
-  for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
+  for (int base = blockIdx.x * WPC; base < n_frames; base += gridDim.x * WPC) {
+    if (WPC > 1) __syncthreads();
+    const int b = base + warp;
+    if (b >= n_frames) continue;
     const int lo = offsets[b];
     int n = offsets[b + 1] - lo;
     unsigned st = 0;
@@ -142,13 +156,13 @@ __global__ void __launch_bounds__(32, 8) sort_match_kernel(DevParams P, int n_fr
       st |= FSD_ST_OVERFLOW;
     }
     if (n < 0) n = 0;
-    const FramePose F = {(double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]};
+    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
     stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
     st |= sort_frame(C.S, n, F, P, O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr);
     store_sort(C.S, b, O);
     if (do_match) {
-      st |= match_from_sort(C.S, C.M, F, P);
-      store_match(C.M, b, O);
+      st |= match_from_sort(C.S, F, P);
+      store_match(C.S.M, b, O);
     }
     if (fsd_lane() == 0) O.status[b] = st;
     __syncwarp();
@@ -163,7 +177,7 @@ __global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, co
   __shared__ MatchSmem M;
   for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
     const T *xy = cones_xy + 2 * (size_t)offsets[b];
-    const FramePose F = {(double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]};
+    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
     int nl = 0, nr = 0;
     for (int q = 0; q < FSD_MAX_SORTED; ++q) {
       nl += left_idx[(size_t)b * FSD_MAX_SORTED + q] >= 0;
@@ -190,13 +204,24 @@ __global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, co
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32, 8) path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O,
-                                                  const int16_t *force_P, const double *prev, int prev_stride,
-                                                  double *out_f64, float *out_f32, int16_t *grid_out) {
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+    path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
+                const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
+                unsigned char *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
-  for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
-    const FramePose F = {(double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]};
+  const int warp = threadIdx.x >> 5;
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * PATH_CTA_STRIDE);
+  if (fsd_lane() == 0) {
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
+  }
+  __syncwarp();
+  for (int base = blockIdx.x * WPC; base < n_frames; base += gridDim.x * WPC) {
+    if (WPC > 1) __syncthreads();
+    const int b = base + warp;
+    if (b >= n_frames) continue;
+    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
     path_from_tensors(S, b, O, F, force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out_f64, out_f32,
                       grid_out);
     __syncwarp();
@@ -204,14 +229,22 @@ __global__ void __launch_bounds__(32, 8) path_kernel(DevParams P, int n_frames, 
 }
 
 __global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *out) {
+  // one warp, once per device: the point buffers sit in shared memory behind the PathSmem image
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
+  if (fsd_lane() == 0) {
+    unsigned char *mine = smem_raw + ((sizeof(PathSmem) + 15) / 16) * 16;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
+  }
+  __syncwarp();
   initial_path_frame(S, P, out);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
 
 constexpr int MAX_DEVICES = 64;
+constexpr size_t INITIAL_SMEM = ((sizeof(PathSmem) + 15) / 16) * 16 + PATH_SCRATCH_BYTES;
 __device__ double g_initial_path[FSD_HORIZON * 4];  // cache of the default-parameter initial path
 
 struct DeviceInfo {
@@ -240,8 +273,13 @@ int device_info(DeviceInfo **out) {
       return FSD_ERR_NO_DEVICE;
     }
     int a = 0, b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float>, 32, sizeof(SortCta));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, 32, sizeof(PathSmem));
+    cudaFuncSetAttribute(sort_match_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
+    cudaFuncSetAttribute(sort_match_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
+    cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
+    cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, WPC * PATH_CTA_STRIDE);
+    cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
     D.sort_ctas = a > 0 ? a : 1;
     D.path_ctas = b > 0 ? b : 1;
     D.sm_count = prop.multiProcessorCount;
@@ -252,7 +290,8 @@ int device_info(DeviceInfo **out) {
 
 int grid_for(int n_frames, int sm_count, int ctas_per_sm) {
   long cap = (long)sm_count * ctas_per_sm;
-  return (int)(n_frames < cap ? n_frames : cap);
+  long need = ((long)n_frames + WPC - 1) / WPC;
+  return (int)(need < cap ? need : cap);
 }
 
 struct Carve {
@@ -267,9 +306,18 @@ struct Carve {
   }
 };
 
+// upper bound of resident path CTAs (each owns PATH_SCRATCH_BYTES of point buffers in the workspace)
+size_t path_grid_bound(int n_frames) {
+  size_t cap = 160 * 16;  // no device visible: any current part
+  DeviceInfo *D = nullptr;
+  if (device_info(&D) == FSD_OK) cap = (size_t)D->sm_count * D->path_ctas * WPC;
+  const size_t B = ((size_t)(n_frames > 0 ? n_frames : 0) + WPC - 1) / WPC * WPC;
+  return B < cap ? B : cap;
+}
+
 size_t workspace_bytes(int n_frames) {
   const size_t B = (size_t)(n_frames > 0 ? n_frames : 0);
-  size_t total = 0;
+  size_t total = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
   total += align_up(B * FSD_HORIZON * 4 * sizeof(double), 256);         // path_f64
   total += align_up(B * 2 * sizeof(int16_t), 256);                      // n_wv
   total += 2 * align_up(B * FSD_MAX_WV * 2 * sizeof(double), 256);      // left_wv, right_wv
@@ -281,13 +329,14 @@ size_t workspace_bytes(int n_frames) {
 
 // resolve every intermediate tensor to user memory or workspace
 int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t workspace_bytes_given,
-            fsd_intermediate *out, double **initial_slot) {
+            fsd_intermediate *out, double **initial_slot, unsigned char **path_scratch) {
   fsd_intermediate r;
   std::memset(&r, 0, sizeof(r));
   if (inter) r = *inter;
   if (!workspace || workspace_bytes_given < workspace_bytes(n_frames)) return FSD_ERR_WORKSPACE;
   Carve cv = {static_cast<unsigned char *>(workspace), 0, workspace_bytes_given};
   const size_t B = (size_t)n_frames;
+  *path_scratch = cv.take<unsigned char>(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES);
   double *w_path = cv.take<double>(B * FSD_HORIZON * 4);
   int16_t *w_nwv = cv.take<int16_t>(B * 2);
   double *w_lwv = cv.take<double>(B * FSD_MAX_WV * 2);
@@ -324,7 +373,7 @@ int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &
   }
   std::lock_guard<std::mutex> lock(g_mutex);
   if (!D.initial_ready) {
-    initial_path_kernel<<<1, 32, sizeof(PathSmem), stream>>>(P, cached);
+    initial_path_kernel<<<1, 32, INITIAL_SMEM, stream>>>(P, cached);
     if (check_launch() != FSD_OK) return FSD_ERR_LAUNCH;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return FSD_ERR_LAUNCH;  // once per device
     D.initial_ready = true;
@@ -335,7 +384,7 @@ int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &
     return FSD_OK;
   }
   if (!scratch) return FSD_ERR_ARG;  // non-default spline parameters: the caller must pass prev_path
-  initial_path_kernel<<<1, 32, sizeof(PathSmem), stream>>>(P, scratch);
+  initial_path_kernel<<<1, 32, INITIAL_SMEM, stream>>>(P, scratch);
   *prev = scratch;
   return check_launch();
 }
@@ -353,7 +402,7 @@ int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, c
   if (rc != FSD_OK) return rc;
   StageOut O = {out_left_idx, out_right_idx, inter->sort_dbg, inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r,   inter->r2l,    out_status};
-  sort_match_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), 32, sizeof(SortCta), stream>>>(
+  sort_match_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
       make_dev_params(*params), n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1);
   return check_launch();
 }
@@ -361,7 +410,8 @@ int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, c
 template <typename T>
 int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
               const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
-              float *out_path, uint32_t *out_status, cudaStream_t stream) {
+              unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream) {
+  if (!path_scratch) return FSD_ERR_WORKSPACE;
   if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
   if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l || !inter->path_f64)
     return FSD_ERR_ARG;
@@ -380,8 +430,8 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   }
   StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r, inter->r2l, out_status};
-  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), 32, sizeof(PathSmem), stream>>>(
-      P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid);
+  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
+      P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch);
   return check_launch();
 }
 
@@ -398,13 +448,14 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   fsd_intermediate R;
   double *init_slot = nullptr;
-  int rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot);
+  unsigned char *path_scratch = nullptr;
+  int rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot, &path_scratch);
   if (rc != FSD_OK) return rc;
   rc = sort_match_impl<T>(params, n_frames, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
                           out_status, stream);
   if (rc != FSD_OK) return rc;
-  return path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev_path, prev_path_stride, init_slot, out_path,
-                      out_status, stream);
+  return path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev_path, prev_path_stride, init_slot, path_scratch,
+                      out_path, out_status, stream);
 }
 
 }  // namespace
@@ -459,7 +510,7 @@ int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stre
   DeviceInfo *D = nullptr;
   int rc = device_info(&D);
   if (rc != FSD_OK) return rc;
-  initial_path_kernel<<<1, 32, sizeof(PathSmem), static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params),
+  initial_path_kernel<<<1, 32, INITIAL_SMEM, static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params),
                                                                                       out_prev_path);
   return check_launch();
 }
@@ -496,7 +547,7 @@ int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy
   int rc = device_info(&D);
   if (rc != FSD_OK) return rc;
   StageOut O = {out_left_idx, out_right_idx, sort_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, out_status};
-  sort_match_kernel<float><<<grid_for(n_frames, D->sm_count, D->sort_ctas), 32, sizeof(SortCta),
+  sort_match_kernel<float><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
                              static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
                                                                   cones_type, offsets, pos, dir, O, 0);
   return check_launch();
@@ -515,7 +566,8 @@ int fsd_match_batch(const fsd_params *params, int n_frames, const float *cones_x
   if (rc != FSD_OK) return rc;
   StageOut O = {nullptr,        nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r,     inter->r2l, out_status};
-  match_kernel<float><<<grid_for(n_frames, D->sm_count, 16), 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int match_grid = n_frames < D->sm_count * 16 ? n_frames : D->sm_count * 16;
+  match_kernel<float><<<match_grid, 32, 0, static_cast<cudaStream_t>(stream)>>>(
       make_dev_params(*params), n_frames, cones_xy, offsets, pos, dir, left_idx, right_idx, O);
   return check_launch();
 }
@@ -536,13 +588,17 @@ int fsd_sort_match_batch(const fsd_params *params, int n_frames, int coords_f64,
 
 int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                    const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
-                   int prev_path_stride, float *out_path, uint32_t *out_status, void *stream) {
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
+                   size_t workspace_bytes_given, void *stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_frames > 0 && (!workspace || workspace_bytes_given < path_grid_bound(n_frames) * PATH_SCRATCH_BYTES))
+    return FSD_ERR_WORKSPACE;
+  unsigned char *scratch = static_cast<unsigned char *>(workspace);
   if (coords_f64)
     return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
-                             force_P, prev_path, prev_path_stride, nullptr, out_path, out_status, st);
+                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
-                          force_P, prev_path, prev_path_stride, nullptr, out_path, out_status, st);
+                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st);
 }
 
 }  // extern "C"

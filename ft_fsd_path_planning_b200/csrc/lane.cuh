@@ -28,7 +28,7 @@
 
 namespace fsd {
 
-struct d2 {
+struct alignas(16) d2 {
   double x, y;
 };
 
@@ -40,7 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 FSD_DEV int fsd_lane() { return (int)(threadIdx.x & 31u); }
 FSD_DEV void wsync() { __syncwarp(); }
 
-FSD_DEV double wsum(double v) {
+FSD_DEVFN double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
@@ -48,7 +48,7 @@ FSD_DEV double wsum(double v) {
 FSD_DEV int wsum_i(int v) { return __reduce_add_sync(FULL, v); }
 FSD_DEV int wmin_i(int v) { return __reduce_min_sync(FULL, v); }
 FSD_DEV int wmax_i(int v) { return __reduce_max_sync(FULL, v); }
-FSD_DEV double wmin_d(double v) {
+FSD_DEVFN double wmin_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
   return v;
@@ -56,7 +56,7 @@ FSD_DEV double wmin_d(double v) {
 FSD_DEV unsigned wballot(bool p) { return __ballot_sync(FULL, p); }
 FSD_DEV bool wany(bool p) { return __any_sync(FULL, p); }
 // argmin with ties -> smallest index; lanes with idx < 0 do not take part
-FSD_DEV void wargmin(double &v, int &idx) {
+FSD_DEVFN void wargmin(double &v, int &idx) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(FULL, v, o);
@@ -69,7 +69,7 @@ FSD_DEV void wargmin(double &v, int &idx) {
   }
 }
 // inclusive prefix sum across the lanes
-FSD_DEV double wscan_incl(double v) {
+FSD_DEVFN double wscan_incl(double v) {
   int lane = fsd_lane();
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -107,8 +107,19 @@ FSD_DEVFN double fsd_atan2(double y, double x) { return atan2(y, x); }
 FSD_DEVFN double fsd_acos(double x) { return acos(x); }
 FSD_DEVFN double fsd_cos(double x) { return cos(x); }
 FSD_DEVFN double fsd_sin(double x) { return sin(x); }
+// fp64 division / square root expand to ~35 / ~25 instructions inline; the kernels are bound by instruction
+// fetch, so every call site shares one out-of-line copy
+FSD_DEVFN double fdiv(double a, double b) { return a / b; }
+FSD_DEVFN double fsqrt(double a) { return sqrt(a); }
+FSD_DEVFN double fnorm(double x, double y) { return sqrt(x * x + y * y); }
+#ifdef FSD_DEVICE_BUILD
+FSD_DEVFN double frsqrt(double a) { return rsqrt(a); }
+#else
+FSD_DEVFN double frsqrt(double a) { return 1.0 / sqrt(a); }
+#endif
 
 FSD_DEV double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
+FSD_DEV int isgn(double v) { return (v > 0.0) - (v < 0.0); }
 
 // (a1 - a2 + 3 pi) mod 2 pi - pi with Python's modulo
 // (reference: fsd_path_planning/utils/math_utils.py:663-676)
@@ -120,8 +131,9 @@ FSD_DEV double angle_difference(double a1, double a2) {
 
 // cosine of the angle between two vectors, clipped like vec_angle_between
 // (fsd_path_planning/utils/math_utils.py:70-100); comparisons `angle < a` become `cos > cos(a)`
-FSD_DEV double cos_between(double ax, double ay, double bx, double by) {
-  double c = (ax * bx + ay * by) / (sqrt(ax * ax + ay * ay) * sqrt(bx * bx + by * by));
+FSD_DEVFN double cos_between(double ax, double ay, double bx, double by) {
+  // one reciprocal square root instead of two square roots and a division
+  double c = (ax * bx + ay * by) * frsqrt((ax * ax + ay * ay) * (bx * bx + by * by));
   if (c < -1.0) c = -1.0;  // NaN (zero-length vector) stays NaN: every comparison is then false,
   if (c > 1.0) c = 1.0;    // as with the reference's arccos(NaN)
   return c;

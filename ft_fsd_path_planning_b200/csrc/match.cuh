@@ -38,9 +38,9 @@ FSD_DEVFN void match_directions(const d2 *c, int n, int side, d2 *out) {
     int b = i == 0 ? 1 : (i == n - 1 ? n - 1 : i + 1);
     double tx = c[b].x - c[a].x, ty = c[b].y - c[a].y;
     double rx = side == FSD_CONE_RIGHT ? -ty : ty, ry = side == FSD_CONE_RIGHT ? tx : -tx;
-    double nrm = sqrt(rx * rx + ry * ry);
-    out[i].x = rx / nrm;
-    out[i].y = ry / nrm;
+    double nrm = fsqrt(rx * rx + ry * ry);
+    out[i].x = fdiv(rx, nrm);
+    out[i].y = fdiv(ry, nrm);
   }
 }
 
@@ -62,7 +62,7 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
     wsync();
     return m == 1;
   }
-  const double inv_major2 = 1.0 / (P.match_major * P.match_major), inv_minor2 = 1.0 / (P.match_minor * P.match_minor);
+  const double inv_major2 = P.match_inv_major2, inv_minor2 = P.match_inv_minor2;
   const double cos_limit = P.cos_match_limit;
   for (int i = lane; i < n; i += FSD_LANES) {
     const double dxi = S.dirs[i].x, dyi = S.dirs[i].y;
@@ -74,7 +74,7 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
       double rx = vx * dxi + vy * dyi, ry = dxi * vy - dyi * vx;
       double r2 = rx * rx + ry * ry;
       bool ok = (rx * rx * inv_major2 + ry * ry * inv_minor2) < 1.0;
-      if (rx / sqrt(r2) < cos_limit) ok = false;                       // :125
+      if (fdiv(rx, fsqrt(r2)) < cos_limit) ok = false;                       // :125
       if (dxi * S.odirs[j].x + dyi * S.odirs[j].y > 0.0) ok = false;  // :127
       any |= ok;
       // the match is the nearest cone of the other side, masked or not (:162)
@@ -127,13 +127,13 @@ FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, cons
     if (ne == 1) {
       // calculate_insert_index_for_one_cone :264-282
       double dvx = cx - F.px, dvy = cy - F.py, dex = S.ex[0].x - F.px, dey = S.ex[0].y - F.py;
-      index = sqrt(dvx * dvx + dvy * dvy) < sqrt(dex * dex + dey * dey) ? 0 : 1;
+      index = fsqrt(dvx * dvx + dvy * dvy) < fsqrt(dex * dex + dey * dey) ? 0 : 1;
     } else {
       int c1 = -1, c2 = -1;
       double d1 = 0.0, d2v = 0.0;
       for (int j = 0; j < ne; ++j) {
         double ddx = S.ex[j].x - cx, ddy = S.ex[j].y - cy;
-        double d = sqrt(ddx * ddx + ddy * ddy);
+        double d = fsqrt(ddx * ddx + ddy * ddy);
         if (c1 < 0 || d < d1) {
           c2 = c1;
           d2v = d1;
@@ -219,7 +219,7 @@ FSD_DEVFN unsigned match_frame(MatchSmem &S, const FramePose &F, const DevParams
     return 0;
   }
   int mn = nl < nr ? nl : nr, mx = nl < nr ? nr : nl;
-  if (mn == 0 || ((double)mx / (double)mn > 2.0)) {
+  if (mn == 0 || mx > 2 * mn) {
     if (nl < nr)
       nl = 0;
     else

@@ -20,9 +20,12 @@ constexpr int GRID_CAP = 128;  // size of the last evaluation grid (P = 120 or 1
 
 enum { RC_OK = 0, RC_VALUE_ERROR = 1, RC_RAISES = 2, RC_UNSUPPORTED = 3 };
 
+// per-frame point buffers live in per-CTA global scratch (L2 resident): PCAP x (16 + 8) bytes
+constexpr size_t PATH_SCRATCH_BYTES = (size_t)PCAP * (sizeof(d2) + sizeof(double));
+
 struct PathSmem {
-  d2 pts[PCAP];
-  double u[PCAP];
+  d2 *pts;    // [PCAP]
+  double *u;  // [PCAP]
   SplineWork W;
   d2 centre[FSD_HORIZON];
   d2 prev_xy[FSD_HORIZON];
@@ -32,7 +35,7 @@ struct PathSmem {
 
 // ---- hyper circle fit -----------------------------------------------------------------------------
 
-FSD_DEV void hyper_from_moments(double mx, double my, double Mxx, double Myy, double Mxy, double Mxz, double Myz,
+FSD_DEVFN void hyper_from_moments(double mx, double my, double Mxx, double Myy, double Mxy, double Mxz, double Myz,
                                 double Mzz, double &cx, double &cy, double &r) {
   const double Mz = Mxx + Myy, Cov_xy = Mxx * Myy - Mxy * Mxy, Var_z = Mzz - Mz * Mz;
   const double A2 = 4.0 * Cov_xy - 3.0 * Mz * Mz - Mzz;
@@ -42,7 +45,7 @@ FSD_DEV void hyper_from_moments(double mx, double my, double Mxx, double Myy, do
   double y = A0, x = 0.0;
   for (int it = 0; it < 99; ++it) {
     double Dy = A1 + x * (A22 + 16.0 * x * x);
-    double xn = x - y / Dy;
+    double xn = x - fdiv(y, Dy);
     if (xn == x || !isfinite(xn)) break;
     double yn = A0 + xn * (A1 + xn * (A2 + 4.0 * xn * xn));
     if (fabs(yn) >= fabs(y)) break;
@@ -50,22 +53,23 @@ FSD_DEV void hyper_from_moments(double mx, double my, double Mxx, double Myy, do
     y = yn;
   }
   const double det = x * x - x * Mz + Cov_xy;
-  const double Xc = (Mxz * (Myy - x) - Myz * Mxy) / det / 2.0;
-  const double Yc = (Myz * (Mxx - x) - Mxz * Mxy) / det / 2.0;
+  const double Xc = fdiv(Mxz * (Myy - x) - Myz * Mxy, det) / 2.0;
+  const double Yc = fdiv(Myz * (Mxx - x) - Mxz * Mxy, det) / 2.0;
   cx = Xc + mx;
   cy = Yc + my;
-  r = sqrt(fabs(Xc * Xc + Yc * Yc + Mz));
+  r = fsqrt(fabs(Xc * Xc + Yc * Yc + Mz));
 }
 
 // one lane fits one window (curvature)
-FSD_DEV double circle_radius_serial(const d2 *p, int n) {
+FSD_DEVFN double circle_radius_serial(const d2 *p, int n) {
   double mx = 0.0, my = 0.0;
   for (int i = 0; i < n; ++i) {
     mx += p[i].x;
     my += p[i].y;
   }
-  mx /= n;
-  my /= n;
+  const double inv_n = fdiv(1.0, (double)n);
+  mx *= inv_n;
+  my *= inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
   for (int i = 0; i < n; ++i) {
     double xi = p[i].x - mx, yi = p[i].y - my, zi = xi * xi + yi * yi;
@@ -77,7 +81,7 @@ FSD_DEV double circle_radius_serial(const d2 *p, int n) {
     Mzz += zi * zi;
   }
   double cx, cy, r;
-  hyper_from_moments(mx, my, Mxx / n, Myy / n, Mxy / n, Mxz / n, Myz / n, Mzz / n, cx, cy, r);
+  hyper_from_moments(mx, my, Mxx * inv_n, Myy * inv_n, Mxy * inv_n, Mxz * inv_n, Myz * inv_n, Mzz * inv_n, cx, cy, r);
   return r;
 }
 
@@ -88,7 +92,8 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
     sx += p[i].x;
     sy += p[i].y;
   }
-  const double mx = wsum(sx) / n, my = wsum(sy) / n;
+  const double inv_n = fdiv(1.0, (double)n);
+  const double mx = wsum(sx) * inv_n, my = wsum(sy) * inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double xi = p[i].x - mx, yi = p[i].y - my, zi = xi * xi + yi * yi;
@@ -99,12 +104,12 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
     Myz += yi * zi;
     Mzz += zi * zi;
   }
-  Mxy = wsum(Mxy) / n;
-  Mxx = wsum(Mxx) / n;
-  Myy = wsum(Myy) / n;
-  Mxz = wsum(Mxz) / n;
-  Myz = wsum(Myz) / n;
-  Mzz = wsum(Mzz) / n;
+  Mxy = wsum(Mxy) * inv_n;
+  Mxx = wsum(Mxx) * inv_n;
+  Myy = wsum(Myy) * inv_n;
+  Mxz = wsum(Mxz) * inv_n;
+  Myz = wsum(Myz) * inv_n;
+  Mzz = wsum(Mzz) * inv_n;
   hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, cx, cy, r);
 }
 
@@ -124,7 +129,7 @@ FSD_DEVFN void chord_params(const d2 *p, int m, double *u) {
     double d = 0.0;
     if (i < m) {
       double ddx = p[i].x - p[i - 1].x, ddy = p[i].y - p[i - 1].y;
-      d = sqrt(ddx * ddx + ddy * ddy);
+      d = fsqrt(ddx * ddx + ddy * ddy);
     }
     double incl = wscan_incl(d) + carry;
     if (i < m) u[i] = incl;
@@ -144,7 +149,7 @@ FSD_DEVFN int fit_predict(PathSmem &S, const d2 *src, double *u, int m, double s
   int ier = fit_curve(S.W, src, u, m, smoothing, status);
   if (ier == 10) return (*status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR;
   const double mu = max_u_override > 0.0 ? max_u_override : S.W.max_u;
-  const double q = ceil(mu / step);  // len(np.arange(0, max_u, step))
+  const double q = ceil(fdiv(mu, step));  // len(np.arange(0, max_u, step))
   const int n = q > 0.0 ? (q > 1e6 ? 1000000 : (int)q) : 0;
   if (n > dst_cap) {
     *status |= FSD_ST_OVERFLOW;
@@ -173,15 +178,15 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
   double len = 0.0, first10 = 0.0;
   for (int i = lane; i + 1 < n; i += FSD_LANES) {
     double ddx = S.pts[i + 1].x - S.pts[i].x, ddy = S.pts[i + 1].y - S.pts[i].y;
-    double d = sqrt(ddx * ddx + ddy * ddy);
+    double d = fsqrt(ddx * ddx + ddy * ddy);
     len += d;
     if (i < 10) first10 += d;
   }
   const double path_length = wsum(len);
   const int nm = n - 1 < 10 ? n - 1 : 10;
-  const double mean_dist = wsum(first10) / nm;
-  const double predict_every = path_length / FSD_HORIZON / 3;
-  const double ratio = predict_every / mean_dist;
+  const double mean_dist = fdiv(wsum(first10), (double)nm);
+  const double predict_every = fdiv(fdiv(path_length, (double)FSD_HORIZON), 3.0);
+  const double ratio = fdiv(predict_every, mean_dist);
   int skip = 1;
   if (isfinite(ratio) && ratio < 1e6 && (int)ratio > 1) skip = (int)ratio;
   int ms = (n + skip - 1) / skip;
@@ -199,7 +204,7 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
   if (force_P > 0) {
     Pn = force_P;
   } else {
-    const double q = S.W.max_u / predict_every;
+    const double q = fdiv(S.W.max_u, predict_every);
     const double r = rint(q);
     if (fabs(q - r) < 1e-9) {
       Pn = (int)r;
@@ -233,13 +238,13 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
     double r = circle_radius_serial(S.pts + lo, cnt);
     r = fmin(fmax(r, 1.0), 3000.0);
     double sg = sgn(orient(S.pts[lo], S.pts[lo + cnt / 2], S.pts[hi]));
-    S.curv[i] = (1.0 / r) * sg;
+    S.curv[i] = fdiv(1.0, r) * sg;
   }
   wsync();
   // uniform_filter1d(size, mode="nearest") evaluated at the 40 sampled indices only;
   // indices np.linspace(0, P-1, 40, dtype=int) (:277-282)
   const int fs = window / 2 > 2 ? window / 2 : 2;
-  const double stp = (double)(Pn - 1) / (double)(FSD_HORIZON - 1);
+  const double stp = fdiv((double)(Pn - 1), (double)(FSD_HORIZON - 1));
   for (int j = lane; j < FSD_HORIZON; j += FSD_LANES) {
     const int idx = j == FSD_HORIZON - 1 ? Pn - 1 : (int)floor((double)j * stp);
     double acc = 0.0;
@@ -250,7 +255,7 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
     out[4 * j + 0] = (double)idx * predict_every;
     out[4 * j + 1] = S.pts[idx].x;
     out[4 * j + 2] = S.pts[idx].y;
-    out[4 * j + 3] = acc / fs;
+    out[4 * j + 3] = fdiv(acc, (double)fs);
   }
   wsync();
   return RC_OK;
@@ -267,13 +272,13 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
   // connect_path_to_car :430-457
   {
     const double fx = path[0].x - F.px, fy = path[0].y - F.py;
-    const double d = sqrt(fx * fx + fy * fy);
+    const double d = fsqrt(fx * fx + fy * fy);
     const bool behind = cos_between(fx, fy, F.dx, F.dy) < 0.0;  // angle > pi/2
     wsync();
     if (!(d < 0.5 || behind)) {
       if (lane == 0) {
-        S.pts[0].x = F.px + fx / d * 0.2;
-        S.pts[0].y = F.py + fy / d * 0.2;
+        S.pts[0].x = F.px + fdiv(fx, d) * 0.2;
+        S.pts[0].y = F.py + fdiv(fy, d) * 0.2;
       }
       path = S.pts;
       n = n_in + 1;
@@ -296,7 +301,7 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
     double part = 0.0;
     for (int i = start + lane; i + 1 < n; i += FSD_LANES) {
       double ddx = path[i + 1].x - path[i].x, ddy = path[i + 1].y - path[i].y;
-      part += sqrt(ddx * ddx + ddy * ddy);
+      part += fsqrt(ddx * ddx + ddy * ddy);
     }
     const double plen = wsum(part);
     if (!(plen > P.mpc_len)) {
@@ -316,7 +321,7 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
            p2 = {rel[nr - 1].x - cx, rel[nr - 1].y - cy};
         const double sg = sgn(orient(p0, p1, p2));
         const double a0 = fsd_atan2(p0.y, p0.x), a1 = a0 + sg * PI;
-        const double stepa = (a1 - a0) / 49.0;  // np.linspace(a0, a1) has 50 samples; the first is dropped
+        const double stepa = fdiv(a1 - a0, 49.0);  // np.linspace(a0, a1) has 50 samples; the first is dropped
         const double r0x = fsd_cos(a0) * r_use, r0y = fsd_sin(a0) * r_use;
         wsync();
         for (int i = 1 + lane; i < 50; i += FSD_LANES) {
@@ -327,9 +332,9 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
         n += 49;
       } else {
         double ddx = lastx - path[n - 2].x, ddy = lasty - path[n - 2].y;
-        const double nrm = sqrt(ddx * ddx + ddy * ddy);
-        ddx /= nrm;
-        ddy /= nrm;
+        const double nrm = fsqrt(ddx * ddx + ddy * ddy);
+        ddx = fdiv(ddx, nrm);
+        ddy = fdiv(ddy, nrm);
         wsync();
         for (int i = 1 + lane; i < 30; i += FSD_LANES) {
           path[n + i - 1].x = lastx + ddx * (double)i;
@@ -347,7 +352,7 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
     int bi = -1;
     for (int i = lane; i < n; i += FSD_LANES) {
       double ddx = F.px - path[i].x, ddy = F.py - path[i].y;
-      double d = sqrt(ddx * ddx + ddy * ddy);
+      double d = fsqrt(ddx * ddx + ddy * ddy);
       if (bi < 0 || d < bv) {
         bv = d;
         bi = i;
@@ -374,7 +379,7 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
       double d = 0.0;
       if (i < nfix - 1) {
         double ddx = S.pts[i + 1].x - S.pts[i].x, ddy = S.pts[i + 1].y - S.pts[i].y;
-        d = sqrt(ddx * ddx + ddy * ddy);
+        d = fsqrt(ddx * ddx + ddy * ddy);
       }
       double incl = wscan_incl(d) + carry;
       if (i < nfix - 1 && incl > P.mpc_len && i < first_over) first_over = i;
@@ -458,7 +463,7 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
     double best = INFINITY;
     for (int i = lane; i < nu; i += FSD_LANES) {
       double ddx = F.px - S.pts[1 + i].x, ddy = F.py - S.pts[1 + i].y;
-      best = fmin(best, sqrt(ddx * ddx + ddy * ddy));
+      best = fmin(best, fsqrt(ddx * ddx + ddy * ddy));
     }
     best = wmin_d(best);
     wsync();

@@ -8,13 +8,27 @@ namespace fsd {
 
 struct FramePose {
   double px, py, dx, dy;  // vehicle position and direction (not normalised)
+  double ux, uy;          // unit direction
 };
+
+FSD_DEV FramePose make_pose(double px, double py, double dx, double dy) {
+  FramePose F;
+  F.px = px;
+  F.py = py;
+  F.dx = dx;
+  F.dy = dy;
+  const double inv = fdiv(1.0, fsqrt(dx * dx + dy * dy));
+  F.ux = dx * inv;
+  F.uy = dy * inv;
+  return F;
+}
 
 struct DevParams {
   int max_n_neighbors, max_length, max_dfs_pops;
   double max_dist, max_dist2, max_dist_to_first, thr_dir, thr_abs, car_size;
   double cos_5deg, cos_150deg, cos_seed_max, cos_seed_min, cos_match_limit, cos_85deg;
   double min_track_width, match_major, match_minor, max_search_angle;
+  double seed_inv_major2, seed_inv_minor2, match_inv_major2, match_inv_minor2;
   double smoothing, predict_every, max_valid_dist, mpc_len, refit_smoothing;
 };
 
@@ -39,6 +53,13 @@ static inline DevParams make_dev_params(const fsd_params &p) {
   d.match_major = p.max_search_range * 1.5;
   d.match_minor = p.min_track_width;
   d.max_search_angle = p.max_search_angle;
+  {
+    const double major = p.max_dist_to_first * 1.5, minor = p.max_dist_to_first / 1.5;  // core_trace_sorter.py:388-394
+    d.seed_inv_major2 = 1.0 / (major * major);
+    d.seed_inv_minor2 = 1.0 / (minor * minor);
+    d.match_inv_major2 = 1.0 / (d.match_major * d.match_major);
+    d.match_inv_minor2 = 1.0 / (d.match_minor * d.match_minor);
+  }
   d.smoothing = p.smoothing;
   d.predict_every = p.predict_every;
   d.max_valid_dist = p.maximal_distance_for_valid_path;

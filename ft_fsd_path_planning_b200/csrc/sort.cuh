@@ -14,6 +14,7 @@
 #pragma once
 
 #include "lane.cuh"
+#include "match.cuh"
 #include "plan_types.cuh"
 
 namespace fsd {
@@ -21,59 +22,74 @@ namespace fsd {
 constexpr int MAX_LEAVES = 64;
 constexpr int STACK_CAP = 64;  // depth <= 12, <= 5 pushes per level
 
+// Shared-memory image of one frame.  Phase-local arrays are overlaid so that 16 frames fit one SM:
+//   region A: fp32 staging of the TMA copy -> k-NN lists (build_knn) -> search / cost scratch (both sides)
+//   region B: adjacency lists + configurations (sorting) -> MatchSmem (matching, after sorting is finished)
 struct SortSmem {
   d2 xy[FSD_MAX_CONES];
-  double dist[FSD_MAX_CONES];
-  double costs[MAX_LEAVES];
-  int16_t leaves[MAX_LEAVES][FSD_MAX_SORTED];
+  uint8_t type[FSD_MAX_CONES];
   int16_t best[2][FSD_MAX_SORTED];
-  int16_t attempt[16];
-  int16_t idxs[FSD_MAX_CONES];   // cone indices used by any configuration (cost term)
-  int16_t close[FSD_MAX_CONES];  // nearby cones (cost term)
-  int32_t n_good[MAX_LEAVES], n_bad[MAX_LEAVES];
   int32_t nbest[2];
   int32_t scratch[8];
-  uint8_t type[FSD_MAX_CONES];
-  uint8_t knn[2][FSD_MAX_CONES][5];
-  uint8_t kcnt[2][FSD_MAX_CONES];
-  uint8_t nbr[2][FSD_MAX_CONES][5];
-  uint8_t deg[2][FSD_MAX_CONES];
-  uint8_t flag[FSD_MAX_CONES];  // seed mask / in-configuration mask
-  uint8_t flag2[FSD_MAX_CONES];
-  uint8_t stack_node[STACK_CAP], stack_pos[STACK_CAP];
-  uint8_t can[8];
+  union {
+    alignas(16) float raw[2 * (FSD_MAX_CONES + 2)];
+    struct {
+      uint8_t knn[2][FSD_MAX_CONES][5];
+      uint8_t kcnt[2][FSD_MAX_CONES];
+    };
+    struct {
+      int16_t idxs[FSD_MAX_CONES];   // cone indices used by any configuration (cost term) / BFS queue
+      int16_t close[FSD_MAX_CONES];  // nearby cones (cost term)
+      int32_t n_good[MAX_LEAVES], n_bad[MAX_LEAVES];
+      uint8_t flag[FSD_MAX_CONES];  // seed mask / in-configuration mask
+      uint8_t flag2[FSD_MAX_CONES];
+      uint8_t stack_node[STACK_CAP], stack_pos[STACK_CAP];
+      int16_t attempt[16];
+      uint8_t can[8];
+    };
+  };
+  union {
+    struct {
+      uint8_t nbr[2][FSD_MAX_CONES][5];
+      uint8_t deg[2][FSD_MAX_CONES];
+      int16_t leaves[MAX_LEAVES][FSD_MAX_SORTED];
+      double costs[MAX_LEAVES];
+    };
+    MatchSmem M;
+  };
 };
 
 // ---- k-NN graph: adjacency_matrix.py:60-110 ------------------------------------------------
 // Both sides in one sweep: the LEFT graph ignores yellow cones, the RIGHT graph ignores blue.
 
-FSD_DEV void top5_insert(double (&d)[5], int (&id)[5], double v, int j) {
-  if (!(v < d[4])) return;
-  d[4] = v;
-  id[4] = j;
-#pragma unroll
-  for (int q = 4; q > 0; --q) {
-    if (d[q] < d[q - 1]) {
-      double td = d[q];
-      d[q] = d[q - 1];
-      d[q - 1] = td;
-      int ti = id[q];
-      id[q] = id[q - 1];
-      id[q - 1] = ti;
-    }
+// sorted insertion into a k-nearest list; rare (a handful of cones lie within max_dist of a row), so it is kept
+// small and out of line rather than unrolled into the distance loop
+FSD_DEVFN void knn_insert(double *d, int *id, int *cnt, int k, double v, int j) {
+  int c = *cnt;
+  if (c == k && !(v < d[k - 1])) return;
+  int p = c < k ? c : k - 1;
+  while (p > 0 && v < d[p - 1]) {
+    d[p] = d[p - 1];
+    id[p] = id[p - 1];
+    --p;
   }
+  d[p] = v;
+  id[p] = j;
+  if (c < k) *cnt = c + 1;
 }
 
 FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
-  const double inf = INFINITY;
   int k = n - 1 < P.max_n_neighbors ? n - 1 : P.max_n_neighbors;
   if (k > 5) k = 5;
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-    double dl[5] = {inf, inf, inf, inf, inf}, dr[5] = {inf, inf, inf, inf, inf};
-    int il[5] = {0, 0, 0, 0, 0}, ir[5] = {0, 0, 0, 0, 0};
+    double dl[5], dr[5];
+    int il[5], ir[5];
+    int cl = 0, cr = 0;
     const double xi = S.xy[i].x, yi = S.xy[i].y;
     const int ti = S.type[i];
     const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
       double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
       double dd = ddx * ddx + ddy * ddy;
@@ -81,29 +97,20 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
       // can never displace a shorter one, so it is dropped before the selection
       if (dd > P.max_dist2 || j == i) continue;
       int tj = S.type[j];
-      if (li && tj != FSD_CONE_RIGHT) top5_insert(dl, il, dd, j);
-      if (ri && tj != FSD_CONE_LEFT) top5_insert(dr, ir, dd, j);
+      if (li && tj != FSD_CONE_RIGHT) knn_insert(dl, il, &cl, k, dd, j);
+      if (ri && tj != FSD_CONE_LEFT) knn_insert(dr, ir, &cr, k, dd, j);
     }
-    int cl = 0, cr = 0;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      if (q < k && dl[q] < inf) {
-        S.knn[0][i][q] = (uint8_t)il[q];
-        cl = q + 1;
-      }
-      if (q < k && dr[q] < inf) {
-        S.knn[1][i][q] = (uint8_t)ir[q];
-        cr = q + 1;
-      }
-    }
+    for (int q = 0; q < cl; ++q) S.knn[0][i][q] = (uint8_t)il[q];
+    for (int q = 0; q < cr; ++q) S.knn[1][i][q] = (uint8_t)ir[q];
     S.kcnt[0][i] = (uint8_t)cl;
     S.kcnt[1][i] = (uint8_t)cr;
   }
   wsync();
   // keep edges present in both directions (:110); neighbour lists in ascending index order, the
   // order np.where gives the CSR lists of end_configurations.py:28-71
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < 2; ++s) {
       int cnt = 0;
       int tmp[5];
@@ -131,21 +138,18 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
 
 FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int *fk) {
   const int opp = side == FSD_CONE_LEFT ? FSD_CONE_RIGHT : FSD_CONE_LEFT;
-  const double dn = sqrt(F.dx * F.dx + F.dy * F.dy);
-  const double c = F.dx / dn, s = F.dy / dn;  // rotation by -yaw
-  const double major = P.max_dist_to_first * 1.5, minor = P.max_dist_to_first / 1.5;
+  const double c = F.ux, s = F.uy;  // rotation by -yaw
   const double cos_max = P.cos_seed_max, cos_min = P.cos_seed_min;
   double bv = 0.0;
   int bi = -1;
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
     double rx = px * c + py * s, ry = -px * s + py * c;
-    double r = sqrt(rx * rx + ry * ry);
-    S.dist[i] = r;
-    bool in_ellipse = (rx * rx / (major * major) + ry * ry / (minor * minor)) < 1.0;
+    double r = fsqrt(rx * rx + ry * ry);
+    bool in_ellipse = (rx * rx * P.seed_inv_major2 + ry * ry * P.seed_inv_minor2) < 1.0;
     // sign(bearing) == +-1, pi/10 < |bearing| < 4pi/5  (:395-399), on the cosine of the bearing
     bool side_ok = side == FSD_CONE_LEFT ? ry > 0.0 : ry < 0.0;
-    double cb = rx / r;
+    double cb = fdiv(rx, r);
     bool ang_ok = cb > cos_max && cb < cos_min;
     int t = S.type[i];
     bool valid = in_ellipse && ((side_ok && ang_ok) || t == side) && t != opp;
@@ -164,7 +168,9 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
   bi = -1;
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     if (!S.flag[i] || S.flag2[i] || i == i1) continue;
-    double r = S.dist[i];
+    double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
+    double rx = px * c + py * s, ry = -px * s + py * c;
+    double r = fsqrt(rx * rx + ry * ry);
     if (bi < 0 || r < bv) {
       bv = r;
       bi = i;
@@ -184,7 +190,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
     i1 = i2;
     i2 = t;
   }
-  double d = sqrt(ex * ex + ey * ey);
+  double d = fsqrt(ex * ex + ey * ey);
   if (d > P.max_dist * 1.1 || d < 1.4) {
     fk[0] = i1;
     return 1;
@@ -241,7 +247,7 @@ FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, 
       overlap = fabs(a0x - b0x) < eps;
       slope = INFINITY;
     } else {
-      slope = ddy / ddx;
+      slope = fdiv(ddy, ddx);
       overlap = fabs((a0y - slope * a0x) - (b0y - slope * b0x)) < eps;
     }
     if (!overlap) return false;
@@ -257,7 +263,8 @@ FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, 
     }
     return left_end >= right_start;
   }
-  double x = ix / iz, y = iy / iz;
+  const double inv = fdiv(1.0, iz);
+  double x = ix * inv, y = iy * inv;
   return (fmin(a0x, a1x) - eps <= x && x <= fmax(a0x, a1x) + eps) &&
          (fmin(b0x, b1x) - eps <= x && x <= fmax(b0x, b1x) + eps) &&
          (fmin(a0y, a1y) - eps <= y && y <= fmax(a0y, a1y) + eps) &&
@@ -280,17 +287,16 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
     const int prev = S.attempt[pos - 1];
     ax = lx - S.xy[prev].x;
     ay = ly - S.xy[prev].y;
-    // ellipse around `last`, major axis 6 m along (last - previous), minor 3 m (:281-300)
-    double an = sqrt(ax * ax + ay * ay);
-    double rx = (bx * ax + by * ay) / an, ry = (by * ax - bx * ay) / an;
-    if (!((rx * rx / 36.0 + ry * ry / 9.0) < 1.0)) return false;
+    // ellipse around `last`, major axis 6 m along (last - previous), minor 3 m (:281-300):
+    // (b.a)^2 / 36 + (b x a)^2 / 9 < |a|^2  -- the rotated-frame test without the normalisation
+    const double dt = bx * ax + by * ay, cr = by * ax - bx * ay;
+    if (!(dt * dt * (1.0 / 36.0) + cr * cr * (1.0 / 9.0) < ax * ax + ay * ay)) return false;
   } else {
     // second cone of the attempt must lie on the expected side of the car, 5 deg tolerance (:260-278)
     double vx = cx - F.px, vy = cy - F.py;
     double cross = F.dx * vy - F.dy * vx;
     bool expected = side == FSD_CONE_LEFT ? cross > 0.0 : cross < 0.0;
-    bool tolerance = cos_between(F.dx, F.dy, vx, vy) > P.cos_5deg;
-    if (!(expected || tolerance)) return false;
+    if (!expected && !(cos_between(F.dx, F.dy, vx, vy) > P.cos_5deg)) return false;
   }
   // another neighbour of `last` lying between `last` and the candidate (:226-257)
   for (int q = 0; q < nnb; ++q) {
@@ -299,37 +305,35 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
     double v1x = lx - S.xy[o].x, v1y = ly - S.xy[o].y;
     double v2x = cx - S.xy[o].x, v2y = cy - S.xy[o].y;
     double d1 = v1x * v1x + v1y * v1y, d2 = v2x * v2x + v2y * v2y;
-    if (sqrt(d2) < 6.0 && sqrt(d1) < 6.0 && cos_between(v1x, v1y, v2x, v2y) < P.cos_150deg) return false;
+    if (d2 < 36.0 && d1 < 36.0 && cos_between(v1x, v1y, v2x, v2y) < P.cos_150deg) return false;
   }
   if (pos >= 1) {
-    double angle_1 = fsd_atan2(ay, ax), angle_2 = fsd_atan2(by, bx);
-    double difference = angle_difference(angle_2, angle_1);
-    double len = sqrt(bx * bx + by * by);
+    // turn angle at `last`: wrap(atan2(b) - atan2(a)) == atan2(a x b, a . b)  (:173-191)
+    double difference = fsd_atan2(ax * by - ay * bx, ax * bx + ay * by);
+    bool short_edge = bx * bx + by * by < 16.0;
     bool ok;
     if (fabs(difference) > P.thr_abs)
       ok = false;
     else if (side == FSD_CONE_LEFT)
-      ok = difference < P.thr_dir || len < 4.0;
+      ok = difference < P.thr_dir || short_edge;
     else
-      ok = difference > -P.thr_dir || len < 4.0;
-    if (pos >= 2) {
+      ok = difference > -P.thr_dir || short_edge;
+    if (ok && pos >= 2) {
       const int prev = S.attempt[pos - 1], pp = S.attempt[pos - 2];
-      double angle_3 = fsd_atan2(S.xy[prev].y - S.xy[pp].y, S.xy[prev].x - S.xy[pp].x);
-      double difference_2 = angle_difference(angle_1, angle_3);
-      if (sgn(difference) != sgn(difference_2) && fabs(difference - difference_2) > 1.3) ok = false;
+      double zx = S.xy[prev].x - S.xy[pp].x, zy = S.xy[prev].y - S.xy[pp].y;
+      double difference_2 = fsd_atan2(zx * ay - zy * ax, zx * ax + zy * ay);
+      if (isgn(difference) != isgn(difference_2) && fabs(difference - difference_2) > 1.3) ok = false;
     }
     if (!ok) return false;
   }
   if (pos == 1) {
     // angle(heading, candidate - first) < pi/2 (:207-211)
     const int first = S.attempt[0];
-    if (!(cos_between(F.dx, F.dy, cx - S.xy[first].x, cy - S.xy[first].y) > 0.0)) return false;
+    if (!(F.dx * (cx - S.xy[first].x) + F.dy * (cy - S.xy[first].y) > 0.0)) return false;
   }
   // the new edge must not cross the car (:213-221)
-  double dn = sqrt(F.dx * F.dx + F.dy * F.dy);
-  double ux = F.dx / dn, uy = F.dy / dn;
-  double csx = F.px - ux * P.car_size / 2.0, csy = F.py - uy * P.car_size / 2.0;
-  double cex = F.px + ux * P.car_size, cey = F.py + uy * P.car_size;
+  double csx = F.px - F.ux * P.car_size / 2.0, csy = F.py - F.uy * P.car_size / 2.0;
+  double cex = F.px + F.ux * P.car_size, cey = F.py + F.uy * P.car_size;
   return !segments_intersect(lx, ly, cx, cy, csx, csy, cex, cey);
 }
 
@@ -483,9 +487,10 @@ FSD_DEV void search_dir(const SortSmem &S, int a, int b, int side, double &ox, d
   // normal of the track direction, +90 deg for RIGHT / -90 deg for LEFT (match_directions.py:7-20)
   double tx = S.xy[b].x - S.xy[a].x, ty = S.xy[b].y - S.xy[a].y;
   double rx = side == FSD_CONE_RIGHT ? -ty : ty, ry = side == FSD_CONE_RIGHT ? tx : -tx;
-  double nrm = sqrt(rx * rx + ry * ry);
-  ox = rx / nrm;
-  oy = ry / nrm;
+  double nrm = fsqrt(rx * rx + ry * ry);
+  double inrm = fdiv(1.0, nrm);
+  ox = rx * inrm;
+  oy = ry * inrm;
 }
 
 // lane-strided stream compaction of the indices i < n with flag[i] != 0 (ascending order)
@@ -619,7 +624,7 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
     double resid = 0.0;
     for (int q = 0; q + 1 < len; ++q) {
       double ddx = px[q + 1] - px[q], ddy = py[q + 1] - py[q];
-      double d = sqrt(ddx * ddx + ddy * ddy) - 3.0;
+      double d = fsqrt(ddx * ddx + ddy * ddy) - 3.0;
       resid += d > 0.0 ? d : 0.0;
     }
     double ncones = 1.0 / (double)len;
@@ -714,7 +719,7 @@ FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
     int pl = left[li - 1], pr = right[ri - 1], ic = left[li];
     double dlx = S.xy[ic].x - S.xy[pl].x, dly = S.xy[ic].y - S.xy[pl].y;
     double drx = S.xy[ic].x - S.xy[pr].x, dry = S.xy[ic].y - S.xy[pr].y;
-    bool l_low = sqrt(dlx * dlx + dly * dly) < 3.0, r_low = sqrt(drx * drx + dry * dry) < 3.0;
+    bool l_low = fsqrt(dlx * dlx + dly * dly) < 3.0, r_low = fsqrt(drx * drx + dry * dry) < 3.0;
     if ((l_low || r_low) && !(l_low && r_low)) {
       have = true;
       if (l_low) {

@@ -23,7 +23,7 @@
 
 namespace fsd {
 
-constexpr int NCAP = 40;  // knots handled per fit (the reference's own data stays below 20)
+constexpr int NCAP = 32;  // knots handled per fit (the reference's own data stays below 20)
 constexpr int BW = 5;     // k + 2 for cubic splines
 
 struct SplineWork {
@@ -35,7 +35,7 @@ struct SplineWork {
   double rhs[NCAP][2];
   double z[NCAP][2];
   double c[NCAP][2];
-  double fpint[NCAP];
+  double fpint[2 * NCAP];  // [0, NCAP): residual per knot interval; [NCAP, 2 NCAP): reciprocal diagonal of G
   int32_t nrdata[NCAP];
   int32_t start[NCAP + 1];
   double rk[NCAP][6];  // reciprocal knot differences of the B-spline recursion, per knot interval
@@ -56,7 +56,7 @@ FSD_DEVFN void knot_reciprocals(SplineWork &W, int n, int k) {
     if (j <= k) {
       const int l = k + ii;
       const double d = W.t[l + i] - W.t[l + i - j];
-      r = d == 0.0 ? 0.0 : 1.0 / d;
+      r = d == 0.0 ? 0.0 : fdiv(1.0, d);
     }
     W.rk[ii][q] = r;
   }
@@ -86,16 +86,31 @@ FSD_DEV void bspl_k(const SplineWork &W, double x, int ii, double (&h)[4]) {
   }
 }
 
+// degrees below 3 only occur for fits of 2 or 3 points: one small out-of-line loop version
+FSD_DEVFN void bspl_low(const SplineWork &W, int k, double x, int ii, double *h) {
+  const int l = k + ii;
+  const double *rk = W.rk[ii];
+  double hh[4];
+  h[0] = 1.0;
+  for (int j = 1; j <= k; ++j) {
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+    for (int i = 1; i <= j; ++i) {
+      const double f = hh[i - 1] * rk[(j * (j - 1)) / 2 + i - 1];
+      h[i - 1] += f * (W.t[l + i] - x);
+      h[i] = f * (x - W.t[l + i - j]);
+    }
+  }
+}
+
 FSD_DEV void bspl(const SplineWork &W, int k, double x, int ii, double (&h)[4]) {
   if (k == 3)
     bspl_k<3>(W, x, ii, h);
-  else if (k == 2)
-    bspl_k<2>(W, x, ii, h);
   else
-    bspl_k<1>(W, x, ii, h);
+    bspl_low(W, k, x, ii, h);
 }
 
-FSD_DEV void spline_point(const SplineWork &W, double x, double &ox, double &oy) {
+FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &oy) {
   // splev with ext=0: the end polynomial pieces extrapolate
   const int k = W.k, nk1 = W.n - k - 1;
   int l = k;
@@ -115,8 +130,10 @@ FSD_DEV void spline_point(const SplineWork &W, double x, double &ox, double &oy)
 
 // banded Cholesky (upper, in place in M), forward and back substitution; lane 0 only.
 // returns false on a non-positive pivot.
-FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2]) {
-  // M[i][0] holds the diagonal of G on return (fppara's p0 needs it); rows are scaled with one reciprocal each
+FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2],
+                          double *rinv_row) {
+  // M[i][0] holds the diagonal of G on return (fppara's p0 needs it).  One reciprocal square root per row replaces
+  // the square root and every division of the textbook algorithm (the solve is dominated by them otherwise).
   for (int i = 0; i < nk1; ++i) {
     double rinv = 0.0;
     for (int d = 0; d < kb; ++d) {
@@ -128,9 +145,9 @@ FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2]
       for (int p = p0; p < i; ++p) s -= M[p][i - p] * M[p][j - p];
       if (d == 0) {
         if (!(s > 0.0)) return false;
-        const double g = sqrt(s);
-        M[i][0] = g;
-        rinv = 1.0 / g;
+        rinv = frsqrt(s);
+        M[i][0] = s * rinv;
+        rinv_row[i] = rinv;
       } else {
         M[i][d] = s * rinv;
       }
@@ -156,7 +173,7 @@ FSD_DEV bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2]
       s0 -= g * c[i + l][0];
       s1 -= g * c[i + l][1];
     }
-    const double rinv = 1.0 / M[i][0];
+    const double rinv = rinv_row[i];
     c[i][0] = s0 * rinv;
     c[i][1] = s1 * rinv;
   }
@@ -196,10 +213,12 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
   for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.N[0][0])[i] = 0.0;
   for (int i = lane; i < nk1 * 2; i += FSD_LANES) (&W.rhs[0][0])[i] = 0.0;
   wsync();
+#pragma unroll 1
   for (int ii = 0; ii < nrint; ++ii) {
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double rx[4] = {0, 0, 0, 0}, ry[4] = {0, 0, 0, 0};
     const int lo = W.start[ii], hi = W.start[ii + 1];
+#pragma unroll 1
     for (int i = lo + lane; i < hi; i += FSD_LANES) {
       double h[4] = {0, 0, 0, 0};
       bspl(W, k, u[i], ii, h);
@@ -243,10 +262,12 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
   const int lane = fsd_lane();
   const int nrint = n - 2 * k - 1;
   double fp = 0.0;
+#pragma unroll 1
   for (int ii = 0; ii < nrint; ++ii) {
     const int lo = W.start[ii], hi = W.start[ii + 1];
     const int last = ii < nrint - 1 ? hi : hi - 1;  // the next interval's first point is shared
     double part = 0.0, full = 0.0;
+#pragma unroll 1
     for (int i = lo + lane; i <= last; i += FSD_LANES) {
       const int li = i >= hi ? ii + 1 : ii;
       double h[4] = {0, 0, 0, 0};
@@ -274,7 +295,7 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
 }
 
 // fpknot: split the interval with the largest residual at its middle data point (lane 0)
-FSD_DEV void add_knot(SplineWork &W, const double *u, int n, int nrint) {
+FSD_DEVFN void add_knot(SplineWork &W, const double *u, int n, int nrint) {
   const int k = (n - nrint - 1) / 2;
   double fpmax = 0.0;
   int jbegin = 1, number = 1, maxpt = 0, maxbeg = 1;
@@ -297,15 +318,15 @@ FSD_DEV void add_knot(SplineWork &W, const double *u, int n, int nrint) {
   W.nrdata[number - 1] = ihalf - 1;
   W.nrdata[next - 1] = maxpt - ihalf;
   const double am = maxpt > 0 ? (double)maxpt : 1.0;
-  W.fpint[number - 1] = fpmax * (double)W.nrdata[number - 1] / am;
-  W.fpint[next - 1] = fpmax * (double)W.nrdata[next - 1] / am;
+  W.fpint[number - 1] = fdiv(fpmax * (double)W.nrdata[number - 1], am);
+  W.fpint[next - 1] = fdiv(fpmax * (double)W.nrdata[next - 1], am);
   W.t[next + k - 1] = u[nrx - 1];
 }
 
 // discontinuity jumps of the k-th derivative at the interior knots (fpdisc), rows lane-strided
 FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
   const int k1 = k + 1, k2 = k + 2, nk1 = n - k1, nrint = nk1 - k;
-  const double fac = (double)nrint / (W.t[nk1] - W.t[k]);
+  const double fac = fdiv((double)nrint, W.t[nk1] - W.t[k]);
   for (int l = k2 + fsd_lane(); l <= nk1; l += FSD_LANES) {  // 1-based row index of FITPACK
     const int lmk = l - k1;
     double h[10];
@@ -321,7 +342,7 @@ FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
         ++jk;
         prod = prod * h[jk - 1] * fac;
       }
-      W.bd[lmk - 1][j - 1] = (W.t[lp + k1 - 1] - W.t[lp - 1]) / prod;
+      W.bd[lmk - 1][j - 1] = fdiv(W.t[lp + k1 - 1] - W.t[lp - 1], prod);
       ++lp;
     }
   }
@@ -370,7 +391,7 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
     if (lane == 0) {
       for (int i = 0; i < nk1; ++i)
         for (int d = 0; d < BW; ++d) W.G[i][d] = W.N[i][d];
-      bool ok = chol_solve(W.G, nk1, k1, W.rhs, W.z, W.c);
+      bool ok = chol_solve(W.G, nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP);
       W.start[NCAP] = ok ? 1 : 0;
     }
     wsync();
@@ -408,7 +429,7 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
     if (ier == 0) {
       int npl1 = nplus * 2;
       double rn = (double)nplus;
-      if (fpold - fp > acc) npl1 = (int)(rn * fpms / (fpold - fp));
+      if (fpold - fp > acc) npl1 = (int)fdiv(rn * fpms, fpold - fp);
       int mx = npl1 > nplus / 2 ? npl1 : nplus / 2;
       if (mx < 1) mx = 1;
       nplus = nplus * 2 < mx ? nplus * 2 : mx;
@@ -454,16 +475,16 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
     wsync();
     double p1 = 0.0, f1 = fp0 - s, p3 = -1.0, f3 = fpms, p = 0.0;
     for (int i = 0; i < nk1; ++i) p += W.G[i][0];
-    p = (double)nk1 / p;
+    p = fdiv((double)nk1, p);
     wsync();
     int ich1 = 0, ich3 = 0;
     const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
     for (int iter = 1; iter <= 20; ++iter) {
-      const double pinv2 = (1.0 / p) * (1.0 / p);
+      const double pinv = fdiv(1.0, p), pinv2 = pinv * pinv;
       for (int i = lane; i < nk1 * BW; i += FSD_LANES)
         (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
       wsync();
-      if (lane == 0) W.start[NCAP] = chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c) ? 1 : 0;
+      if (lane == 0) W.start[NCAP] = chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP) ? 1 : 0;
       wsync();
       if (!W.start[NCAP]) {
         *status |= FSD_ST_UNSUPPORTED;
@@ -494,7 +515,7 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
         if (!((f1 - f2) > acc)) {
           p1 = p2;
           f1 = f2;
-          p = p / con4;
+          p = fdiv(p, con4);
           if (p3 < 0.0) continue;
           if (p >= p3) p = p2 * con1 + p3 * con9;
           continue;
@@ -509,9 +530,9 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
       double pn;
       if (p3 > 0.0) {
         double h1 = f1 * (f2 - f3), h2 = f2 * (f3 - f1), h3 = f3 * (f1 - f2);
-        pn = -(p1 * p2 * h3 + p2 * p3 * h1 + p3 * p1 * h2) / (p1 * h1 + p2 * h2 + p3 * h3);
+        pn = -fdiv(p1 * p2 * h3 + p2 * p3 * h1 + p3 * p1 * h2, p1 * h1 + p2 * h2 + p3 * h3);
       } else {
-        pn = (p1 * (f1 - f3) * f2 - p2 * (f2 - f3) * f1) / ((f1 - f2) * f3);
+        pn = fdiv(p1 * (f1 - f3) * f2 - p2 * (f2 - f3) * f1, (f1 - f2) * f3);
       }
       if (f2 < 0.0) {
         p3 = p2;

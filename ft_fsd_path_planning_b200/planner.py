@@ -160,7 +160,7 @@ class BatchPlanner:
                 rc = self.lib.fsd_path_batch(
                     C.byref(self.params), B, int(f64), pos.data_ptr(), direction.data_ptr(), C.byref(inter),
                     _ptr(force_P), prev_path.data_ptr(), stride, bufs["path"].data_ptr(), bufs["status"].data_ptr(),
-                    stream)
+                    bufs["workspace"].data_ptr(), bufs["workspace"].numel(), stream)
                 ev[2].record()
                 self.kernel_events.append(ev)
             else:

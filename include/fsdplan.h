@@ -164,11 +164,13 @@ int fsd_sort_match_batch(const fsd_params *params, int n_frames, int coords_f64,
                          uint32_t *out_status, void *stream);
 
 /* fsd_path_batch: CalculatePath on given matching results.  inter->n_wv, left_wv, right_wv, l2r, r2l (inputs) and
- * path_f64 (output) must be non-NULL (grid optional).  Status bits are OR-ed INTO out_status (zero it when the
+ * path_f64 (output) must be non-NULL (grid optional); workspace as for fsd_plan_batch (fsd_workspace_bytes).
+ * Status bits are OR-ed INTO out_status (zero it when the
  * stage is used on its own).  prev_path NULL = initial path of a fresh planner (default spline parameters only). */
 int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                    const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
-                   int prev_path_stride, float *out_path, uint32_t *out_status, void *stream);
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
+                   size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

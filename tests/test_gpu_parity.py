@@ -163,8 +163,9 @@ def test_stage_entry_points_compose(planner):
     out = torch.empty((B, 40, 4), dtype=torch.float32, device=dev)
     st3 = torch.zeros_like(st)
     prev = planner.initial_path()
+    ws = torch.empty((int(lib.fsd_workspace_bytes(B, 0)),), dtype=torch.uint8, device=dev)
     _lib.check(lib.fsd_path_batch(C.byref(p), B, 0, pos.data_ptr(), dr.data_ptr(), C.byref(inter), None,
-                                  prev.data_ptr(), 0, out.data_ptr(), st3.data_ptr(), stream))
+                                  prev.data_ptr(), 0, out.data_ptr(), st3.data_ptr(), ws.data_ptr(), ws.numel(), stream))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), full["path"])
     assert np.array_equal((st.cpu().numpy() | st2.cpu().numpy() | st3.cpu().numpy()), full["status"])
