@@ -37,12 +37,17 @@ class Result(C.Structure):
     ]
 
 
+class Reloc(C.Structure):
+    _fields_ = [("relocalized", C.c_int), ("n_accepted", C.c_int), ("translation", C.c_double * 2),
+                ("rotation", C.c_double), ("right_ref", C.c_double * 2), ("right_calc", C.c_double * 2)]
+
+
 RESULT_DTYPE = np.dtype(Result)
 
 
 def build(force: bool = False) -> str:
     """Compile the C restatement (gcc) if the shared object is missing or stale."""
-    srcs = [os.path.join(_HERE, f) for f in ("fitpack.c", "sort.c", "match.c", "path.c", "api.c",
+    srcs = [os.path.join(_HERE, f) for f in ("fitpack.c", "sort.c", "match.c", "path.c", "api.c", "skidpad.c",
                                              "fsd_oracle.h", "oracle_internal.h", "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
@@ -129,3 +134,76 @@ def splev(x: np.ndarray, t: np.ndarray, c: np.ndarray, k: int) -> np.ndarray:
     y = np.zeros(len(x))
     lib().fsd_oracle_splev(_dp(t), len(t), _dp(cc), k, _dp(x), len(x), _dp(y))
     return y
+
+
+# ---- skidpad mission ---------------------------------------------------------------------------------------------
+
+def skidpad_constants(path_table: np.ndarray):
+    """(global path = table[::2], reference centres [right, left], jitter) -- host-side constants.
+    Reference centres: hyper circle fit of the table's points with y < -2 / y > 2
+    (skidpad_relocalizer.py:172-183); jitter: numpy RandomState(42).randn (skidpad_relocalizer.py:38, 53)."""
+    def fit(pts):
+        x, y = pts[:, 0], pts[:, 1]
+        xi, yi = x - x.mean(), y - y.mean()
+        zi = xi * xi + yi * yi
+        n = len(x)
+        mxy, mxx, myy = (xi * yi).sum() / n, (xi * xi).sum() / n, (yi * yi).sum() / n
+        mxz, myz, mzz = (xi * zi).sum() / n, (yi * zi).sum() / n, (zi * zi).sum() / n
+        mz = mxx + myy
+        cov = mxx * myy - mxy * mxy
+        var = mzz - mz * mz
+        a2 = 4 * cov - 3 * mz * mz - mzz
+        a1 = var * mz + 4.0 * cov * mz - mxz * mxz - myz * myz
+        a0 = mxz * (mxz * myy - myz * mxy) + myz * (myz * mxx - mxz * mxy) - var * cov
+        a22 = a2 + a2
+        yv, xv = a0, 0.0
+        for _ in range(99):
+            dy = a1 + xv * (a22 + 16.0 * xv * xv)
+            xn = xv - yv / dy
+            if xn == xv or not np.isfinite(xn):
+                break
+            yn = a0 + xn * (a1 + xn * (a2 + 4.0 * xn * xn))
+            if abs(yn) >= abs(yv):
+                break
+            xv, yv = xn, yn
+        det = xv * xv - xv * mz + cov
+        return np.array([(mxz * (myy - xv) - myz * mxy) / det / 2.0 + x.mean(),
+                         (myz * (mxx - xv) - mxz * mxy) / det / 2.0 + y.mean()])
+
+    ref = np.stack([fit(path_table[path_table[:, 1] < -2]), fit(path_table[path_table[:, 1] > 2])])
+    jitter = np.random.RandomState(42).randn(1140 * 6)
+    return np.ascontiguousarray(path_table[::2]), ref, jitter
+
+
+class SkidpadOracle:
+    """Sequential skidpad planner (one trajectory), mirroring PathPlanner(MissionTypes.skidpad)."""
+
+    def __init__(self, path_table: np.ndarray):
+        self.path, self.ref, self.jitter = skidpad_constants(np.asarray(path_table, dtype=np.float64))
+        self.reloc = Reloc()
+        self.orig = None
+        self.index = C.c_int(0)
+        self.prev = initial_path()
+        L = lib()
+        dp = C.POINTER(C.c_double)
+        L.fsd_oracle_skidpad_relocalize.argtypes = [dp, C.c_int, dp, dp, dp, dp, dp, C.POINTER(Reloc)]
+        L.fsd_oracle_skidpad_step.argtypes = [dp, C.c_int, C.POINTER(C.c_int), C.POINTER(Reloc), dp, dp, C.c_int, dp,
+                                              dp, C.POINTER(Result)]
+
+    def step(self, cones_by_type, pos, direction, force_P=0):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        direction = np.ascontiguousarray(direction, dtype=np.float64)
+        if not self.reloc.relocalized:
+            if self.orig is None:
+                self.orig = (pos.copy(), direction.copy())
+            xy = np.ascontiguousarray(np.concatenate([np.asarray(c, float).reshape(-1, 2) for c in cones_by_type]))
+            lib().fsd_oracle_skidpad_relocalize(_dp(xy), len(xy), _dp(pos), _dp(self.orig[0]), _dp(self.orig[1]),
+                                                _dp(self.jitter), _dp(np.ascontiguousarray(self.ref)),
+                                                C.byref(self.reloc))
+        res = Result()
+        internal = np.zeros((HORIZON, 4))
+        lib().fsd_oracle_skidpad_step(_dp(self.path), len(self.path), C.byref(self.index), C.byref(self.reloc),
+                                      _dp(pos), _dp(direction), int(force_P), _dp(self.prev), _dp(internal),
+                                      C.byref(res))
+        self.prev = internal
+        return np.ctypeslib.as_array(res.path).copy(), res

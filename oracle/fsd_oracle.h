@@ -76,6 +76,22 @@ int fsd_oracle_path(const double *left_wv, int nl, const double *right_wv, int n
                     const double *pos, const double *dir, int force_P, const double *prev_path,
                     fsd_oracle_result *out);
 
+/* ---- skidpad mission (oracle/skidpad.c) ---- */
+typedef struct {
+  int relocalized, n_accepted;
+  double translation[2], rotation, right_ref[2], right_calc[2];
+} fsd_oracle_reloc;
+
+/* jitter: RandomState(42).randn(1140 * 6); ref_centers: [right(x,y), left(x,y)] of the canonical path */
+int fsd_oracle_skidpad_relocalize(const double *cones_xy, int n, const double *pos, const double *orig_pos,
+                                  const double *orig_dir, const double *jitter, const double *ref_centers,
+                                  fsd_oracle_reloc *out);
+/* one planner step; path = canonical path [::2]; index_along_path in/out; reloc may be NULL (not relocalised);
+ * path_internal: the (40,4) path before the transform back to the SLAM frame (next step's prev_path) */
+int fsd_oracle_skidpad_step(const double *path, int n_path, int *index_along_path, const fsd_oracle_reloc *reloc,
+                            const double *pos, const double *dir, int force_P, const double *prev_path,
+                            double *path_internal, fsd_oracle_result *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,10 @@
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
+int fsd_o_path_from_update(double *update, int nu, const double *pos, const double *dir, int force_P,
+                           const double *prev_path, fsd_oracle_result *out);
+void fsd_o_almost_straight_path(double *chord40x2);
+
 #endif
 
 #define FSD_O_UNKNOWN 0
@@ -36,5 +40,9 @@ int fsd_o_match(const double *left, int nl, const double *right, int nr, const d
                 fsd_oracle_result *out);
 int fsd_o_path(const double *left_wv, int nl, const double *right_wv, int nr, const int *l2r, const int *r2l,
                const double *pos, const double *dir, int force_P, const double *prev_path, fsd_oracle_result *out);
+
+int fsd_o_path_from_update(double *update, int nu, const double *pos, const double *dir, int force_P,
+                           const double *prev_path, fsd_oracle_result *out);
+void fsd_o_almost_straight_path(double *chord40x2);
 
 #endif

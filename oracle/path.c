@@ -417,9 +417,8 @@ static int mpc_tail(const double *update, int n_in, const double *pos, const dou
 static double g_initial[HORIZON][4];
 static pthread_once_t g_initial_once = PTHREAD_ONCE_INIT;
 
-static void compute_initial(void) {
+void fsd_o_almost_straight_path(double *chord) {
   /* calculate_almost_straight_path, path_calculator_helpers.py:26-68 */
-  double chord[2 * HORIZON];
   double max_angle = M_PI / 50.0, radius = 1000.0;
   double step = max_angle / (HORIZON - 1);
   for (int i = 0; i < HORIZON; ++i) {
@@ -429,6 +428,11 @@ static void compute_initial(void) {
     chord[2 * i] = rx;
     chord[2 * i + 1] = ry * 1.0;
   }
+}
+
+static void compute_initial(void) {
+  double chord[2 * HORIZON];
+  fsd_o_almost_straight_path(chord);
   double *dense = (double *)malloc(sizeof(double) * 2 * MAXP);
   int nd = 0, P = 0;
   unsigned st = 0;
@@ -440,6 +444,48 @@ static void compute_initial(void) {
 void fsd_oracle_initial_path(double *out40x4) {
   pthread_once(&g_initial_once, compute_initial);
   memcpy(out40x4, g_initial, sizeof(g_initial));
+}
+
+/* second half of run_path_calculation (core_calculate_path.py:555-575): validity check, MPC tail, fallback.
+ * update: path update (capacity >= 40 points), modified in place. */
+int fsd_o_path_from_update(double *update, int nu, const double *pos, const double *dir, int force_P,
+                           const double *prev_path, fsd_oracle_result *out) {
+  double prev[HORIZON][4];
+  memcpy(prev, prev_path, sizeof(prev));
+  double prev_xy[2 * HORIZON];
+  for (int i = 0; i < HORIZON; ++i) {
+    prev_xy[2 * i] = prev[i][1];
+    prev_xy[2 * i + 1] = prev[i][2];
+  }
+  int rc;
+  /* overwrite_path_if_it_is_too_far_away :225-237 */
+  {
+    double best = INFINITY;
+    for (int i = 0; i < nu; ++i) {
+      double dx = pos[0] - update[2 * i], dy = pos[1] - update[2 * i + 1];
+      double d = sqrt(dx * dx + dy * dy);
+      if (d < best) best = d;
+    }
+    if (best > 5.0) {
+      out->status |= FSD_O_PATH_TOO_FAR;
+      memcpy(update, prev_xy, sizeof(prev_xy));
+      nu = HORIZON;
+    }
+  }
+  /* do_all_mpc_parameter_calculations with the ValueError fallback :561-570 */
+  unsigned st = 0;
+  rc = mpc_tail(update, nu, pos, dir, force_P, out->path, &out->P, &out->n_trim, &st);
+  if (rc == VALUE_ERROR) {
+    out->status |= FSD_O_MPC_FAILED;
+    st = 0;
+    rc = mpc_tail(prev_xy, HORIZON, pos, dir, force_P, out->path, &out->P, &out->n_trim, &st);
+  }
+  out->status |= st;
+  if (rc != OK) {
+    out->status |= rc == UNSUPPORTED ? FSD_O_UNSUPPORTED : FSD_O_REF_RAISES;
+    memcpy(out->path, prev, sizeof(prev));
+  }
+  return 0;
 }
 
 /* ---- CalculatePath.run_path_calculation (core_calculate_path.py:514-575), global_path None ---- */
@@ -508,33 +554,7 @@ int fsd_o_path(const double *left, int nl, const double *right, int nr, const in
     free(update);
     return 0;
   }
-  /* overwrite_path_if_it_is_too_far_away :225-237 */
-  {
-    double best = INFINITY;
-    for (int i = 0; i < nu; ++i) {
-      double dx = pos[0] - update[2 * i], dy = pos[1] - update[2 * i + 1];
-      double d = sqrt(dx * dx + dy * dy);
-      if (d < best) best = d;
-    }
-    if (best > 5.0) {
-      out->status |= FSD_O_PATH_TOO_FAR;
-      memcpy(update, prev_xy, sizeof(prev_xy));
-      nu = HORIZON;
-    }
-  }
-  /* do_all_mpc_parameter_calculations with the ValueError fallback :561-570 */
-  unsigned st = 0;
-  rc = mpc_tail(update, nu, pos, dir, force_P, out->path, &out->P, &out->n_trim, &st);
-  if (rc == VALUE_ERROR) {
-    out->status |= FSD_O_MPC_FAILED;
-    st = 0;
-    rc = mpc_tail(prev_xy, HORIZON, pos, dir, force_P, out->path, &out->P, &out->n_trim, &st);
-  }
-  out->status |= st;
-  if (rc != OK) {
-    out->status |= rc == UNSUPPORTED ? FSD_O_UNSUPPORTED : FSD_O_REF_RAISES;
-    memcpy(out->path, prev, sizeof(prev));
-  }
+  fsd_o_path_from_update(update, nu, pos, dir, force_P, &prev[0][0], out);
   free(update);
   return 0;
 }
