@@ -9,7 +9,8 @@ from .enums import ConeTypes, MissionTypes  # noqa: F401
 from .synth import FrameBatch, gen_autocross, gen_mixed, pack_frames, remove_color_info  # noqa: F401
 
 __all__ = ["ConeTypes", "MissionTypes", "FrameBatch", "gen_autocross", "gen_mixed", "pack_frames",
-           "remove_color_info", "PathPlanner", "BatchPlanner", "PlanResult", "RelocalizationInformation", "build"]
+           "remove_color_info", "PathPlanner", "BatchPlanner", "SkidpadBatchPlanner", "PlanResult",
+           "RelocalizationInformation", "build"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -25,4 +26,8 @@ def __getattr__(name):
         from . import planner
 
         return getattr(planner, name)
+    if name == "SkidpadBatchPlanner":
+        from . import skidpad
+
+        return skidpad.SkidpadBatchPlanner
     raise AttributeError(name)

@@ -90,6 +90,11 @@ def lib():
                                            C.POINTER(Intermediate), vp, vp]
         L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp,
                                      vp, sz, vp]
+        L.fsd_skidpad_workspace_bytes.restype = sz
+        L.fsd_skidpad_workspace_bytes.argtypes = [i32]
+        L.fsd_skidpad_relocalize_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.fsd_skidpad_plan_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp,
+                                             vp, vp, vp, vp, vp, vp, sz, vp]
         if L.fsd_abi_version() != 1:
             raise RuntimeError("libfsdplan.so ABI version mismatch")
         _lib = L

@@ -10,6 +10,7 @@
 #include <new>
 
 #include "frame.cuh"
+#include "skidpad.cuh"
 
 using namespace fsd;
 
@@ -114,4 +115,40 @@ extern "C" int fsd_hostcheck_fit(const double *pts, int m, double s, double *t, 
   }
   free_path_smem(Q);
   return ier;
+}
+
+// ---- skidpad mission ------------------------------------------------------------------------------------------
+extern "C" int fsd_hostcheck_skidpad_relocalize(const double *cones, int n, const double *pos, const double *orig_pos,
+                                                const double *orig_dir, const double *jitter, const double *ref,
+                                                double *out8, int *n_accepted) {
+  SkidSmem *S = new SkidSmem();
+  SkidReloc R;
+  std::memset(&R, 0, sizeof(R));
+  skidpad_relocalize(*S, cones, n, pos[0], pos[1], orig_pos[0], orig_pos[1], orig_dir[0], orig_dir[1], jitter, ref, &R,
+                     n_accepted);
+  std::memcpy(out8, &R, sizeof(R));
+  delete S;
+  return 0;
+}
+
+extern "C" int fsd_hostcheck_skidpad_steps(const fsd_params *params, const double *reloc8, const double *table,
+                                           int n_table, const double *pos, const double *dir, int n_steps, int *state,
+                                           const int16_t *force_P, const double *prev, int prev_stride, double *out,
+                                           double *out_internal, int *index_out, uint32_t *status, int16_t *grid) {
+  DevParams P = make_dev_params(*params);
+  SkidReloc R;
+  std::memcpy(&R, reloc8, sizeof(R));
+  PathSmem *Q = new_path_smem();
+  double *known = new double[4 * (size_t)n_steps];
+  skidpad_track(R, table, n_table, pos, dir, n_steps, state, known, index_out);
+  for (int s = 0; s < n_steps; ++s) {
+    int g[2] = {0, 0};
+    status[s] = skidpad_step(*Q, R, table, n_table, index_out[s], known + 4 * s, force_P ? force_P[s] : 0,
+                             prev + (size_t)s * prev_stride, P, out + 160 * (size_t)s, out_internal + 160 * (size_t)s, g);
+    grid[2 * s] = (int16_t)g[0];
+    grid[2 * s + 1] = (int16_t)g[1];
+  }
+  delete[] known;
+  free_path_smem(Q);
+  return 0;
 }

@@ -18,6 +18,7 @@
 #include <mutex>
 
 #include "frame.cuh"
+#include "skidpad.cuh"
 
 using namespace fsd;
 
@@ -241,6 +242,119 @@ __global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *o
   initial_path_frame(S, P, out);
 }
 
+// ---- skidpad mission -----------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32) skid_reloc_kernel(int n_traj, const double *cones_xy, const int32_t *offsets,
+                                                        const double *pos, const double *orig_pos,
+                                                        const double *orig_dir, const double *jitter,
+                                                        const double *ref, double *reloc, int32_t *n_accepted) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SkidSmem &S = *reinterpret_cast<SkidSmem *>(smem_raw);
+  for (int t = blockIdx.x; t < n_traj; t += gridDim.x) {
+    const int lo = offsets[t], n = offsets[t + 1] - lo;
+    SkidReloc *R = reinterpret_cast<SkidReloc *>(reloc + 8 * (size_t)t);
+    int nacc = 0;
+    skidpad_relocalize(S, cones_xy + 2 * (size_t)lo, n, pos[2 * t], pos[2 * t + 1], orig_pos[2 * t], orig_pos[2 * t + 1],
+                       orig_dir[2 * t], orig_dir[2 * t + 1], jitter, ref, R, &nacc);
+    if (fsd_lane() == 0 && n_accepted) n_accepted[t] = nacc;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32) skid_track_kernel(int n_traj, const int32_t *step_offsets, const double *pos,
+                                                        const double *dir, const double *reloc, int32_t *index_state,
+                                                        const double *table, int n_table, double *known,
+                                                        int32_t *index, int32_t *traj_of_step) {
+  for (int t = blockIdx.x; t < n_traj; t += gridDim.x) {
+    const int s0 = step_offsets[t], n = step_offsets[t + 1] - s0;
+    const SkidReloc R = *reinterpret_cast<const SkidReloc *>(reloc + 8 * (size_t)t);
+    int state = index_state[t];
+    skidpad_track(R, table, n_table, pos + 2 * (size_t)s0, dir + 2 * (size_t)s0, n, &state, known + 4 * (size_t)s0,
+                  index + s0);
+    for (int s = fsd_lane(); s < n; s += 32) traj_of_step[s0 + s] = t;
+    if (fsd_lane() == 0) index_state[t] = state;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+    skid_step_kernel(DevParams P, int n_steps, const double *reloc, const int32_t *traj_of_step, const double *table,
+                     int n_table, const int32_t *index, const double *known, const int16_t *force_P,
+                     const double *prev, int prev_stride, double *out_f64, double *out_internal, float *out_f32,
+                     int16_t *grid_out, uint32_t *status, unsigned char *scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * PATH_CTA_STRIDE);
+  if (fsd_lane() == 0) {
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
+  }
+  __syncwarp();
+  for (int base = blockIdx.x * WPC; base < n_steps; base += gridDim.x * WPC) {
+    if (WPC > 1) __syncthreads();
+    const int s = base + warp;
+    if (s >= n_steps) continue;
+    const SkidReloc R = *reinterpret_cast<const SkidReloc *>(reloc + 8 * (size_t)traj_of_step[s]);
+    int grid[2] = {0, 0};
+    double *out = out_f64 + (size_t)s * FSD_HORIZON * 4;
+    unsigned st = skidpad_step(S, R, table, n_table, index[s], known + 4 * (size_t)s, force_P ? (int)force_P[s] : 0,
+                               prev + (size_t)s * prev_stride, P, out, out_internal + (size_t)s * FSD_HORIZON * 4, grid);
+    if (out_f32)
+      for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += 32) out_f32[(size_t)s * FSD_HORIZON * 4 + i] = (float)out[i];
+    if (fsd_lane() == 0) {
+      status[s] = st;
+      if (grid_out) {
+        grid_out[2 * (size_t)s] = (int16_t)grid[0];
+        grid_out[2 * (size_t)s + 1] = (int16_t)grid[1];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Sequential semantics inside a trajectory: a step whose previous-path fallback fired (path too far from the car,
+// failed tail, ...) must see the PREVIOUS STEP's path (core_calculate_path.py:573), which the step-parallel launch
+// cannot know.  One warp per trajectory walks its steps in order and recomputes only the flagged ones.
+__global__ void __launch_bounds__(32) skid_fixup_kernel(DevParams P, int n_traj, const int32_t *step_offsets,
+                                                        const double *reloc, const double *table, int n_table,
+                                                        const int32_t *index, const double *known,
+                                                        const int16_t *force_P, double *out_f64, double *out_internal,
+                                                        float *out_f32, int16_t *grid_out, uint32_t *status,
+                                                        unsigned char *scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
+  if (fsd_lane() == 0) {
+    unsigned char *mine = scratch + (size_t)blockIdx.x * PATH_SCRATCH_BYTES;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
+  }
+  __syncwarp();
+  const unsigned uses_prev = FSD_ST_FEW_CONES | FSD_ST_FEW_MATCHES | FSD_ST_FIT1_FAILED | FSD_ST_PATH_TOO_FAR |
+                             FSD_ST_MPC_FAILED | FSD_ST_REF_RAISES | FSD_ST_UNSUPPORTED;
+  for (int t = blockIdx.x; t < n_traj; t += gridDim.x) {
+    const SkidReloc R = *reinterpret_cast<const SkidReloc *>(reloc + 8 * (size_t)t);
+    for (int s = step_offsets[t] + 1; s < step_offsets[t + 1]; ++s) {
+      if (!(status[s] & uses_prev)) continue;
+      int grid[2] = {0, 0};
+      double *out = out_f64 + (size_t)s * FSD_HORIZON * 4;
+      unsigned st = skidpad_step(S, R, table, n_table, index[s], known + 4 * (size_t)s, force_P ? (int)force_P[s] : 0,
+                                 out_internal + (size_t)(s - 1) * FSD_HORIZON * 4, P, out,
+                                 out_internal + (size_t)s * FSD_HORIZON * 4, grid);
+      if (out_f32)
+        for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += 32) out_f32[(size_t)s * FSD_HORIZON * 4 + i] = (float)out[i];
+      if (fsd_lane() == 0) {
+        status[s] = st;
+        if (grid_out) {
+          grid_out[2 * (size_t)s] = (int16_t)grid[0];
+          grid_out[2 * (size_t)s + 1] = (int16_t)grid[1];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 
 constexpr int MAX_DEVICES = 64;
@@ -277,6 +391,7 @@ int device_info(DeviceInfo **out) {
     cudaFuncSetAttribute(sort_match_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
     cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
     cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
+    cudaFuncSetAttribute(skid_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, WPC * PATH_CTA_STRIDE);
     cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
@@ -599,6 +714,75 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
                              force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
                           force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st);
+}
+
+size_t fsd_skidpad_workspace_bytes(int n_steps) {
+  const size_t S = (size_t)(n_steps > 0 ? n_steps : 0);
+  return align_up(path_grid_bound(n_steps) * PATH_SCRATCH_BYTES, 256) + align_up(S * 4 * sizeof(double), 256) +
+         align_up(S * sizeof(int32_t), 256);
+}
+
+int fsd_skidpad_relocalize_batch(const fsd_params *params, int n_traj, const double *cones_xy, const int32_t *offsets,
+                                 const double *pos, const double *orig_pos, const double *orig_dir,
+                                 const double *jitter, const double *ref_centers, double *reloc, int32_t *n_accepted,
+                                 void *stream) {
+  if (!params || n_traj < 0) return FSD_ERR_ARG;
+  if (n_traj == 0) return FSD_OK;
+  if (!cones_xy || !offsets || !pos || !orig_pos || !orig_dir || !jitter || !ref_centers || !reloc) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  const int grid = n_traj < D->sm_count * 4 ? n_traj : D->sm_count * 4;
+  skid_reloc_kernel<<<grid, 32, sizeof(SkidSmem), static_cast<cudaStream_t>(stream)>>>(
+      n_traj, cones_xy, offsets, pos, orig_pos, orig_dir, jitter, ref_centers, reloc, n_accepted);
+  return check_launch();
+}
+
+int fsd_skidpad_plan_batch(const fsd_params *params, int n_traj, int n_steps, const int32_t *step_offsets,
+                           const double *pos, const double *dir, const double *reloc, int32_t *index_state,
+                           const double *path_table, int n_table, const int16_t *force_P, const double *prev_path,
+                           int prev_path_stride, float *out_path, double *out_path_f64, double *out_internal_f64,
+                           int32_t *out_index, int16_t *out_grid, uint32_t *out_status, void *workspace,
+                           size_t workspace_bytes_given, void *stream_v) {
+  if (!params || n_traj < 0 || n_steps < 0) return FSD_ERR_ARG;
+  if (n_traj == 0 || n_steps == 0) return FSD_OK;
+  if (!step_offsets || !pos || !dir || !reloc || !index_state || !path_table || n_table < 16 || !out_path_f64 ||
+      !out_internal_f64 || !out_index || !out_status)
+    return FSD_ERR_ARG;
+  if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
+  if (!workspace || workspace_bytes_given < fsd_skidpad_workspace_bytes(n_steps)) return FSD_ERR_WORKSPACE;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const DevParams P = make_dev_params(*params);
+  Carve cv = {static_cast<unsigned char *>(workspace), 0, workspace_bytes_given};
+  unsigned char *scratch = cv.take<unsigned char>(path_grid_bound(n_steps) * PATH_SCRATCH_BYTES);
+  double *known = cv.take<double>((size_t)n_steps * 4);
+  int32_t *traj_of_step = cv.take<int32_t>((size_t)n_steps);
+  const double *prev = prev_path;
+  int stride = prev_path_stride;
+  if (!prev) {
+    rc = default_prev_path(params, P, *D, nullptr, stream, &prev);
+    if (rc != FSD_OK) return rc;
+    stride = 0;
+  }
+  const int tgrid = n_traj < D->sm_count * 8 ? n_traj : D->sm_count * 8;
+  skid_track_kernel<<<tgrid, 32, 0, stream>>>(n_traj, step_offsets, pos, dir, reloc, index_state, path_table, n_table,
+                                              known, out_index, traj_of_step);
+  rc = check_launch();
+  if (rc != FSD_OK) return rc;
+  skid_step_kernel<<<grid_for(n_steps, D->sm_count, D->path_ctas), CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
+      P, n_steps, reloc, traj_of_step, path_table, n_table, out_index, known, force_P, prev, stride, out_path_f64,
+      out_internal_f64, out_path, out_grid, out_status, scratch);
+  rc = check_launch();
+  if (rc != FSD_OK || stride != 0) return rc;  // per-step previous paths given: the caller owns the chaining
+  const long bound = (long)path_grid_bound(n_steps);
+  const int fgrid = (int)(n_traj < bound ? n_traj : bound);
+  skid_fixup_kernel<<<fgrid, 32, PATH_CTA_STRIDE, stream>>>(P, n_traj, step_offsets, reloc, path_table, n_table,
+                                                            out_index, known, force_P, out_path_f64, out_internal_f64,
+                                                            out_path, out_grid, out_status, scratch);
+  return check_launch();
 }
 
 }  // extern "C"

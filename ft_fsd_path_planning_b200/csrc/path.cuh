@@ -392,6 +392,61 @@ FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, c
   return parameterize(S, keep, force_P, P, out, P_out, status);
 }
 
+// ---- second half of run_path_calculation (core_calculate_path.py:555-575) -----------------------------------------
+// The path update sits in S.pts[1 .. 1+nu), S.prev_xy holds the previous path's xy.  Validity check, MPC tail,
+// fallbacks.  out: 40 x 4 fp64; grid[0] = P, grid[1] = points entering the last re-fit.
+
+FSD_DEVFN unsigned path_from_update(PathSmem &S, int nu, const FramePose &F, int force_P, const double *prev,
+                                    const DevParams &P, double *out, int *grid) {
+  const int lane = fsd_lane();
+  unsigned status = 0;
+  int P_grid = 0, n_trim = 0;
+  bool ok = true;
+  int rc;
+  {
+    // overwrite_path_if_it_is_too_far_away :225-237
+    double best = INFINITY;
+    for (int i = lane; i < nu; i += FSD_LANES) {
+      double ddx = F.px - S.pts[1 + i].x, ddy = F.py - S.pts[1 + i].y;
+      best = fmin(best, fsqrt(ddx * ddx + ddy * ddy));
+    }
+    best = wmin_d(best);
+    wsync();
+    if (best > P.max_valid_dist) {
+      status |= FSD_ST_PATH_TOO_FAR;
+      for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
+      nu = FSD_HORIZON;
+      wsync();
+    }
+    // do_all_mpc_parameter_calculations, ValueError -> redo with the previous path (:561-570)
+    unsigned st = 0;
+    rc = mpc_tail(S, nu, F, force_P, P, out, &P_grid, &n_trim, &st);
+    if (rc == RC_VALUE_ERROR) {
+      status |= FSD_ST_MPC_FAILED;
+      st = 0;
+      wsync();
+      for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
+      wsync();
+      rc = mpc_tail(S, FSD_HORIZON, F, force_P, P, out, &P_grid, &n_trim, &st);
+    }
+    status |= st;
+    if (rc != RC_OK) {
+      status |= rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES;
+      ok = false;
+    }
+  }
+  if (!ok) {
+    wsync();
+    for (int i = lane; i < FSD_HORIZON * 4; i += FSD_LANES) out[i] = prev[i];
+  }
+  if (grid && lane == 0) {
+    grid[0] = P_grid;
+    grid[1] = n_trim;
+  }
+  wsync();
+  return status;
+}
+
 // ---- CalculatePath.run_path_calculation (core_calculate_path.py:514-575), global_path is None ------------
 // Inputs: the with-virtual cone lists and matches (any memory space).  prev: previous path (40 x 4 fp64).
 // out: 40 x 4 fp64.  grid[0] = P, grid[1] = points entering the last re-fit.
@@ -447,7 +502,6 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
       ncl = nc;
     }
   }
-  int P_grid = 0, n_trim = 0;
   // fit_matches_as_spline :207-223 (path update lives in S.pts[1..], slot 0 is kept for connect_path_to_car)
   int nu = 0;
   int rc = fit_predict(S, cl, S.u, ncl, P.smoothing, P.predict_every, -1.0, S.pts + 1, PCAP - 1, &nu, &status);
@@ -456,50 +510,15 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
     rc = fit_predict(S, S.prev_xy, S.u, FSD_HORIZON, P.smoothing, P.predict_every, -1.0, S.pts + 1, PCAP - 1, &nu,
                      &status);
   }
-  bool ok = rc == RC_OK && nu >= 1;
-  if (!ok) status |= rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES;
-  if (ok) {
-    // overwrite_path_if_it_is_too_far_away :225-237
-    double best = INFINITY;
-    for (int i = lane; i < nu; i += FSD_LANES) {
-      double ddx = F.px - S.pts[1 + i].x, ddy = F.py - S.pts[1 + i].y;
-      best = fmin(best, fsqrt(ddx * ddx + ddy * ddy));
-    }
-    best = wmin_d(best);
-    wsync();
-    if (best > P.max_valid_dist) {
-      status |= FSD_ST_PATH_TOO_FAR;
-      for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
-      nu = FSD_HORIZON;
-      wsync();
-    }
-    // do_all_mpc_parameter_calculations, ValueError -> redo with the previous path (:561-570)
-    unsigned st = 0;
-    rc = mpc_tail(S, nu, F, force_P, P, out, &P_grid, &n_trim, &st);
-    if (rc == RC_VALUE_ERROR) {
-      status |= FSD_ST_MPC_FAILED;
-      st = 0;
-      wsync();
-      for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
-      wsync();
-      rc = mpc_tail(S, FSD_HORIZON, F, force_P, P, out, &P_grid, &n_trim, &st);
-    }
-    status |= st;
-    if (rc != RC_OK) {
-      status |= rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES;
-      ok = false;
-    }
-  }
-  if (!ok) {
+  if (!(rc == RC_OK && nu >= 1)) {
+    status |= rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES;
     wsync();
     for (int i = lane; i < FSD_HORIZON * 4; i += FSD_LANES) out[i] = prev[i];
+    if (grid && lane == 0) grid[0] = grid[1] = 0;
+    wsync();
+    return status;
   }
-  if (grid && lane == 0) {
-    grid[0] = P_grid;
-    grid[1] = n_trim;
-  }
-  wsync();
-  return status;
+  return status | path_from_update(S, nu, F, force_P, prev, P, out, grid);
 }
 
 // ---- initial path of a fresh planner (core_calculate_path.py:103-121) -------------------------------------

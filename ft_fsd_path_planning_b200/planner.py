@@ -216,15 +216,25 @@ class PathPlanner:
     def __init__(self, mission: MissionTypes, experimental_performance_improvements: bool = False,
                  device: Union[str, torch.device, int] = "cuda") -> None:
         self.mission = MissionTypes(mission)
-        if self.mission in (MissionTypes.skidpad, MissionTypes.acceleration, MissionTypes.ebs_test):
+        if self.mission in (MissionTypes.acceleration, MissionTypes.ebs_test):
             raise NotImplementedError(
-                f"mission {self.mission.name} needs relocalization, which is outside the batched hot path "
-                "(SURVEY.md section 8f); use trackdrive / autocross")
+                f"mission {self.mission.name}: the acceleration relocalizer draws from an unseeded RNG in the reference "
+                "and is out of scope (SURVEY.md section 2); use trackdrive / autocross / skidpad")
         # the experimental sorting cache of the reference changes results and is not reproduced
         self.experimental_performance_improvements = experimental_performance_improvements
         self._planner = BatchPlanner(device, mission=_lib.MISSION_TRACKDRIVE)
         self.global_path = None
         self._prev_path: Optional[torch.Tensor] = None  # previous_paths[-1] of the reference
+        self._skid = None
+        if self.mission == MissionTypes.skidpad:
+            from .skidpad import SkidpadBatchPlanner
+
+            dev = self._planner.device
+            self._skid = SkidpadBatchPlanner(dev)
+            self._reloc = torch.zeros((1, 8), dtype=torch.float64, device=dev)
+            self._reloc_host = np.zeros(8)
+            self._orig_pose = None
+            self._index_state = torch.zeros((1,), dtype=torch.int32, device=dev)
 
     @staticmethod
     def _convert_direction_to_array(direction: Any) -> np.ndarray:
@@ -241,7 +251,38 @@ class PathPlanner:
 
     @property
     def relocalization_info(self) -> Optional[RelocalizationInformation]:
-        return None
+        """relocalization_information.py:13-35: where the SLAM origin and the x axis land in the map frame."""
+        if self._skid is None or self._reloc_host[7] == 0.0:
+            return None
+        from .skidpad import to_known_frame
+
+        o = to_known_frame(self._reloc_host, np.zeros(2))
+        e = to_known_frame(self._reloc_host, np.array([1.0, 0.0]))
+        return RelocalizationInformation(o, float(np.arctan2(e[1] - o[1], e[0] - o[0])))
+
+    def _skidpad_step(self, cones, position, direction, return_intermediate_results):
+        """full_pipeline.py:122-140, 165-194 for MissionTypes.skidpad (sorting and matching are skipped)."""
+        dev = self._planner.device
+        t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+        pos_d, dir_d = t(position.reshape(1, 2)), t(direction.reshape(1, 2))
+        if self._reloc_host[7] == 0.0:
+            if self._orig_pose is None:
+                self._orig_pose = (pos_d.clone(), dir_d.clone())
+            xy = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in cones])
+            if len(xy) > 0:
+                off = t(np.array([0, len(xy)]), torch.int32)
+                self._reloc, _ = self._skid.relocalize(t(xy), off, pos_d, self._orig_pose[0], self._orig_pose[1])
+                self._reloc_host = self._reloc[0].cpu().numpy()
+        if self._prev_path is None:
+            self._prev_path = self._planner.initial_path()
+        res = self._skid.plan(t(np.array([0, 1]), torch.int32), pos_d, dir_d, self._reloc, self._index_state,
+                              prev_path=self._prev_path)
+        self._prev_path = res["internal"][0].clone()
+        path = res["path_f64"][0].cpu().numpy()
+        if not return_intermediate_results:
+            return path
+        e2, ei = np.zeros((0, 2)), np.zeros(0, dtype=int)
+        return path, e2, e2, e2, e2, ei, ei
 
     def calculate_path_in_global_frame(
         self,
@@ -253,6 +294,9 @@ class PathPlanner:
         """Same contract as the reference: returns a (40, 4) float64 array [u, x, y, curvature], or the
         7-tuple (path, sorted_left, sorted_right, left_with_virtual, right_with_virtual, l2r, r2l)."""
         direction = self._convert_direction_to_array(vehicle_direction)
+        if self._skid is not None:
+            return self._skidpad_step(cones, np.asarray(vehicle_position, dtype=np.float64).reshape(2), direction,
+                                      return_intermediate_results)
         if self.global_path is not None:
             raise NotImplementedError("global-path tracking belongs to the skidpad mission")
         batch = pack_frames([(cones, np.asarray(vehicle_position, dtype=np.float64).reshape(2), direction)],

@@ -237,3 +237,42 @@ def gen_mixed(seed: int, n_frames: int, start: int = 0, dtype=np.float32) -> Fra
             cones = new
         frames.append((cones, pos, direction))
     return pack_frames(frames, dtype=dtype)
+
+
+# ---- skidpad (BASELINE config 4) ------------------------------------------------------------------------------------
+
+def gen_skidpad(seed: int, n_traj: int, n_steps: int):
+    """Synthetic skidpad trajectories: the skidpad cone map under a random rigid motion per
+    trajectory plus sigma = 0.03 m cone noise; poses follow the canonical path (every k-th point) mapped through the same
+    motion, with N(0, 0.15 m) lateral noise and 2 deg heading noise.
+
+    Returns (cones_xy [sum n, 2], cones_type, offsets [T+1], pos [T, S, 2], dir [T, S, 2]) as float64 / uint8 / int32."""
+    import os
+
+    data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    table = np.load(os.path.join(data, "skidpad_path.npy"))
+    cones = np.load(os.path.join(data, "skidpad_cones.npy"))
+    k = max((int(0.85 * len(table)) - 200) // n_steps, 1)  # stop well before the end of the track table
+    centre = table[100 : 100 + k * n_steps : k][:n_steps]
+    tangent = np.gradient(table, axis=0)[100 : 100 + k * n_steps : k][:n_steps]
+    tangent /= np.linalg.norm(tangent, axis=1, keepdims=True)
+    normal = np.stack([-tangent[:, 1], tangent[:, 0]], 1)
+    xy_all, ty_all, offsets = [], [], [0]
+    pos = np.zeros((n_traj, n_steps, 2))
+    dirs = np.zeros((n_traj, n_steps, 2))
+    for t in range(n_traj):
+        rng = np.random.default_rng([int(seed), t])
+        th = rng.uniform(-np.pi, np.pi)
+        tr = rng.uniform(-300.0, 300.0, 2)
+        c, s_ = np.cos(th), np.sin(th)
+        rot = np.array([[c, -s_], [s_, c]])
+        xy = cones[:, :2] @ rot.T + tr + rng.normal(0.0, 0.03, (len(cones), 2))
+        p = centre + normal * rng.normal(0.0, 0.15, (n_steps, 1))
+        yaw = np.arctan2(tangent[:, 1], tangent[:, 0]) + rng.normal(0.0, np.deg2rad(2.0), n_steps)
+        d = np.stack([np.cos(yaw), np.sin(yaw)], 1)
+        pos[t] = p @ rot.T + tr
+        dirs[t] = d @ rot.T
+        xy_all.append(xy)
+        ty_all.append(cones[:, 2].astype(np.uint8))
+        offsets.append(offsets[-1] + len(xy))
+    return (np.ascontiguousarray(np.concatenate(xy_all)), np.concatenate(ty_all), np.asarray(offsets, np.int32), pos, dirs)

@@ -172,6 +172,41 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
                    int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/*
+ * Skidpad mission (MissionTypes.skidpad): relocalization + stateful tracking of the canonical skidpad path.
+ *   SkidpadRelocalizer.do_relocalization_once   fsd_path_planning/relocalization/skidpad/skidpad_relocalizer.py:198-240
+ *   SkidpadCalculatePath.fit_matches_as_spline  fsd_path_planning/calculate_path/skidpad_calculate_path.py:49-71
+ *   pose into / path out of the map frame       fsd_path_planning/full_pipeline/full_pipeline.py:122-140, 178-194
+ * Coordinates are fp64 (SLAM frames sit hundreds of metres from the origin).
+ *
+ * fsd_skidpad_relocalize_batch: one relocalization attempt for each of n_traj trajectories.
+ *   cones_xy [total][2] / offsets [T+1]: the cones seen by each trajectory; pos [T][2] current position;
+ *   orig_pos / orig_dir [T][2]: pose at the FIRST attempt of the trajectory; jitter [1140*6]: numpy
+ *   RandomState(42).randn (skidpad_relocalizer.py:38, 53); ref_centers [4]: right (x, y), left (x, y) circle centres of
+ *   the canonical path; reloc [T][8] out: translation(2), rotation, right reference centre(2), right calculated
+ *   centre(2), success flag (1.0 / 0.0); n_accepted [T] (nullable): circles that passed the filters.
+ */
+int fsd_skidpad_relocalize_batch(const fsd_params *params, int n_traj, const double *cones_xy, const int32_t *offsets,
+                                 const double *pos, const double *orig_pos, const double *orig_dir,
+                                 const double *jitter, const double *ref_centers, double *reloc, int32_t *n_accepted,
+                                 void *stream);
+
+/*
+ * fsd_skidpad_plan_batch: n_steps planner steps of n_traj trajectories (steps of trajectory t are
+ * step_offsets[t] .. step_offsets[t+1]-1, in time order).  index_state [T] in/out: index_along_path of each
+ * trajectory.  path_table [n_table][2]: the canonical path the planner tracks (every 2nd point of the track table).
+ * prev_path: as for fsd_plan_batch, in the MAP frame (= out_internal_f64 of the previous step).  Outputs per step:
+ * out_path fp32 (nullable) and out_path_f64 in the SLAM frame, out_internal_f64 in the map frame, out_index (path
+ * index used, -1 before relocalization), out_grid (nullable), out_status.
+ */
+size_t fsd_skidpad_workspace_bytes(int n_steps);
+int fsd_skidpad_plan_batch(const fsd_params *params, int n_traj, int n_steps, const int32_t *step_offsets,
+                           const double *pos, const double *dir, const double *reloc, int32_t *index_state,
+                           const double *path_table, int n_table, const int16_t *force_P, const double *prev_path,
+                           int prev_path_stride, float *out_path, double *out_path_f64, double *out_internal_f64,
+                           int32_t *out_index, int16_t *out_grid, uint32_t *out_status, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

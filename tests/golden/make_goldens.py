@@ -148,6 +148,45 @@ def fitpack_goldens():
     print(f"[fitpack] {len(calls)} fits")
 
 
+def skidpad_goldens():
+    """Sequential (stateful) reference runs of MissionTypes.skidpad: the recorded log and 6 synthetic trajectories."""
+    mod = rh.load_reference()
+    rec = rh._state["rec"]
+
+    def run(frames):
+        pp = mod.PathPlanner(mod.MissionTypes.skidpad)
+        paths, Ps, reloc_flag, index = [], [], [], []
+        for cones, pos, direction in frames:
+            rec.clear()
+            paths.append(pp.calculate_path_in_global_frame(cones, pos, direction))
+            Ps.append(int(rec.get("P", 0)))
+            reloc_flag.append(bool(pp.relocalizer.is_relocalized))
+            index.append(int(pp.pathing.index_along_path))
+        info = pp.relocalization_info
+        return (np.array(paths), np.array(Ps, np.int16), np.array(reloc_flag), np.array(index, np.int32),
+                np.zeros(3) if info is None else np.array([info.translation[0], info.translation[1], info.rotation]))
+
+    log = rh.load_demo_log("skidpad.json")
+    batch = synth.pack_frames(log)
+    paths, Ps, flag, index, info = run(log)
+    out = {"log_cones_xy": batch.cones_xy, "log_cones_type": batch.cones_type, "log_offsets": batch.offsets,
+           "log_pos": batch.pos, "log_dir": batch.dir, "log_path": paths, "log_P": Ps, "log_relocalized": flag,
+           "log_index": index, "log_info": info}
+    T, S = 6, 96
+    xy, ty, off, pos, dirs = synth.gen_skidpad(4, T, S)
+    syn_paths, syn_P, syn_flag, syn_index, syn_info = [], [], [], [], []
+    for t in range(T):
+        c = xy[off[t]:off[t + 1]]
+        cones = [c[ty[off[t]:off[t + 1]] == k] for k in range(5)]
+        p, P, f, ix, info_t = run([(cones, pos[t, s], dirs[t, s]) for s in range(S)])
+        syn_paths.append(p), syn_P.append(P), syn_flag.append(f), syn_index.append(ix), syn_info.append(info_t)
+        print(f"  skidpad synthetic trajectory {t}: relocalized at step {int(np.argmax(f)) if f.any() else -1}", flush=True)
+    out.update({"syn_T": T, "syn_S": S, "syn_path": np.array(syn_paths), "syn_P": np.array(syn_P),
+                "syn_relocalized": np.array(syn_flag), "syn_index": np.array(syn_index), "syn_info": np.array(syn_info)})
+    np.savez_compressed(os.path.join(HERE, "skidpad.npz"), **out)
+    print("[skidpad] log", len(log), "frames; synthetic", T, "x", S)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:] or None
     fsg = synth.pack_frames(rh.load_demo_log("fsg_19_2_laps.json"))
@@ -162,6 +201,7 @@ if __name__ == "__main__":
         "synth_colorless": lambda: save("synth_colorless", synth.remove_color_info(synth.gen_autocross(3, 256)).astype(np.float64)),
         "synth_mixed": lambda: save("synth_mixed", synth.gen_mixed(5, 256).astype(np.float64)),
         "fitpack": fitpack_goldens,
+        "skidpad": skidpad_goldens,
     }
     for name, fn in jobs.items():
         if only is None or name in only:

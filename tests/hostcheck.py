@@ -116,3 +116,42 @@ def fit(points: np.ndarray, s: float):
     nn, kk = n.value, k.value
     cc = c[: 2 * (nn - kk - 1)].reshape(-1, 2)
     return t[:nn].copy(), cc[:, 0].copy(), cc[:, 1].copy(), kk, ier
+
+
+# ---- skidpad ------------------------------------------------------------------------------------------------------
+
+def skidpad_relocalize(cones_xy, pos, orig_pos, orig_dir, jitter, ref):
+    xy = np.ascontiguousarray(cones_xy, dtype=np.float64)
+    out = np.zeros(8)
+    nacc = C.c_int(0)
+    d = lambda a: _p(np.ascontiguousarray(a, dtype=np.float64), C.c_double)
+    lib().fsd_hostcheck_skidpad_relocalize(_p(xy, C.c_double), len(xy), d(pos), d(orig_pos), d(orig_dir), d(jitter),
+                                           d(ref), _p(out, C.c_double), C.byref(nacc))
+    return out, nacc.value
+
+
+def skidpad_steps(reloc8, table, pos, direction, state, force_P=None, prev=None):
+    """Steps of ONE trajectory; prev: [40,4] shared or [n,40,4]; returns dict."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    direction = np.ascontiguousarray(direction, dtype=np.float64)
+    table = np.ascontiguousarray(table, dtype=np.float64)
+    n = len(pos)
+    out = np.zeros((n, HORIZON, 4))
+    internal = np.zeros((n, HORIZON, 4))
+    index = np.zeros(n, np.int32)
+    status = np.zeros(n, np.uint32)
+    grid = np.zeros((n, 2), np.int16)
+    st = C.c_int(int(state))
+    prev = np.ascontiguousarray(prev if prev is not None else initial_path(), dtype=np.float64)
+    stride = 0 if prev.size == HORIZON * 4 else HORIZON * 4
+    fp = None
+    if force_P is not None:
+        fpa = np.ascontiguousarray(force_P, dtype=np.int16)
+        fp = _p(fpa, C.c_int16)
+    p = default_params()
+    r8 = np.ascontiguousarray(reloc8, dtype=np.float64)
+    lib().fsd_hostcheck_skidpad_steps(C.byref(p), _p(r8, C.c_double), _p(table, C.c_double), len(table),
+                                      _p(pos, C.c_double), _p(direction, C.c_double), n, C.byref(st), fp,
+                                      _p(prev, C.c_double), stride, _p(out, C.c_double), _p(internal, C.c_double),
+                                      _p(index, C.c_int32), _p(status, C.c_uint32), _p(grid, C.c_int16))
+    return {"path": out, "internal": internal, "index": index, "status": status, "grid": grid, "state": st.value}

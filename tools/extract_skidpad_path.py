@@ -18,3 +18,19 @@ from fsd_path_planning.relocalization.skidpad.skidpad_path_data import BASE_SKID
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "ft_fsd_path_planning_b200", "data", "skidpad_path.npy")
 np.save(out, np.asarray(BASE_SKIDPAD_PATH, dtype=np.float64))
 print(BASE_SKIDPAD_PATH.shape, "->", out)
+
+# canonical-frame cone map of the skidpad track (data for the synthetic config-4 generator): the cones of the last
+# frame of the reference's recorded skidpad log, moved into the map frame with the reference's own relocalization
+mod = rh.load_reference()
+frames = rh.load_demo_log("skidpad.json")
+pp = mod.PathPlanner(mod.MissionTypes.skidpad)
+for cones, pos, direction in frames[:40]:
+    pp.calculate_path_in_global_frame(cones, pos, direction)
+assert pp.relocalizer.is_relocalized
+cones = frames[-1][0]
+xy = np.concatenate([c.reshape(-1, 2) for c in cones])
+ty = np.concatenate([np.full(len(c), t) for t, c in enumerate(cones)])
+known = np.array([pp.relocalizer.transform_to_known_map_frame(p, 0.0)[0] for p in xy])
+out2 = os.path.join(os.path.dirname(out), "skidpad_cones.npy")
+np.save(out2, np.concatenate([known, ty[:, None].astype(np.float64)], axis=1))
+print(known.shape, "->", out2)
