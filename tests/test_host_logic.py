@@ -71,3 +71,31 @@ def test_direction_conversion_like_reference():
     assert np.allclose(conv(np.array([[0.3]])), [np.cos(0.3), np.sin(0.3)])
     with pytest.raises(ValueError, match="direction must be a float or a 2 element array"):
         conv([1.0, 2.0, 3.0])
+
+
+def test_json_log_round_trip(tmp_path):
+    from ft_fsd_path_planning_b200.io import load_data_json, save_data_json
+
+    batch = synth.gen_autocross(9, 4).astype(np.float64)
+    save_data_json(batch, tmp_path / "log.json")
+    again = load_data_json(tmp_path / "log.json")
+    assert np.array_equal(again.cones_xy, batch.cones_xy) and np.array_equal(again.offsets, batch.offsets)
+    assert np.array_equal(again.cones_type, batch.cones_type) and np.array_equal(again.pos, batch.pos)
+    unknown = load_data_json(tmp_path / "log.json", remove_color_info=True)
+    assert (unknown.cones_type == 0).all() and np.array_equal(unknown.cones_xy, batch.cones_xy)
+
+
+def test_json_loader_reads_reference_log_format():
+    """The goldens were packed from the reference's own logs; loading the same file through io.py gives the same batch
+    (only where the reference tree is present)."""
+    import os
+
+    from conftest import load_golden
+    from ft_fsd_path_planning_b200.io import load_data_json
+
+    path = "/root/reference/fsd_path_planning/demo/fsg_19_2_laps.json"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    batch, _ = load_golden("fsg_color")
+    loaded = load_data_json(path)
+    assert np.array_equal(loaded.cones_xy, batch.cones_xy) and np.array_equal(loaded.offsets, batch.offsets)
