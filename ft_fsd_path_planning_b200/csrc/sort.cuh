@@ -78,9 +78,11 @@ FSD_DEVFN void knn_insert(double *d, int *id, int *cnt, int k, double v, int j) 
   if (c < k) *cnt = c + 1;
 }
 
-FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
+// returns true when a cone had more in-range neighbours than the candidate buffer holds (FSD_ST_OVERFLOW)
+FSD_DEVFN bool build_knn(SortSmem &S, int n, const DevParams &P) {
   int k = n - 1 < P.max_n_neighbors ? n - 1 : P.max_n_neighbors;
   if (k > 5) k = 5;
+  bool over = false;
 #pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double dl[5], dr[5];
@@ -89,14 +91,29 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
     const double xi = S.xy[i].x, yi = S.xy[i].y;
     const int ti = S.type[i];
     const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
-#pragma unroll 1
+    // pass 1: a tight, call-free distance sweep that only collects the cones within max_dist of cone i (a handful);
+    // edges longer than max_dist are removed after the k-NN selection in the reference (:102-107) and a longer edge
+    // can never displace a shorter one, so they are dropped before the selection
+    constexpr int CAND_CAP = 48;
+    uint8_t cand[CAND_CAP];
+    int nc = 0;
+#pragma unroll 2
     for (int j = 0; j < n; ++j) {
-      double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
-      double dd = ddx * ddx + ddy * ddy;
-      // edges longer than max_dist are removed after the k-NN selection (:102-107): a longer edge
-      // can never displace a shorter one, so it is dropped before the selection
-      if (dd > P.max_dist2 || j == i) continue;
-      int tj = S.type[j];
+      const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
+      const double dd = ddx * ddx + ddy * ddy;
+      if (dd <= P.max_dist2 && j != i) {
+        if (nc < CAND_CAP)
+          cand[nc++] = (uint8_t)j;
+        else
+          over = true;
+      }
+    }
+    // pass 2: exact selection among the candidates, ascending j (ties keep the lower index first)
+    for (int q = 0; q < nc; ++q) {
+      const int j = cand[q];
+      const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
+      const double dd = ddx * ddx + ddy * ddy;
+      const int tj = S.type[j];
       if (li && tj != FSD_CONE_RIGHT) knn_insert(dl, il, &cl, k, dd, j);
       if (ri && tj != FSD_CONE_LEFT) knn_insert(dr, ir, &cr, k, dd, j);
     }
@@ -132,6 +149,7 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
     }
   }
   wsync();
+  return wany(over);
 }
 
 // ---- seeds: core_trace_sorter.py:344-465 ----------------------------------------------------
@@ -782,7 +800,7 @@ FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
 
 FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg) {
   unsigned status = 0;
-  if (n >= 3) build_knn(S, n, P);
+  if (n >= 3 && build_knn(S, n, P)) status |= FSD_ST_OVERFLOW;
   int nl = sort_one_side(S, n, F, FSD_CONE_LEFT, P, dbg, &status);
   int nr = sort_one_side(S, n, F, FSD_CONE_RIGHT, P, dbg, &status);
   if (nl == 0) status |= FSD_ST_NO_LEFT;

@@ -130,52 +130,58 @@ FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &o
 
 // banded Cholesky (upper, in place in M), forward and back substitution; lane 0 only.
 // returns false on a non-positive pivot.
+// Banded Cholesky G^T G = M (upper band, in place), z = G^-T rhs, c = G^-1 z, cooperative over the warp:
+// right-looking elimination, one matrix row per step; the <= 10 trailing updates of the band and the <= 8 updates of
+// the two right-hand sides are one task per lane; one reciprocal square root per row replaces the square root and
+// every division.  M[i][0] holds the diagonal of G on return (fppara's p0 needs it).  All lanes return the same flag.
 FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2],
                           double *rinv_row) {
-  // M[i][0] holds the diagonal of G on return (fppara's p0 needs it).  One reciprocal square root per row replaces
-  // the square root and every division of the textbook algorithm (the solve is dominated by them otherwise).
+  const int lane = fsd_lane();
+  const int kbm = kb - 1, npairs = kbm * (kbm + 1) / 2;
+  for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&z[0][0])[e] = (&rhs[0][0])[e];
+  wsync();
   for (int i = 0; i < nk1; ++i) {
-    double rinv = 0.0;
-    for (int d = 0; d < kb; ++d) {
-      int j = i + d;
-      if (j >= nk1) break;
-      double s = M[i][d];
-      int p0 = j - kb + 1;
-      if (p0 < 0) p0 = 0;
-      for (int p = p0; p < i; ++p) s -= M[p][i - p] * M[p][j - p];
-      if (d == 0) {
-        if (!(s > 0.0)) return false;
-        rinv = frsqrt(s);
+    const double s = M[i][0];
+    if (!(s > 0.0)) return false;
+    const double rinv = frsqrt(s);
+    wsync();
+    for (int e = lane; e < kbm + 4; e += FSD_LANES) {
+      if (e < kbm) {
+        if (i + 1 + e < nk1) M[i][1 + e] *= rinv;
+      } else if (e < kbm + 2) {
+        z[i][e - kbm] *= rinv;
+      } else if (e == kbm + 2) {
         M[i][0] = s * rinv;
-        rinv_row[i] = rinv;
       } else {
-        M[i][d] = s * rinv;
+        rinv_row[i] = rinv;
       }
     }
-    // forward substitution of row i rides along: z = G^-T rhs
-    double s0 = rhs[i][0], s1 = rhs[i][1];
-    int p0 = i - kb + 1;
-    if (p0 < 0) p0 = 0;
-    for (int p = p0; p < i; ++p) {
-      double g = M[p][i - p];
-      s0 -= g * z[p][0];
-      s1 -= g * z[p][1];
+    wsync();
+    for (int e = lane; e < npairs + 2 * kbm; e += FSD_LANES) {
+      if (e < npairs) {
+        int a = 1, rem = e;
+        while (rem >= kbm - a + 1) {
+          rem -= kbm - a + 1;
+          ++a;
+        }
+        const int b = a + rem;
+        if (i + b < nk1) M[i + a][b - a] -= M[i][a] * M[i][b];
+      } else {
+        const int a = 1 + ((e - npairs) >> 1), col = (e - npairs) & 1;
+        if (i + a < nk1) z[i + a][col] -= M[i][a] * z[i][col];
+      }
     }
-    z[i][0] = s0 * rinv;
-    z[i][1] = s1 * rinv;
+    wsync();
   }
   for (int i = nk1 - 1; i >= 0; --i) {
-    double s0 = z[i][0], s1 = z[i][1];
-    int l1 = nk1 - 1 - i;
-    if (l1 > kb - 1) l1 = kb - 1;
-    for (int l = 1; l <= l1; ++l) {
-      double g = M[i][l];
-      s0 -= g * c[i + l][0];
-      s1 -= g * c[i + l][1];
+    for (int col = lane; col < 2; col += FSD_LANES) {
+      double s = z[i][col];
+      int l1 = nk1 - 1 - i;
+      if (l1 > kbm) l1 = kbm;
+      for (int l = 1; l <= l1; ++l) s -= M[i][l] * c[i + l][col];
+      c[i][col] = s * rinv_row[i];
     }
-    const double rinv = rinv_row[i];
-    c[i][0] = s0 * rinv;
-    c[i][1] = s1 * rinv;
+    wsync();
   }
   return true;
 }
@@ -388,14 +394,9 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
     interval_starts(W, u, m, n, k);
     knot_reciprocals(W, n, k);
     assemble_normal(W, pts, u, n, k);
-    if (lane == 0) {
-      for (int i = 0; i < nk1; ++i)
-        for (int d = 0; d < BW; ++d) W.G[i][d] = W.N[i][d];
-      bool ok = chol_solve(W.G, nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP);
-      W.start[NCAP] = ok ? 1 : 0;
-    }
+    for (int e = lane; e < nk1 * BW; e += FSD_LANES) (&W.G[0][0])[e] = (&W.N[0][0])[e];
     wsync();
-    if (!W.start[NCAP]) {
+    if (!chol_solve(W.G, nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP)) {
       *status |= FSD_ST_UNSUPPORTED;
       return 10;
     }
@@ -484,9 +485,7 @@ FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, do
       for (int i = lane; i < nk1 * BW; i += FSD_LANES)
         (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
       wsync();
-      if (lane == 0) W.start[NCAP] = chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP) ? 1 : 0;
-      wsync();
-      if (!W.start[NCAP]) {
+      if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP)) {
         *status |= FSD_ST_UNSUPPORTED;
         return 10;
       }
