@@ -211,25 +211,66 @@ __global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, co
   }
 }
 
+// Path stage.  The WPC warps of a CTA run their frames' path machines (path.cuh) in LOCKSTEP: one machine step per
+// loop iteration (a pass of a spline fit, or one stage between fits), a CTA barrier per iteration, and a warp that
+// reaches an alignment state (a fit is finished) waits there until no other warp of the CTA is behind it.  The warps
+// therefore execute the same few kilobytes of code at the same time and share every instruction-cache fill; measured
+// with 16 identical frames per CTA (perfect sharing) the kernel is 1.7x faster than with free-running warps
+// (profiles/r1_lockstep_probe.txt).
 template <typename T>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
                 unsigned char *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  __shared__ int s_state[WPC];
+  const int warp = threadIdx.x >> 5, lane = fsd_lane();
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * PATH_CTA_STRIDE);
-  if (fsd_lane() == 0) {
+  if (lane == 0) {
     unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
     S.pts = reinterpret_cast<d2 *>(mine);
     S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
   }
   __syncwarp();
-  FSD_FRAME_LOOP(b, n_frames) {
-    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
-    path_from_tensors(S, b, O, F, force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out_f64, out_f32,
-                      grid_out);
-    __syncwarp();
+  for (int base = (int)blockIdx.x * WPC; base < n_frames; base += (int)gridDim.x * WPC) {
+    const int b = base + warp;
+    const bool active = b < n_frames;
+    PathMachine M;
+    M.state = PS_DONE;
+    M.status = 0;
+    M.P_grid = M.n_trim = 0;
+    double *out = out_f64 + (size_t)(active ? b : 0) * FSD_HORIZON * 4;
+    if (active) {
+      const FramePose F =
+          make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
+      const int nl = O.n_wv[2 * (size_t)b], nr = O.n_wv[2 * (size_t)b + 1];
+      const d2 *left = reinterpret_cast<const d2 *>(O.left_wv + (size_t)b * WV_CAP * 2);
+      const d2 *right = reinterpret_cast<const d2 *>(O.right_wv + (size_t)b * WV_CAP * 2);
+      pm_begin_frame(S, M, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F,
+                     force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out);
+    }
+    for (;;) {
+      if (lane == 0) s_state[warp] = M.state;
+      __syncthreads();
+      int behind = PS_DONE;
+#pragma unroll
+      for (int w = 0; w < WPC; ++w) behind = min(behind, s_state[w]);
+      __syncthreads();
+      if (behind == PS_DONE) break;
+      if (M.state != PS_DONE && !(pm_is_alignment_state(M.state) && behind < M.state)) pm_step(S, M, P);
+    }
+    if (active) {
+      __syncwarp();
+      if (out_f32)
+        for (int i = lane; i < FSD_HORIZON * 4; i += 32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)out[i];
+      if (lane == 0) {
+        O.status[b] |= M.status;
+        if (grid_out) {
+          grid_out[2 * (size_t)b] = (int16_t)M.P_grid;
+          grid_out[2 * (size_t)b + 1] = (int16_t)M.n_trim;
+        }
+      }
+    }
   }
 }
 

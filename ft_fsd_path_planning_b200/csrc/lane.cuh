@@ -80,6 +80,16 @@ FSD_DEVFN double wscan_incl(double v) {
 }
 // value of the last lane
 FSD_DEV double wlast(double v) { return __shfl_sync(FULL, v, 31); }
+// N sums at once, butterfly steps interleaved across the N values (independent shuffles issue back to back, so
+// the latency is that of ONE reduction instead of N)
+template <int N>
+FSD_DEV void wsum_vec(double (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] += __shfl_xor_sync(FULL, v[e], o);
+  }
+}
 
 #else  // host-check build: a warp of one lane
 
@@ -97,6 +107,8 @@ FSD_DEV bool wany(bool p) { return p; }
 FSD_DEV void wargmin(double &, int &) {}
 FSD_DEV double wscan_incl(double v) { return v; }
 FSD_DEV double wlast(double v) { return v; }
+template <int N>
+FSD_DEV void wsum_vec(double (&)[N]) {}
 
 #endif
 

@@ -138,23 +138,44 @@ FSD_DEVFN void chord_params(const d2 *p, int m, double *u) {
   wsync();
 }
 
-// ---- SplineFitterFactory.fit(...).predict(der=0) ------------------------------------------------------
-// fits src[0..m) and evaluates every `step` up to max_u (the fit's own when max_u_override <= 0) into
-// dst[0..*n_out).  dst may alias src (the evaluation only needs the coefficients).
+// ---- the path pipeline as a resumable state machine -----------------------------------------------------------------
+// One frame's path calculation = fit #1 -> validity / connect / extend / cut -> fit #2 -> trim -> fit #3 -> curvature
+// and sampling, with the reference's fallbacks (re-fit of the previous path, redo of the tail with the previous
+// path) as backward transitions.  pm_step advances ONE unit: a pass of a spline fit (spline.cuh) or one stage between
+// fits.  The path kernel keeps the warps of a CTA in lockstep at this granularity (they wait for each other at the
+// *_DONE states), the blocking wrappers below (path_frame, path_from_update, initial_path_frame) simply run the
+// machine to completion.  Every lane holds an identical copy of the machine state.
 
-FSD_DEVFN int fit_predict(PathSmem &S, const d2 *src, double *u, int m, double smoothing, double step,
-                          double max_u_override, d2 *dst, int dst_cap, int *n_out, unsigned *status) {
-  if (m < 2) return RC_RAISES;  // NullSplineEvaluator
-  chord_params(src, m, u);
-  int ier = fit_curve(S.W, src, u, m, smoothing, status);
-  if (ier == 10) return (*status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR;
-  const double mu = max_u_override > 0.0 ? max_u_override : S.W.max_u;
-  const double q = ceil(fdiv(mu, step));  // len(np.arange(0, max_u, step))
+enum {
+  PS_FIT1 = 1,
+  PS_FIT1_DONE = 2,  // alignment point
+  PS_TAIL = 3,
+  PS_FIT2 = 4,
+  PS_FIT2_DONE = 5,  // alignment point
+  PS_FIT3 = 6,
+  PS_FIT3_DONE = 7,  // alignment point
+  PS_DONE = 100
+};
+
+struct PathMachine {
+  int state, mode;  // mode 0: planner frame, 1: initial path (fit #1 on the chord, then the parameterisation only)
+  FitState fit;
+  FramePose F;
+  const double *prev;  // previous path, 40 x 4
+  double *out;         // 40 x 4
+  int force_P, nu, P_grid, n_trim;
+  unsigned status, tail_status;
+  bool fit1_retry, tail_retry;
+  double predict_every;
+};
+
+FSD_DEV bool pm_is_alignment_state(int st) { return st == PS_FIT1_DONE || st == PS_FIT2_DONE || st == PS_FIT3_DONE; }
+
+// evaluate the fitted spline every `step` up to max_u into dst (len(np.arange(0, max_u, step)) points)
+FSD_DEVFN int pm_evaluate(PathSmem &S, double max_u, double step, d2 *dst, int dst_cap) {
+  const double q = ceil(fdiv(max_u, step));
   const int n = q > 0.0 ? (q > 1e6 ? 1000000 : (int)q) : 0;
-  if (n > dst_cap) {
-    *status |= FSD_ST_OVERFLOW;
-    return RC_UNSUPPORTED;
-  }
+  if (n > dst_cap) return -1;
   wsync();
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double x, y;
@@ -163,33 +184,84 @@ FSD_DEVFN int fit_predict(PathSmem &S, const d2 *src, double *u, int m, double s
     dst[i].y = y;
   }
   wsync();
-  *n_out = n;
-  return RC_OK;
+  return n;
 }
 
-// ---- PathParameterizer.parameterize_path (path_parameterization.py:297-328) ----------------------------
-// path = S.pts[0..n).  Writes the (40, 4) result to out (lane-strided) and P to *P_out.
+FSD_DEVFN void pm_finish_with_prev(PathMachine &M, unsigned bits) {
+  M.status |= bits;
+  wsync();
+  for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += FSD_LANES) M.out[i] = M.prev[i];
+  M.P_grid = 0;
+  M.n_trim = 0;
+  M.state = PS_DONE;
+  wsync();
+}
 
-FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, double *out, int *P_out,
-                           unsigned *status) {
+// the tail failed with return code rc: ValueError -> once more with the previous path (:561-570), else give up
+FSD_DEVFN void pm_tail_failed(PathSmem &S, PathMachine &M, int rc) {
+  if (M.mode == 1) {
+    M.status |= FSD_ST_UNSUPPORTED;
+    M.state = PS_DONE;
+    return;
+  }
+  if (rc == RC_VALUE_ERROR && !M.tail_retry) {
+    M.status |= FSD_ST_MPC_FAILED;
+    M.tail_retry = true;
+    M.tail_status = 0;
+    wsync();
+    for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
+    M.nu = FSD_HORIZON;
+    M.state = PS_TAIL;
+    wsync();
+    return;
+  }
+  pm_finish_with_prev(M, M.tail_status | (rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES));
+}
+
+FSD_DEVFN void pm_start_fit1(PathSmem &S, PathMachine &M, const d2 *src, int m, const DevParams &P) {
+  if (m >= 2) chord_params(src, m, S.u);
+  fit_init(S.W, M.fit, src, S.u, m, P.smoothing);
+  M.state = PS_FIT1;
+}
+
+// overwrite_path_if_it_is_too_far_away :225-237 on the path update S.pts[1 .. 1+nu), then the tail
+FSD_DEVFN void pm_enter_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   const int lane = fsd_lane();
-  if (n < 2) return RC_RAISES;
-  // _refit_spline :125-161
+  double best = INFINITY;
+  for (int i = lane; i < M.nu; i += FSD_LANES) best = fmin(best, fnorm(M.F.px - S.pts[1 + i].x, M.F.py - S.pts[1 + i].y));
+  best = wmin_d(best);
+  wsync();
+  if (best > P.max_valid_dist) {
+    M.status |= FSD_ST_PATH_TOO_FAR;
+    for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
+    M.nu = FSD_HORIZON;
+    wsync();
+  }
+  M.tail_status = 0;
+  M.state = PS_TAIL;
+}
+
+// _refit_spline :125-161 on S.pts[0..n): path length, sub-sampling, start of fit #3
+FSD_DEVFN void pm_start_fit3(PathSmem &S, PathMachine &M, int n, const DevParams &P) {
+  const int lane = fsd_lane();
+  if (n < 2) {
+    pm_tail_failed(S, M, RC_RAISES);
+    return;
+  }
   double len = 0.0, first10 = 0.0;
   for (int i = lane; i + 1 < n; i += FSD_LANES) {
-    double ddx = S.pts[i + 1].x - S.pts[i].x, ddy = S.pts[i + 1].y - S.pts[i].y;
-    double d = fsqrt(ddx * ddx + ddy * ddy);
+    const double d = fnorm(S.pts[i + 1].x - S.pts[i].x, S.pts[i + 1].y - S.pts[i].y);
     len += d;
     if (i < 10) first10 += d;
   }
   const double path_length = wsum(len);
   const int nm = n - 1 < 10 ? n - 1 : 10;
   const double mean_dist = fdiv(wsum(first10), (double)nm);
-  const double predict_every = fdiv(fdiv(path_length, (double)FSD_HORIZON), 3.0);
-  const double ratio = fdiv(predict_every, mean_dist);
+  M.predict_every = fdiv(fdiv(path_length, (double)FSD_HORIZON), 3.0);
+  const double ratio = fdiv(M.predict_every, mean_dist);
   int skip = 1;
   if (isfinite(ratio) && ratio < 1e6 && (int)ratio > 1) skip = (int)ratio;
-  int ms = (n + skip - 1) / skip;
+  const int ms = (n + skip - 1) / skip;
   wsync();
   if (skip > 1) {
     if (lane == 0)
@@ -197,27 +269,176 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
     wsync();
   }
   chord_params(S.pts, ms, S.u);
-  int ier = fit_curve(S.W, S.pts, S.u, ms, P.refit_smoothing, status);
-  if (ier == 10) return (*status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR;
+  fit_init(S.W, M.fit, S.pts, S.u, ms, P.refit_smoothing);
+  M.state = PS_FIT3;
+}
+
+// connect_path_to_car, extend_path, remove_path_behind_car (core_calculate_path.py:430-465, 261-334), start of fit #2
+FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
+  const int lane = fsd_lane();
+  const FramePose &F = M.F;
+  if (M.nu < 1) {
+    pm_tail_failed(S, M, RC_RAISES);
+    return;
+  }
+  d2 *path = S.pts + 1;
+  int n = M.nu;
+  {
+    const double fx = path[0].x - F.px, fy = path[0].y - F.py;
+    const double d = fnorm(fx, fy);
+    const bool behind = cos_between(fx, fy, F.dx, F.dy) < 0.0;  // angle > pi/2
+    wsync();
+    if (!(d < 0.5 || behind)) {
+      if (lane == 0) {
+        S.pts[0].x = F.px + fdiv(fx, d) * 0.2;
+        S.pts[0].y = F.py + fdiv(fy, d) * 0.2;
+      }
+      path = S.pts;
+      n = M.nu + 1;
+    }
+    wsync();
+  }
+  {
+    int first = n;
+    for (int i = lane; i < n; i += FSD_LANES)
+      if ((path[i].x - F.px) * F.dx + (path[i].y - F.py) * F.dy > 0.0) {
+        first = i;
+        break;
+      }
+    first = wmin_i(first);
+    int start = n - 20 < 0 ? 0 : n - 20;
+    if (first < start) start = first;
+    const int nf = n - start;
+    if (nf < 2) {
+      pm_tail_failed(S, M, RC_RAISES);
+      return;
+    }
+    double part = 0.0;
+    for (int i = start + lane; i + 1 < n; i += FSD_LANES) part += fnorm(path[i + 1].x - path[i].x, path[i + 1].y - path[i].y);
+    const double plen = wsum(part);
+    if (!(plen > P.mpc_len)) {
+      const int nr = nf < 20 ? nf : 20;
+      const d2 *rel = path + (n - nr);
+      double cx, cy, radius;
+      circle_fit_warp(rel, nr, cx, cy, radius);
+      const double r_use = fmin(fmax(radius, 10.0), 100.0);
+      const double lastx = path[n - 1].x, lasty = path[n - 1].y;
+      const int room = PCAP - (int)(path - S.pts) - n;
+      if (room < 49) {
+        M.tail_status |= FSD_ST_OVERFLOW;
+        pm_tail_failed(S, M, RC_UNSUPPORTED);
+        return;
+      }
+      if (r_use < 80.0) {
+        d2 p0 = {rel[0].x - cx, rel[0].y - cy}, p1 = {rel[nr / 2].x - cx, rel[nr / 2].y - cy},
+           p2 = {rel[nr - 1].x - cx, rel[nr - 1].y - cy};
+        const double sg = sgn(orient(p0, p1, p2));
+        const double a0 = fsd_atan2(p0.y, p0.x), a1 = a0 + sg * PI;
+        const double stepa = fdiv(a1 - a0, 49.0);  // np.linspace(a0, a1) has 50 samples; the first is dropped
+        const double r0x = fsd_cos(a0) * r_use, r0y = fsd_sin(a0) * r_use;
+        wsync();
+        for (int i = 1 + lane; i < 50; i += FSD_LANES) {
+          const double ang = i == 49 ? a1 : (double)i * stepa + a0;
+          path[n + i - 1].x = fsd_cos(ang) * r_use - r0x + lastx;
+          path[n + i - 1].y = fsd_sin(ang) * r_use - r0y + lasty;
+        }
+        n += 49;
+      } else {
+        double ddx = lastx - path[n - 2].x, ddy = lasty - path[n - 2].y;
+        const double nrm = fnorm(ddx, ddy);
+        ddx = fdiv(ddx, nrm);
+        ddy = fdiv(ddy, nrm);
+        wsync();
+        for (int i = 1 + lane; i < 30; i += FSD_LANES) {
+          path[n + i - 1].x = lastx + ddx * (double)i;
+          path[n + i - 1].y = lasty + ddy * (double)i;
+        }
+        n += 29;
+      }
+      wsync();
+    }
+  }
+  // first point of minimal distance to the car
+  double bv = 0.0;
+  int bi = -1;
+  for (int i = lane; i < n; i += FSD_LANES) {
+    const double d = fnorm(F.px - path[i].x, F.py - path[i].y);
+    if (bi < 0 || d < bv) {
+      bv = d;
+      bi = i;
+    }
+  }
+  wargmin(bv, bi);
+  // refit_path_for_mpc_with_safety_factor :239-259
+  const int off = (int)(path - S.pts) + bi, m2 = n - bi;
+  if (m2 < 2) {
+    pm_tail_failed(S, M, RC_UNSUPPORTED);  // the reference re-parameterises a (40, 4) array here (latent bug)
+    return;
+  }
+  chord_params(S.pts + off, m2, S.u + off);
+  fit_init(S.W, M.fit, S.pts + off, S.u + off, m2, P.smoothing);
+  M.state = PS_FIT2;
+}
+
+// fit #2 is done: evaluate up to 1.5 x the MPC length, keep the first mpc_path_length metres (:467-499), start fit #3
+FSD_DEVFN void pm_stage_after_fit2(PathSmem &S, PathMachine &M, const DevParams &P) {
+  const int lane = fsd_lane();
+  if (M.fit.ier == 10) {
+    pm_tail_failed(S, M, (M.tail_status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR);
+    return;
+  }
+  const int nfix = pm_evaluate(S, P.mpc_len * 1.5, P.predict_every, S.pts, PCAP);
+  if (nfix < 0 || nfix - 1 <= 1) {
+    if (nfix < 0) M.tail_status |= FSD_ST_OVERFLOW;
+    pm_tail_failed(S, M, RC_UNSUPPORTED);
+    return;
+  }
+  int first_over = nfix;
+  double carry = 0.0;
+  for (int base = 0; base < nfix - 1; base += FSD_LANES) {
+    const int i = base + lane;
+    double d = 0.0;
+    if (i < nfix - 1) d = fnorm(S.pts[i + 1].x - S.pts[i].x, S.pts[i + 1].y - S.pts[i].y);
+    const double incl = wscan_incl(d) + carry;
+    if (i < nfix - 1 && incl > P.mpc_len && i < first_over) first_over = i;
+    carry = wlast(incl);
+  }
+  first_over = wmin_i(first_over);
+  M.n_trim = first_over >= nfix ? nfix - 1 : first_over;
+  pm_start_fit3(S, M, M.n_trim, P);
+}
+
+// fit #3 is done: evaluation grid, curvature, 40 samples (path_parameterization.py:163-295)
+FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams &P) {
+  const int lane = fsd_lane();
+  if (M.fit.ier == 10) {
+    pm_tail_failed(S, M, (M.tail_status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR);
+    return;
+  }
+  const double predict_every = M.predict_every;
   // size of the evaluation grid np.arange(0, max_u, predict_every): SURVEY.md Q13
   int Pn;
-  if (force_P > 0) {
-    Pn = force_P;
+  if (M.force_P > 0) {
+    Pn = M.force_P;
   } else {
     const double q = fdiv(S.W.max_u, predict_every);
     const double r = rint(q);
     if (fabs(q - r) < 1e-9) {
       Pn = (int)r;
-      *status |= FSD_ST_TIE_P;
+      M.tail_status |= FSD_ST_TIE_P;
     } else {
       Pn = q < 1e6 ? (int)ceil(q) : 1000000;
     }
   }
-  *P_out = Pn;
-  if (Pn < FSD_HORIZON) return RC_VALUE_ERROR;  // repeated sample indices (:284-285)
+  M.P_grid = Pn;
+  if (Pn < FSD_HORIZON) {  // repeated sample indices (:284-285)
+    pm_tail_failed(S, M, RC_VALUE_ERROR);
+    return;
+  }
   if (Pn > GRID_CAP) {
-    *status |= FSD_ST_OVERFLOW;
-    return RC_UNSUPPORTED;
+    M.tail_status |= FSD_ST_OVERFLOW;
+    pm_tail_failed(S, M, RC_UNSUPPORTED);
+    return;
   }
   wsync();
   for (int i = lane; i < Pn; i += FSD_LANES) {
@@ -232,12 +453,12 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
   if (window % 2 == 0) window += 1;
   const int hw = window / 2;
   for (int i = lane; i < Pn; i += FSD_LANES) {
-    int lo = i - hw < 0 ? 0 : i - hw;
-    int hi = i + hw > Pn - 1 ? Pn - 1 : i + hw;
+    const int lo = i - hw < 0 ? 0 : i - hw;
+    const int hi = i + hw > Pn - 1 ? Pn - 1 : i + hw;
     const int cnt = hi - lo + 1;
     double r = circle_radius_serial(S.pts + lo, cnt);
     r = fmin(fmax(r, 1.0), 3000.0);
-    double sg = sgn(orient(S.pts[lo], S.pts[lo + cnt / 2], S.pts[hi]));
+    const double sg = sgn(orient(S.pts[lo], S.pts[lo + cnt / 2], S.pts[hi]));
     S.curv[i] = fdiv(1.0, r) * sg;
   }
   wsync();
@@ -249,222 +470,124 @@ FSD_DEVFN int parameterize(PathSmem &S, int n, int force_P, const DevParams &P, 
     const int idx = j == FSD_HORIZON - 1 ? Pn - 1 : (int)floor((double)j * stp);
     double acc = 0.0;
     for (int q = idx - fs / 2; q <= idx + fs - fs / 2 - 1; ++q) {
-      int qq = q < 0 ? 0 : (q > Pn - 1 ? Pn - 1 : q);
+      const int qq = q < 0 ? 0 : (q > Pn - 1 ? Pn - 1 : q);
       acc += S.curv[qq];
     }
-    out[4 * j + 0] = (double)idx * predict_every;
-    out[4 * j + 1] = S.pts[idx].x;
-    out[4 * j + 2] = S.pts[idx].y;
-    out[4 * j + 3] = fdiv(acc, (double)fs);
+    M.out[4 * j + 0] = (double)idx * predict_every;
+    M.out[4 * j + 1] = S.pts[idx].x;
+    M.out[4 * j + 2] = S.pts[idx].y;
+    M.out[4 * j + 3] = fdiv(acc, (double)fs);
   }
   wsync();
-  return RC_OK;
+  M.status |= M.tail_status;
+  M.state = PS_DONE;
 }
 
-// ---- CalculatePath MPC tail (core_calculate_path.py:336-417) on path = S.pts[1 .. 1+n_in) -----------------
-
-FSD_DEVFN int mpc_tail(PathSmem &S, int n_in, const FramePose &F, int force_P, const DevParams &P, double *out,
-                       int *P_out, int *n_trim, unsigned *status) {
-  const int lane = fsd_lane();
-  if (n_in < 1) return RC_RAISES;
-  d2 *path = S.pts + 1;
-  int n = n_in;
-  // connect_path_to_car :430-457
-  {
-    const double fx = path[0].x - F.px, fy = path[0].y - F.py;
-    const double d = fsqrt(fx * fx + fy * fy);
-    const bool behind = cos_between(fx, fy, F.dx, F.dy) < 0.0;  // angle > pi/2
-    wsync();
-    if (!(d < 0.5 || behind)) {
-      if (lane == 0) {
-        S.pts[0].x = F.px + fdiv(fx, d) * 0.2;
-        S.pts[0].y = F.py + fdiv(fy, d) * 0.2;
-      }
-      path = S.pts;
-      n = n_in + 1;
+// fit #1 is done (fit_matches_as_spline :207-223): evaluate the path update every predict_every metres
+FSD_DEVFN void pm_stage_after_fit1(PathSmem &S, PathMachine &M, const DevParams &P) {
+  if (M.fit.ier == 10) {
+    const bool unsupported = (M.status & FSD_ST_UNSUPPORTED) != 0;
+    if (!unsupported && !M.fit1_retry && M.mode == 0) {
+      M.status |= FSD_ST_FIT1_FAILED;  // ValueError -> the previous path is fitted instead
+      M.fit1_retry = true;
+      pm_start_fit1(S, M, S.prev_xy, FSD_HORIZON, P);
+      return;
     }
-    wsync();
+    if (M.mode == 1) {
+      M.status |= FSD_ST_UNSUPPORTED;
+      M.state = PS_DONE;
+    } else {
+      pm_finish_with_prev(M, unsupported ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES);
+    }
+    return;
   }
-  // extend_path :261-334
-  {
-    int first = n;
-    for (int i = lane; i < n; i += FSD_LANES)
-      if ((path[i].x - F.px) * F.dx + (path[i].y - F.py) * F.dy > 0.0) {
-        first = i;
-        break;
-      }
-    first = wmin_i(first);
-    int start = n - 20 < 0 ? 0 : n - 20;
-    if (first < start) start = first;
-    const int nf = n - start;
-    if (nf < 2) return RC_RAISES;
-    double part = 0.0;
-    for (int i = start + lane; i + 1 < n; i += FSD_LANES) {
-      double ddx = path[i + 1].x - path[i].x, ddy = path[i + 1].y - path[i].y;
-      part += fsqrt(ddx * ddx + ddy * ddy);
+  if (M.mode == 1) {
+    const int nd = pm_evaluate(S, S.W.max_u, P.predict_every, S.pts, PCAP);
+    if (nd < 0) {
+      M.status |= FSD_ST_UNSUPPORTED | FSD_ST_OVERFLOW;
+      M.state = PS_DONE;
+      return;
     }
-    const double plen = wsum(part);
-    if (!(plen > P.mpc_len)) {
-      const int nr = nf < 20 ? nf : 20;
-      const d2 *rel = path + (n - nr);
-      double cx, cy, radius;
-      circle_fit_warp(rel, nr, cx, cy, radius);
-      const double r_use = fmin(fmax(radius, 10.0), 100.0);
-      const double lastx = path[n - 1].x, lasty = path[n - 1].y;
-      const int room = PCAP - (int)(path - S.pts) - n;
-      if (room < 49) {
-        *status |= FSD_ST_OVERFLOW;
-        return RC_UNSUPPORTED;
-      }
-      if (r_use < 80.0) {
-        d2 p0 = {rel[0].x - cx, rel[0].y - cy}, p1 = {rel[nr / 2].x - cx, rel[nr / 2].y - cy},
-           p2 = {rel[nr - 1].x - cx, rel[nr - 1].y - cy};
-        const double sg = sgn(orient(p0, p1, p2));
-        const double a0 = fsd_atan2(p0.y, p0.x), a1 = a0 + sg * PI;
-        const double stepa = fdiv(a1 - a0, 49.0);  // np.linspace(a0, a1) has 50 samples; the first is dropped
-        const double r0x = fsd_cos(a0) * r_use, r0y = fsd_sin(a0) * r_use;
-        wsync();
-        for (int i = 1 + lane; i < 50; i += FSD_LANES) {
-          double ang = i == 49 ? a1 : (double)i * stepa + a0;
-          path[n + i - 1].x = fsd_cos(ang) * r_use - r0x + lastx;
-          path[n + i - 1].y = fsd_sin(ang) * r_use - r0y + lasty;
-        }
-        n += 49;
-      } else {
-        double ddx = lastx - path[n - 2].x, ddy = lasty - path[n - 2].y;
-        const double nrm = fsqrt(ddx * ddx + ddy * ddy);
-        ddx = fdiv(ddx, nrm);
-        ddy = fdiv(ddy, nrm);
-        wsync();
-        for (int i = 1 + lane; i < 30; i += FSD_LANES) {
-          path[n + i - 1].x = lastx + ddx * (double)i;
-          path[n + i - 1].y = lasty + ddy * (double)i;
-        }
-        n += 29;
-      }
-      wsync();
-    }
+    M.tail_status = 0;
+    pm_start_fit3(S, M, nd, P);
+    return;
   }
-  // remove_path_behind_car :459-465: first point of minimal distance to the car
-  int i0;
-  {
-    double bv = 0.0;
-    int bi = -1;
-    for (int i = lane; i < n; i += FSD_LANES) {
-      double ddx = F.px - path[i].x, ddy = F.py - path[i].y;
-      double d = fsqrt(ddx * ddx + ddy * ddy);
-      if (bi < 0 || d < bv) {
-        bv = d;
-        bi = i;
-      }
-    }
-    wargmin(bv, bi);
-    i0 = bi;
+  // the path update lives in S.pts[1..], slot 0 is kept for connect_path_to_car
+  const int nu = pm_evaluate(S, S.W.max_u, P.predict_every, S.pts + 1, PCAP - 1);
+  if (nu < 1) {
+    pm_finish_with_prev(M, nu < 0 ? (FSD_ST_UNSUPPORTED | FSD_ST_OVERFLOW) : FSD_ST_REF_RAISES);
+    return;
   }
-  // refit_path_for_mpc_with_safety_factor :239-259: evaluate up to u = 1.5 * mpc_path_length
-  int nfix = 0;
-  const int off = (int)(path - S.pts) + i0;
-  int rc = fit_predict(S, S.pts + off, S.u + off, n - i0, P.smoothing, P.predict_every, P.mpc_len * 1.5, S.pts, PCAP,
-                       &nfix, status);
-  if (rc == RC_RAISES) rc = RC_UNSUPPORTED;  // the reference re-parameterises a (40, 4) array here (latent bug)
-  if (rc != RC_OK) return rc;
-  // remove_path_not_in_prediction_horizon :467-499
-  int keep;
-  {
-    if (nfix - 1 <= 1) return RC_UNSUPPORTED;
-    int first_over = nfix;
-    double carry = 0.0;
-    for (int base = 0; base < nfix - 1; base += FSD_LANES) {
-      const int i = base + lane;
-      double d = 0.0;
-      if (i < nfix - 1) {
-        double ddx = S.pts[i + 1].x - S.pts[i].x, ddy = S.pts[i + 1].y - S.pts[i].y;
-        d = fsqrt(ddx * ddx + ddy * ddy);
-      }
-      double incl = wscan_incl(d) + carry;
-      if (i < nfix - 1 && incl > P.mpc_len && i < first_over) first_over = i;
-      carry = wlast(incl);
-    }
-    first_over = wmin_i(first_over);
-    keep = first_over >= nfix ? nfix - 1 : first_over;
-  }
-  *n_trim = keep;
-  return parameterize(S, keep, force_P, P, out, P_out, status);
+  M.nu = nu;
+  pm_enter_tail(S, M, P);
 }
 
-// ---- second half of run_path_calculation (core_calculate_path.py:555-575) -----------------------------------------
-// The path update sits in S.pts[1 .. 1+nu), S.prev_xy holds the previous path's xy.  Validity check, MPC tail,
-// fallbacks.  out: 40 x 4 fp64; grid[0] = P, grid[1] = points entering the last re-fit.
+// advance the machine by one unit
+FSD_DEVFN void pm_step(PathSmem &S, PathMachine &M, const DevParams &P) {
+  switch (M.state) {
+    case PS_FIT1:
+    case PS_FIT2:
+    case PS_FIT3:
+      if (M.fit.phase != FIT_DONE) fit_step(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
+      if (M.fit.phase == FIT_DONE) M.state += 1;
+      break;
+    case PS_FIT1_DONE:
+      pm_stage_after_fit1(S, M, P);
+      break;
+    case PS_TAIL:
+      pm_stage_tail(S, M, P);
+      break;
+    case PS_FIT2_DONE:
+      pm_stage_after_fit2(S, M, P);
+      break;
+    case PS_FIT3_DONE:
+      pm_stage_after_fit3(S, M, P);
+      break;
+    default:
+      break;
+  }
+}
 
-FSD_DEVFN unsigned path_from_update(PathSmem &S, int nu, const FramePose &F, int force_P, const double *prev,
-                                    const DevParams &P, double *out, int *grid) {
-  const int lane = fsd_lane();
-  unsigned status = 0;
-  int P_grid = 0, n_trim = 0;
-  bool ok = true;
-  int rc;
-  {
-    // overwrite_path_if_it_is_too_far_away :225-237
-    double best = INFINITY;
-    for (int i = lane; i < nu; i += FSD_LANES) {
-      double ddx = F.px - S.pts[1 + i].x, ddy = F.py - S.pts[1 + i].y;
-      best = fmin(best, fsqrt(ddx * ddx + ddy * ddy));
+FSD_DEVFN void pm_init(PathSmem &S, PathMachine &M, int mode, const FramePose &F, int force_P, const double *prev,
+                       double *out) {
+  M.mode = mode;
+  M.F = F;
+  M.force_P = force_P;
+  M.prev = prev;
+  M.out = out;
+  M.status = 0;
+  M.tail_status = 0;
+  M.fit1_retry = false;
+  M.tail_retry = false;
+  M.nu = 0;
+  M.P_grid = 0;
+  M.n_trim = 0;
+  M.predict_every = 0.0;
+  M.fit.phase = FIT_DONE;
+  M.fit.ier = 10;
+  M.state = PS_DONE;
+  if (prev) {
+    for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
+      S.prev_xy[i].x = prev[4 * i + 1];
+      S.prev_xy[i].y = prev[4 * i + 2];
     }
-    best = wmin_d(best);
     wsync();
-    if (best > P.max_valid_dist) {
-      status |= FSD_ST_PATH_TOO_FAR;
-      for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
-      nu = FSD_HORIZON;
-      wsync();
-    }
-    // do_all_mpc_parameter_calculations, ValueError -> redo with the previous path (:561-570)
-    unsigned st = 0;
-    rc = mpc_tail(S, nu, F, force_P, P, out, &P_grid, &n_trim, &st);
-    if (rc == RC_VALUE_ERROR) {
-      status |= FSD_ST_MPC_FAILED;
-      st = 0;
-      wsync();
-      for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
-      wsync();
-      rc = mpc_tail(S, FSD_HORIZON, F, force_P, P, out, &P_grid, &n_trim, &st);
-    }
-    status |= st;
-    if (rc != RC_OK) {
-      status |= rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES;
-      ok = false;
-    }
   }
-  if (!ok) {
-    wsync();
-    for (int i = lane; i < FSD_HORIZON * 4; i += FSD_LANES) out[i] = prev[i];
-  }
-  if (grid && lane == 0) {
-    grid[0] = P_grid;
-    grid[1] = n_trim;
-  }
-  wsync();
-  return status;
 }
 
 // ---- CalculatePath.run_path_calculation (core_calculate_path.py:514-575), global_path is None ------------
 // Inputs: the with-virtual cone lists and matches (any memory space).  prev: previous path (40 x 4 fp64).
-// out: 40 x 4 fp64.  grid[0] = P, grid[1] = points entering the last re-fit.
+// Sets the machine up to the start of fit #1.
 
-FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *right, int nr, const int16_t *l2r,
-                              const int16_t *r2l, const FramePose &F, int force_P, const double *prev,
-                              const DevParams &P, double *out, int *grid) {
+FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int nl, const d2 *right, int nr,
+                              const int16_t *l2r, const int16_t *r2l, const FramePose &F, int force_P,
+                              const double *prev, const DevParams &P, double *out) {
   const int lane = fsd_lane();
-  unsigned status = 0;
-  for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) {
-    S.prev_xy[i].x = prev[4 * i + 1];
-    S.prev_xy[i].y = prev[4 * i + 2];
-  }
-  wsync();
+  pm_init(S, M, 0, F, force_P, prev, out);
   const d2 *cl = S.prev_xy;
   int ncl = FSD_HORIZON;
   if (nl < 3 && nr < 3) {
-    status |= FSD_ST_FEW_CONES;
+    M.status |= FSD_ST_FEW_CONES;
   } else {
     if (lane == 0) {
       // select_side_to_use :165-183: max over (number of matches, sum of match indices), ties -> left
@@ -496,50 +619,78 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
     wsync();
     const int nc = S.si[0];
     if (nc < 2) {
-      status |= FSD_ST_FEW_MATCHES;
+      M.status |= FSD_ST_FEW_MATCHES;
     } else {
       cl = S.centre;
       ncl = nc;
     }
   }
-  // fit_matches_as_spline :207-223 (path update lives in S.pts[1..], slot 0 is kept for connect_path_to_car)
-  int nu = 0;
-  int rc = fit_predict(S, cl, S.u, ncl, P.smoothing, P.predict_every, -1.0, S.pts + 1, PCAP - 1, &nu, &status);
-  if (rc == RC_VALUE_ERROR) {
-    status |= FSD_ST_FIT1_FAILED;
-    rc = fit_predict(S, S.prev_xy, S.u, FSD_HORIZON, P.smoothing, P.predict_every, -1.0, S.pts + 1, PCAP - 1, &nu,
-                     &status);
-  }
-  if (!(rc == RC_OK && nu >= 1)) {
-    status |= rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES;
-    wsync();
-    for (int i = lane; i < FSD_HORIZON * 4; i += FSD_LANES) out[i] = prev[i];
-    if (grid && lane == 0) grid[0] = grid[1] = 0;
-    wsync();
-    return status;
-  }
-  return status | path_from_update(S, nu, F, force_P, prev, P, out, grid);
+  pm_start_fit1(S, M, cl, ncl, P);
 }
 
-// ---- initial path of a fresh planner (core_calculate_path.py:103-121) -------------------------------------
+// second half of run_path_calculation only: the path update already sits in S.pts[1 .. 1+nu) (skidpad)
+FSD_DEVFN void pm_begin_update(PathSmem &S, PathMachine &M, int nu, const FramePose &F, int force_P, const double *prev,
+                               const DevParams &P, double *out) {
+  pm_init(S, M, 0, F, force_P, prev, out);
+  M.nu = nu;
+  pm_enter_tail(S, M, P);
+}
 
-FSD_DEVFN unsigned initial_path_frame(PathSmem &S, const DevParams &P, double *out) {
-  unsigned status = 0;
-  // calculate_almost_straight_path: 40 points of a chord, radius 1000 m, angle pi/50, turned by -pi/2
+// the constant path of a fresh planner (core_calculate_path.py:103-121): fit of the "almost straight" chord
+// (path_calculator_helpers.py:26-68: 40 points, radius 1000 m, angle pi/50, turned by -pi/2), then the parameterisation
+FSD_DEVFN void pm_begin_initial(PathSmem &S, PathMachine &M, const DevParams &P, double *out) {
+  FramePose F = {0, 0, 1, 0, 1, 0};
+  pm_init(S, M, 1, F, 0, nullptr, out);
   const double max_angle = PI / 50.0, radius = 1000.0, stp = max_angle / (FSD_HORIZON - 1);
   const double c = fsd_cos(-PI / 2.0), s = fsd_sin(-PI / 2.0);
   for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
-    double a = i == FSD_HORIZON - 1 ? max_angle : (double)i * stp;
-    double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;
+    const double a = i == FSD_HORIZON - 1 ? max_angle : (double)i * stp;
+    const double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;
     S.centre[i].x = px * c - py * s;
     S.centre[i].y = px * s + py * c;
   }
   wsync();
-  int nd = 0, Pg = 0;
-  int rc = fit_predict(S, S.centre, S.u, FSD_HORIZON, P.smoothing, P.predict_every, -1.0, S.pts, PCAP, &nd, &status);
-  if (rc == RC_OK) rc = parameterize(S, nd, 0, P, out, &Pg, &status);
-  if (rc != RC_OK) status |= FSD_ST_UNSUPPORTED;
-  return status;
+  pm_start_fit1(S, M, S.centre, FSD_HORIZON, P);
+}
+
+FSD_DEVFN void pm_run(PathSmem &S, PathMachine &M, const DevParams &P) {
+  while (M.state != PS_DONE) pm_step(S, M, P);
+}
+
+// ---- blocking wrappers -------------------------------------------------------------------------------------------
+
+FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *right, int nr, const int16_t *l2r,
+                              const int16_t *r2l, const FramePose &F, int force_P, const double *prev,
+                              const DevParams &P, double *out, int *grid) {
+  PathMachine M;
+  pm_begin_frame(S, M, left, nl, right, nr, l2r, r2l, F, force_P, prev, P, out);
+  pm_run(S, M, P);
+  if (grid && fsd_lane() == 0) {
+    grid[0] = M.P_grid;
+    grid[1] = M.n_trim;
+  }
+  wsync();
+  return M.status;
+}
+
+FSD_DEVFN unsigned path_from_update(PathSmem &S, int nu, const FramePose &F, int force_P, const double *prev,
+                                    const DevParams &P, double *out, int *grid) {
+  PathMachine M;
+  pm_begin_update(S, M, nu, F, force_P, prev, P, out);
+  pm_run(S, M, P);
+  if (grid && fsd_lane() == 0) {
+    grid[0] = M.P_grid;
+    grid[1] = M.n_trim;
+  }
+  wsync();
+  return M.status;
+}
+
+FSD_DEVFN unsigned initial_path_frame(PathSmem &S, const DevParams &P, double *out) {
+  PathMachine M;
+  pm_begin_initial(S, M, P, out);
+  pm_run(S, M, P);
+  return M.status;
 }
 
 }  // namespace fsd

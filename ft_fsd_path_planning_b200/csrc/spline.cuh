@@ -186,28 +186,19 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
   return true;
 }
 
-// first data index of every knot interval: start[ii] = first i with u[i] >= t[k + ii]
-FSD_DEVFN void interval_starts(SplineWork &W, const double *u, int m, int n, int k) {
+// first data index of every knot interval.  Interior knots are data abscissae (fpknot puts every new knot on a data
+// point) and nrdata[ii] counts the data points strictly inside interval ii, so start[ii+1] = start[ii] + nrdata[ii] + 1
+// -- no search over the data.
+FSD_DEVFN void interval_starts(SplineWork &W, int m, int n, int k) {
   const int nrint = n - 2 * k - 1;
-  for (int ii = fsd_lane(); ii <= nrint; ii += FSD_LANES) {
-    int v;
-    if (ii == 0)
-      v = 0;
-    else if (ii == nrint)
-      v = m;
-    else {
-      double tk = W.t[k + ii];
-      int lo = 0, hi = m;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (u[mid] < tk)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      v = lo;
+  if (fsd_lane() == 0) {
+    int s = 0;
+    W.start[0] = 0;
+    for (int ii = 0; ii + 1 < nrint; ++ii) {
+      s += W.nrdata[ii] + 1;
+      W.start[ii + 1] = s;
     }
-    W.start[ii] = v;
+    W.start[nrint] = m;
   }
   wsync();
 }
@@ -238,23 +229,27 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
         ry[a] += h[a] * y;
       }
     }
+    double red[18];
 #pragma unroll
-    for (int e = 0; e < 10; ++e) acc[e] = wsum(acc[e]);
+    for (int e = 0; e < 10; ++e) red[e] = acc[e];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      rx[a] = wsum(rx[a]);
-      ry[a] = wsum(ry[a]);
+      red[10 + a] = rx[a];
+      red[14 + a] = ry[a];
     }
+    wsum_vec(red);
     if (lane == 0) {
       int e = 0;
+#pragma unroll
       for (int a = 0; a < 4; ++a) {
+#pragma unroll
         for (int b = a; b < 4; ++b) {
-          if (b < k1) W.N[ii + a][b - a] += acc[e];
+          if (b < k1) W.N[ii + a][b - a] += red[e];
           ++e;
         }
         if (a < k1) {
-          W.rhs[ii + a][0] += rx[a];
-          W.rhs[ii + a][1] += ry[a];
+          W.rhs[ii + a][0] += red[10 + a];
+          W.rhs[ii + a][1] += red[14 + a];
         }
       }
     }
@@ -291,13 +286,43 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
       part += wgt * term;
       if (i < hi) full += term;
     }
-    part = wsum(part);
-    full = wsum(full);
-    fp += full;
-    if (per_interval && lane == 0) W.fpint[ii] = part;
+    double red[2] = {part, full};
+    wsum_vec(red);
+    fp += red[1];
+    if (per_interval && lane == 0) W.fpint[ii] = red[0];
   }
   wsync();
   return fp;
+}
+
+// F(p) only (smoothing iterations): one lane-strided sweep over ALL data points, the knot interval of a point is
+// looked up in start[]; a single reduction at the end
+FSD_DEVFN double residual_total(const SplineWork &W, const d2 *pts, const double *u, int m, int n, int k) {
+  const int nrint = n - 2 * k - 1;
+  double part = 0.0;
+#pragma unroll 2
+  for (int i = fsd_lane(); i < m; i += FSD_LANES) {
+    int lo = 0, hi = nrint - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (W.start[mid] <= i)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    double h[4] = {0, 0, 0, 0};
+    bspl(W, k, u[i], lo, h);
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j <= k) {
+        sx += W.c[lo + j][0] * h[j];
+        sy += W.c[lo + j][1] * h[j];
+      }
+    const double ex = sx - pts[i].x, ey = sy - pts[i].y;
+    part += ex * ex + ey * ey;
+  }
+  return wsum(part);
 }
 
 // fpknot: split the interval with the largest residual at its middle data point (lane 0)
@@ -355,197 +380,276 @@ FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
   wsync();
 }
 
-// The fit.  pts/u: m data points and their (strictly increasing) parameters.  Result in W.t, W.c,
-// W.n, W.k, W.max_u.  Returns FITPACK's ier (10 = invalid input, the reference's ValueError).
-FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, double s, unsigned *status) {
+// ---- the fit as a resumable state machine -----------------------------------------------------------------------
+// fit_init + repeated fit_step == FITPACK's fppara.  One step is ONE least-squares pass over the data (knot-selection
+// phase) or ONE evaluation of F(p) (smoothing phase): the unit at which the warps of a CTA are kept in lockstep by
+// the path kernel, so that they execute the same code at the same time (instruction-cache sharing).  Every lane
+// holds an identical copy of the state.
+
+enum { FIT_KNOTS = 0, FIT_SMOOTH_SETUP = 1, FIT_SMOOTH = 2, FIT_DONE = 3 };
+
+struct FitState {
+  const d2 *pts;
+  const double *u;
+  int m, k, n, nest, nmax, nplus, ier, nk1, phase, iter, ich1, ich3;
+  bool capped;
+  double s, acc, fp, fpold, fp0, fpms, p, p1, f1, p3, f3;
+};
+
+// pts/u: m data points and their (strictly increasing) parameters.  ier = 10 (phase FIT_DONE) on invalid input,
+// the reference's ValueError.
+FSD_DEVFN void fit_init(SplineWork &W, FitState &F, const d2 *pts, const double *u, int m, double s) {
   const int lane = fsd_lane();
+  F.pts = pts;
+  F.u = u;
+  F.m = m;
+  F.s = s;
+  F.phase = FIT_DONE;
+  F.ier = 10;
+  F.n = 0;
+  if (m < 2) return;
   const int k = m - 1 < 1 ? 1 : (m - 1 > 3 ? 3 : m - 1);
-  const int k1 = k + 1, k2 = k + 2, nmin = 2 * k1;
-  int nest = m + 2 * k;
-  const int nmax = m + k1;
-  if (m < 2) return 10;
+  F.k = k;
   // u strictly increasing (parcur's input check)
   int bad = 0;
   for (int i = 1 + lane; i < m; i += FSD_LANES) bad |= !(u[i - 1] < u[i]);
-  if (wany(bad != 0)) return 10;
-  const double tol = 1e-3, acc = tol * s;
-  const double ub = u[0], ue = u[m - 1];
-  bool capped = false;
-  if (nest > NCAP) {
-    nest = NCAP;
-    capped = true;
+  if (wany(bad != 0)) return;
+  F.acc = 1e-3 * s;
+  F.nest = m + 2 * k;
+  F.capped = false;
+  if (F.nest > NCAP) {
+    F.nest = NCAP;
+    F.capped = true;
   }
-  int n = nmin, nplus = 0, ier = 0, nk1 = 0;
-  double fp = 0.0, fpold = 0.0, fp0 = 0.0, fpms = 0.0;
-  if (lane == 0) W.nrdata[0] = m - 2;
-  W.k = k;
-  W.max_u = ue;
-  bool done = false, part2 = false;
-  for (int iter = 1; iter <= m; ++iter) {
-    if (n == nmin) ier = -2;
-    int nrint = n - nmin + 1;
-    nk1 = n - k1;
-    if (lane == 0)
-      for (int j = 0; j < k1; ++j) {
-        W.t[j] = ub;
-        W.t[n - 1 - j] = ue;
-      }
-    wsync();
-    interval_starts(W, u, m, n, k);
-    knot_reciprocals(W, n, k);
-    assemble_normal(W, pts, u, n, k);
-    for (int e = lane; e < nk1 * BW; e += FSD_LANES) (&W.G[0][0])[e] = (&W.N[0][0])[e];
-    wsync();
-    if (!chol_solve(W.G, nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP)) {
-      *status |= FSD_ST_UNSUPPORTED;
-      return 10;
-    }
-    fp = residuals(W, pts, u, n, k, true);
-    if (ier == -2) fp0 = fp;
-    if (lane == 0) {
-      W.fpint[n - 1] = fp0;
-      W.fpint[n - 2] = fpold;
-      W.nrdata[n - 1] = nplus;
-    }
-    fpms = fp - s;
-    if (fabs(fpms) < acc) {
-      done = true;
-      break;
-    }
-    if (fpms < 0.0) {
-      part2 = true;
-      break;
-    }
-    if (n == nmax) {
-      ier = -1;
-      done = true;
-      break;
-    }
-    if (n == nest) {
-      ier = 1;
-      if (capped) *status |= FSD_ST_OVERFLOW;
-      done = true;
-      break;
-    }
-    if (ier == 0) {
-      int npl1 = nplus * 2;
-      double rn = (double)nplus;
-      if (fpold - fp > acc) npl1 = (int)fdiv(rn * fpms, fpold - fp);
-      int mx = npl1 > nplus / 2 ? npl1 : nplus / 2;
-      if (mx < 1) mx = 1;
-      nplus = nplus * 2 < mx ? nplus * 2 : mx;
-    } else {
-      nplus = 1;
-      ier = 0;
-    }
-    fpold = fp;
-    wsync();
-    for (int l = 1; l <= nplus; ++l) {
-      if (lane == 0) add_knot(W, u, n, nrint);
-      ++n;
-      ++nrint;
-      if (n == nmax) {
-        // every data abscissa becomes a knot (interpolating curve); k is odd whenever interior knots exist
-        if (lane == 0) {
-          const int k3 = k / 2;
-          int i = k2, j = k3 + 2;
-          for (int l2 = 0; l2 < m - k1; ++l2) {
-            W.t[i - 1] = (k3 * 2 != k) ? u[j - 1] : (u[j - 1] + u[j - 2]) * 0.5;
-            ++i;
-            ++j;
-          }
-        }
-        break;
-      }
-      if (n == nest) break;
-    }
-    wsync();
+  F.nmax = m + k + 1;
+  F.n = 2 * (k + 1);
+  F.nplus = 0;
+  F.ier = 0;
+  F.nk1 = 0;
+  F.fp = F.fpold = F.fp0 = F.fpms = 0.0;
+  F.iter = 0;
+  F.phase = FIT_KNOTS;
+  if (lane == 0) {
+    W.nrdata[0] = m - 2;
+    W.k = k;
+    W.max_u = u[m - 1];
   }
-  (void)done;
-  if (part2 && ier != -2) {
-    // smoothing parameter p with F(p) = s
-    disc_jumps(W, n, k);
-    const int n8 = n - nmin;
-    if (lane == 0) {
-      for (int i = 0; i < nk1; ++i)
-        for (int d = 0; d < BW; ++d) W.DtD[i][d] = 0.0;
-      for (int r = 0; r < n8; ++r)
-        for (int a = 0; a < k2 && r + a < nk1; ++a)
-          for (int b = a; b < k2 && r + b < nk1; ++b) W.DtD[r + a][b - a] += W.bd[r][a] * W.bd[r][b];
-    }
-    wsync();
-    double p1 = 0.0, f1 = fp0 - s, p3 = -1.0, f3 = fpms, p = 0.0;
-    for (int i = 0; i < nk1; ++i) p += W.G[i][0];
-    p = fdiv((double)nk1, p);
-    wsync();
-    int ich1 = 0, ich3 = 0;
-    const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
-    for (int iter = 1; iter <= 20; ++iter) {
-      const double pinv = fdiv(1.0, p), pinv2 = pinv * pinv;
-      for (int i = lane; i < nk1 * BW; i += FSD_LANES)
-        (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
-      wsync();
-      if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP)) {
-        *status |= FSD_ST_UNSUPPORTED;
-        return 10;
-      }
-      fp = residuals(W, pts, u, n, k, false);
-      fpms = fp - s;
-      if (fabs(fpms) < acc) {
-        ier = 0;
-        break;
-      }
-      if (iter == 20) {
-        ier = 3;
-        break;
-      }
-      const double p2 = p, f2 = fpms;
-      if (ich3 == 0) {
-        if (!((f2 - f3) > acc)) {
-          p3 = p2;
-          f3 = f2;
-          p = p * con4;
-          if (p <= p1) p = p1 * con9 + p2 * con1;
-          continue;
-        }
-        if (f2 < 0.0) ich3 = 1;
-      }
-      if (ich1 == 0) {
-        if (!((f1 - f2) > acc)) {
-          p1 = p2;
-          f1 = f2;
-          p = fdiv(p, con4);
-          if (p3 < 0.0) continue;
-          if (p >= p3) p = p2 * con1 + p3 * con9;
-          continue;
-        }
-        if (f2 > 0.0) ich1 = 1;
-      }
-      if (f2 >= f1 || f2 <= f3) {
-        ier = 2;
-        break;
-      }
-      // fprati: rational interpolation through (p1,f1), (p2,f2), (p3,f3)
-      double pn;
-      if (p3 > 0.0) {
-        double h1 = f1 * (f2 - f3), h2 = f2 * (f3 - f1), h3 = f3 * (f1 - f2);
-        pn = -fdiv(p1 * p2 * h3 + p2 * p3 * h1 + p3 * p1 * h2, p1 * h1 + p2 * h2 + p3 * h3);
-      } else {
-        pn = fdiv(p1 * (f1 - f3) * f2 - p2 * (f2 - f3) * f1, (f1 - f2) * f3);
-      }
-      if (f2 < 0.0) {
-        p3 = p2;
-        f3 = f2;
-      } else {
-        p1 = p2;
-        f1 = f2;
-      }
-      p = pn;
-    }
-  }
-  if (lane == 0) W.n = n;
   wsync();
-  return ier;
+}
+
+FSD_DEVFN void fit_finish(SplineWork &W, FitState &F, int ier) {
+  F.ier = ier;
+  F.phase = FIT_DONE;
+  if (fsd_lane() == 0) W.n = F.n;
+  wsync();
+}
+
+// one least-squares pass for the current knots + FITPACK's decision what to do next
+FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
+  const int lane = fsd_lane();
+  const int k = F.k, k1 = k + 1, k2 = k + 2, nmin = 2 * k1, m = F.m;
+  const double *u = F.u;
+  int n = F.n;
+  if (n == nmin) F.ier = -2;
+  int nrint = n - nmin + 1;
+  F.nk1 = n - k1;
+  if (lane == 0)
+    for (int j = 0; j < k1; ++j) {
+      W.t[j] = u[0];
+      W.t[n - 1 - j] = u[m - 1];
+    }
+  wsync();
+  interval_starts(W, m, n, k);
+  knot_reciprocals(W, n, k);
+  assemble_normal(W, F.pts, u, n, k);
+  for (int e = lane; e < F.nk1 * BW; e += FSD_LANES) (&W.G[0][0])[e] = (&W.N[0][0])[e];
+  wsync();
+  if (!chol_solve(W.G, F.nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP)) {
+    *status |= FSD_ST_UNSUPPORTED;
+    fit_finish(W, F, 10);
+    return;
+  }
+  F.fp = residuals(W, F.pts, u, n, k, true);
+  if (F.ier == -2) F.fp0 = F.fp;
+  if (lane == 0) {
+    W.fpint[n - 1] = F.fp0;
+    W.fpint[n - 2] = F.fpold;
+    W.nrdata[n - 1] = F.nplus;
+  }
+  F.fpms = F.fp - F.s;
+  if (fabs(F.fpms) < F.acc) {
+    fit_finish(W, F, F.ier);
+    return;
+  }
+  if (F.fpms < 0.0) {
+    if (F.ier == -2)
+      fit_finish(W, F, -2);  // the polynomial already satisfies fp <= s
+    else
+      F.phase = FIT_SMOOTH_SETUP;
+    return;
+  }
+  if (n == F.nmax) {
+    fit_finish(W, F, -1);
+    return;
+  }
+  if (n == F.nest) {
+    if (F.capped) *status |= FSD_ST_OVERFLOW;
+    fit_finish(W, F, 1);
+    return;
+  }
+  if (F.ier == 0) {
+    int npl1 = F.nplus * 2;
+    const double rn = (double)F.nplus;
+    if (F.fpold - F.fp > F.acc) npl1 = (int)fdiv(rn * F.fpms, F.fpold - F.fp);
+    int mx = npl1 > F.nplus / 2 ? npl1 : F.nplus / 2;
+    if (mx < 1) mx = 1;
+    F.nplus = F.nplus * 2 < mx ? F.nplus * 2 : mx;
+  } else {
+    F.nplus = 1;
+    F.ier = 0;
+  }
+  F.fpold = F.fp;
+  wsync();
+  for (int l = 1; l <= F.nplus; ++l) {
+    if (lane == 0) add_knot(W, u, n, nrint);
+    ++n;
+    ++nrint;
+    if (n == F.nmax) {
+      // every data abscissa becomes a knot (interpolating curve); k is odd whenever interior knots exist
+      if (lane == 0) {
+        const int k3 = k / 2;
+        int i = k2, j = k3 + 2;
+        for (int l2 = 0; l2 < m - k1; ++l2) {
+          W.t[i - 1] = (k3 * 2 != k) ? u[j - 1] : (u[j - 1] + u[j - 2]) * 0.5;
+          ++i;
+          ++j;
+        }
+        // data points strictly inside each interval of the interpolating knot set (k is odd here): the first
+        // interior knot is data point k3 + 1 (0-based), consecutive knots are consecutive data points
+        const int nint = m - k1 + 1;
+        for (int q = 0; q < nint; ++q) W.nrdata[q] = 0;
+        W.nrdata[0] = k3;
+        W.nrdata[nint - 1] = m - 1 - (k3 + 1 + (m - k1 - 1)) - 1;
+      }
+      break;
+    }
+    if (n == F.nest) break;
+  }
+  F.n = n;
+  if (++F.iter >= m) fit_finish(W, F, F.ier);  // fppara's outer loop bound (never reached in practice)
+  wsync();
+}
+
+// smoothing phase, set-up: discontinuity jumps, D^T D, initial p
+FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
+  const int lane = fsd_lane();
+  const int k = F.k, k2 = k + 2, nmin = 2 * (k + 1), n = F.n, nk1 = F.nk1;
+  disc_jumps(W, n, k);
+  const int n8 = n - nmin;
+  if (lane == 0) {
+    for (int i = 0; i < nk1; ++i)
+      for (int d = 0; d < BW; ++d) W.DtD[i][d] = 0.0;
+    for (int r = 0; r < n8; ++r)
+      for (int a = 0; a < k2 && r + a < nk1; ++a)
+        for (int b = a; b < k2 && r + b < nk1; ++b) W.DtD[r + a][b - a] += W.bd[r][a] * W.bd[r][b];
+  }
+  wsync();
+  F.p1 = 0.0;
+  F.f1 = F.fp0 - F.s;
+  F.p3 = -1.0;
+  F.f3 = F.fpms;
+  double p = 0.0;
+  for (int i = 0; i < nk1; ++i) p += W.G[i][0];
+  F.p = fdiv((double)nk1, p);
+  F.ich1 = F.ich3 = 0;
+  F.iter = 0;
+  F.phase = FIT_SMOOTH;
+  wsync();
+}
+
+// smoothing phase, one evaluation of F(p) and the next p (fppara's iteration incl. fprati)
+FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
+  const int lane = fsd_lane();
+  const int k = F.k, k2 = k + 2, nk1 = F.nk1;
+  const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
+  ++F.iter;
+  const double pinv = fdiv(1.0, F.p), pinv2 = pinv * pinv;
+  for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
+  wsync();
+  if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP)) {
+    *status |= FSD_ST_UNSUPPORTED;
+    fit_finish(W, F, 10);
+    return;
+  }
+  F.fp = residual_total(W, F.pts, F.u, F.m, F.n, k);
+  F.fpms = F.fp - F.s;
+  if (fabs(F.fpms) < F.acc) {
+    fit_finish(W, F, 0);
+    return;
+  }
+  if (F.iter == 20) {
+    fit_finish(W, F, 3);
+    return;
+  }
+  const double p2 = F.p, f2 = F.fpms;
+  if (F.ich3 == 0) {
+    if (!((f2 - F.f3) > F.acc)) {
+      F.p3 = p2;
+      F.f3 = f2;
+      F.p = F.p * con4;
+      if (F.p <= F.p1) F.p = F.p1 * con9 + p2 * con1;
+      return;
+    }
+    if (f2 < 0.0) F.ich3 = 1;
+  }
+  if (F.ich1 == 0) {
+    if (!((F.f1 - f2) > F.acc)) {
+      F.p1 = p2;
+      F.f1 = f2;
+      F.p = fdiv(F.p, con4);
+      if (F.p3 < 0.0) return;
+      if (F.p >= F.p3) F.p = p2 * con1 + F.p3 * con9;
+      return;
+    }
+    if (f2 > 0.0) F.ich1 = 1;
+  }
+  if (f2 >= F.f1 || f2 <= F.f3) {
+    fit_finish(W, F, 2);
+    return;
+  }
+  // fprati: rational interpolation through (p1,f1), (p2,f2), (p3,f3)
+  double pn;
+  if (F.p3 > 0.0) {
+    const double h1 = F.f1 * (f2 - F.f3), h2 = f2 * (F.f3 - F.f1), h3 = F.f3 * (F.f1 - f2);
+    pn = -fdiv(F.p1 * p2 * h3 + p2 * F.p3 * h1 + F.p3 * F.p1 * h2, F.p1 * h1 + p2 * h2 + F.p3 * h3);
+  } else {
+    pn = fdiv(F.p1 * (F.f1 - F.f3) * f2 - p2 * (f2 - F.f3) * F.f1, (F.f1 - f2) * F.f3);
+  }
+  if (f2 < 0.0) {
+    F.p3 = p2;
+    F.f3 = f2;
+  } else {
+    F.p1 = p2;
+    F.f1 = f2;
+  }
+  F.p = pn;
+}
+
+FSD_DEVFN void fit_step(SplineWork &W, FitState &F, unsigned *status) {
+  if (F.phase == FIT_KNOTS)
+    fit_step_knots(W, F, status);
+  else if (F.phase == FIT_SMOOTH_SETUP)
+    fit_step_smooth_setup(W, F);
+  else if (F.phase == FIT_SMOOTH)
+    fit_step_smooth(W, F, status);
+}
+
+// blocking form.  Result in W.t, W.c, W.n, W.k, W.max_u.  Returns FITPACK's ier.
+FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, double s, unsigned *status) {
+  FitState F;
+  fit_init(W, F, pts, u, m, s);
+  while (F.phase != FIT_DONE) fit_step(W, F, status);
+  return F.ier;
 }
 
 }  // namespace fsd
