@@ -155,25 +155,45 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   if (fsd_lane() == 0) mbar_init(&C.mbar, 1);
   __syncwarp();
   uint32_t phase = 0;
-  FSD_FRAME_LOOP(b, n_frames) {
-    const int lo = offsets[b];
-    int n = offsets[b + 1] - lo;
+  // The warps of a CTA start every frame together and meet again after the k-NN graph and after each side's search:
+  // they then run the same phase (the same code) at the same time and share instruction-cache fills, like the path
+  // kernel's lockstep machine.
+  for (int base = (int)blockIdx.x * WPC; base < n_frames; base += (int)gridDim.x * WPC) {
+    const int b = base + warp;
+    const bool active = b < n_frames;
+    int n = 0, nl = 0, nr = 0;
     unsigned st = 0;
-    if (n > FSD_MAX_CONES) {
-      n = FSD_MAX_CONES;
-      st |= FSD_ST_OVERFLOW;
+    FramePose F = make_pose(0.0, 0.0, 1.0, 0.0);
+    int16_t *dbg = nullptr;
+    if (WPC > 1) __syncthreads();
+    if (active) {
+      const int lo = offsets[b];
+      n = offsets[b + 1] - lo;
+      if (n > FSD_MAX_CONES) {
+        n = FSD_MAX_CONES;
+        st |= FSD_ST_OVERFLOW;
+      }
+      if (n < 0) n = 0;
+      F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
+      dbg = O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr;
+      stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
+      if (n >= 3 && build_knn(C.S, n, P)) st |= FSD_ST_OVERFLOW;
     }
-    if (n < 0) n = 0;
-    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
-    stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
-    st |= sort_frame(C.S, n, F, P, O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr);
-    store_sort(C.S, b, O);
-    if (do_match) {
-      st |= match_from_sort(C.S, F, P);
-      store_match(C.S.M, b, O);
+    if (WPC > 1) __syncthreads();
+    if (active) nl = sort_one_side(C.S, n, F, FSD_CONE_LEFT, P, dbg, &st);
+    if (WPC > 1) __syncthreads();
+    if (active) nr = sort_one_side(C.S, n, F, FSD_CONE_RIGHT, P, dbg, &st);
+    if (WPC > 1) __syncthreads();
+    if (active) {
+      st |= sort_finish(C.S, nl, nr);
+      store_sort(C.S, b, O);
+      if (do_match) {
+        st |= match_from_sort(C.S, F, P);
+        store_match(C.S.M, b, O);
+      }
+      if (fsd_lane() == 0) O.status[b] = st;
+      __syncwarp();
     }
-    if (fsd_lane() == 0) O.status[b] = st;
-    __syncwarp();
   }
 }
 
@@ -250,6 +270,11 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
                      force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out);
     }
     for (;;) {
+#ifndef FSD_LOCKSTEP_PER_STEP
+      // free-run to the next alignment point (the end of a spline fit): the warps of the CTA are then inside the same
+      // fit at the same time -- the same ~40 KB of code -- without waiting for each other after every pass
+      while (M.state != PS_DONE && !pm_is_alignment_state(M.state)) pm_step(S, M, P);
+#endif
       if (lane == 0) s_state[warp] = M.state;
       __syncthreads();
       int behind = PS_DONE;

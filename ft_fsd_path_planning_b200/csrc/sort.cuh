@@ -798,11 +798,9 @@ FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
 // ---- whole frame: TraceSorter.sort_left_right, core_trace_sorter.py:148-216 -----------------------
 // S.xy / S.type must hold the frame's n cones.  On return S.best[0..1] / S.nbest hold the sort indices.
 
-FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg) {
+// last part of sort_left_right: conflict resolution and the final index lists
+FSD_DEVFN unsigned sort_finish(SortSmem &S, int nl, int nr) {
   unsigned status = 0;
-  if (n >= 3 && build_knn(S, n, P)) status |= FSD_ST_OVERFLOW;
-  int nl = sort_one_side(S, n, F, FSD_CONE_LEFT, P, dbg, &status);
-  int nr = sort_one_side(S, n, F, FSD_CONE_RIGHT, P, dbg, &status);
   if (nl == 0) status |= FSD_ST_NO_LEFT;
   if (nr == 0) status |= FSD_ST_NO_RIGHT;
   if (nl > 0 && nr > 0) combine_sides(S, nl, nr);
@@ -814,6 +812,14 @@ FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevP
   }
   wsync();
   return status;
+}
+
+FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg) {
+  unsigned status = 0;
+  if (n >= 3 && build_knn(S, n, P)) status |= FSD_ST_OVERFLOW;
+  int nl = sort_one_side(S, n, F, FSD_CONE_LEFT, P, dbg, &status);
+  int nr = sort_one_side(S, n, F, FSD_CONE_RIGHT, P, dbg, &status);
+  return status | sort_finish(S, nl, nr);
 }
 
 }  // namespace fsd
