@@ -235,6 +235,12 @@ def run_ours(args):
         alg_bytes = batch.algorithmic_bytes()  # per launch of this rank's shard: 9 B/cone + 708 B/frame
         dom_ms, dom_name = (path_ms, "path_kernel") if path_ms >= sort_ms else (sort_ms, "sort_match_kernel")
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            t = json.load(open(tpath)).get(dom_name)
+            if t:
+                traffic = t["read_bytes"] + t["write_bytes"]  # per launch, from the committed ncu --set full capture
         cpu_threads = os.cpu_count() or 1
         cpu_value, cpu_dt = cpu_oracle_throughput(batch, cpu_threads, passes=2)
         out = {
@@ -246,7 +252,7 @@ def run_ours(args):
                        "parallelism": f"frames block-sharded over {world} GPU(s), one NCCL all-gather of the paths per step"
                        if distributed else "single GPU", "frames_flagged_overflow_or_unsupported": flagged},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": dom_name, "kernel_ms": dom_ms,
+                         "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms,
                          "other_kernel_ms": sort_ms if dom_name == "path_kernel" else path_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "note": "latency/issue-bound integer+fp64 work: the HBM fraction is reported as required, "

@@ -28,7 +28,7 @@ namespace {
 // frame): frames walk through the same phases at roughly the same time, so the SM's instruction cache serves
 // all of them from one copy of the phase's code (the kernels are instruction-fetch bound).
 #ifndef FSD_WARPS_PER_CTA
-#define FSD_WARPS_PER_CTA 16
+#define FSD_WARPS_PER_CTA 8
 #endif
 constexpr int WPC = FSD_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WPC;
