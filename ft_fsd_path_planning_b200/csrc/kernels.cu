@@ -33,6 +33,9 @@ namespace {
 constexpr int WPC = FSD_WARPS_PER_CTA;
 constexpr int CTA_THREADS = 32 * WPC;
 constexpr int CTAS_PER_SM = 16 / WPC;
+#ifndef FSD_PATH_CTAS_PER_SM
+#define FSD_PATH_CTAS_PER_SM CTAS_PER_SM
+#endif
 
 // Frame scheduling inside a kernel: the warps of a CTA take frames in rounds of WPC (CTA-strided over the batch) with
 // one __syncthreads per round, so that the frames of a round walk through the same phases together and share the
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, co
 // with 16 identical frames per CTA (perfect sharing) the kernel is 1.7x faster than with free-running warps
 // (profiles/r1_lockstep_probe.txt).
 template <typename T>
-__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+__global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
                 unsigned char *scratch) {

@@ -36,6 +36,8 @@ struct alignas(16) d2 {
 
 constexpr int FSD_LANES = 32;
 constexpr unsigned FULL = 0xffffffffu;
+// `count` (<= 32) independent tasks, one per lane
+#define FSD_FOR_TASKS(e, count) if (const int e = (int)(threadIdx.x & 31u); e < (count))
 
 FSD_DEV int fsd_lane() { return (int)(threadIdx.x & 31u); }
 FSD_DEV void wsync() { __syncwarp(); }
@@ -91,9 +93,28 @@ FSD_DEV void wsum_vec(double (&v)[N]) {
   }
 }
 
+// Warp totals of 16 values with 16 shuffles instead of 80: in every butterfly step a lane hands over the half of the
+// values its partner becomes responsible for and adds the partner's copy of its own half.  On return v[0] of lane L
+// holds the total of value (L >> 1) & 15 (both lanes of a pair hold the same total).
+FSD_DEV void wsum16_transposed(double (&v)[16]) {
+  const int lane = fsd_lane();
+#pragma unroll
+  for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < h; ++j) {
+      const double send = up ? v[j] : v[j + h];
+      const double keep = up ? v[j + h] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULL, send, o);
+    }
+  }
+  v[0] += __shfl_xor_sync(FULL, v[0], 1);
+}
+
 #else  // host-check build: a warp of one lane
 
 constexpr int FSD_LANES = 1;
+#define FSD_FOR_TASKS(e, count) for (int e = 0; e < (count); ++e)
 
 FSD_DEV int fsd_lane() { return 0; }
 FSD_DEV void wsync() {}
@@ -126,8 +147,10 @@ FSD_DEVFN double fsqrt(double a) { return sqrt(a); }
 FSD_DEVFN double fnorm(double x, double y) { return sqrt(x * x + y * y); }
 #ifdef FSD_DEVICE_BUILD
 FSD_DEVFN double frsqrt(double a) { return rsqrt(a); }
+FSD_DEV double frcp(double a) { return __drcp_rn(a); }
 #else
 FSD_DEVFN double frsqrt(double a) { return 1.0 / sqrt(a); }
+FSD_DEV double frcp(double a) { return 1.0 / a; }
 #endif
 
 FSD_DEV double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }

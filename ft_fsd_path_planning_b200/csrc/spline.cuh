@@ -23,7 +23,10 @@
 
 namespace fsd {
 
-constexpr int NCAP = 32;  // knots handled per fit (the reference's own data stays below 20)
+#ifndef FSD_NCAP
+#define FSD_NCAP 32
+#endif
+constexpr int NCAP = FSD_NCAP;  // knots handled per fit (the reference's own data stays below 20)
 constexpr int BW = 5;     // k + 2 for cubic splines
 
 struct SplineWork {
@@ -35,7 +38,8 @@ struct SplineWork {
   double rhs[NCAP][2];
   double z[NCAP][2];
   double c[NCAP][2];
-  double fpint[2 * NCAP];  // [0, NCAP): residual per knot interval; [NCAP, 2 NCAP): reciprocal diagonal of G
+  double c0[NCAP][2];      // least-squares coefficients of the final knot set (smoothing phase: F(p) as a quadratic form)
+  double fpint[2 * NCAP];  // [0, NCAP): residual per knot interval; [NCAP, 2 NCAP): reciprocal pivots of chol_solve
   int32_t nrdata[NCAP];
   int32_t start[NCAP + 1];
   double rk[NCAP][6];  // reciprocal knot differences of the B-spline recursion, per knot interval
@@ -128,58 +132,69 @@ FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &o
   oy = sy;
 }
 
-// banded Cholesky (upper, in place in M), forward and back substitution; lane 0 only.
-// returns false on a non-positive pivot.
-// Banded Cholesky G^T G = M (upper band, in place), z = G^-T rhs, c = G^-1 z, cooperative over the warp:
-// right-looking elimination, one matrix row per step; the <= 10 trailing updates of the band and the <= 8 updates of
-// the two right-hand sides are one task per lane; one reciprocal square root per row replaces the square root and
-// every division.  M[i][0] holds the diagonal of G on return (fppara's p0 needs it).  All lanes return the same flag.
+// Task (a, b) of lane/task index e in the elimination step of chol_solve: e < npairs -> band update (a, b), 1 <= a <= b <=
+// kbm, in row-major order; otherwise right-hand-side update (a, column)
+FSD_DEV void chol_task(int e, int kbm, int npairs, int &ta, int &tb) {
+  if (e < npairs) {
+    int a = 1, rem = e;
+    while (rem >= kbm - a + 1) {
+      rem -= kbm - a + 1;
+      ++a;
+    }
+    ta = a;
+    tb = a + rem;
+  } else {
+    ta = 1 + ((e - npairs) >> 1);
+    tb = (e - npairs) & 1;
+  }
+}
+
+// Banded symmetric solve M c = rhs (upper band of M in place, two right-hand sides), cooperative over the warp, as the
+// square-root-free factorisation M = L D L^T: right-looking elimination, one matrix row per step; the <= 10 trailing
+// updates of the band and the <= 8 updates of the two right-hand sides are ONE task per lane (decoded once, the task of a
+// lane never changes), one reciprocal per row and one warp barrier per row.  On return M[i][0] holds the pivot d_i (the
+// diagonal of the Cholesky factor G with G^T G = M is sqrt(d_i): fppara's p0 needs it), M[i][1..] the unscaled rows
+// d_i L[i+a][i], rpiv[i] = 1 / d_i.  Back substitution c = L^-T D^-1 L^-1 rhs as a column sweep (<= 10 tasks per row).
+// All lanes return the same flag: false on a non-positive pivot.
 FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2],
-                          double *rinv_row) {
+                          double *rpiv) {
   const int lane = fsd_lane();
-  const int kbm = kb - 1, npairs = kbm * (kbm + 1) / 2;
+  const int kbm = kb - 1, npairs = kbm * (kbm + 1) / 2, ntasks = npairs + 2 * kbm;
   for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&z[0][0])[e] = (&rhs[0][0])[e];
+  int ta = 0, tb = 0;
+#ifdef FSD_DEVICE_BUILD
+  chol_task(lane, kbm, npairs, ta, tb);
+#endif
   wsync();
+#pragma unroll 1
   for (int i = 0; i < nk1; ++i) {
     const double s = M[i][0];
     if (!(s > 0.0)) return false;
-    const double rinv = frsqrt(s);
-    wsync();
-    for (int e = lane; e < kbm + 4; e += FSD_LANES) {
-      if (e < kbm) {
-        if (i + 1 + e < nk1) M[i][1 + e] *= rinv;
-      } else if (e < kbm + 2) {
-        z[i][e - kbm] *= rinv;
-      } else if (e == kbm + 2) {
-        M[i][0] = s * rinv;
-      } else {
-        rinv_row[i] = rinv;
-      }
-    }
-    wsync();
-    for (int e = lane; e < npairs + 2 * kbm; e += FSD_LANES) {
+    const double rs = frcp(s);
+    FSD_FOR_TASKS(e, ntasks) {
+#ifndef FSD_DEVICE_BUILD
+      chol_task(e, kbm, npairs, ta, tb);
+#endif
+      const double f = M[i][ta] * rs;
       if (e < npairs) {
-        int a = 1, rem = e;
-        while (rem >= kbm - a + 1) {
-          rem -= kbm - a + 1;
-          ++a;
-        }
-        const int b = a + rem;
-        if (i + b < nk1) M[i + a][b - a] -= M[i][a] * M[i][b];
+        if (i + tb < nk1) M[i + ta][tb - ta] -= f * M[i][tb];
       } else {
-        const int a = 1 + ((e - npairs) >> 1), col = (e - npairs) & 1;
-        if (i + a < nk1) z[i + a][col] -= M[i][a] * z[i][col];
+        if (i + ta < nk1) z[i + ta][tb] -= f * z[i][tb];
       }
+      if (e == 0) rpiv[i] = rs;
     }
     wsync();
   }
+  const int nback = 2 * kb;
+#pragma unroll 1
   for (int i = nk1 - 1; i >= 0; --i) {
-    for (int col = lane; col < 2; col += FSD_LANES) {
-      double s = z[i][col];
-      int l1 = nk1 - 1 - i;
-      if (l1 > kbm) l1 = kbm;
-      for (int l = 1; l <= l1; ++l) s -= M[i][l] * c[i + l][col];
-      c[i][col] = s * rinv_row[i];
+    FSD_FOR_TASKS(e, nback) {
+      const int l = e >> 1, col = e & 1;
+      const double ci = z[i][col] * rpiv[i];
+      if (l == 0)
+        c[i][col] = ci;
+      else if (i - l >= 0)
+        z[i - l][col] -= M[i - l][l] * ci;
     }
     wsync();
   }
@@ -209,6 +224,29 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
   const int nk1 = n - k - 1, nrint = n - 2 * k - 1, k1 = k + 1;
   for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.N[0][0])[i] = 0.0;
   for (int i = lane; i < nk1 * 2; i += FSD_LANES) (&W.rhs[0][0])[i] = 0.0;
+#ifdef FSD_DEVICE_BUILD
+  // the sum this lane owns after the transposed reduction below and where it goes (relative to knot interval 0)
+  double *own_base = &W.N[0][0];
+  int own_stride = BW;
+  bool own_ok = (lane & 1) == 0;
+  {
+    const int e = lane >> 1;
+    if (e < 10) {
+      int a = 0, rem = e;
+      while (rem >= 4 - a) {
+        rem -= 4 - a;
+        ++a;
+      }
+      own_base = &W.N[a][rem];  // entry (a, b = a + rem) of the 4 x 4 block -> N[ii + a][b - a]
+      own_ok = own_ok && a + rem < k1;
+    } else {
+      const int a = e < 14 ? e - 10 : e - 14;
+      own_base = &W.rhs[a][e < 14 ? 0 : 1];
+      own_stride = 2;
+      own_ok = own_ok && a < k1;
+    }
+  }
+#endif
   wsync();
 #pragma unroll 1
   for (int ii = 0; ii < nrint; ++ii) {
@@ -229,6 +267,22 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
         ry[a] += h[a] * y;
       }
     }
+#ifdef FSD_DEVICE_BUILD
+    // 16 of the 18 sums through the transposed reduction (the lane pair 2e, 2e+1 ends up with sum e), ry[2..3] through
+    // a plain butterfly; every sum is added to the matrix by the lane that owns it
+    double red[16], tail[2] = {ry[2], ry[3]};
+#pragma unroll
+    for (int e = 0; e < 10; ++e) red[e] = acc[e];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) red[10 + a] = rx[a];
+    red[14] = ry[0];
+    red[15] = ry[1];
+    wsum16_transposed(red);
+    wsum_vec(tail);
+    if (own_ok) own_base[ii * own_stride] += red[0];
+    if (lane == 1 && 2 < k1) W.rhs[ii + 2][1] += tail[0];
+    if (lane == 3 && 3 < k1) W.rhs[ii + 3][1] += tail[1];
+#else
     double red[18];
 #pragma unroll
     for (int e = 0; e < 10; ++e) red[e] = acc[e];
@@ -237,7 +291,6 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
       red[10 + a] = rx[a];
       red[14 + a] = ry[a];
     }
-    wsum_vec(red);
     if (lane == 0) {
       int e = 0;
 #pragma unroll
@@ -253,6 +306,7 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
         }
       }
     }
+#endif
     wsync();
   }
 }
@@ -295,33 +349,27 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
   return fp;
 }
 
-// F(p) only (smoothing iterations): one lane-strided sweep over ALL data points, the knot interval of a point is
-// looked up in start[]; a single reduction at the end
-FSD_DEVFN double residual_total(const SplineWork &W, const d2 *pts, const double *u, int m, int n, int k) {
-  const int nrint = n - 2 * k - 1;
+// F(p) - F(inf) of the smoothing iterations without touching the data: the least-squares spline c0 of the knot set is
+// the orthogonal projection of the data onto the spline space, so for any coefficients c
+//     sum |B c - x|^2 = sum |B c0 - x|^2 + (c - c0)^T N (c - c0),      N = B^T B (already assembled, banded)
+// -- a sum of two non-negative terms, no cancellation.  One row of N per lane; z is free after chol_solve.
+FSD_DEVFN double smoothing_excess(SplineWork &W, int nk1, int k) {
+  const int lane = fsd_lane();
+  for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.z[0][0])[e] = (&W.c[0][0])[e] - (&W.c0[0][0])[e];
+  wsync();
   double part = 0.0;
-#pragma unroll 2
-  for (int i = fsd_lane(); i < m; i += FSD_LANES) {
-    int lo = 0, hi = nrint - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (W.start[mid] <= i)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    double h[4] = {0, 0, 0, 0};
-    bspl(W, k, u[i], lo, h);
-    double sx = 0.0, sy = 0.0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j <= k) {
-        sx += W.c[lo + j][0] * h[j];
-        sy += W.c[lo + j][1] * h[j];
+  for (int i = lane; i < nk1; i += FSD_LANES) {
+    const double dx = W.z[i][0], dy = W.z[i][1];
+    double ax = W.N[i][0] * dx, ay = W.N[i][0] * dy;
+    for (int d = 1; d <= k; ++d)
+      if (i + d < nk1) {
+        const double w2 = W.N[i][d] + W.N[i][d];
+        ax += w2 * W.z[i + d][0];
+        ay += w2 * W.z[i + d][1];
       }
-    const double ex = sx - pts[i].x, ey = sy - pts[i].y;
-    part += ex * ex + ey * ey;
+    part += dx * ax + dy * ay;
   }
+  wsync();
   return wsum(part);
 }
 
@@ -393,7 +441,7 @@ struct FitState {
   const double *u;
   int m, k, n, nest, nmax, nplus, ier, nk1, phase, iter, ich1, ich3;
   bool capped;
-  double s, acc, fp, fpold, fp0, fpms, p, p1, f1, p3, f3;
+  double s, acc, fp, fpold, fp0, fpms, p, p1, f1, p3, f3, fp_ls;
 };
 
 // pts/u: m data points and their (strictly increasing) parameters.  ier = 10 (phase FIT_DONE) on invalid input,
@@ -558,8 +606,14 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   F.f1 = F.fp0 - F.s;
   F.p3 = -1.0;
   F.f3 = F.fpms;
+  // the least-squares spline of this knot set: its coefficients and residual anchor F(p) below
+  F.fp_ls = F.fp;
+  for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.c0[0][0])[e] = (&W.c[0][0])[e];
+  // p0 = nk1 / trace of the Cholesky factor of N (chol_solve leaves the pivots d_i = G_ii^2 on the diagonal)
+  for (int i = lane; i < nk1; i += FSD_LANES) W.z[i][0] = fsqrt(W.G[i][0]);
+  wsync();
   double p = 0.0;
-  for (int i = 0; i < nk1; ++i) p += W.G[i][0];
+  for (int i = 0; i < nk1; ++i) p += W.z[i][0];
   F.p = fdiv((double)nk1, p);
   F.ich1 = F.ich3 = 0;
   F.iter = 0;
@@ -581,7 +635,7 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
     fit_finish(W, F, 10);
     return;
   }
-  F.fp = residual_total(W, F.pts, F.u, F.m, F.n, k);
+  F.fp = F.fp_ls + smoothing_excess(W, nk1, k);
   F.fpms = F.fp - F.s;
   if (fabs(F.fpms) < F.acc) {
     fit_finish(W, F, 0);
