@@ -24,6 +24,7 @@ struct StageOut {
 // plain (non-TMA) frame load with widening to fp64; the CUDA sort kernel stages xy with a bulk copy instead
 template <typename T>
 FSD_DEVFN void load_frame_plain(SortSmem &S, const T *xy, const uint8_t *type, int n) {
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     S.xy[i].x = (double)xy[2 * i];
     S.xy[i].y = (double)xy[2 * i + 1];
@@ -33,6 +34,7 @@ FSD_DEVFN void load_frame_plain(SortSmem &S, const T *xy, const uint8_t *type, i
 }
 
 FSD_DEVFN void store_sort(const SortSmem &S, int b, const StageOut &O) {
+#pragma unroll 1
   for (int q = fsd_lane(); q < 2 * FSD_MAX_SORTED; q += FSD_LANES) {
     const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
     int16_t *dst = s == 0 ? O.left_idx : O.right_idx;
@@ -45,6 +47,7 @@ FSD_DEVFN void store_sort(const SortSmem &S, int b, const StageOut &O) {
 FSD_DEVFN unsigned match_from_sort(SortSmem &S, const FramePose &F, const DevParams &P) {
   MatchSmem &M = S.M;
   wsync();
+#pragma unroll 1
   for (int q = fsd_lane(); q < 2 * FSD_MAX_SORTED; q += FSD_LANES) {
     const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
     if (j < S.nbest[s]) M.side[s][j] = S.xy[S.best[s][j]];
@@ -63,6 +66,7 @@ FSD_DEVFN void store_match(const MatchSmem &M, int b, const StageOut &O) {
     O.n_wv[2 * (size_t)b] = (int16_t)M.nwv[0];
     O.n_wv[2 * (size_t)b + 1] = (int16_t)M.nwv[1];
   }
+#pragma unroll 1
   for (int q = lane; q < 2 * WV_CAP; q += FSD_LANES) {
     const int s = q / WV_CAP, j = q % WV_CAP;
     double *wv = s == 0 ? O.left_wv : O.right_wv;
@@ -89,6 +93,7 @@ FSD_DEVFN void path_from_tensors(PathSmem &S, int b, const StageOut &O, const Fr
                            prev, P, out, grid);
   wsync();
   if (out_f32)
+#pragma unroll 1
     for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += FSD_LANES)
       out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)out[i];
   if (fsd_lane() == 0) {

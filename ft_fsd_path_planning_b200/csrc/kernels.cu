@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
       pm_begin_frame(S, M, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F,
                      force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out);
     }
+#ifdef FSD_NO_LOCKSTEP
+    while (M.state != PS_DONE) pm_step(S, M, P);  // A/B only: free-running warps
+    __syncthreads();
+#else
     for (;;) {
 #ifndef FSD_LOCKSTEP_PER_STEP
       // free-run to the next alignment point (the end of a spline fit): the warps of the CTA are then inside the same
@@ -287,6 +291,7 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
       if (behind == PS_DONE) break;
       if (M.state != PS_DONE && !(pm_is_alignment_state(M.state) && behind < M.state)) pm_step(S, M, P);
     }
+#endif
     if (active) {
       __syncwarp();
       if (out_f32)

@@ -33,6 +33,7 @@ struct MatchSmem {
 
 FSD_DEVFN void match_directions(const d2 *c, int n, int side, d2 *out) {
   // calculate_match_search_direction, match_directions.py:23-44
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     int a = i == 0 ? 0 : (i == n - 1 ? n - 2 : i - 1);
     int b = i == 0 ? 1 : (i == n - 1 ? n - 1 : i + 1);
@@ -50,6 +51,7 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
                                 int16_t *match, const DevParams &P) {
   const int lane = fsd_lane();
   if (n <= 1) {
+#pragma unroll 1
     for (int i = lane; i < n; i += FSD_LANES) match[i] = -1;
     wsync();
     return false;
@@ -58,12 +60,14 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
   if (m > 1) match_directions(other, m, side == FSD_CONE_RIGHT ? FSD_CONE_LEFT : FSD_CONE_RIGHT, S.odirs);
   wsync();
   if (m <= 1) {
+#pragma unroll 1
     for (int i = lane; i < n; i += FSD_LANES) match[i] = -1;
     wsync();
     return m == 1;
   }
   const double inv_major2 = P.match_inv_major2, inv_minor2 = P.match_inv_minor2;
   const double cos_limit = P.cos_match_limit;
+#pragma unroll 1
   for (int i = lane; i < n; i += FSD_LANES) {
     const double dxi = S.dirs[i].x, dyi = S.dirs[i].y;
     bool any = false;
@@ -230,12 +234,14 @@ FSD_DEVFN unsigned match_frame(MatchSmem &S, const FramePose &F, const DevParams
   if (nl >= 2) {
     nrw = cones_for_other_side(S, S.side[0], nl, FSD_CONE_LEFT, S.side[1], nr, S.wv[1], F, P, &raises);
   } else {
+#pragma unroll 1
     for (int i = fsd_lane(); i < nr; i += FSD_LANES) S.wv[1][i] = S.side[1][i];
     nrw = nr;
   }
   if (nr >= 2) {
     nlw = cones_for_other_side(S, S.side[1], nr, FSD_CONE_RIGHT, S.side[0], nl, S.wv[0], F, P, &raises);
   } else {
+#pragma unroll 1
     for (int i = fsd_lane(); i < nl; i += FSD_LANES) S.wv[0][i] = S.side[0][i];
     nlw = nl;
   }

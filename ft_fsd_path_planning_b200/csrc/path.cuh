@@ -88,6 +88,7 @@ FSD_DEVFN double circle_radius_serial(const d2 *p, int n) {
 // the whole warp fits one point set (path extension)
 FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, double &r) {
   double sx = 0.0, sy = 0.0;
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     sx += p[i].x;
     sy += p[i].y;
@@ -95,6 +96,7 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
   const double inv_n = fdiv(1.0, (double)n);
   const double mx = wsum(sx) * inv_n, my = wsum(sy) * inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double xi = p[i].x - mx, yi = p[i].y - my, zi = xi * xi + yi * yi;
     Mxy += xi * yi;
@@ -177,6 +179,7 @@ FSD_DEVFN int pm_evaluate(PathSmem &S, double max_u, double step, d2 *dst, int d
   const int n = q > 0.0 ? (q > 1e6 ? 1000000 : (int)q) : 0;
   if (n > dst_cap) return -1;
   wsync();
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double x, y;
     spline_point(S.W, (double)i * step, x, y);
@@ -190,6 +193,7 @@ FSD_DEVFN int pm_evaluate(PathSmem &S, double max_u, double step, d2 *dst, int d
 FSD_DEVFN void pm_finish_with_prev(PathMachine &M, unsigned bits) {
   M.status |= bits;
   wsync();
+#pragma unroll 1
   for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += FSD_LANES) M.out[i] = M.prev[i];
   M.P_grid = 0;
   M.n_trim = 0;
@@ -209,6 +213,7 @@ FSD_DEVFN void pm_tail_failed(PathSmem &S, PathMachine &M, int rc) {
     M.tail_retry = true;
     M.tail_status = 0;
     wsync();
+#pragma unroll 1
     for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
     M.nu = FSD_HORIZON;
     M.state = PS_TAIL;
@@ -228,11 +233,13 @@ FSD_DEVFN void pm_start_fit1(PathSmem &S, PathMachine &M, const d2 *src, int m, 
 FSD_DEVFN void pm_enter_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   const int lane = fsd_lane();
   double best = INFINITY;
+#pragma unroll 1
   for (int i = lane; i < M.nu; i += FSD_LANES) best = fmin(best, fnorm(M.F.px - S.pts[1 + i].x, M.F.py - S.pts[1 + i].y));
   best = wmin_d(best);
   wsync();
   if (best > P.max_valid_dist) {
     M.status |= FSD_ST_PATH_TOO_FAR;
+#pragma unroll 1
     for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
     M.nu = FSD_HORIZON;
     wsync();
@@ -249,6 +256,7 @@ FSD_DEVFN void pm_start_fit3(PathSmem &S, PathMachine &M, int n, const DevParams
     return;
   }
   double len = 0.0, first10 = 0.0;
+#pragma unroll 1
   for (int i = lane; i + 1 < n; i += FSD_LANES) {
     const double d = fnorm(S.pts[i + 1].x - S.pts[i].x, S.pts[i + 1].y - S.pts[i].y);
     len += d;
@@ -300,6 +308,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   }
   {
     int first = n;
+#pragma unroll 1
     for (int i = lane; i < n; i += FSD_LANES)
       if ((path[i].x - F.px) * F.dx + (path[i].y - F.py) * F.dy > 0.0) {
         first = i;
@@ -314,6 +323,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
       return;
     }
     double part = 0.0;
+#pragma unroll 1
     for (int i = start + lane; i + 1 < n; i += FSD_LANES) part += fnorm(path[i + 1].x - path[i].x, path[i + 1].y - path[i].y);
     const double plen = wsum(part);
     if (!(plen > P.mpc_len)) {
@@ -337,6 +347,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
         const double stepa = fdiv(a1 - a0, 49.0);  // np.linspace(a0, a1) has 50 samples; the first is dropped
         const double r0x = fsd_cos(a0) * r_use, r0y = fsd_sin(a0) * r_use;
         wsync();
+#pragma unroll 1
         for (int i = 1 + lane; i < 50; i += FSD_LANES) {
           const double ang = i == 49 ? a1 : (double)i * stepa + a0;
           path[n + i - 1].x = fsd_cos(ang) * r_use - r0x + lastx;
@@ -349,6 +360,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
         ddx = fdiv(ddx, nrm);
         ddy = fdiv(ddy, nrm);
         wsync();
+#pragma unroll 1
         for (int i = 1 + lane; i < 30; i += FSD_LANES) {
           path[n + i - 1].x = lastx + ddx * (double)i;
           path[n + i - 1].y = lasty + ddy * (double)i;
@@ -361,6 +373,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   // first point of minimal distance to the car
   double bv = 0.0;
   int bi = -1;
+#pragma unroll 1
   for (int i = lane; i < n; i += FSD_LANES) {
     const double d = fnorm(F.px - path[i].x, F.py - path[i].y);
     if (bi < 0 || d < bv) {
@@ -441,6 +454,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
     return;
   }
   wsync();
+#pragma unroll 1
   for (int i = lane; i < Pn; i += FSD_LANES) {
     double x, y;
     spline_point(S.W, (double)i * predict_every, x, y);
@@ -452,6 +466,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   int window = Pn / 5 < 30 ? Pn / 5 : 30;
   if (window % 2 == 0) window += 1;
   const int hw = window / 2;
+#pragma unroll 1
   for (int i = lane; i < Pn; i += FSD_LANES) {
     const int lo = i - hw < 0 ? 0 : i - hw;
     const int hi = i + hw > Pn - 1 ? Pn - 1 : i + hw;
@@ -466,6 +481,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   // indices np.linspace(0, P-1, 40, dtype=int) (:277-282)
   const int fs = window / 2 > 2 ? window / 2 : 2;
   const double stp = fdiv((double)(Pn - 1), (double)(FSD_HORIZON - 1));
+#pragma unroll 1
   for (int j = lane; j < FSD_HORIZON; j += FSD_LANES) {
     const int idx = j == FSD_HORIZON - 1 ? Pn - 1 : (int)floor((double)j * stp);
     double acc = 0.0;
@@ -567,6 +583,7 @@ FSD_DEVFN void pm_init(PathSmem &S, PathMachine &M, int mode, const FramePose &F
   M.fit.ier = 10;
   M.state = PS_DONE;
   if (prev) {
+#pragma unroll 1
     for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
       S.prev_xy[i].x = prev[4 * i + 1];
       S.prev_xy[i].y = prev[4 * i + 2];
@@ -643,6 +660,7 @@ FSD_DEVFN void pm_begin_initial(PathSmem &S, PathMachine &M, const DevParams &P,
   pm_init(S, M, 1, F, 0, nullptr, out);
   const double max_angle = PI / 50.0, radius = 1000.0, stp = max_angle / (FSD_HORIZON - 1);
   const double c = fsd_cos(-PI / 2.0), s = fsd_sin(-PI / 2.0);
+#pragma unroll 1
   for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
     const double a = i == FSD_HORIZON - 1 ? max_angle : (double)i * stp;
     const double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;

@@ -39,6 +39,7 @@ struct SkidSmem {
 FSD_DEVFN double select_rank(SkidSmem &S, int n, int lab, int coord, int r) {
   double out = 0.0;
   int found = 0;
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     if (S.label[i] != lab) continue;
     const double v = coord == 0 ? S.cen[i].x : S.cen[i].y;
@@ -70,12 +71,14 @@ FSD_DEVFN void skidpad_relocalize(SkidSmem &S, const double *cones, int n, doubl
   const int lane = fsd_lane();
   if (n > FSD_MAX_CONES) n = FSD_MAX_CONES;
   const int m = n < SKID_NEAR ? n : SKID_NEAR;
+#pragma unroll 1
   for (int i = lane; i < n; i += FSD_LANES) S.used[i] = 0;
   wsync();
   // the 20 cones nearest to the vehicle, nearest first (:207-212)
   for (int q = 0; q < m; ++q) {
     double bv = 0.0;
     int bi = -1;
+#pragma unroll 1
     for (int i = lane; i < n; i += FSD_LANES) {
       if (S.used[i]) continue;
       double d = fnorm(cones[2 * i] - px, cones[2 * i + 1] - py);
@@ -167,10 +170,12 @@ FSD_DEVFN void skidpad_relocalize(SkidSmem &S, const double *cones, int n, doubl
   if (nacc < 3) return;
   // DBSCAN(eps=3, min_samples=1) == connected components; label = smallest member index, i.e. clusters are
   // numbered in order of first appearance like sklearn's
+#pragma unroll 1
   for (int i = lane; i < nacc; i += FSD_LANES) S.label[i] = (int16_t)i;
   wsync();
   for (int iter = 0; iter < nacc; ++iter) {
     bool changed = false;
+#pragma unroll 1
     for (int i = lane; i < nacc; i += FSD_LANES) {
       int best = S.label[i];
       for (int j = 0; j < nacc; ++j) {
@@ -200,6 +205,7 @@ FSD_DEVFN void skidpad_relocalize(SkidSmem &S, const double *cones, int n, doubl
   for (int rep = 0; rep < nacc; ++rep) {
     if (S.label[rep] != rep) continue;
     int count = 0;
+#pragma unroll 1
     for (int i = lane; i < nacc; i += FSD_LANES) count += S.label[i] == rep;
     count = wsum_i(count);
     const double mxv = cluster_median(S, nacc, rep, 0, count);
@@ -288,6 +294,7 @@ FSD_DEVFN void skidpad_track(const SkidReloc &R, const double *table, int n_tabl
       const int lo = cur - mac < 0 ? 0 : cur - mac, hi = cur + mac > n_table ? n_table : cur + mac;
       double bv = 0.0;
       int bi = -1;
+#pragma unroll 1
       for (int i = lo + lane; i < hi; i += FSD_LANES) {
         double d = fnorm(kx - table[2 * i], ky - table[2 * i + 1]);
         if (bi < 0 || d < bv) {
@@ -327,6 +334,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     if (fin > n_table) fin = n_table;
     nu = fin - index;
     if (nu > PCAP - 64) nu = PCAP - 64;
+#pragma unroll 1
     for (int i = lane; i < nu; i += FSD_LANES) {
       S.pts[1 + i].x = table[2 * (index + i)];
       S.pts[1 + i].y = table[2 * (index + i) + 1];
@@ -337,6 +345,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     const double c0 = fsd_cos(-PI / 2.0), s0 = fsd_sin(-PI / 2.0);
     const double yaw = fsd_atan2(F.dy, F.dx), cy = fsd_cos(yaw), sy = fsd_sin(yaw);
     nu = FSD_HORIZON - 1;
+#pragma unroll 1
     for (int i = lane; i < nu; i += FSD_LANES) {
       const int k = i + 1;
       const double a = k == FSD_HORIZON - 1 ? max_angle : (double)k * stp;
@@ -347,6 +356,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     }
   }
   wsync();
+#pragma unroll 1
   for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) {
     S.prev_xy[i].x = prev[4 * i + 1];
     S.prev_xy[i].y = prev[4 * i + 2];
@@ -354,6 +364,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
   wsync();
   unsigned status = path_from_update(S, nu, F, force_P, prev, P, out_internal, grid);
   wsync();
+#pragma unroll 1
   for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) {
     double x = out_internal[4 * i + 1], y = out_internal[4 * i + 2];
     if (index >= 0) skid_to_original(R, x, y, x, y);

@@ -160,6 +160,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
   const double cos_max = P.cos_seed_max, cos_min = P.cos_seed_min;
   double bv = 0.0;
   int bi = -1;
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
     double rx = px * c + py * s, ry = -px * s + py * c;
@@ -184,6 +185,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
   int i1 = bi;
   bv = 0.0;
   bi = -1;
+#pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     if (!S.flag[i] || S.flag2[i] || i == i1) continue;
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
@@ -388,6 +390,7 @@ FSD_DEVFN int find_leaves(SortSmem &S, const FramePose &F, int side, int sidx, c
     }
     wsync();
     const int nnb = S.deg[sidx][node];
+#pragma unroll 1
     for (int i = lane; i < nnb; i += FSD_LANES) S.can[i] = can_be_added(S, F, side, sidx, pos, i, P) ? 1 : 0;
     wsync();
     int n_ok = 0;
@@ -530,6 +533,7 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
   // nearby_cone_search.py:212-297, search distance 6 m, search angle 120 deg
   const int lane = fsd_lane();
   const double range2 = 36.0;
+#pragma unroll 1
   for (int i = lane; i < n; i += FSD_LANES) S.flag[i] = 0;
   wsync();
   if (lane == 0)
@@ -539,6 +543,7 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
   wsync();
   int nidx = compact_flags(S.flag, n, S.idxs);
   // cones within 6 m of any configuration cone (:97-103)
+#pragma unroll 1
   for (int j = lane; j < n; j += FSD_LANES) {
     bool near = false;
     for (int q = 0; q < nidx && !near; ++q) {
@@ -553,8 +558,10 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
   // `close` first holds all nearby cones, then loses the entries hit by the reference's
   // sorted_set_diff (:88-94): mask[searchsorted(all, idxs)] = False, no membership test
   int nall = compact_flags(S.flag2, n, S.close);
+#pragma unroll 1
   for (int j = lane; j < n; j += FSD_LANES) S.flag2[j] = 0;
   wsync();
+#pragma unroll 1
   for (int q = lane; q < nidx; q += FSD_LANES) {
     int v = S.idxs[q], lo = 0, hi = nall;
     while (lo < hi) {
@@ -582,6 +589,7 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
       const int cj = c[j];
       const double x0 = S.xy[cj].x, y0 = S.xy[cj].y;
       // other = close (minus removed) ++ configuration cones of OTHER configurations
+#pragma unroll 1
       for (int q = lane; q < nall + nidx; q += FSD_LANES) {
         int o;
         if (q < nall) {
@@ -621,6 +629,7 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
     int d = S.n_good[r] - S.n_bad[r];
     if (r == 0 || d < mn) mn = d;
   }
+#pragma unroll 1
   for (int r = fsd_lane(); r < C; r += FSD_LANES) {
     const int16_t *c = S.leaves[r];
     const int len = row_len(c);

@@ -52,6 +52,7 @@ struct SplineWork {
 // (1,1) (2,1) (2,2) (3,1) (3,2) (3,3).  One division per table entry instead of six per evaluated point.
 FSD_DEVFN void knot_reciprocals(SplineWork &W, int n, int k) {
   const int nrint = n - 2 * k - 1;
+#pragma unroll 1
   for (int e = fsd_lane(); e < nrint * 6; e += FSD_LANES) {
     const int ii = e / 6, q = e % 6;
     const int j = q == 0 ? 1 : (q < 3 ? 2 : 3);
@@ -160,6 +161,7 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
                           double *rpiv) {
   const int lane = fsd_lane();
   const int kbm = kb - 1, npairs = kbm * (kbm + 1) / 2, ntasks = npairs + 2 * kbm;
+#pragma unroll 1
   for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&z[0][0])[e] = (&rhs[0][0])[e];
   int ta = 0, tb = 0;
 #ifdef FSD_DEVICE_BUILD
@@ -222,7 +224,9 @@ FSD_DEVFN void interval_starts(SplineWork &W, int m, int n, int k) {
 FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, int n, int k) {
   const int lane = fsd_lane();
   const int nk1 = n - k - 1, nrint = n - 2 * k - 1, k1 = k + 1;
+#pragma unroll 1
   for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.N[0][0])[i] = 0.0;
+#pragma unroll 1
   for (int i = lane; i < nk1 * 2; i += FSD_LANES) (&W.rhs[0][0])[i] = 0.0;
 #ifdef FSD_DEVICE_BUILD
   // the sum this lane owns after the transposed reduction below and where it goes (relative to knot interval 0)
@@ -355,9 +359,11 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
 // -- a sum of two non-negative terms, no cancellation.  One row of N per lane; z is free after chol_solve.
 FSD_DEVFN double smoothing_excess(SplineWork &W, int nk1, int k) {
   const int lane = fsd_lane();
+#pragma unroll 1
   for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.z[0][0])[e] = (&W.c[0][0])[e] - (&W.c0[0][0])[e];
   wsync();
   double part = 0.0;
+#pragma unroll 1
   for (int i = lane; i < nk1; i += FSD_LANES) {
     const double dx = W.z[i][0], dy = W.z[i][1];
     double ax = W.N[i][0] * dx, ay = W.N[i][0] * dy;
@@ -406,6 +412,7 @@ FSD_DEVFN void add_knot(SplineWork &W, const double *u, int n, int nrint) {
 FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
   const int k1 = k + 1, k2 = k + 2, nk1 = n - k1, nrint = nk1 - k;
   const double fac = fdiv((double)nrint, W.t[nk1] - W.t[k]);
+#pragma unroll 1
   for (int l = k2 + fsd_lane(); l <= nk1; l += FSD_LANES) {  // 1-based row index of FITPACK
     const int lmk = l - k1;
     double h[10];
@@ -460,6 +467,7 @@ FSD_DEVFN void fit_init(SplineWork &W, FitState &F, const d2 *pts, const double 
   F.k = k;
   // u strictly increasing (parcur's input check)
   int bad = 0;
+#pragma unroll 1
   for (int i = 1 + lane; i < m; i += FSD_LANES) bad |= !(u[i - 1] < u[i]);
   if (wany(bad != 0)) return;
   F.acc = 1e-3 * s;
@@ -510,6 +518,7 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
   interval_starts(W, m, n, k);
   knot_reciprocals(W, n, k);
   assemble_normal(W, F.pts, u, n, k);
+#pragma unroll 1
   for (int e = lane; e < F.nk1 * BW; e += FSD_LANES) (&W.G[0][0])[e] = (&W.N[0][0])[e];
   wsync();
   if (!chol_solve(W.G, F.nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP)) {
@@ -608,8 +617,10 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   F.f3 = F.fpms;
   // the least-squares spline of this knot set: its coefficients and residual anchor F(p) below
   F.fp_ls = F.fp;
+#pragma unroll 1
   for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.c0[0][0])[e] = (&W.c[0][0])[e];
   // p0 = nk1 / trace of the Cholesky factor of N (chol_solve leaves the pivots d_i = G_ii^2 on the diagonal)
+#pragma unroll 1
   for (int i = lane; i < nk1; i += FSD_LANES) W.z[i][0] = fsqrt(W.G[i][0]);
   wsync();
   double p = 0.0;
@@ -628,6 +639,7 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
   const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
   ++F.iter;
   const double pinv = fdiv(1.0, F.p), pinv2 = pinv * pinv;
+#pragma unroll 1
   for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
   wsync();
   if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP)) {

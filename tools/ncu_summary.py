@@ -2,7 +2,8 @@
 import collections, csv, io, re, subprocess, sys
 
 rep, tag = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kfilter = ["--kernel-name", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []  # reports holding several kernels
+raw = subprocess.run(["ncu", "-i", rep, *kfilter, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[-1]
 keep = ["gpu__time_duration.sum", "launch__", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -13,7 +14,7 @@ with open(f"profiles/{tag}_ncu_raw.txt", "w") as f:
     for h, v in zip(hdr, vals):
         if any(w in h for w in keep) and "not_issued" not in h:
             f.write(f"{h} = {v}\n")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, *kfilter, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 funcs = {}
 import glob, os
