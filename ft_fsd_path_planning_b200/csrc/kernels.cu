@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
       F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
       dbg = O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr;
       stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
-      if (n >= 3 && build_knn(C.S, n, P)) st |= FSD_ST_OVERFLOW;
+      if (n >= 3) build_knn(C.S, n, P);
     }
     if (WPC > 1) __syncthreads();
     if (active) nl = sort_one_side(C.S, n, F, FSD_CONE_LEFT, P, dbg, &st);

@@ -27,6 +27,7 @@ struct DevParams {
   int max_n_neighbors, max_length, max_dfs_pops;
   double max_dist, max_dist2, max_dist_to_first, thr_dir, thr_abs, car_size;
   double cos_5deg, cos_150deg, cos_seed_max, cos_seed_min, cos_match_limit, cos_85deg;
+  double cos_thr_dir, cos_thr_abs, cos_1p3;
   double min_track_width, match_major, match_minor, max_search_angle;
   double seed_inv_major2, seed_inv_minor2, match_inv_major2, match_inv_minor2;
   double smoothing, predict_every, max_valid_dist, mpc_len, refit_smoothing;
@@ -49,6 +50,9 @@ static inline DevParams make_dev_params(const fsd_params &p) {
   d.cos_seed_min = cos(PI / 10.0);        // |bearing| > pi / 10
   d.cos_match_limit = cos(2.0 * p.max_search_angle);
   d.cos_85deg = cos(85.0 * PI / 180.0);
+  d.cos_thr_dir = cos(p.threshold_directional_angle);
+  d.cos_thr_abs = cos(p.threshold_absolute_angle);
+  d.cos_1p3 = cos(1.3);
   d.min_track_width = p.min_track_width;
   d.match_major = p.max_search_range * 1.5;
   d.match_minor = p.min_track_width;
@@ -70,8 +74,10 @@ static inline DevParams make_dev_params(const fsd_params &p) {
 
 #ifdef FSD_DEVICE_BUILD
 #define FSD_POPC(x) __popc(x)
+#define FSD_FFS(x) __ffs((int)(x))
 #else
 #define FSD_POPC(x) __builtin_popcount(x)
+#define FSD_FFS(x) __builtin_ffs((int)(x))
 #endif
 
 }  // namespace fsd

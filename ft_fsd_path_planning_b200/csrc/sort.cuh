@@ -62,9 +62,8 @@ struct SortSmem {
 // ---- k-NN graph: adjacency_matrix.py:60-110 ------------------------------------------------
 // Both sides in one sweep: the LEFT graph ignores yellow cones, the RIGHT graph ignores blue.
 
-// sorted insertion into a k-nearest list; rare (a handful of cones lie within max_dist of a row), so it is kept
-// small and out of line rather than unrolled into the distance loop
-FSD_DEVFN void knn_insert(double *d, int *id, int *cnt, int k, double v, int j) {
+// sorted insertion into a k-nearest list (ascending distance; ties keep the earlier, i.e. lower, index first)
+FSD_DEV void knn_insert(double *d, int *id, int *cnt, int k, double v, int j) {
   int c = *cnt;
   if (c == k && !(v < d[k - 1])) return;
   int p = c < k ? c : k - 1;
@@ -78,49 +77,60 @@ FSD_DEVFN void knn_insert(double *d, int *id, int *cnt, int k, double v, int j) 
   if (c < k) *cnt = c + 1;
 }
 
-// returns true when a cone had more in-range neighbours than the candidate buffer holds (FSD_ST_OVERFLOW)
-FSD_DEVFN bool build_knn(SortSmem &S, int n, const DevParams &P) {
+struct KnnLists {
+  double d[2][5];
+  int id[2][5];
+  int cnt[2];
+};
+
+// cone j lies within max_dist of the row's cone: offer it to the row's LEFT and RIGHT lists.  Rare (a handful of the
+// frame's cones per row) and deliberately out of line, so that the distance sweep below stays a tight loop.
+FSD_DEVFN void knn_consider(KnnLists &K, int k, bool li, bool ri, int tj, double dd, int j) {
+  if (li && tj != FSD_CONE_RIGHT) knn_insert(K.d[0], K.id[0], &K.cnt[0], k, dd, j);
+  if (ri && tj != FSD_CONE_LEFT) knn_insert(K.d[1], K.id[1], &K.cnt[1], k, dd, j);
+}
+
+FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
   int k = n - 1 < P.max_n_neighbors ? n - 1 : P.max_n_neighbors;
   if (k > 5) k = 5;
-  bool over = false;
 #pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-    double dl[5], dr[5];
-    int il[5], ir[5];
-    int cl = 0, cr = 0;
+    KnnLists K;
+    K.cnt[0] = K.cnt[1] = 0;
     const double xi = S.xy[i].x, yi = S.xy[i].y;
     const int ti = S.type[i];
     const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
-    // pass 1: a tight, call-free distance sweep that only collects the cones within max_dist of cone i (a handful);
-    // edges longer than max_dist are removed after the k-NN selection in the reference (:102-107) and a longer edge
-    // can never displace a shorter one, so they are dropped before the selection
-    constexpr int CAND_CAP = 48;
-    uint8_t cand[CAND_CAP];
-    int nc = 0;
-#pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-      const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
-      const double dd = ddx * ddx + ddy * ddy;
-      if (dd <= P.max_dist2 && j != i) {
-        if (nc < CAND_CAP)
-          cand[nc++] = (uint8_t)j;
-        else
-          over = true;
+    // Edges longer than max_dist are removed after the k-NN selection in the reference (:102-107) and a longer edge can
+    // never displace a shorter one, so they are dropped before the selection.  The frame is swept in chunks of 32
+    // cones: a branch-free distance loop leaves the chunk's in-range cones as a bit mask, then the handful of set bits
+    // is offered to the row's lists in ascending j (the tie order of the selection).  Lanes stay converged through
+    // the sweep and diverge only by the number of in-range cones per chunk.
+#pragma unroll 1
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int jn = n - j0 < 32 ? n - j0 : 32;
+      unsigned mask = 0;
+#pragma unroll 4
+      for (int jj = 0; jj < jn; ++jj) {
+        const double ddx = S.xy[j0 + jj].x - xi, ddy = S.xy[j0 + jj].y - yi;
+        mask |= (ddx * ddx + ddy * ddy <= P.max_dist2 ? 1u : 0u) << jj;
+      }
+      if ((unsigned)(i - j0) < 32u) mask &= ~(1u << (i - j0));
+      while (mask) {
+        const int jj = FSD_FFS(mask) - 1;
+        mask &= mask - 1;
+        const int j = j0 + jj;
+        const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
+        knn_consider(K, k, li, ri, S.type[j], ddx * ddx + ddy * ddy, j);
       }
     }
-    // pass 2: exact selection among the candidates, ascending j (ties keep the lower index first)
-    for (int q = 0; q < nc; ++q) {
-      const int j = cand[q];
-      const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
-      const double dd = ddx * ddx + ddy * ddy;
-      const int tj = S.type[j];
-      if (li && tj != FSD_CONE_RIGHT) knn_insert(dl, il, &cl, k, dd, j);
-      if (ri && tj != FSD_CONE_LEFT) knn_insert(dr, ir, &cr, k, dd, j);
+    // unused slots hold the row's own index: a cone is never its own neighbour, so they match nothing below
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      S.knn[0][i][q] = (uint8_t)(q < K.cnt[0] ? K.id[0][q] : i);
+      S.knn[1][i][q] = (uint8_t)(q < K.cnt[1] ? K.id[1][q] : i);
     }
-    for (int q = 0; q < cl; ++q) S.knn[0][i][q] = (uint8_t)il[q];
-    for (int q = 0; q < cr; ++q) S.knn[1][i][q] = (uint8_t)ir[q];
-    S.kcnt[0][i] = (uint8_t)cl;
-    S.kcnt[1][i] = (uint8_t)cr;
+    S.kcnt[0][i] = (uint8_t)K.cnt[0];
+    S.kcnt[1][i] = (uint8_t)K.cnt[1];
   }
   wsync();
   // keep edges present in both directions (:110); neighbour lists in ascending index order, the
@@ -131,10 +141,12 @@ FSD_DEVFN bool build_knn(SortSmem &S, int n, const DevParams &P) {
     for (int s = 0; s < 2; ++s) {
       int cnt = 0;
       int tmp[5];
-      for (int q = 0; q < S.kcnt[s][i]; ++q) {
-        int j = S.knn[s][i][q];
-        bool back = false;
-        for (int r = 0; r < S.kcnt[s][j]; ++r) back |= S.knn[s][j][r] == i;
+      const int kc = S.kcnt[s][i];
+#pragma unroll 1
+      for (int q = 0; q < kc; ++q) {
+        const int j = S.knn[s][i][q];
+        const uint8_t *kj = S.knn[s][j];
+        const bool back = (kj[0] == i) | (kj[1] == i) | (kj[2] == i) | (kj[3] == i) | (kj[4] == i);
         if (back) {
           int p = cnt++;
           while (p > 0 && tmp[p - 1] > j) {
@@ -149,7 +161,6 @@ FSD_DEVFN bool build_knn(SortSmem &S, int n, const DevParams &P) {
     }
   }
   wsync();
-  return wany(over);
 }
 
 // ---- seeds: core_trace_sorter.py:344-465 ----------------------------------------------------
@@ -291,6 +302,16 @@ FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, 
          (fmin(b0y, b1y) - eps <= y && y <= fmax(b0y, b1y) + eps);
 }
 
+// x < c sqrt(v2) and x > c sqrt(v2) for v2 >= 0, without the square root
+FSD_DEV bool lt_scaled(double x, double c, double v2) {
+  const double x2 = x * x, cv = c * c * v2;
+  return c >= 0.0 ? (x < 0.0 || x2 < cv) : (x < 0.0 && x2 > cv);
+}
+FSD_DEV bool gt_scaled(double x, double c, double v2) {
+  const double x2 = x * x, cv = c * c * v2;
+  return c >= 0.0 ? (x > 0.0 && x2 > cv) : (x >= 0.0 || x2 < cv);
+}
+
 FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int sidx, int pos, int i,
                             const DevParams &P) {
   const int last = S.attempt[pos];
@@ -328,23 +349,27 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
     if (d2 < 36.0 && d1 < 36.0 && cos_between(v1x, v1y, v2x, v2y) < P.cos_150deg) return false;
   }
   if (pos >= 1) {
-    // turn angle at `last`: wrap(atan2(b) - atan2(a)) == atan2(a x b, a . b)  (:173-191)
-    double difference = fsd_atan2(ax * by - ay * bx, ax * bx + ay * by);
-    bool short_edge = bx * bx + by * by < 16.0;
-    bool ok;
-    if (fabs(difference) > P.thr_abs)
-      ok = false;
-    else if (side == FSD_CONE_LEFT)
-      ok = difference < P.thr_dir || short_edge;
-    else
-      ok = difference > -P.thr_dir || short_edge;
-    if (ok && pos >= 2) {
+    // turn angle at `last` (:173-191): difference = wrap(atan2(b) - atan2(a)) has sine cr / v and cosine dt / v with
+    // v = |a| |b|, so the three threshold tests are evaluated on cr, dt and v^2 -- no arctangent, no square root:
+    //   |difference| > t        <=>  dt < cos(t) v
+    //   difference >= t (t > 0) <=>  cr >= 0 and dt <= cos(t) v
+    const double cr = ax * by - ay * bx, dt = ax * bx + ay * by, v2 = cr * cr + dt * dt;
+    if (lt_scaled(dt, P.cos_thr_abs, v2)) return false;
+    const bool short_edge = bx * bx + by * by < 16.0;
+    const bool beyond = (side == FSD_CONE_LEFT ? cr >= 0.0 : cr <= 0.0) && !gt_scaled(dt, P.cos_thr_dir, v2);
+    if (beyond && !short_edge) return false;
+    if (pos >= 2) {
+      // change of turning direction (:193-205): sign(difference) != sign(difference_2) and |difference -
+      // difference_2| = |difference| + |difference_2| > 1.3, on the sine and cosine of the sum of the two magnitudes
       const int prev = S.attempt[pos - 1], pp = S.attempt[pos - 2];
-      double zx = S.xy[prev].x - S.xy[pp].x, zy = S.xy[prev].y - S.xy[pp].y;
-      double difference_2 = fsd_atan2(zx * ay - zy * ax, zx * ax + zy * ay);
-      if (isgn(difference) != isgn(difference_2) && fabs(difference - difference_2) > 1.3) ok = false;
+      const double zx = S.xy[prev].x - S.xy[pp].x, zy = S.xy[prev].y - S.xy[pp].y;
+      const double cr2 = zx * ay - zy * ax, dt2 = zx * ax + zy * ay, w2 = cr2 * cr2 + dt2 * dt2;
+      if (isgn(cr) != isgn(cr2)) {
+        const double sa = fabs(cr), sb = fabs(cr2);
+        const double sn = sa * dt2 + dt * sb, cs = dt * dt2 - sa * sb;
+        if (sn < 0.0 || lt_scaled(cs, P.cos_1p3, v2 * w2)) return false;
+      }
     }
-    if (!ok) return false;
   }
   if (pos == 1) {
     // angle(heading, candidate - first) < pi/2 (:207-211)
@@ -384,27 +409,31 @@ FSD_DEVFN int find_leaves(SortSmem &S, const FramePose &F, int side, int sidx, c
     const int node = S.stack_node[sp], pos = S.stack_pos[sp];
     --sp;
     wsync();
-    if (lane == 0) {
-      S.attempt[pos] = (int16_t)node;
-      for (int q = pos + 1; q < L; ++q) S.attempt[q] = -1;
-    }
-    wsync();
-    const int nnb = S.deg[sidx][node];
+    // the popped node becomes entry `pos` of the attempt, everything behind it is cleared (one entry per lane)
 #pragma unroll 1
-    for (int i = lane; i < nnb; i += FSD_LANES) S.can[i] = can_be_added(S, F, side, sidx, pos, i, P) ? 1 : 0;
+    for (int q = pos + lane; q < L; q += FSD_LANES) S.attempt[q] = (int16_t)(q == pos ? node : -1);
     wsync();
-    int n_ok = 0;
-    for (int i = 0; i < nnb; ++i) n_ok += S.can[i];
+    // one candidate neighbour per lane; the admissible ones as a bit mask
+    const int nnb = S.deg[sidx][node];
+    unsigned ok_mask = 0;
+#pragma unroll 1
+    for (int base = 0; base < nnb; base += FSD_LANES) {
+      const int i = base + lane;
+      const bool ok = i < nnb && can_be_added(S, F, side, sidx, pos, i, P);
+      ok_mask |= wballot(ok) << base;
+    }
+    const int n_ok = FSD_POPC(ok_mask);
     if (pos < L - 1 && n_ok > 0) {
-      if (lane == 0) {
-        int w = sp;
-        for (int i = 0; i < nnb; ++i)
-          if (S.can[i] && w + 1 < STACK_CAP) {
-            ++w;
+      // push the admissible neighbours in list order (each lane writes its own slot)
+#pragma unroll 1
+      for (int i = lane; i < nnb; i += FSD_LANES)
+        if ((ok_mask >> i) & 1u) {
+          const int w = sp + 1 + FSD_POPC(ok_mask & ((1u << i) - 1u));
+          if (w < STACK_CAP) {
             S.stack_node[w] = S.nbr[sidx][node][i];
             S.stack_pos[w] = (uint8_t)(pos + 1);
           }
-      }
+        }
       sp += n_ok;
       if (sp >= STACK_CAP) {
         sp = STACK_CAP - 1;
@@ -412,8 +441,8 @@ FSD_DEVFN int find_leaves(SortSmem &S, const FramePose &F, int side, int sidx, c
       }
     } else {
       if (n_leaves < MAX_LEAVES) {
-        if (lane == 0)
-          for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[n_leaves][q] = q < L ? S.attempt[q] : (int16_t)-1;
+#pragma unroll 1
+        for (int q = lane; q < FSD_MAX_SORTED; q += FSD_LANES) S.leaves[n_leaves][q] = q < L ? S.attempt[q] : (int16_t)-1;
         ++n_leaves;
       } else {
         *status |= FSD_ST_OVERFLOW;
@@ -825,7 +854,7 @@ FSD_DEVFN unsigned sort_finish(SortSmem &S, int nl, int nr) {
 
 FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg) {
   unsigned status = 0;
-  if (n >= 3 && build_knn(S, n, P)) status |= FSD_ST_OVERFLOW;
+  if (n >= 3) build_knn(S, n, P);
   int nl = sort_one_side(S, n, F, FSD_CONE_LEFT, P, dbg, &status);
   int nr = sort_one_side(S, n, F, FSD_CONE_RIGHT, P, dbg, &status);
   return status | sort_finish(S, nl, nr);

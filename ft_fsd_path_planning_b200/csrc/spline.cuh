@@ -163,30 +163,48 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
   const int kbm = kb - 1, npairs = kbm * (kbm + 1) / 2, ntasks = npairs + 2 * kbm;
 #pragma unroll 1
   for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&z[0][0])[e] = (&rhs[0][0])[e];
-  int ta = 0, tb = 0;
 #ifdef FSD_DEVICE_BUILD
+  // this lane's task as three running pointers (factor, multiplier, target) and the first row without a target
+  int ta = 0, tb = 0;
   chol_task(lane, kbm, npairs, ta, tb);
-#endif
+  const bool is_pair = lane < npairs, has_task = lane < ntasks;
+  const double *pa = &M[0][has_task ? ta : 0];
+  const double *pb = is_pair ? &M[0][tb] : &z[0][tb & 1];
+  double *pt = is_pair ? &M[ta][tb - ta] : &z[ta][tb & 1];
+  const int sb = is_pair ? BW : 2;
+  const int ilim = has_task ? nk1 - (is_pair ? tb : ta) : 0;
   wsync();
 #pragma unroll 1
   for (int i = 0; i < nk1; ++i) {
     const double s = M[i][0];
     if (!(s > 0.0)) return false;
     const double rs = frcp(s);
-    FSD_FOR_TASKS(e, ntasks) {
-#ifndef FSD_DEVICE_BUILD
+    if (i < ilim) *pt -= *pa * rs * *pb;
+    if (lane == 0) rpiv[i] = rs;
+    pa += BW;
+    pb += sb;
+    pt += sb;
+    wsync();
+  }
+#else
+  wsync();
+  for (int i = 0; i < nk1; ++i) {
+    const double s = M[i][0];
+    if (!(s > 0.0)) return false;
+    const double rs = frcp(s);
+    for (int e = 0; e < ntasks; ++e) {
+      int ta, tb;
       chol_task(e, kbm, npairs, ta, tb);
-#endif
       const double f = M[i][ta] * rs;
       if (e < npairs) {
         if (i + tb < nk1) M[i + ta][tb - ta] -= f * M[i][tb];
       } else {
         if (i + ta < nk1) z[i + ta][tb] -= f * z[i][tb];
       }
-      if (e == 0) rpiv[i] = rs;
     }
-    wsync();
+    rpiv[i] = rs;
   }
+#endif
   const int nback = 2 * kb;
 #pragma unroll 1
   for (int i = nk1 - 1; i >= 0; --i) {
