@@ -162,11 +162,12 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
+        step()
         step(events=True)
     barrier()
     planner.kernel_times_ms()  # drop the warm-up events
 
-    # ---- device-resident throughput: K steps, CUDA events per step, L2 flushed between steps ----------------
+    # ---- device-resident throughput: K steps through fsd_plan_batch, CUDA events per step, L2 flushed between steps --
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -175,12 +176,17 @@ def run_ours(args):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step(events=True)
+        step()
         e1.record()
         evs.append((e0, e1))
     barrier()
     clocks = sampler.stop()
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    # ---- per-kernel launch durations (roofline): the two stage entry points, whole batch per launch, events between --
+    for _ in range(args.steps):
+        flush.zero_()
+        step(events=True)
+    barrier()
     ktimes = planner.kernel_times_ms()
     sort_ms = float(np.mean([t[0] for t in ktimes]))
     path_ms = float(np.mean([t[1] for t in ktimes]))
@@ -262,7 +268,7 @@ def run_ours(args):
                                        f"{cpu_threads} pthreads"},
             "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": int(planner.lib.fsd_plan_launches(B)) * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(out))

@@ -79,6 +79,8 @@ def lib():
         L.fsd_params_default.argtypes = [C.POINTER(Params)]
         L.fsd_workspace_bytes.restype = sz
         L.fsd_workspace_bytes.argtypes = [i32, i32]
+        L.fsd_plan_launches.restype = i32
+        L.fsd_plan_launches.argtypes = [i32]
         L.fsd_initial_path.argtypes = [C.POINTER(Params), vp, vp]
         plan_args = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Intermediate), vp, vp, i32,
                      vp, vp, sz, vp]

@@ -31,6 +31,10 @@ namespace {
 #define FSD_WARPS_PER_CTA 8
 #endif
 constexpr int WPC = FSD_WARPS_PER_CTA;
+// CTA barriers per frame in the sort kernel (phase alignment of the warps of a CTA): A/B knob
+#ifndef FSD_SORT_BARRIERS
+#define FSD_SORT_BARRIERS 4
+#endif
 constexpr int CTA_THREADS = 32 * WPC;
 constexpr int CTAS_PER_SM = 16 / WPC;
 #ifndef FSD_PATH_CTAS_PER_SM
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     unsigned st = 0;
     FramePose F = make_pose(0.0, 0.0, 1.0, 0.0);
     int16_t *dbg = nullptr;
-    if (WPC > 1) __syncthreads();
+    if (WPC > 1 && FSD_SORT_BARRIERS >= 1) __syncthreads();
     if (active) {
       const int lo = offsets[b];
       n = offsets[b + 1] - lo;
@@ -182,11 +186,11 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
       stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
       if (n >= 3) build_knn(C.S, n, P);
     }
-    if (WPC > 1) __syncthreads();
+    if (WPC > 1 && FSD_SORT_BARRIERS >= 2) __syncthreads();
     if (active) nl = sort_one_side(C.S, n, F, FSD_CONE_LEFT, P, dbg, &st);
-    if (WPC > 1) __syncthreads();
+    if (WPC > 1 && FSD_SORT_BARRIERS >= 3) __syncthreads();
     if (active) nr = sort_one_side(C.S, n, F, FSD_CONE_RIGHT, P, dbg, &st);
-    if (WPC > 1) __syncthreads();
+    if (WPC > 1 && FSD_SORT_BARRIERS >= 4) __syncthreads();
     if (active) {
       st |= sort_finish(C.S, nl, nr);
       store_sort(C.S, b, O);
@@ -436,11 +440,20 @@ constexpr int MAX_DEVICES = 64;
 constexpr size_t INITIAL_SMEM = ((sizeof(PathSmem) + 15) / 16) * 16 + PATH_SCRATCH_BYTES;
 __device__ double g_initial_path[FSD_HORIZON * 4];  // cache of the default-parameter initial path
 
+// a side stream with its fork / join events: the second chunk of a large batch runs on it (plan_batch_impl)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool busy = false;
+};
+constexpr int SIDE_STREAMS = 8;
+
 struct DeviceInfo {
   int sm_count = 0;
   int sort_ctas = 0, path_ctas = 0;  // resident CTAs per SM
   bool initial_ready = false;
   double key[3] = {0, 0, 0};
+  SideStream side[SIDE_STREAMS];
 };
 DeviceInfo g_dev[MAX_DEVICES];
 std::mutex g_mutex;
@@ -505,9 +518,25 @@ size_t path_grid_bound(int n_frames) {
   return B < cap ? B : cap;
 }
 
+// A batch of at least two full waves of resident warps is planned as two chunks on two streams (the caller's and a side
+// stream): the ragged last wave of one kernel then overlaps the first wave of the next launch instead of leaving SMs
+// idle (persistent CTAs stride statically over their chunk).  Returns the size of the first chunk (n_frames: no split).
+int first_chunk(int n_frames) {
+  DeviceInfo *D = nullptr;
+  if (device_info(&D) != FSD_OK) return n_frames;
+  const long wave = (long)D->sm_count * (D->path_ctas < D->sort_ctas ? D->path_ctas : D->sort_ctas) * WPC;
+  if ((long)n_frames < 2 * wave) return n_frames;
+  return (n_frames / 2 + WPC - 1) / WPC * WPC;
+}
+
+size_t path_scratch_bytes(int n_frames) {
+  const int a = first_chunk(n_frames);
+  return align_up(path_grid_bound(a) * PATH_SCRATCH_BYTES, 256) + align_up(path_grid_bound(n_frames - a) * PATH_SCRATCH_BYTES, 256);
+}
+
 size_t workspace_bytes(int n_frames) {
   const size_t B = (size_t)(n_frames > 0 ? n_frames : 0);
-  size_t total = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
+  size_t total = align_up(path_scratch_bytes(n_frames), 256);
   total += align_up(B * FSD_HORIZON * 4 * sizeof(double), 256);         // path_f64
   total += align_up(B * 2 * sizeof(int16_t), 256);                      // n_wv
   total += 2 * align_up(B * FSD_MAX_WV * 2 * sizeof(double), 256);      // left_wv, right_wv
@@ -526,7 +555,7 @@ int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t
   if (!workspace || workspace_bytes_given < workspace_bytes(n_frames)) return FSD_ERR_WORKSPACE;
   Carve cv = {static_cast<unsigned char *>(workspace), 0, workspace_bytes_given};
   const size_t B = (size_t)n_frames;
-  *path_scratch = cv.take<unsigned char>(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES);
+  *path_scratch = cv.take<unsigned char>(path_scratch_bytes(n_frames));
   double *w_path = cv.take<double>(B * FSD_HORIZON * 4);
   int16_t *w_nwv = cv.take<int16_t>(B * 2);
   double *w_lwv = cv.take<double>(B * FSD_MAX_WV * 2);
@@ -625,6 +654,43 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   return check_launch();
 }
 
+// take / return a side stream of the current device (created on first use)
+SideStream *acquire_side(DeviceInfo &D) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  for (SideStream &s : D.side) {
+    if (s.busy) continue;
+    if (!s.stream) {
+      if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    }
+    s.busy = true;
+    return &s;
+  }
+  return nullptr;
+}
+
+void release_side(SideStream *s) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  s->busy = false;
+}
+
+fsd_intermediate shift_intermediate(const fsd_intermediate &R, size_t h) {
+  fsd_intermediate r = R;
+  if (r.path_f64) r.path_f64 += h * FSD_HORIZON * 4;
+  if (r.n_wv) r.n_wv += h * 2;
+  if (r.left_wv) r.left_wv += h * FSD_MAX_WV * 2;
+  if (r.right_wv) r.right_wv += h * FSD_MAX_WV * 2;
+  if (r.l2r) r.l2r += h * FSD_MAX_WV;
+  if (r.r2l) r.r2l += h * FSD_MAX_WV;
+  if (r.grid) r.grid += h * 2;
+  if (r.sort_dbg) r.sort_dbg += h * 8;
+  return r;
+}
+
 template <typename T>
 int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T *cones_xy, const uint8_t *cones_type,
                     const int32_t *offsets, const T *pos, const T *dir, float *out_path, int16_t *out_left_idx,
@@ -635,17 +701,65 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
   if (mission != FSD_MISSION_AUTOCROSS && mission != FSD_MISSION_TRACKDRIVE) return FSD_ERR_MISSION;
   if (n_frames == 0) return FSD_OK;
   if (!offsets || !pos || !dir || !out_status) return FSD_ERR_ARG;
+  if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   fsd_intermediate R;
   double *init_slot = nullptr;
   unsigned char *path_scratch = nullptr;
   int rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot, &path_scratch);
   if (rc != FSD_OK) return rc;
-  rc = sort_match_impl<T>(params, n_frames, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
-                          out_status, stream);
+  DeviceInfo *D = nullptr;
+  rc = device_info(&D);
   if (rc != FSD_OK) return rc;
-  return path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev_path, prev_path_stride, init_slot, path_scratch,
-                      out_path, out_status, stream);
+  // the previous path both chunks fall back to (resolved once, on the caller's stream, before the fork)
+  const double *prev = prev_path;
+  int stride = prev_path_stride;
+  if (!prev) {
+    rc = default_prev_path(params, make_dev_params(*params), *D, init_slot, stream, &prev);
+    if (rc != FSD_OK) return rc;
+    stride = 0;
+  }
+  const int na = first_chunk(n_frames), nb = n_frames - na;
+  SideStream *side = nb > 0 ? acquire_side(*D) : nullptr;
+  if (!side) {
+    rc = sort_match_impl<T>(params, n_frames, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
+                            out_status, stream);
+    if (rc != FSD_OK) return rc;
+    return path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
+                        out_status, stream);
+  }
+  // chunk A = frames [0, na) on the caller's stream, chunk B = [na, n_frames) on the side stream; the CSR offsets are
+  // absolute, so chunk B simply starts further into the same arrays
+  const size_t h = (size_t)na;
+  const fsd_intermediate RB = shift_intermediate(R, h);
+  unsigned char *scratch_b = path_scratch + align_up(path_grid_bound(na) * PATH_SCRATCH_BYTES, 256);
+  bool ok = cudaEventRecord(side->fork, stream) == cudaSuccess &&
+            cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess;
+  if (ok) {
+    rc = sort_match_impl<T>(params, na, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
+                            out_status, stream);
+    if (rc == FSD_OK)
+      rc = sort_match_impl<T>(params, nb, cones_xy, cones_type, offsets + h, pos + 2 * h, dir + 2 * h,
+                              out_left_idx ? out_left_idx + h * FSD_MAX_SORTED : nullptr,
+                              out_right_idx ? out_right_idx + h * FSD_MAX_SORTED : nullptr, &RB, out_status + h,
+                              side->stream);
+    if (rc == FSD_OK)
+      rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
+                        stream);
+    if (rc == FSD_OK)
+      rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
+                        prev + h * (size_t)stride, stride, init_slot, scratch_b,
+                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream);
+  }
+  // always join, so that the caller's stream never runs ahead of work queued on the side stream
+  ok = cudaEventRecord(side->join, side->stream) == cudaSuccess && ok;
+  ok = cudaStreamWaitEvent(stream, side->join, 0) == cudaSuccess && ok;
+  release_side(side);
+  if (!ok) {
+    cudaGetLastError();
+    return FSD_ERR_LAUNCH;
+  }
+  return rc;
 }
 
 }  // namespace
@@ -693,6 +807,11 @@ int fsd_params_default(fsd_params *p) {
 size_t fsd_workspace_bytes(int n_frames, int total_cones) {
   (void)total_cones;
   return workspace_bytes(n_frames);
+}
+
+int fsd_plan_launches(int n_frames) {
+  if (n_frames <= 0) return 0;
+  return first_chunk(n_frames) < n_frames ? 4 : 2;
 }
 
 int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stream) {

@@ -115,6 +115,12 @@ int fsd_params_default(fsd_params *params);
 /* bytes of scratch needed by the batch entry points below for B frames */
 size_t fsd_workspace_bytes(int n_frames, int total_cones);
 
+/* Kernel launches one fsd_plan_batch call makes for n_frames frames on the current device: 2 (sort+match, path), or 4
+ * when the batch is large enough to be planned as two chunks -- the second one on an internal side stream that is
+ * forked from and joined back into the caller's stream with events, so the call stays asynchronous and ordered on
+ * the caller's stream (and capturable in a CUDA graph). */
+int fsd_plan_launches(int n_frames);
+
 /* The constant initial path of a fresh planner (core_calculate_path.py:103-107), computed on the
  * device with the path kernels; out_prev_path: device, [40][4] fp64. */
 int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stream);
