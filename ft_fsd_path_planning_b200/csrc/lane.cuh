@@ -156,6 +156,16 @@ FSD_DEV double frcp(double a) { return 1.0 / a; }
 FSD_DEV double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 FSD_DEV int isgn(double v) { return (v > 0.0) - (v < 0.0); }
 
+// x < c sqrt(v2) and x > c sqrt(v2) for v2 >= 0, without the square root
+FSD_DEV bool lt_scaled(double x, double c, double v2) {
+  const double x2 = x * x, cv = c * c * v2;
+  return c >= 0.0 ? (x < 0.0 || x2 < cv) : (x < 0.0 && x2 > cv);
+}
+FSD_DEV bool gt_scaled(double x, double c, double v2) {
+  const double x2 = x * x, cv = c * c * v2;
+  return c >= 0.0 ? (x > 0.0 && x2 > cv) : (x >= 0.0 || x2 < cv);
+}
+
 // (a1 - a2 + 3 pi) mod 2 pi - pi with Python's modulo
 // (reference: fsd_path_planning/utils/math_utils.py:663-676)
 FSD_DEV double angle_difference(double a1, double a2) {

@@ -78,7 +78,7 @@ FSD_DEVFN bool matches_for_side(MatchSmem &S, const d2 *cones, int n, int side, 
       double rx = vx * dxi + vy * dyi, ry = dxi * vy - dyi * vx;
       double r2 = rx * rx + ry * ry;
       bool ok = (rx * rx * inv_major2 + ry * ry * inv_minor2) < 1.0;
-      if (fdiv(rx, fsqrt(r2)) < cos_limit) ok = false;                       // :125
+      if (lt_scaled(rx, cos_limit, r2)) ok = false;                          // cos(angle) < limit :125
       if (dxi * S.odirs[j].x + dyi * S.odirs[j].y > 0.0) ok = false;  // :127
       any |= ok;
       // the match is the nearest cone of the other side, masked or not (:162)

@@ -168,19 +168,19 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
 FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int *fk) {
   const int opp = side == FSD_CONE_LEFT ? FSD_CONE_RIGHT : FSD_CONE_LEFT;
   const double c = F.ux, s = F.uy;  // rotation by -yaw
-  const double cos_max = P.cos_seed_max, cos_min = P.cos_seed_min;
+  const double cos_max = P.cos_seed_max, cos_min = P.cos_seed_min, max_first2 = P.max_dist_to_first * P.max_dist_to_first;
   double bv = 0.0;
   int bi = -1;
 #pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
     double rx = px * c + py * s, ry = -px * s + py * c;
-    double r = fsqrt(rx * rx + ry * ry);
+    // distances to the car are compared squared (monotone, no square root)
+    double r = rx * rx + ry * ry;
     bool in_ellipse = (rx * rx * P.seed_inv_major2 + ry * ry * P.seed_inv_minor2) < 1.0;
-    // sign(bearing) == +-1, pi/10 < |bearing| < 4pi/5  (:395-399), on the cosine of the bearing
+    // sign(bearing) == +-1, pi/10 < |bearing| < 4pi/5  (:395-399), on the cosine rx / |r| of the bearing
     bool side_ok = side == FSD_CONE_LEFT ? ry > 0.0 : ry < 0.0;
-    double cb = fdiv(rx, r);
-    bool ang_ok = cb > cos_max && cb < cos_min;
+    bool ang_ok = gt_scaled(rx, cos_max, r) && lt_scaled(rx, cos_min, r);
     int t = S.type[i];
     bool valid = in_ellipse && ((side_ok && ang_ok) || t == side) && t != opp;
     S.flag[i] = valid ? 1 : 0;
@@ -192,7 +192,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
   }
   wargmin(bv, bi);
   wsync();
-  if (bi < 0 || bv > P.max_dist_to_first) return 0;
+  if (bi < 0 || bv > max_first2) return 0;
   int i1 = bi;
   bv = 0.0;
   bi = -1;
@@ -201,7 +201,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
     if (!S.flag[i] || S.flag2[i] || i == i1) continue;
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
     double rx = px * c + py * s, ry = -px * s + py * c;
-    double r = fsqrt(rx * rx + ry * ry);
+    double r = rx * rx + ry * ry;
     if (bi < 0 || r < bv) {
       bv = r;
       bi = i;
@@ -209,7 +209,7 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
   }
   wargmin(bv, bi);
   wsync();
-  if (bi < 0 || bv > P.max_dist_to_first) {
+  if (bi < 0 || bv > max_first2) {
     fk[0] = i1;
     return 1;
   }
@@ -221,8 +221,8 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
     i1 = i2;
     i2 = t;
   }
-  double d = fsqrt(ex * ex + ey * ey);
-  if (d > P.max_dist * 1.1 || d < 1.4) {
+  const double d2 = ex * ex + ey * ey, dmax = P.max_dist * 1.1;
+  if (d2 > dmax * dmax || d2 < 1.4 * 1.4) {
     fk[0] = i1;
     return 1;
   }
@@ -234,9 +234,11 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
 // ---- reachability: common.py:36-67; only min(#reachable, max_length) is used ----------------
 
 FSD_DEVFN int reachable_count(SortSmem &S, int n, int sidx, int start, int cap) {
+  // flag2 doubles as the visited mask, idxs as the queue
+#pragma unroll 1
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) S.flag2[i] = 0;
+  wsync();
   if (fsd_lane() == 0) {
-    // flag2 doubles as the visited mask, idxs as the queue
-    for (int i = 0; i < n; ++i) S.flag2[i] = 0;
     int head = 0, tail = 0;
     S.idxs[tail++] = (int16_t)start;
     S.flag2[start] = 1;
@@ -302,24 +304,13 @@ FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, 
          (fmin(b0y, b1y) - eps <= y && y <= fmax(b0y, b1y) + eps);
 }
 
-// x < c sqrt(v2) and x > c sqrt(v2) for v2 >= 0, without the square root
-FSD_DEV bool lt_scaled(double x, double c, double v2) {
-  const double x2 = x * x, cv = c * c * v2;
-  return c >= 0.0 ? (x < 0.0 || x2 < cv) : (x < 0.0 && x2 > cv);
-}
-FSD_DEV bool gt_scaled(double x, double c, double v2) {
-  const double x2 = x * x, cv = c * c * v2;
-  return c >= 0.0 ? (x > 0.0 && x2 > cv) : (x >= 0.0 || x2 < cv);
-}
-
 FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int sidx, int pos, int i,
                             const DevParams &P) {
   const int last = S.attempt[pos];
   const uint8_t *nb = S.nbr[sidx][last];
   const int nnb = S.deg[sidx][last];
   const int cand = nb[i];
-  for (int q = 0; q <= pos; ++q)
-    if (S.attempt[q] == cand) return false;  // already in the attempt (:126)
+  if (S.flag[cand]) return false;  // already in the attempt (:126); find_leaves keeps the membership flags
   const double lx = S.xy[last].x, ly = S.xy[last].y;
   const double cx = S.xy[cand].x, cy = S.xy[cand].y;
   const double bx = cx - lx, by = cy - ly;  // last -> candidate
@@ -385,14 +376,19 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
 // ---- exhaustive search: end_configurations.py:320-431 ----------------------------------------
 // returns the number of raw leaves in S.leaves (rows padded with -1 up to FSD_MAX_SORTED)
 
-FSD_DEVFN int find_leaves(SortSmem &S, const FramePose &F, int side, int sidx, const int *fk, int nfk, int L,
+FSD_DEVFN int find_leaves(SortSmem &S, int n, const FramePose &F, int side, int sidx, const int *fk, int nfk, int L,
                           const DevParams &P, int *pops_out, unsigned *status) {
   const int lane = fsd_lane();
   int sp = 0, n_leaves = 0, pops = 0;
+  // S.flag[c] == 1 <=> cone c is in the current attempt
+#pragma unroll 1
+  for (int i = lane; i < n; i += FSD_LANES) S.flag[i] = 0;
+  wsync();
   if (lane == 0) {
     for (int q = 0; q < 16; ++q) S.attempt[q] = -1;
     if (nfk > 1) {
       S.attempt[0] = (int16_t)fk[0];
+      S.flag[fk[0]] = 1;
       S.stack_node[0] = (uint8_t)fk[1];
       S.stack_pos[0] = 1;
     } else {
@@ -411,7 +407,13 @@ FSD_DEVFN int find_leaves(SortSmem &S, const FramePose &F, int side, int sidx, c
     wsync();
     // the popped node becomes entry `pos` of the attempt, everything behind it is cleared (one entry per lane)
 #pragma unroll 1
-    for (int q = pos + lane; q < L; q += FSD_LANES) S.attempt[q] = (int16_t)(q == pos ? node : -1);
+    for (int q = pos + lane; q < L; q += FSD_LANES) {
+      const int old = S.attempt[q];
+      if (old >= 0) S.flag[old] = 0;
+      S.attempt[q] = (int16_t)(q == pos ? node : -1);
+    }
+    wsync();
+    if (lane == 0) S.flag[node] = 1;
     wsync();
     // one candidate neighbour per lane; the admissible ones as a bit mask
     const int nnb = S.deg[sidx][node];
@@ -724,7 +726,7 @@ FSD_DEVFN int sort_one_side(SortSmem &S, int n, const FramePose &F, int side, co
     int R = reachable_count(S, n, sidx, fk[0], P.max_length);
     int L = R < P.max_length ? R : P.max_length;  // find_configs_and_scores.py:76
     if (L >= 3) {
-      int n_leaves = find_leaves(S, F, side, sidx, fk, nfk, L, P, &pops, status);
+      int n_leaves = find_leaves(S, n, F, side, sidx, fk, nfk, L, P, &pops, status);
       n_cfg = post_filter(S, n_leaves, side, fk, nfk);
       if (n_cfg > 0) {
         int arg = best_configuration(S, n, n_cfg, side, F);
@@ -755,20 +757,21 @@ FSD_DEV double angle_change_at(const SortSmem &S, const int16_t *cfg, int p) {
 
 FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
   const int16_t *left = S.best[0], *right = S.best[1];
-  int li = -1, ri = -1;
-  for (int a = 0; a < nl && li < 0; ++a)
-    for (int b = 0; b < nr; ++b)
-      if (left[a] == right[b]) {
-        li = a;
-        break;
-      }
-  if (li < 0) return;
-  for (int b = 0; b < nr && ri < 0; ++b)
-    for (int a = 0; a < nl; ++a)
-      if (left[a] == right[b]) {
-        ri = b;
-        break;
-      }
+  // first entry of each side that also appears in the other one (one entry per lane)
+  unsigned ml = 0, mr = 0;
+#pragma unroll 1
+  for (int base = 0; base < nl || base < nr; base += FSD_LANES) {
+    const int e = base + fsd_lane();
+    bool hl = false, hr = false;
+    if (e < nl)
+      for (int b = 0; b < nr; ++b) hl |= left[e] == right[b];
+    if (e < nr)
+      for (int a = 0; a < nl; ++a) hr |= right[e] == left[a];
+    ml |= wballot(hl) << base;
+    mr |= wballot(hr) << base;
+  }
+  if (!ml) return;
+  const int li = FSD_FFS(ml) - 1, ri = FSD_FFS(mr) - 1;
   int ls = -1, rs = -1;
   bool have = false;
   if (li > 0 && ri > 0) {
