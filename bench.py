@@ -198,18 +198,13 @@ def run_ours(args):
     h_li = torch.empty((B, 12), dtype=torch.int16).pin_memory()
     h_ri = torch.empty((B, 12), dtype=torch.int16).pin_memory()
     h_st = torch.empty((B,), dtype=torch.int32).pin_memory()
-    d_xy, d_ty, d_off, d_pos, d_dir = (torch.empty_like(t, device=dev) for t in (h_xy, h_ty, h_off, h_pos, h_dir))
 
     def e2e_step():
-        for d, h in ((d_xy, h_xy), (d_ty, h_ty), (d_off, h_off), (d_pos, h_pos), (d_dir, h_dir)):
-            d.copy_(h, non_blocking=True)
-        res = planner.plan(d_xy, d_ty, d_off, d_pos, d_dir)
-        h_path.copy_(res.path, non_blocking=True)
-        h_li.copy_(res.left_idx, non_blocking=True)
-        h_ri.copy_(res.right_idx, non_blocking=True)
-        h_st.copy_(res.status, non_blocking=True)
+        # the host-to-host entry point: per chunk H2D of the inputs, the planner launches, D2H of paths / sort indices /
+        # status, chunks on streams of their own (copies overlap kernels)
+        planner.plan_pinned(h_xy, h_ty, h_off, h_pos, h_dir, h_path, h_li, h_ri, h_st)
         if distributed:
-            all_gather_frames(res.path, n_global)
+            all_gather_frames(planner._pinned["path"], n_global)
 
     for _ in range(3):
         e2e_step()

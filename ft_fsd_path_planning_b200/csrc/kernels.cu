@@ -186,10 +186,18 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
       stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
       if (n >= 3) build_knn(C.S, n, P);
     }
-    if (WPC > 1 && FSD_SORT_BARRIERS >= 2) __syncthreads();
-    if (active) nl = sort_one_side(C.S, n, F, FSD_CONE_LEFT, P, dbg, &st);
-    if (WPC > 1 && FSD_SORT_BARRIERS >= 3) __syncthreads();
-    if (active) nr = sort_one_side(C.S, n, F, FSD_CONE_RIGHT, P, dbg, &st);
+    // each side in three stages (seeds / exhaustive search / filter + cost), a CTA barrier before every stage
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int side = pass == 0 ? FSD_CONE_LEFT : FSD_CONE_RIGHT;
+      SideSearch Q;
+      if (WPC > 1 && FSD_SORT_BARRIERS >= 2) __syncthreads();
+      if (active) side_seeds(C.S, n, F, side, P, Q);
+      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) __syncthreads();
+      if (active) side_search(C.S, n, F, side, P, Q, &st);
+      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) __syncthreads();
+      if (active) (side == FSD_CONE_LEFT ? nl : nr) = side_select(C.S, n, F, side, Q, dbg);
+    }
     if (WPC > 1 && FSD_SORT_BARRIERS >= 4) __syncthreads();
     if (active) {
       st |= sort_finish(C.S, nl, nr);

@@ -716,34 +716,61 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
 
 // ---- one side: core_trace_sorter.py:252-327 -----------------------------------------------------
 
-FSD_DEVFN int sort_one_side(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int16_t *dbg,
-                            unsigned *status) {
+// The side's search in three stages, so that the sort kernel can align the warps of a CTA between them (they then run
+// the same stage -- the same code -- at the same time).  `SideSearch` carries the state from stage to stage; every lane
+// holds an identical copy.
+struct SideSearch {
+  int fk[2], nfk, L, n_leaves, pops;
+};
+
+// stage 1: seeds and search depth
+FSD_DEVFN void side_seeds(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, SideSearch &Q) {
   const int sidx = side == FSD_CONE_LEFT ? 0 : 1;
-  int fk[2] = {-1, -1};
-  int len = 0, n_cfg = 0, pops = 0;
-  int nfk = n < 3 ? 0 : select_first_k(S, n, F, side, P, fk);
-  if (nfk > 0) {
-    int R = reachable_count(S, n, sidx, fk[0], P.max_length);
-    int L = R < P.max_length ? R : P.max_length;  // find_configs_and_scores.py:76
-    if (L >= 3) {
-      int n_leaves = find_leaves(S, n, F, side, sidx, fk, nfk, L, P, &pops, status);
-      n_cfg = post_filter(S, n_leaves, side, fk, nfk);
-      if (n_cfg > 0) {
-        int arg = best_configuration(S, n, n_cfg, side, F);
-        len = row_len(S.leaves[arg]);
-        if (fsd_lane() == 0)
-          for (int q = 0; q < FSD_MAX_SORTED; ++q) S.best[sidx][q] = S.leaves[arg][q];
-        wsync();
-      }
+  Q.fk[0] = Q.fk[1] = -1;
+  Q.L = Q.n_leaves = Q.pops = 0;
+  Q.nfk = n < 3 ? 0 : select_first_k(S, n, F, side, P, Q.fk);
+  if (Q.nfk > 0) {
+    const int R = reachable_count(S, n, sidx, Q.fk[0], P.max_length);
+    Q.L = R < P.max_length ? R : P.max_length;  // find_configs_and_scores.py:76
+  }
+}
+
+// stage 2: exhaustive search
+FSD_DEVFN void side_search(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, SideSearch &Q,
+                           unsigned *status) {
+  if (Q.nfk > 0 && Q.L >= 3)
+    Q.n_leaves = find_leaves(S, n, F, side, side == FSD_CONE_LEFT ? 0 : 1, Q.fk, Q.nfk, Q.L, P, &Q.pops, status);
+}
+
+// stage 3: filter, cost, the side's result in S.best; returns its length
+FSD_DEVFN int side_select(SortSmem &S, int n, const FramePose &F, int side, const SideSearch &Q, int16_t *dbg) {
+  const int sidx = side == FSD_CONE_LEFT ? 0 : 1;
+  int len = 0, n_cfg = 0;
+  if (Q.nfk > 0 && Q.L >= 3) {
+    n_cfg = post_filter(S, Q.n_leaves, side, Q.fk, Q.nfk);
+    if (n_cfg > 0) {
+      const int arg = best_configuration(S, n, n_cfg, side, F);
+      len = row_len(S.leaves[arg]);
+      if (fsd_lane() == 0)
+        for (int q = 0; q < FSD_MAX_SORTED; ++q) S.best[sidx][q] = S.leaves[arg][q];
+      wsync();
     }
   }
   if (dbg && fsd_lane() == 0) {
-    dbg[2 * sidx] = (int16_t)fk[0];
-    dbg[2 * sidx + 1] = (int16_t)(nfk > 1 ? fk[1] : -1);
+    dbg[2 * sidx] = (int16_t)Q.fk[0];
+    dbg[2 * sidx + 1] = (int16_t)(Q.nfk > 1 ? Q.fk[1] : -1);
     dbg[4 + sidx] = (int16_t)n_cfg;
-    dbg[6 + sidx] = (int16_t)(pops > 32767 ? 32767 : pops);
+    dbg[6 + sidx] = (int16_t)(Q.pops > 32767 ? 32767 : Q.pops);
   }
   return len;
+}
+
+FSD_DEVFN int sort_one_side(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int16_t *dbg,
+                            unsigned *status) {
+  SideSearch Q;
+  side_seeds(S, n, F, side, P, Q);
+  side_search(S, n, F, side, P, Q, status);
+  return side_select(S, n, F, side, Q, dbg);
 }
 
 // ---- left/right conflict: combine_traces.py:115-257 (lane 0) --------------------------------------

@@ -64,6 +64,8 @@ class BatchPlanner:
         self.mission = int(mission)
         self._bufs = {}
         self._prev0: Optional[torch.Tensor] = None
+        self._pinned_key = None
+        self._pinned: dict = {}
         self.kernel_events: list = []
 
     def _default_prev(self) -> torch.Tensor:
@@ -192,6 +194,79 @@ class BatchPlanner:
             xy = torch.zeros((1, 2), dtype=dt, device=dev)
             ty = torch.zeros((1,), dtype=torch.uint8, device=dev)
         return self.plan(xy, ty, off, pos, dr, force_P=fp, prev_path=pv, intermediates=intermediates)
+
+    def plan_pinned(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
+                    direction: torch.Tensor, out_path: torch.Tensor, out_left_idx: torch.Tensor,
+                    out_right_idx: torch.Tensor, out_status: torch.Tensor, *, chunks: Optional[int] = None) -> None:
+        """Host-to-host entry point: all arguments are PINNED host tensors (inputs as for `plan`, outputs
+        [B, 40, 4] float32 / [B, 12] int16 / [B, 12] int16 / [B] int32).  The batch is cut into `chunks` contiguous
+        chunks (default: one per ~2 500 frames, at most 4); each chunk's host->device copies, its planner launches
+        and its device->host copies are queued on a stream of its own, so the copies of one chunk overlap the
+        kernels of the others.  Asynchronous: the caller's current stream waits for all chunks (synchronize it
+        before reading the outputs)."""
+        B = offsets.numel() - 1
+        if B <= 0:
+            return
+        for t in (cones_xy, cones_type, offsets, pos, direction, out_path, out_left_idx, out_right_idx, out_status):
+            if t.device.type != "cpu" or not t.is_pinned() or not t.is_contiguous():
+                raise ValueError("plan_pinned takes contiguous pinned host tensors")
+        if cones_xy.dtype not in (torch.float32, torch.float64) or pos.dtype != cones_xy.dtype or \
+                direction.dtype != cones_xy.dtype or cones_type.dtype != torch.uint8 or offsets.dtype != torch.int32:
+            raise ValueError("inputs must have the dtypes documented for plan()")
+        if out_path.dtype != torch.float32 or out_left_idx.dtype != torch.int16 or out_right_idx.dtype != torch.int16 \
+                or out_status.dtype != torch.int32 or out_path.numel() != B * HORIZON * 4 \
+                or out_left_idx.numel() != B * MAX_SORTED or out_right_idx.numel() != B * MAX_SORTED \
+                or out_status.numel() != B:
+            raise ValueError("outputs must be [B,40,4] float32, [B,12] int16, [B,12] int16, [B] int32")
+        f64 = cones_xy.dtype == torch.float64
+        K = chunks if chunks is not None else max(1, min(4, B // 2500))
+        K = max(1, min(int(K), B))
+        dev = self.device
+        key = ("pinned", B, int(cones_xy.shape[0]), f64, K)
+        if self._pinned_key != key:
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            bounds = [B * k // K for k in range(K + 1)]
+            self._pinned = {
+                "xy": e((max(int(cones_xy.shape[0]), 1), 2), cones_xy.dtype), "ty": e((max(int(cones_xy.shape[0]), 1),), torch.uint8),
+                "off": e((B + 1,), torch.int32), "pos": e((B, 2), cones_xy.dtype), "dir": e((B, 2), cones_xy.dtype),
+                "path": e((B, HORIZON, 4), torch.float32), "li": e((B, MAX_SORTED), torch.int16),
+                "ri": e((B, MAX_SORTED), torch.int16), "st": e((B,), torch.int32), "bounds": bounds,
+                "ws": [e((int(self.lib.fsd_workspace_bytes(bounds[k + 1] - bounds[k], 0)),), torch.uint8) for k in range(K)],
+                "streams": [torch.cuda.Stream(dev) for _ in range(K)],
+            }
+            self._pinned_key = key
+        P = self._pinned
+        fn = self.lib.fsd_plan_batch_f64 if f64 else self.lib.fsd_plan_batch
+        esz = cones_xy.element_size()
+        off_host = offsets.numpy()
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            for k in range(K):
+                lo, hi = P["bounds"][k], P["bounds"][k + 1]
+                c0, c1 = int(off_host[lo]), int(off_host[hi])
+                st = P["streams"][k]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    if c1 > c0:
+                        P["xy"][c0:c1].copy_(cones_xy[c0:c1], non_blocking=True)
+                        P["ty"][c0:c1].copy_(cones_type[c0:c1], non_blocking=True)
+                    P["off"][lo:hi + 1].copy_(offsets[lo:hi + 1], non_blocking=True)
+                    P["pos"][lo:hi].copy_(pos[lo:hi], non_blocking=True)
+                    P["dir"][lo:hi].copy_(direction[lo:hi], non_blocking=True)
+                    # the CSR offsets are absolute: a chunk is the same arrays entered at frame `lo`
+                    rc = fn(C.byref(self.params), self.mission, hi - lo, P["xy"].data_ptr(), P["ty"].data_ptr(),
+                            P["off"].data_ptr() + 4 * lo, P["pos"].data_ptr() + 2 * esz * lo,
+                            P["dir"].data_ptr() + 2 * esz * lo, P["path"].data_ptr() + 4 * HORIZON * 4 * lo,
+                            P["li"].data_ptr() + 2 * MAX_SORTED * lo, P["ri"].data_ptr() + 2 * MAX_SORTED * lo, None,
+                            None, None, 0, P["st"].data_ptr() + 4 * lo, P["ws"][k].data_ptr(), P["ws"][k].numel(),
+                            st.cuda_stream)
+                    _lib.check(rc)
+                    out_path[lo:hi].copy_(P["path"][lo:hi], non_blocking=True)
+                    out_left_idx[lo:hi].copy_(P["li"][lo:hi], non_blocking=True)
+                    out_right_idx[lo:hi].copy_(P["ri"][lo:hi], non_blocking=True)
+                    out_status[lo:hi].copy_(P["st"][lo:hi], non_blocking=True)
+            for k in range(K):
+                cur.wait_stream(P["streams"][k])
 
     def initial_path(self) -> torch.Tensor:
         """The constant path of a fresh planner (core_calculate_path.py:103-107), computed on the device."""

@@ -184,6 +184,46 @@ def test_kernel_event_mode_equals_single_call(planner):
     assert np.array_equal(res.path.cpu().numpy(), a["path"]) and np.array_equal(res.status.cpu().numpy(), a["status"])
 
 
+def test_two_chunk_plan_equals_stage_entry_points(planner):
+    """fsd_plan_batch plans a large batch as two chunks on two streams (fsd_plan_launches == 4); the result must be
+    bit-identical to the unsplit stage entry points, and the call must stay ordered on the caller's stream."""
+    B = 6000
+    batch = synth.gen_mixed(42, B)
+    dev = planner.device
+    assert planner.lib.fsd_plan_launches(B) == 4 and planner.lib.fsd_plan_launches(256) == 2
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    args = (t(batch.cones_xy), t(batch.cones_type), t(batch.offsets), t(batch.pos), t(batch.dir))
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):  # a non-default caller stream; outputs are read on it right after the call
+        res = planner.plan(*args, intermediates=True)
+        a = {k: getattr(res, k).clone() for k in ("path", "left_idx", "right_idx", "status", "path_f64", "l2r", "r2l")}
+    side.synchronize()
+    res = planner.plan(*args, kernel_events=True)
+    torch.cuda.synchronize()
+    planner.kernel_times_ms()
+    for k, v in a.items():
+        assert torch.equal(v, getattr(res, k)), f"{k} differs between the chunked call and the stage entry points"
+
+
+def test_plan_pinned_equals_plan(planner):
+    """The pipelined host-to-host entry point (chunks on streams of their own) gives the same bytes as plan()."""
+    B = 7000
+    batch = synth.gen_autocross(43, B)
+    ref = _np(planner.plan_host(batch, intermediates=True))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(a) for a in (batch.cones_xy, batch.cones_type, batch.offsets, batch.pos, batch.dir)]
+    for chunks in (None, 1, 3):
+        out = [torch.zeros((B, 40, 4), dtype=torch.float32).pin_memory(), torch.zeros((B, 12), dtype=torch.int16).pin_memory(),
+               torch.zeros((B, 12), dtype=torch.int16).pin_memory(), torch.zeros((B,), dtype=torch.int32).pin_memory()]
+        planner.plan_pinned(*h, *out, chunks=chunks)
+        torch.cuda.synchronize()
+        assert np.array_equal(out[0].numpy(), ref["path"]) and np.array_equal(out[1].numpy(), ref["left_idx"])
+        assert np.array_equal(out[2].numpy(), ref["right_idx"]) and np.array_equal(out[3].numpy(), ref["status"])
+    with pytest.raises(ValueError):
+        planner.plan_pinned(torch.zeros((4, 2)), *h[1:], *out)  # not pinned
+
+
 def test_edge_cases(planner):
     """Empty batch, frames without cones, ragged frames, more than FSD_MAX_CONES cones."""
     z = np.zeros((0, 2))
