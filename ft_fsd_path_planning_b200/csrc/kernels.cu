@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
                 unsigned char *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_state[WPC];
+#ifdef FSD_ALIGN_SLACK
+  __shared__ volatile int s_prog[WPC];
+  int round = 0;
+  if (threadIdx.x < WPC) s_prog[threadIdx.x] = 0;
+  __syncthreads();
+#endif
   const int warp = threadIdx.x >> 5, lane = fsd_lane();
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * PATH_CTA_STRIDE);
   if (lane == 0) {
@@ -284,7 +290,26 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
       pm_begin_frame(S, M, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F,
                      force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out);
     }
-#ifdef FSD_NO_LOCKSTEP
+#if defined(FSD_ALIGN_SLACK)
+    // Elastic lockstep (A/B): no CTA barrier; a warp that reaches an alignment state publishes its progress and waits
+    // there only while more than FSD_ALIGN_SLACK warps of the CTA are behind it
+    for (;;) {
+      while (M.state != PS_DONE && !pm_is_alignment_state(M.state)) pm_step(S, M, P);
+      const int my = M.state == PS_DONE ? round * 256 + 255 : round * 256 + M.state;
+      if (lane == 0) s_prog[warp] = my;
+      __syncwarp();
+      if (M.state == PS_DONE) break;
+      for (;;) {
+        int behind = 0;
+#pragma unroll
+        for (int w = 0; w < WPC; ++w) behind += s_prog[w] < my;
+        if (behind <= FSD_ALIGN_SLACK) break;
+        __nanosleep(200);
+      }
+      pm_step(S, M, P);
+    }
+    ++round;
+#elif defined(FSD_NO_LOCKSTEP)
     while (M.state != PS_DONE) pm_step(S, M, P);  // A/B only: free-running warps
     __syncthreads();
 #else
@@ -317,6 +342,9 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
       }
     }
   }
+#ifdef FSD_ALIGN_SLACK
+  if (lane == 0) s_prog[warp] = 0x7fffffff;  // retired: nobody waits for this warp any more
+#endif
 }
 
 __global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *out) {

@@ -43,6 +43,7 @@ FSD_DEVFN void hyper_from_moments(double mx, double my, double Mxx, double Myy, 
   const double A0 = Mxz * (Mxz * Myy - Myz * Mxy) + Myz * (Myz * Mxx - Mxz * Mxy) - Var_z * Cov_xy;
   const double A22 = A2 + A2;
   double y = A0, x = 0.0;
+#pragma unroll 1
   for (int it = 0; it < 99; ++it) {
     double Dy = A1 + x * (A22 + 16.0 * x * x);
     double xn = x - fdiv(y, Dy);
@@ -63,6 +64,7 @@ FSD_DEVFN void hyper_from_moments(double mx, double my, double Mxx, double Myy, 
 // one lane fits one window (curvature)
 FSD_DEVFN double circle_radius_serial(const d2 *p, int n) {
   double mx = 0.0, my = 0.0;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     mx += p[i].x;
     my += p[i].y;
@@ -71,6 +73,7 @@ FSD_DEVFN double circle_radius_serial(const d2 *p, int n) {
   mx *= inv_n;
   my *= inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     double xi = p[i].x - mx, yi = p[i].y - my, zi = xi * xi + yi * yi;
     Mxy += xi * yi;
@@ -126,6 +129,7 @@ FSD_DEVFN void chord_params(const d2 *p, int m, double *u) {
   const int lane = fsd_lane();
   double carry = 0.0;
   if (lane == 0) u[0] = 0.0;
+#pragma unroll 1
   for (int base = 1; base < m; base += FSD_LANES) {
     const int i = base + lane;
     double d = 0.0;
@@ -408,6 +412,7 @@ FSD_DEVFN void pm_stage_after_fit2(PathSmem &S, PathMachine &M, const DevParams 
   }
   int first_over = nfix;
   double carry = 0.0;
+#pragma unroll 1
   for (int base = 0; base < nfix - 1; base += FSD_LANES) {
     const int i = base + lane;
     double d = 0.0;
@@ -485,6 +490,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   for (int j = lane; j < FSD_HORIZON; j += FSD_LANES) {
     const int idx = j == FSD_HORIZON - 1 ? Pn - 1 : (int)floor((double)j * stp);
     double acc = 0.0;
+#pragma unroll 1
     for (int q = idx - fs / 2; q <= idx + fs - fs / 2 - 1; ++q) {
       const int qq = q < 0 ? 0 : (q > Pn - 1 ? Pn - 1 : q);
       acc += S.curv[qq];
@@ -609,11 +615,13 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
     if (lane == 0) {
       // select_side_to_use :165-183: max over (number of matches, sum of match indices), ties -> left
       int nml = 0, nmr = 0, sl = 0, sr = 0;
+#pragma unroll 1
       for (int i = 0; i < nl; ++i)
         if (l2r[i] != -1) {
           ++nml;
           sl += l2r[i];
         }
+#pragma unroll 1
       for (int i = 0; i < nr; ++i)
         if (r2l[i] != -1) {
           ++nmr;
@@ -625,6 +633,7 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
       const int ns = use_left ? nl : nr;
       int nc = 0;
       // calculate_centerline_points_of_matches :185-205
+#pragma unroll 1
       for (int i = 0; i < ns; ++i)
         if (mt[i] != -1 && nc < FSD_HORIZON) {
           S.centre[nc].x = (a[i].x + b[mt[i]].x) / 2.0;
@@ -672,6 +681,7 @@ FSD_DEVFN void pm_begin_initial(PathSmem &S, PathMachine &M, const DevParams &P,
 }
 
 FSD_DEVFN void pm_run(PathSmem &S, PathMachine &M, const DevParams &P) {
+#pragma unroll 1
   while (M.state != PS_DONE) pm_step(S, M, P);
 }
 

@@ -97,9 +97,12 @@ FSD_DEVFN void bspl_low(const SplineWork &W, int k, double x, int ii, double *h)
   const double *rk = W.rk[ii];
   double hh[4];
   h[0] = 1.0;
+#pragma unroll 1
   for (int j = 1; j <= k; ++j) {
+#pragma unroll 1
     for (int i = 0; i < j; ++i) hh[i] = h[i];
     h[0] = 0.0;
+#pragma unroll 1
     for (int i = 1; i <= j; ++i) {
       const double f = hh[i - 1] * rk[(j * (j - 1)) / 2 + i - 1];
       h[i - 1] += f * (W.t[l + i] - x);
@@ -119,6 +122,7 @@ FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &o
   // splev with ext=0: the end polynomial pieces extrapolate
   const int k = W.k, nk1 = W.n - k - 1;
   int l = k;
+#pragma unroll 1
   while (l < nk1 - 1 && x >= W.t[l + 1]) ++l;
   double h[4] = {0, 0, 0, 0};
   bspl(W, k, x, l - k, h);
@@ -138,6 +142,7 @@ FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &o
 FSD_DEV void chol_task(int e, int kbm, int npairs, int &ta, int &tb) {
   if (e < npairs) {
     int a = 1, rem = e;
+#pragma unroll 1
     while (rem >= kbm - a + 1) {
       rem -= kbm - a + 1;
       ++a;
@@ -188,10 +193,12 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
   }
 #else
   wsync();
+#pragma unroll 1
   for (int i = 0; i < nk1; ++i) {
     const double s = M[i][0];
     if (!(s > 0.0)) return false;
     const double rs = frcp(s);
+#pragma unroll 1
     for (int e = 0; e < ntasks; ++e) {
       int ta, tb;
       chol_task(e, kbm, npairs, ta, tb);
@@ -229,6 +236,7 @@ FSD_DEVFN void interval_starts(SplineWork &W, int m, int n, int k) {
   if (fsd_lane() == 0) {
     int s = 0;
     W.start[0] = 0;
+#pragma unroll 1
     for (int ii = 0; ii + 1 < nrint; ++ii) {
       s += W.nrdata[ii] + 1;
       W.start[ii + 1] = s;
@@ -255,6 +263,7 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
     const int e = lane >> 1;
     if (e < 10) {
       int a = 0, rem = e;
+#pragma unroll 1
       while (rem >= 4 - a) {
         rem -= 4 - a;
         ++a;
@@ -385,6 +394,7 @@ FSD_DEVFN double smoothing_excess(SplineWork &W, int nk1, int k) {
   for (int i = lane; i < nk1; i += FSD_LANES) {
     const double dx = W.z[i][0], dy = W.z[i][1];
     double ax = W.N[i][0] * dx, ay = W.N[i][0] * dy;
+#pragma unroll 1
     for (int d = 1; d <= k; ++d)
       if (i + d < nk1) {
         const double w2 = W.N[i][d] + W.N[i][d];
@@ -402,6 +412,7 @@ FSD_DEVFN void add_knot(SplineWork &W, const double *u, int n, int nrint) {
   const int k = (n - nrint - 1) / 2;
   double fpmax = 0.0;
   int jbegin = 1, number = 1, maxpt = 0, maxbeg = 1;
+#pragma unroll 1
   for (int j = 1; j <= nrint; ++j) {
     int jpoint = W.nrdata[j - 1];
     if (!(fpmax >= W.fpint[j - 1] || jpoint == 0)) {
@@ -413,6 +424,7 @@ FSD_DEVFN void add_knot(SplineWork &W, const double *u, int n, int nrint) {
     jbegin += jpoint + 1;
   }
   const int ihalf = maxpt / 2 + 1, nrx = maxbeg + ihalf, next = number + 1;
+#pragma unroll 1
   for (int j = nrint; j >= next; --j) {
     W.fpint[j] = W.fpint[j - 1];
     W.nrdata[j] = W.nrdata[j - 1];
@@ -434,14 +446,17 @@ FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
   for (int l = k2 + fsd_lane(); l <= nk1; l += FSD_LANES) {  // 1-based row index of FITPACK
     const int lmk = l - k1;
     double h[10];
+#pragma unroll 1
     for (int j = 1; j <= k1; ++j) {
       h[j - 1] = W.t[l - 1] - W.t[l + j - k2 - 1];
       h[j + k1 - 1] = W.t[l - 1] - W.t[l + j - 1];
     }
     int lp = lmk;
+#pragma unroll 1
     for (int j = 1; j <= k2; ++j) {
       int jk = j;
       double prod = h[j - 1];
+#pragma unroll 1
       for (int i = 1; i <= k; ++i) {
         ++jk;
         prod = prod * h[jk - 1] * fac;
@@ -585,6 +600,7 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
   }
   F.fpold = F.fp;
   wsync();
+#pragma unroll 1
   for (int l = 1; l <= F.nplus; ++l) {
     if (lane == 0) add_knot(W, u, n, nrint);
     ++n;
@@ -594,6 +610,7 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
       if (lane == 0) {
         const int k3 = k / 2;
         int i = k2, j = k3 + 2;
+#pragma unroll 1
         for (int l2 = 0; l2 < m - k1; ++l2) {
           W.t[i - 1] = (k3 * 2 != k) ? u[j - 1] : (u[j - 1] + u[j - 2]) * 0.5;
           ++i;
@@ -602,6 +619,7 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
         // data points strictly inside each interval of the interpolating knot set (k is odd here): the first
         // interior knot is data point k3 + 1 (0-based), consecutive knots are consecutive data points
         const int nint = m - k1 + 1;
+#pragma unroll 1
         for (int q = 0; q < nint; ++q) W.nrdata[q] = 0;
         W.nrdata[0] = k3;
         W.nrdata[nint - 1] = m - 1 - (k3 + 1 + (m - k1 - 1)) - 1;
@@ -622,8 +640,10 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   disc_jumps(W, n, k);
   const int n8 = n - nmin;
   if (lane == 0) {
+#pragma unroll 1
     for (int i = 0; i < nk1; ++i)
       for (int d = 0; d < BW; ++d) W.DtD[i][d] = 0.0;
+#pragma unroll 1
     for (int r = 0; r < n8; ++r)
       for (int a = 0; a < k2 && r + a < nk1; ++a)
         for (int b = a; b < k2 && r + b < nk1; ++b) W.DtD[r + a][b - a] += W.bd[r][a] * W.bd[r][b];
@@ -642,6 +662,7 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   for (int i = lane; i < nk1; i += FSD_LANES) W.z[i][0] = fsqrt(W.G[i][0]);
   wsync();
   double p = 0.0;
+#pragma unroll 1
   for (int i = 0; i < nk1; ++i) p += W.z[i][0];
   F.p = fdiv((double)nk1, p);
   F.ich1 = F.ich3 = 0;
@@ -732,6 +753,7 @@ FSD_DEVFN void fit_step(SplineWork &W, FitState &F, unsigned *status) {
 FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, double s, unsigned *status) {
   FitState F;
   fit_init(W, F, pts, u, m, s);
+#pragma unroll 1
   while (F.phase != FIT_DONE) fit_step(W, F, status);
   return F.ier;
 }
