@@ -29,7 +29,6 @@ struct PathSmem {
   SplineWork W;
   d2 centre[FSD_HORIZON];
   d2 prev_xy[FSD_HORIZON];
-  double curv[GRID_CAP];
   int32_t si[4];
 };
 
@@ -467,7 +466,10 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
     S.pts[i].y = y;
   }
   wsync();
-  // _calculate_path_curvature :163-193 / calculate_path_curvature :49-93 (open path)
+  // _calculate_path_curvature :163-193 / calculate_path_curvature :49-93 (open path).  The curvature samples live in the
+  // fit's normal-equation storage: the fits are over, only knots and coefficients of the last one are still needed.
+  static_assert(sizeof(S.W.N) >= GRID_CAP * sizeof(double), "curvature samples alias SplineWork::N");
+  double *curv = &S.W.N[0][0];
   int window = Pn / 5 < 30 ? Pn / 5 : 30;
   if (window % 2 == 0) window += 1;
   const int hw = window / 2;
@@ -479,7 +481,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
     double r = circle_radius_serial(S.pts + lo, cnt);
     r = fmin(fmax(r, 1.0), 3000.0);
     const double sg = sgn(orient(S.pts[lo], S.pts[lo + cnt / 2], S.pts[hi]));
-    S.curv[i] = fdiv(1.0, r) * sg;
+    curv[i] = fdiv(1.0, r) * sg;
   }
   wsync();
   // uniform_filter1d(size, mode="nearest") evaluated at the 40 sampled indices only;
@@ -493,7 +495,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
 #pragma unroll 1
     for (int q = idx - fs / 2; q <= idx + fs - fs / 2 - 1; ++q) {
       const int qq = q < 0 ? 0 : (q > Pn - 1 ? Pn - 1 : q);
-      acc += S.curv[qq];
+      acc += curv[qq];
     }
     M.out[4 * j + 0] = (double)idx * predict_every;
     M.out[4 * j + 1] = S.pts[idx].x;

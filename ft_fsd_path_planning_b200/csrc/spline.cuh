@@ -32,9 +32,11 @@ constexpr int BW = 5;     // k + 2 for cubic splines
 struct SplineWork {
   double t[NCAP];
   double N[NCAP][BW];
-  double G[NCAP][BW];
+  union {
+    double G[NCAP][BW];   // banded system being solved (factorised in place)
+    double bd[NCAP][BW];  // discontinuity jumps: dead once D^T D is built, before the first smoothing solve
+  };
   double DtD[NCAP][BW];
-  double bd[NCAP][BW];
   double rhs[NCAP][2];
   double z[NCAP][2];
   double c[NCAP][2];
@@ -637,16 +639,30 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
 FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   const int lane = fsd_lane();
   const int k = F.k, k2 = k + 2, nmin = 2 * (k + 1), n = F.n, nk1 = F.nk1;
+  // p0 = nk1 / trace of the Cholesky factor of N (chol_solve leaves the pivots d_i = G_ii^2 on the diagonal); read
+  // before the jump matrix overwrites G (they share storage)
+#pragma unroll 1
+  for (int i = lane; i < nk1; i += FSD_LANES) W.z[i][0] = fsqrt(W.G[i][0]);
+  wsync();
+  double p = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < nk1; ++i) p += W.z[i][0];
+  F.p = fdiv((double)nk1, p);
+  wsync();
   disc_jumps(W, n, k);
+  // D^T D, one band entry per lane: (D^T D)[i][i+d] = sum over the jump rows r = i - a of bd[r][a] bd[r][a+d]
   const int n8 = n - nmin;
-  if (lane == 0) {
 #pragma unroll 1
-    for (int i = 0; i < nk1; ++i)
-      for (int d = 0; d < BW; ++d) W.DtD[i][d] = 0.0;
+  for (int e = lane; e < nk1 * BW; e += FSD_LANES) {
+    const int i = e / BW, d = e % BW;
+    double acc = 0.0;
+    if (i + d < nk1)
 #pragma unroll 1
-    for (int r = 0; r < n8; ++r)
-      for (int a = 0; a < k2 && r + a < nk1; ++a)
-        for (int b = a; b < k2 && r + b < nk1; ++b) W.DtD[r + a][b - a] += W.bd[r][a] * W.bd[r][b];
+      for (int a = k2 - 1 - d; a >= 0; --a) {  // ascending r
+        const int r = i - a;
+        if (r >= 0 && r < n8) acc += W.bd[r][a] * W.bd[r][a + d];
+      }
+    W.DtD[i][d] = acc;
   }
   wsync();
   F.p1 = 0.0;
@@ -657,14 +673,6 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   F.fp_ls = F.fp;
 #pragma unroll 1
   for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.c0[0][0])[e] = (&W.c[0][0])[e];
-  // p0 = nk1 / trace of the Cholesky factor of N (chol_solve leaves the pivots d_i = G_ii^2 on the diagonal)
-#pragma unroll 1
-  for (int i = lane; i < nk1; i += FSD_LANES) W.z[i][0] = fsqrt(W.G[i][0]);
-  wsync();
-  double p = 0.0;
-#pragma unroll 1
-  for (int i = 0; i < nk1; ++i) p += W.z[i][0];
-  F.p = fdiv((double)nk1, p);
   F.ich1 = F.ich3 = 0;
   F.iter = 0;
   F.phase = FIT_SMOOTH;
