@@ -34,8 +34,7 @@ struct SortSmem {
   union {
     alignas(16) float raw[2 * (FSD_MAX_CONES + 2)];
     struct {
-      uint8_t knn[2][FSD_MAX_CONES][5];
-      uint8_t kcnt[2][FSD_MAX_CONES];
+      uint8_t knn[2][FSD_MAX_CONES][5];  // unused slots hold the row's own index
     };
     struct {
       int16_t idxs[FSD_MAX_CONES];   // cone indices used by any configuration (cost term) / BFS queue
@@ -129,8 +128,6 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
       S.knn[0][i][q] = (uint8_t)(q < K.cnt[0] ? K.id[0][q] : i);
       S.knn[1][i][q] = (uint8_t)(q < K.cnt[1] ? K.id[1][q] : i);
     }
-    S.kcnt[0][i] = (uint8_t)K.cnt[0];
-    S.kcnt[1][i] = (uint8_t)K.cnt[1];
   }
   wsync();
   // keep edges present in both directions (:110); neighbour lists in ascending index order, the
@@ -141,10 +138,10 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
     for (int s = 0; s < 2; ++s) {
       int cnt = 0;
       int tmp[5];
-      const int kc = S.kcnt[s][i];
 #pragma unroll 1
-      for (int q = 0; q < kc; ++q) {
+      for (int q = 0; q < 5; ++q) {
         const int j = S.knn[s][i][q];
+        if (j == i) break;  // end of the list
         const uint8_t *kj = S.knn[s][j];
         const bool back = (kj[0] == i) | (kj[1] == i) | (kj[2] == i) | (kj[3] == i) | (kj[4] == i);
         if (back) {
