@@ -61,32 +61,41 @@ struct SortSmem {
 // ---- k-NN graph: adjacency_matrix.py:60-110 ------------------------------------------------
 // Both sides in one sweep: the LEFT graph ignores yellow cones, the RIGHT graph ignores blue.
 
-// sorted insertion into a k-nearest list (ascending distance; ties keep the earlier, i.e. lower, index first)
-FSD_DEV void knn_insert(double *d, int *id, int *cnt, int k, double v, int j) {
-  int c = *cnt;
-  if (c == k && !(v < d[k - 1])) return;
-  int p = c < k ? c : k - 1;
-  while (p > 0 && v < d[p - 1]) {
-    d[p] = d[p - 1];
-    id[p] = id[p - 1];
-    --p;
-  }
-  d[p] = v;
-  id[p] = j;
-  if (c < k) *cnt = c + 1;
-}
-
-struct KnnLists {
-  double d[2][5];
-  int id[2][5];
-  int cnt[2];
+// The k <= 5 nearest neighbours of one cone for one side, ascending distance, held in registers (no indexing by a
+// run-time value, so nothing lands in local memory).  Empty slots hold +inf.
+struct KnnList {
+  double d0, d1, d2, d3, d4;
+  int i0, i1, i2, i3, i4;
 };
 
-// cone j lies within max_dist of the row's cone: offer it to the row's LEFT and RIGHT lists.  Rare (a handful of the
-// frame's cones per row) and deliberately out of line, so that the distance sweep below stays a tight loop.
-FSD_DEVFN void knn_consider(KnnLists &K, int k, bool li, bool ri, int tj, double dd, int j) {
-  if (li && tj != FSD_CONE_RIGHT) knn_insert(K.d[0], K.id[0], &K.cnt[0], k, dd, j);
-  if (ri && tj != FSD_CONE_LEFT) knn_insert(K.d[1], K.id[1], &K.cnt[1], k, dd, j);
+FSD_DEV void knn_clear(KnnList &L) {
+  L.d0 = L.d1 = L.d2 = L.d3 = L.d4 = INFINITY;
+  L.i0 = L.i1 = L.i2 = L.i3 = L.i4 = -1;
+}
+
+// insert (v, j); ties keep the earlier, i.e. lower, index first (candidates arrive in ascending j)
+FSD_DEV void knn_insert(KnnList &L, double v, int j) {
+  if (!(v < L.d4)) return;
+  const bool c3 = v < L.d3, c2 = v < L.d2, c1 = v < L.d1, c0 = v < L.d0;
+  L.d4 = c3 ? L.d3 : v;
+  L.i4 = c3 ? L.i3 : j;
+  L.d3 = c3 ? (c2 ? L.d2 : v) : L.d3;
+  L.i3 = c3 ? (c2 ? L.i2 : j) : L.i3;
+  L.d2 = c2 ? (c1 ? L.d1 : v) : L.d2;
+  L.i2 = c2 ? (c1 ? L.i1 : j) : L.i2;
+  L.d1 = c1 ? (c0 ? L.d0 : v) : L.d1;
+  L.i1 = c1 ? (c0 ? L.i0 : j) : L.i1;
+  L.d0 = c0 ? v : L.d0;
+  L.i0 = c0 ? j : L.i0;
+}
+
+// the first k entries of the list (fewer when the list is shorter); unused slots get the row's own index
+FSD_DEV void knn_store(const KnnList &L, int k, int own, uint8_t *out) {
+  out[0] = (uint8_t)(k > 0 && L.i0 >= 0 ? L.i0 : own);
+  out[1] = (uint8_t)(k > 1 && L.i1 >= 0 ? L.i1 : own);
+  out[2] = (uint8_t)(k > 2 && L.i2 >= 0 ? L.i2 : own);
+  out[3] = (uint8_t)(k > 3 && L.i3 >= 0 ? L.i3 : own);
+  out[4] = (uint8_t)(k > 4 && L.i4 >= 0 ? L.i4 : own);
 }
 
 FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
@@ -94,8 +103,9 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
   if (k > 5) k = 5;
 #pragma unroll 1
   for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-    KnnLists K;
-    K.cnt[0] = K.cnt[1] = 0;
+    KnnList KL, KR;
+    knn_clear(KL);
+    knn_clear(KR);
     const double xi = S.xy[i].x, yi = S.xy[i].y;
     const int ti = S.type[i];
     const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
@@ -119,15 +129,15 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
         mask &= mask - 1;
         const int j = j0 + jj;
         const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
-        knn_consider(K, k, li, ri, S.type[j], ddx * ddx + ddy * ddy, j);
+        const double dd = ddx * ddx + ddy * ddy;
+        const int tj = S.type[j];
+        if (li && tj != FSD_CONE_RIGHT) knn_insert(KL, dd, j);
+        if (ri && tj != FSD_CONE_LEFT) knn_insert(KR, dd, j);
       }
     }
     // unused slots hold the row's own index: a cone is never its own neighbour, so they match nothing below
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      S.knn[0][i][q] = (uint8_t)(q < K.cnt[0] ? K.id[0][q] : i);
-      S.knn[1][i][q] = (uint8_t)(q < K.cnt[1] ? K.id[1][q] : i);
-    }
+    knn_store(KL, k, i, S.knn[0][i]);
+    knn_store(KR, k, i, S.knn[1][i]);
   }
   wsync();
   // keep edges present in both directions (:110); neighbour lists in ascending index order, the
@@ -137,7 +147,7 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
       int cnt = 0;
-      int tmp[5];
+      int t0 = 256, t1 = 256, t2 = 256, t3 = 256, t4 = 256;  // ascending, 256 = empty
 #pragma unroll 1
       for (int q = 0; q < 5; ++q) {
         const int j = S.knn[s][i][q];
@@ -145,15 +155,21 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
         const uint8_t *kj = S.knn[s][j];
         const bool back = (kj[0] == i) | (kj[1] == i) | (kj[2] == i) | (kj[3] == i) | (kj[4] == i);
         if (back) {
-          int p = cnt++;
-          while (p > 0 && tmp[p - 1] > j) {
-            tmp[p] = tmp[p - 1];
-            --p;
-          }
-          tmp[p] = j;
+          ++cnt;
+          const bool c3 = j < t3, c2 = j < t2, c1 = j < t1, c0 = j < t0;
+          t4 = c3 ? t3 : j;
+          t3 = c3 ? (c2 ? t2 : j) : t3;
+          t2 = c2 ? (c1 ? t1 : j) : t2;
+          t1 = c1 ? (c0 ? t0 : j) : t1;
+          t0 = c0 ? j : t0;
         }
       }
-      for (int q = 0; q < cnt; ++q) S.nbr[s][i][q] = (uint8_t)tmp[q];
+      uint8_t *ni = S.nbr[s][i];
+      ni[0] = (uint8_t)t0;
+      ni[1] = (uint8_t)t1;
+      ni[2] = (uint8_t)t2;
+      ni[3] = (uint8_t)t3;
+      ni[4] = (uint8_t)t4;
       S.deg[s][i] = (uint8_t)cnt;
     }
   }
