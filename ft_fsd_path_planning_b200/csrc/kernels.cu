@@ -94,6 +94,12 @@ struct SortCta {
 };
 constexpr size_t SORT_CTA_STRIDE = (sizeof(SortCta) + 15) / 16 * 16;
 constexpr size_t PATH_CTA_STRIDE = (sizeof(PathSmem) + 15) / 16 * 16;
+constexpr size_t PATH_MACHINE_STRIDE = (sizeof(PathMachine) + 15) / 16 * 16;
+#ifdef FSD_MACHINE_IN_SMEM
+constexpr size_t PATH_KERNEL_SMEM = WPC * (PATH_CTA_STRIDE + PATH_MACHINE_STRIDE);
+#else
+constexpr size_t PATH_KERNEL_SMEM = WPC * PATH_CTA_STRIDE;
+#endif
 
 // Stage the frame's coordinates into S.xy (fp64).  The 16-byte aligned interior of the frame's slice goes
 // through the TMA bulk copy; a leading / trailing cone that is not 16-byte aligned (fp32 input, odd offset)
@@ -276,7 +282,14 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
   for (int base = (int)blockIdx.x * WPC; base < n_frames; base += (int)gridDim.x * WPC) {
     const int b = base + warp;
     const bool active = b < n_frames;
+#ifdef FSD_MACHINE_IN_SMEM
+    // one copy of the machine state per warp in shared memory (every lane reads it, every lane writes the same values)
+    // instead of 32 identical per-lane copies in local memory
+    PathMachine &M = *reinterpret_cast<PathMachine *>(smem_raw + (size_t)WPC * PATH_CTA_STRIDE + (size_t)warp * PATH_MACHINE_STRIDE);
+    __syncwarp();
+#else
     PathMachine M;
+#endif
     M.state = PS_DONE;
     M.status = 0;
     M.P_grid = M.n_trim = 0;
@@ -513,11 +526,11 @@ int device_info(DeviceInfo **out) {
     int a = 0, b = 0;
     cudaFuncSetAttribute(sort_match_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
     cudaFuncSetAttribute(sort_match_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
-    cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
-    cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
+    cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
+    cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(skid_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, WPC * PATH_CTA_STRIDE);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
     D.sort_ctas = a > 0 ? a : 1;
     D.path_ctas = b > 0 ? b : 1;
@@ -685,7 +698,7 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   }
   StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r, inter->r2l, out_status};
-  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
+  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), CTA_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch);
   return check_launch();
 }

@@ -114,10 +114,17 @@ FSD_DEVFN void bspl_low(const SplineWork &W, int k, double x, int ii, double *h)
 }
 
 FSD_DEV void bspl(const SplineWork &W, int k, double x, int ii, double (&h)[4]) {
-  if (k == 3)
+  if (k == 3) {
     bspl_k<3>(W, x, ii, h);
-  else
-    bspl_low(W, k, x, ii, h);
+  } else {
+    // the out-of-line version gets a buffer of its own: handing it `h` would pin the caller's h to local memory
+    double low[4] = {0, 0, 0, 0};
+    bspl_low(W, k, x, ii, low);
+    h[0] = low[0];
+    h[1] = low[1];
+    h[2] = low[2];
+    h[3] = low[3];
+  }
 }
 
 FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &oy) {
