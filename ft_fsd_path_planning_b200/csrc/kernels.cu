@@ -51,6 +51,22 @@ constexpr int CTAS_PER_SM = 16 / WPC;
       continue;                                                                                              \
     else
 
+// Alignment group: the warps of a CTA that wait for each other at the phase boundaries.  Default: the whole CTA.
+// Smaller groups (A/B knob) keep the warps that share an SM sub-partition together: warp w sits on sub-partition w % 4,
+// so a group is the set of warps with the same index modulo WPC / FSD_ALIGN_GROUP.
+#ifndef FSD_ALIGN_GROUP
+#define FSD_ALIGN_GROUP FSD_WARPS_PER_CTA
+#endif
+constexpr int AG = FSD_ALIGN_GROUP;
+__device__ __forceinline__ void group_sync() {
+  if (AG == WPC) {
+    __syncthreads();
+  } else {
+    const unsigned id = 1u + ((threadIdx.x >> 5) % (WPC / AG));
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(AG * 32) : "memory");
+  }
+}
+
 // ---- TMA bulk copy helpers (raw PTX) ------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,7 +194,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     unsigned st = 0;
     FramePose F = make_pose(0.0, 0.0, 1.0, 0.0);
     int16_t *dbg = nullptr;
-    if (WPC > 1 && FSD_SORT_BARRIERS >= 1) __syncthreads();
+    if (WPC > 1 && FSD_SORT_BARRIERS >= 1) group_sync();
     if (active) {
       const int lo = offsets[b];
       n = offsets[b + 1] - lo;
@@ -197,14 +213,14 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     for (int pass = 0; pass < 2; ++pass) {
       const int side = pass == 0 ? FSD_CONE_LEFT : FSD_CONE_RIGHT;
       SideSearch Q;
-      if (WPC > 1 && FSD_SORT_BARRIERS >= 2) __syncthreads();
+      if (WPC > 1 && FSD_SORT_BARRIERS >= 2) group_sync();
       if (active) side_seeds(C.S, n, F, side, P, Q);
-      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) __syncthreads();
+      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
       if (active) side_search(C.S, n, F, side, P, Q, &st);
-      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) __syncthreads();
+      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
       if (active) (side == FSD_CONE_LEFT ? nl : nr) = side_select(C.S, n, F, side, Q, dbg);
     }
-    if (WPC > 1 && FSD_SORT_BARRIERS >= 4) __syncthreads();
+    if (WPC > 1 && FSD_SORT_BARRIERS >= 4) group_sync();
     if (active) {
       st |= sort_finish(C.S, nl, nr);
       store_sort(C.S, b, O);
@@ -333,11 +349,11 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
       while (M.state != PS_DONE && !pm_is_alignment_state(M.state)) pm_step(S, M, P);
 #endif
       if (lane == 0) s_state[warp] = M.state;
-      __syncthreads();
+      group_sync();
       int behind = PS_DONE;
 #pragma unroll
-      for (int w = 0; w < WPC; ++w) behind = min(behind, s_state[w]);
-      __syncthreads();
+      for (int w = warp % (WPC / AG); w < WPC; w += WPC / AG) behind = min(behind, s_state[w]);
+      group_sync();
       if (behind == PS_DONE) break;
       if (M.state != PS_DONE && !(pm_is_alignment_state(M.state) && behind < M.state)) pm_step(S, M, P);
     }
