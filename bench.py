@@ -244,12 +244,21 @@ def run_ours(args):
         alg_bytes = batch.algorithmic_bytes()  # per launch of this rank's shard: 9 B/cone + 708 B/frame
         dom_ms, dom_name = (path_ms, "path_kernel") if path_ms >= sort_ms else (sort_ms, "sort_match_kernel")
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and world == 1:
+        if os.path.exists(tpath):
             t = json.load(open(tpath)).get(dom_name)
             if t:
                 traffic = t["read_bytes"] + t["write_bytes"]  # per launch, from the committed ncu --set full capture
+                if "warp_inst" in t:
+                    # what actually bounds the kernel: warp instructions issued per SM cycle (4 schedulers per SM).
+                    # Instruction count from the committed ncu capture of the same launch, time measured live here.
+                    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                    ipc = t["warp_inst"] / (dom_ms * 1e-3 * sm_clock * n_sm)
+                    issue = {"warp_inst_per_launch": t["warp_inst"], "warp_inst_per_frame": t["warp_inst"] / B,
+                             "achieved_ipc_per_sm": ipc, "peak_ipc_per_sm": 4.0, "frac": ipc / 4.0,
+                             "source": "profiles/ncu_traffic.json (ncu inst_executed) / live kernel time"}
         cpu_threads = os.cpu_count() or 1
         cpu_value, cpu_dt = cpu_oracle_throughput(batch, cpu_threads, passes=2)
         out = {
@@ -261,7 +270,7 @@ def run_ours(args):
                        "parallelism": f"frames block-sharded over {world} GPU(s), one NCCL all-gather of the paths per step"
                        if distributed else "single GPU", "frames_flagged_overflow_or_unsupported": flagged},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms,
+                         "traffic": traffic, "issue": issue, "kernel": dom_name, "kernel_ms": dom_ms,
                          "other_kernel_ms": sort_ms if dom_name == "path_kernel" else path_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "note": "latency/issue-bound integer+fp64 work: the HBM fraction is reported as required, "

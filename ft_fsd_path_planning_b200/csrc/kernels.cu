@@ -374,6 +374,17 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
 #ifdef FSD_ALIGN_SLACK
   if (lane == 0) s_prog[warp] = 0x7fffffff;  // retired: nobody waits for this warp any more
 #endif
+  // The point buffers are dead now: drop their lines from L2 instead of letting the dirty data be written back to HBM
+  // (scratch traffic was 5x the algorithmic bytes of the whole step).  discard.L2 works on whole 128-byte lines; the
+  // buffers are 256-byte aligned and a multiple of 128 bytes long.
+  {
+    __syncwarp();
+    static_assert(PATH_SCRATCH_BYTES % 128 == 0, "per-warp point buffers must be whole L2 lines");
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+    if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)  // never touch a line shared with a neighbour's buffer
+      for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
+  }
 }
 
 __global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *out) {

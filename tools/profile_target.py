@@ -13,7 +13,8 @@ bp = BatchPlanner("cuda:0")
 dev = bp.device
 xy, ty, off = (torch.from_numpy(a).to(dev) for a in (batch.cones_xy, batch.cones_type, batch.offsets))
 pos, dr = torch.from_numpy(batch.pos).to(dev), torch.from_numpy(batch.dir).to(dev)
+stage = len(sys.argv) > 3 and sys.argv[3] == "stage"  # the two stage entry points over the whole batch (no chunking)
 for _ in range(iters):
-    bp.plan(xy, ty, off, pos, dr)
+    bp.plan(xy, ty, off, pos, dr, kernel_events=stage)
 torch.cuda.synchronize()
 print("done", n, iters)
