@@ -27,8 +27,6 @@ struct PathSmem {
   d2 *pts;    // [PCAP]
   double *u;  // [PCAP]
   SplineWork W;
-  d2 centre[FSD_HORIZON];
-  d2 prev_xy[FSD_HORIZON];
   int32_t si[4];
 };
 
@@ -176,6 +174,18 @@ struct PathMachine {
 
 FSD_DEV bool pm_is_alignment_state(int st) { return st == PS_FIT1_DONE || st == PS_FIT2_DONE || st == PS_FIT3_DONE; }
 
+// x, y of the previous path (40 x 4, global memory) into dst[0 .. 40): only the fallbacks need them, so they are read
+// when a fallback fires instead of being kept in shared memory
+FSD_DEVFN void pm_prev_to(const PathMachine &M, d2 *dst) {
+  wsync();
+#pragma unroll 1
+  for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
+    dst[i].x = M.prev[4 * i + 1];
+    dst[i].y = M.prev[4 * i + 2];
+  }
+  wsync();
+}
+
 // evaluate the fitted spline every `step` up to max_u into dst (len(np.arange(0, max_u, step)) points)
 FSD_DEVFN int pm_evaluate(PathSmem &S, double max_u, double step, d2 *dst, int dst_cap) {
   const double q = ceil(fdiv(max_u, step));
@@ -215,12 +225,9 @@ FSD_DEVFN void pm_tail_failed(PathSmem &S, PathMachine &M, int rc) {
     M.status |= FSD_ST_MPC_FAILED;
     M.tail_retry = true;
     M.tail_status = 0;
-    wsync();
-#pragma unroll 1
-    for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
+    pm_prev_to(M, S.pts + 1);
     M.nu = FSD_HORIZON;
     M.state = PS_TAIL;
-    wsync();
     return;
   }
   pm_finish_with_prev(M, M.tail_status | (rc == RC_UNSUPPORTED ? FSD_ST_UNSUPPORTED : FSD_ST_REF_RAISES));
@@ -242,10 +249,8 @@ FSD_DEVFN void pm_enter_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   wsync();
   if (best > P.max_valid_dist) {
     M.status |= FSD_ST_PATH_TOO_FAR;
-#pragma unroll 1
-    for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) S.pts[1 + i] = S.prev_xy[i];
+    pm_prev_to(M, S.pts + 1);
     M.nu = FSD_HORIZON;
-    wsync();
   }
   M.tail_status = 0;
   M.state = PS_TAIL;
@@ -514,7 +519,8 @@ FSD_DEVFN void pm_stage_after_fit1(PathSmem &S, PathMachine &M, const DevParams 
     if (!unsupported && !M.fit1_retry && M.mode == 0) {
       M.status |= FSD_ST_FIT1_FAILED;  // ValueError -> the previous path is fitted instead
       M.fit1_retry = true;
-      pm_start_fit1(S, M, S.prev_xy, FSD_HORIZON, P);
+      pm_prev_to(M, S.pts);  // the point buffer is free until the fit has been evaluated
+      pm_start_fit1(S, M, S.pts, FSD_HORIZON, P);
       return;
     }
     if (M.mode == 1) {
@@ -590,14 +596,6 @@ FSD_DEVFN void pm_init(PathSmem &S, PathMachine &M, int mode, const FramePose &F
   M.fit.phase = FIT_DONE;
   M.fit.ier = 10;
   M.state = PS_DONE;
-  if (prev) {
-#pragma unroll 1
-    for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
-      S.prev_xy[i].x = prev[4 * i + 1];
-      S.prev_xy[i].y = prev[4 * i + 2];
-    }
-    wsync();
-  }
 }
 
 // ---- CalculatePath.run_path_calculation (core_calculate_path.py:514-575), global_path is None ------------
@@ -609,51 +607,53 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
                               const double *prev, const DevParams &P, double *out) {
   const int lane = fsd_lane();
   pm_init(S, M, 0, F, force_P, prev, out);
-  const d2 *cl = S.prev_xy;
-  int ncl = FSD_HORIZON;
+  // the data of fit #1 (centre line of the matches, or the previous path) lives at the start of the point buffer, which
+  // is free until the fit has been evaluated
+  int ncl = 0;
   if (nl < 3 && nr < 3) {
     M.status |= FSD_ST_FEW_CONES;
   } else {
-    if (lane == 0) {
-      // select_side_to_use :165-183: max over (number of matches, sum of match indices), ties -> left
-      int nml = 0, nmr = 0, sl = 0, sr = 0;
+    // select_side_to_use :165-183: max over (number of matches, sum of match indices), ties -> left; one cone per lane
+    int nml = 0, nmr = 0, sl = 0, sr = 0;
 #pragma unroll 1
-      for (int i = 0; i < nl; ++i)
-        if (l2r[i] != -1) {
-          ++nml;
-          sl += l2r[i];
-        }
-#pragma unroll 1
-      for (int i = 0; i < nr; ++i)
-        if (r2l[i] != -1) {
-          ++nmr;
-          sr += r2l[i];
-        }
-      const bool use_left = !(nmr > nml || (nmr == nml && sr > sl));
-      const d2 *a = use_left ? left : right, *b = use_left ? right : left;
-      const int16_t *mt = use_left ? l2r : r2l;
-      const int ns = use_left ? nl : nr;
-      int nc = 0;
-      // calculate_centerline_points_of_matches :185-205
-#pragma unroll 1
-      for (int i = 0; i < ns; ++i)
-        if (mt[i] != -1 && nc < FSD_HORIZON) {
-          S.centre[nc].x = (a[i].x + b[mt[i]].x) / 2.0;
-          S.centre[nc].y = (a[i].y + b[mt[i]].y) / 2.0;
-          ++nc;
-        }
-      S.si[0] = nc;
+    for (int base = 0; base < nl || base < nr; base += FSD_LANES) {
+      const int i = base + lane;
+      const int ml = i < nl ? (int)l2r[i] : -1, mr = i < nr ? (int)r2l[i] : -1;
+      nml += FSD_POPC(wballot(ml != -1));
+      nmr += FSD_POPC(wballot(mr != -1));
+      sl += wsum_i(ml != -1 ? ml : 0);
+      sr += wsum_i(mr != -1 ? mr : 0);
     }
+    const bool use_left = !(nmr > nml || (nmr == nml && sr > sl));
+    const d2 *a = use_left ? left : right, *b = use_left ? right : left;
+    const int16_t *mt = use_left ? l2r : r2l;
+    const int ns = use_left ? nl : nr;
+    // calculate_centerline_points_of_matches :185-205: the matched cones in order, compacted by ballot
+    int nc = 0;
+#pragma unroll 1
+    for (int base = 0; base < ns; base += FSD_LANES) {
+      const int i = base + lane;
+      const int m = i < ns ? (int)mt[i] : -1;
+      const unsigned mask = wballot(m != -1);
+      const int slot = nc + FSD_POPC(mask & ((1u << lane) - 1u));
+      if (m != -1 && slot < FSD_HORIZON) {
+        S.pts[slot].x = (a[i].x + b[m].x) / 2.0;
+        S.pts[slot].y = (a[i].y + b[m].y) / 2.0;
+      }
+      nc += FSD_POPC(mask);
+    }
+    if (nc > FSD_HORIZON) nc = FSD_HORIZON;
     wsync();
-    const int nc = S.si[0];
-    if (nc < 2) {
+    if (nc < 2)
       M.status |= FSD_ST_FEW_MATCHES;
-    } else {
-      cl = S.centre;
+    else
       ncl = nc;
-    }
   }
-  pm_start_fit1(S, M, cl, ncl, P);
+  if (ncl == 0) {
+    pm_prev_to(M, S.pts);
+    ncl = FSD_HORIZON;
+  }
+  pm_start_fit1(S, M, S.pts, ncl, P);
 }
 
 // second half of run_path_calculation only: the path update already sits in S.pts[1 .. 1+nu) (skidpad)
@@ -675,11 +675,11 @@ FSD_DEVFN void pm_begin_initial(PathSmem &S, PathMachine &M, const DevParams &P,
   for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
     const double a = i == FSD_HORIZON - 1 ? max_angle : (double)i * stp;
     const double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;
-    S.centre[i].x = px * c - py * s;
-    S.centre[i].y = px * s + py * c;
+    S.pts[i].x = px * c - py * s;
+    S.pts[i].y = px * s + py * c;
   }
   wsync();
-  pm_start_fit1(S, M, S.centre, FSD_HORIZON, P);
+  pm_start_fit1(S, M, S.pts, FSD_HORIZON, P);
 }
 
 FSD_DEVFN void pm_run(PathSmem &S, PathMachine &M, const DevParams &P) {

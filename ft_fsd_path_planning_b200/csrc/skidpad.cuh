@@ -356,12 +356,6 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     }
   }
   wsync();
-#pragma unroll 1
-  for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) {
-    S.prev_xy[i].x = prev[4 * i + 1];
-    S.prev_xy[i].y = prev[4 * i + 2];
-  }
-  wsync();
   unsigned status = path_from_update(S, nu, F, force_P, prev, P, out_internal, grid);
   wsync();
 #pragma unroll 1

@@ -40,10 +40,15 @@ struct SplineWork {
   double rhs[NCAP][2];
   double z[NCAP][2];
   double c[NCAP][2];
-  double c0[NCAP][2];      // least-squares coefficients of the final knot set (smoothing phase: F(p) as a quadratic form)
-  double fpint[2 * NCAP];  // [0, NCAP): residual per knot interval; [NCAP, 2 NCAP): reciprocal pivots of chol_solve
-  int32_t nrdata[NCAP];
-  int32_t start[NCAP + 1];
+  double rpiv[NCAP];  // reciprocal pivots of chol_solve
+  union {
+    struct {  // knot-selection phase only
+      double fpint[NCAP];         // residual per knot interval
+      int32_t nrdata[NCAP];       // data points strictly inside each knot interval
+      int32_t start[NCAP + 1];    // first data index of each knot interval
+    };
+    double c0[NCAP][2];  // smoothing phase only: least-squares coefficients of the final knot set (F(p) as a quadratic form)
+  };
   double rk[NCAP][6];  // reciprocal knot differences of the B-spline recursion, per knot interval
   int32_t n, k;   // result: knot count, degree
   double max_u;   // last parameter value of the fitted data
@@ -563,7 +568,7 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
 #pragma unroll 1
   for (int e = lane; e < F.nk1 * BW; e += FSD_LANES) (&W.G[0][0])[e] = (&W.N[0][0])[e];
   wsync();
-  if (!chol_solve(W.G, F.nk1, k1, W.rhs, W.z, W.c, W.fpint + NCAP)) {
+  if (!chol_solve(W.G, F.nk1, k1, W.rhs, W.z, W.c, W.rpiv)) {
     *status |= FSD_ST_UNSUPPORTED;
     fit_finish(W, F, 10);
     return;
@@ -696,7 +701,7 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
 #pragma unroll 1
   for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
   wsync();
-  if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.fpint + NCAP)) {
+  if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.rpiv)) {
     *status |= FSD_ST_UNSUPPORTED;
     fit_finish(W, F, 10);
     return;
