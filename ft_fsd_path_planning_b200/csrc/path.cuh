@@ -66,7 +66,7 @@ FSD_DEVFN double circle_radius_serial(const d2 *p, int n) {
     mx += p[i].x;
     my += p[i].y;
   }
-  const double inv_n = fdiv(1.0, (double)n);
+  const double inv_n = frcp((double)n);
   mx *= inv_n;
   my *= inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
@@ -93,7 +93,7 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
     sx += p[i].x;
     sy += p[i].y;
   }
-  const double inv_n = fdiv(1.0, (double)n);
+  const double inv_n = frcp((double)n);
   const double mx = wsum(sx) * inv_n, my = wsum(sy) * inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
 #pragma unroll 1
@@ -486,7 +486,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
     double r = circle_radius_serial(S.pts + lo, cnt);
     r = fmin(fmax(r, 1.0), 3000.0);
     const double sg = sgn(orient(S.pts[lo], S.pts[lo + cnt / 2], S.pts[hi]));
-    curv[i] = fdiv(1.0, r) * sg;
+    curv[i] = frcp(r) * sg;
   }
   wsync();
   // uniform_filter1d(size, mode="nearest") evaluated at the 40 sampled indices only;

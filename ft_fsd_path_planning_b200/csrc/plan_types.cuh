@@ -17,7 +17,7 @@ FSD_DEV FramePose make_pose(double px, double py, double dx, double dy) {
   F.py = py;
   F.dx = dx;
   F.dy = dy;
-  const double inv = fdiv(1.0, fsqrt(dx * dx + dy * dy));
+  const double inv = frcp(fsqrt(dx * dx + dy * dy));
   F.ux = dx * inv;
   F.uy = dy * inv;
   return F;

@@ -309,7 +309,7 @@ FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, 
     }
     return left_end >= right_start;
   }
-  const double inv = fdiv(1.0, iz);
+  const double inv = frcp(iz);
   double x = ix * inv, y = iy * inv;
   return (fmin(a0x, a1x) - eps <= x && x <= fmax(a0x, a1x) + eps) &&
          (fmin(b0x, b1x) - eps <= x && x <= fmax(b0x, b1x) + eps) &&
@@ -553,7 +553,7 @@ FSD_DEV void search_dir(const SortSmem &S, int a, int b, int side, double &ox, d
   double tx = S.xy[b].x - S.xy[a].x, ty = S.xy[b].y - S.xy[a].y;
   double rx = side == FSD_CONE_RIGHT ? -ty : ty, ry = side == FSD_CONE_RIGHT ? tx : -tx;
   double nrm = fsqrt(rx * rx + ry * ry);
-  double inrm = fdiv(1.0, nrm);
+  double inrm = frcp(nrm);
   ox = rx * inrm;
   oy = ry * inrm;
 }

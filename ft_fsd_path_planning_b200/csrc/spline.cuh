@@ -68,7 +68,7 @@ FSD_DEVFN void knot_reciprocals(SplineWork &W, int n, int k) {
     if (j <= k) {
       const int l = k + ii;
       const double d = W.t[l + i] - W.t[l + i - j];
-      r = d == 0.0 ? 0.0 : fdiv(1.0, d);
+      r = d == 0.0 ? 0.0 : frcp(d);
     }
     W.rk[ii][q] = r;
   }
@@ -697,7 +697,7 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
   const int k = F.k, k2 = k + 2, nk1 = F.nk1;
   const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
   ++F.iter;
-  const double pinv = fdiv(1.0, F.p), pinv2 = pinv * pinv;
+  const double pinv = frcp(F.p), pinv2 = pinv * pinv;
 #pragma unroll 1
   for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
   wsync();
