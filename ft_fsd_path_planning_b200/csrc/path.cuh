@@ -558,7 +558,12 @@ FSD_DEVFN void pm_step(PathSmem &S, PathMachine &M, const DevParams &P) {
     case PS_FIT1:
     case PS_FIT2:
     case PS_FIT3:
+#ifdef FSD_LOCKSTEP_PER_STEP
       if (M.fit.phase != FIT_DONE) fit_step(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
+#else
+      // the whole fit in one machine step (the kernel aligns its warps at the fit boundaries only)
+      while (M.fit.phase != FIT_DONE) fit_step(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
+#endif
       if (M.fit.phase == FIT_DONE) M.state += 1;
       break;
     case PS_FIT1_DONE:
