@@ -562,7 +562,7 @@ FSD_DEVFN void pm_step(PathSmem &S, PathMachine &M, const DevParams &P) {
       if (M.fit.phase != FIT_DONE) fit_step(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
 #else
       // the whole fit in one machine step (the kernel aligns its warps at the fit boundaries only)
-      while (M.fit.phase != FIT_DONE) fit_step(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
+      if (M.fit.phase != FIT_DONE) fit_run(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
 #endif
       if (M.fit.phase == FIT_DONE) M.state += 1;
       break;

@@ -769,6 +769,13 @@ FSD_DEVFN void fit_step(SplineWork &W, FitState &F, unsigned *status) {
     fit_step_smooth(W, F, status);
 }
 
+// the rest of the fit, phase by phase (no dispatch per pass)
+FSD_DEVFN void fit_run(SplineWork &W, FitState &F, unsigned *status) {
+  while (F.phase == FIT_KNOTS) fit_step_knots(W, F, status);
+  if (F.phase == FIT_SMOOTH_SETUP) fit_step_smooth_setup(W, F);
+  while (F.phase == FIT_SMOOTH) fit_step_smooth(W, F, status);
+}
+
 // blocking form.  Result in W.t, W.c, W.n, W.k, W.max_u.  Returns FITPACK's ier.
 FSD_DEVFN int fit_curve(SplineWork &W, const d2 *pts, const double *u, int m, double s, unsigned *status) {
   FitState F;
