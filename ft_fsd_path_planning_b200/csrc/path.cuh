@@ -58,31 +58,66 @@ FSD_DEVFN void hyper_from_moments(double mx, double my, double Mxx, double Myy, 
   r = fsqrt(fabs(Xc * Xc + Yc * Yc + Mz));
 }
 
-// one lane fits one window (curvature)
-FSD_DEVFN double circle_radius_serial(const d2 *p, int n) {
-  double mx = 0.0, my = 0.0;
+FSD_DEV double orient(const d2 &p0, const d2 &p1, const d2 &p2) {
+  // sign of det [[1, p0], [1, p1], [1, p2]] (np.linalg.det in the reference)
+  return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+
+// Curvature windows (calculate_path_curvature :49-93, open path): one hyper circle fit per path point over the points
+// within +-hw of it.  Neighbouring windows share all but two points, so a lane takes a run of consecutive windows and
+// SLIDES the raw moment sums (10 monomials up to degree 4, in coordinates local to the run: |x|, |y| < 3 m, so the
+// shift to the window mean below cancels a few digits at most) instead of re-reading 25 points per window: 31 point
+// visits per lane instead of 100.  curv[i] = sign / clamp(radius, 1, 3000).
+FSD_DEVFN void curvature_windows(const d2 *p, int Pn, int hw, double *curv) {
+  const int per = (Pn + FSD_LANES - 1) / FSD_LANES;
+  const int i0 = fsd_lane() * per, i1 = i0 + per < Pn ? i0 + per : Pn;
+  if (i0 >= i1) return;
+  const double ox = p[i0].x, oy = p[i0].y;
+  double s1x = 0, s1y = 0, sxx = 0, sxy = 0, syy = 0, sxxx = 0, sxxy = 0, sxyy = 0, syyy = 0, sz2 = 0;
+  int lo = i0 - hw < 0 ? 0 : i0 - hw, hi = lo - 1;  // the window [lo, hi] covered by the sums (empty)
 #pragma unroll 1
-  for (int i = 0; i < n; ++i) {
-    mx += p[i].x;
-    my += p[i].y;
-  }
-  const double inv_n = frcp((double)n);
-  mx *= inv_n;
-  my *= inv_n;
-  double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
+  for (int i = i0; i < i1; ++i) {
+    const int nlo = i - hw < 0 ? 0 : i - hw, nhi = i + hw > Pn - 1 ? Pn - 1 : i + hw;
 #pragma unroll 1
-  for (int i = 0; i < n; ++i) {
-    double xi = p[i].x - mx, yi = p[i].y - my, zi = xi * xi + yi * yi;
-    Mxy += xi * yi;
-    Mxx += xi * xi;
-    Myy += yi * yi;
-    Mxz += xi * zi;
-    Myz += yi * zi;
-    Mzz += zi * zi;
+    while (hi < nhi || lo < nlo) {
+      // one point enters (sign +1) or leaves (sign -1)
+      const bool enter = hi < nhi;
+      const int q = enter ? ++hi : lo++;
+      const double sg = enter ? 1.0 : -1.0;
+      const double x = p[q].x - ox, y = p[q].y - oy;
+      const double xx = x * x, yy = y * y, z = xx + yy;
+      const double sx = sg * x, sy = sg * y;
+      s1x += sx;
+      s1y += sy;
+      sxx += sx * x;
+      sxy += sx * y;
+      syy += sy * y;
+      sxxx += sx * xx;
+      sxxy += sy * xx;
+      sxyy += sx * yy;
+      syyy += sy * yy;
+      sz2 += sg * z * z;
+    }
+    // central moments about the window mean from the raw sums
+    const double n = (double)(nhi - nlo + 1), inv = frcp(n);
+    const double mx = s1x * inv, my = s1y * inv;
+    const double Mxx = sxx * inv - mx * mx, Myy = syy * inv - my * my, Mxy = sxy * inv - mx * my;
+    const double n2 = n + n;
+    const double c3x = sxxx - 3.0 * mx * sxx + n2 * mx * mx * mx;
+    const double cxxy = sxxy - my * sxx - 2.0 * mx * sxy + n2 * mx * mx * my;
+    const double cxyy = sxyy - mx * syy - 2.0 * my * sxy + n2 * mx * my * my;
+    const double c3y = syyy - 3.0 * my * syy + n2 * my * my * my;
+    const double Mxz = (c3x + cxyy) * inv, Myz = (cxxy + c3y) * inv;
+    const double q2 = mx * mx + my * my;
+    const double sl2 = mx * mx * sxx + 2.0 * mx * my * sxy + my * my * syy;
+    const double szl = mx * (sxxx + sxyy) + my * (sxxy + syyy);
+    const double Mzz = (sz2 + 4.0 * sl2 - 4.0 * szl + 2.0 * q2 * (sxx + syy) - 3.0 * n * q2 * q2) * inv;
+    double cx, cy, r;
+    hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, cx, cy, r);
+    r = fmin(fmax(r, 1.0), 3000.0);
+    const int cnt = nhi - nlo + 1;
+    curv[i] = frcp(r) * sgn(orient(p[nlo], p[nlo + cnt / 2], p[nhi]));
   }
-  double cx, cy, r;
-  hyper_from_moments(mx, my, Mxx * inv_n, Myy * inv_n, Mxy * inv_n, Mxz * inv_n, Myz * inv_n, Mzz * inv_n, cx, cy, r);
-  return r;
 }
 
 // the whole warp fits one point set (path extension)
@@ -113,11 +148,6 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
   Myz = wsum(Myz) * inv_n;
   Mzz = wsum(Mzz) * inv_n;
   hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, cx, cy, r);
-}
-
-FSD_DEV double orient(const d2 &p0, const d2 &p1, const d2 &p2) {
-  // sign of det [[1, p0], [1, p1], [1, p2]] (np.linalg.det in the reference)
-  return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
 }
 
 // ---- chord-length parameters: u[0] = 0, u[i] = u[i-1] + |p_i - p_{i-1}| (np.cumsum) -------------------
@@ -478,16 +508,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   int window = Pn / 5 < 30 ? Pn / 5 : 30;
   if (window % 2 == 0) window += 1;
   const int hw = window / 2;
-#pragma unroll 1
-  for (int i = lane; i < Pn; i += FSD_LANES) {
-    const int lo = i - hw < 0 ? 0 : i - hw;
-    const int hi = i + hw > Pn - 1 ? Pn - 1 : i + hw;
-    const int cnt = hi - lo + 1;
-    double r = circle_radius_serial(S.pts + lo, cnt);
-    r = fmin(fmax(r, 1.0), 3000.0);
-    const double sg = sgn(orient(S.pts[lo], S.pts[lo + cnt / 2], S.pts[hi]));
-    curv[i] = frcp(r) * sg;
-  }
+  curvature_windows(S.pts, Pn, hw, curv);
   wsync();
   // uniform_filter1d(size, mode="nearest") evaluated at the 40 sampled indices only;
   // indices np.linspace(0, P-1, 40, dtype=int) (:277-282)
