@@ -155,14 +155,11 @@ FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &o
 // kbm, in row-major order; otherwise right-hand-side update (a, column)
 FSD_DEV void chol_task(int e, int kbm, int npairs, int &ta, int &tb) {
   if (e < npairs) {
-    int a = 1, rem = e;
-#pragma unroll 1
-    while (rem >= kbm - a + 1) {
-      rem -= kbm - a + 1;
-      ++a;
-    }
-    ta = a;
-    tb = a + rem;
+    // (a, b) of the e-th pair, one nibble each, for kbm = 1 .. 4 (row-major over 1 <= a <= b <= kbm)
+    const unsigned long long lut_a = kbm == 4 ? 0x4332221111ull : (kbm == 3 ? 0x322111ull : (kbm == 2 ? 0x211ull : 0x1ull));
+    const unsigned long long lut_b = kbm == 4 ? 0x4434324321ull : (kbm == 3 ? 0x332321ull : (kbm == 2 ? 0x221ull : 0x1ull));
+    ta = (int)((lut_a >> (4 * e)) & 15ull);
+    tb = (int)((lut_b >> (4 * e)) & 15ull);
   } else {
     ta = 1 + ((e - npairs) >> 1);
     tb = (e - npairs) & 1;
