@@ -243,6 +243,24 @@ def test_two_chunk_plan_equals_stage_entry_points(planner):
         assert torch.equal(v, getattr(res, k)), f"{k} differs between the chunked call and the stage entry points"
 
 
+def test_two_chunk_plan_offsets_every_per_frame_argument(planner):
+    """The second chunk of a large batch must see its own slice of force_P and of a per-frame prev_path: the chunked
+    call equals two unsplit calls on the halves."""
+    B = 6000
+    batch = synth.gen_autocross(44, B)
+    rng = np.random.default_rng(44)
+    force = np.where(rng.random(B) < 0.5, 120, 121).astype(np.int16)
+    prev0 = planner.initial_path().cpu().numpy()
+    prev = np.repeat(prev0[None], B, 0)
+    prev[:, :, 1] += rng.normal(0, 0.5, (B, 1))  # a different previous path per frame
+    whole = _np(planner.plan_host(batch, force_P=force, prev_path=prev, intermediates=True))
+    assert (whole["grid"][:, 0] == force).all()
+    for lo, hi in ((0, 3000), (3000, 6000)):
+        part = _np(planner.plan_host(batch.slice(lo, hi), force_P=force[lo:hi], prev_path=prev[lo:hi], intermediates=True))
+        for k in ("path", "path_f64", "left_idx", "right_idx", "status", "grid"):
+            assert np.array_equal(part[k], whole[k][lo:hi]), f"{k} differs in frames [{lo}, {hi})"
+
+
 def test_plan_pinned_equals_plan(planner):
     """The pipelined host-to-host entry point (chunks on streams of their own) gives the same bytes as plan()."""
     B = 7000
