@@ -181,6 +181,10 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   SortCta &C = *reinterpret_cast<SortCta *>(smem_raw + (size_t)warp * SORT_CTA_STRIDE);
+#ifdef FSD_POOLED_KNN
+  __shared__ int s_n[WPC];
+  const int lane = fsd_lane();
+#endif
   if (fsd_lane() == 0) mbar_init(&C.mbar, 1);
   __syncwarp();
   uint32_t phase = 0;
@@ -206,8 +210,34 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
       F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
       dbg = O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr;
       stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
+#ifndef FSD_POOLED_KNN
       if (n >= 3) build_knn(C.S, n, P);
+#endif
     }
+#ifdef FSD_POOLED_KNN
+    // The k-NN graph costs N^2 per frame and N varies 3x inside a batch: the rows of all frames of the CTA are pooled and
+    // dealt out evenly to its threads (a thread may work on another warp's frame - every slice is in this CTA's shared
+    // memory), so no warp waits for the frame with the most cones.
+    if (lane == 0) s_n[warp] = (active && n >= 3) ? n : 0;
+    __syncthreads();
+    for (int stage = 0; stage < 2; ++stage) {
+      int total = 0;
+#pragma unroll
+      for (int w = 0; w < WPC; ++w) total += s_n[w];
+#pragma unroll 1
+      for (int r = (int)threadIdx.x; r < total; r += CTA_THREADS) {
+        int f = 0, base = 0;
+        while (r >= base + s_n[f]) base += s_n[f++];
+        SortSmem &Sf = reinterpret_cast<SortCta *>(smem_raw + (size_t)f * SORT_CTA_STRIDE)->S;
+        const int nf = s_n[f];
+        if (stage == 0)
+          knn_row(Sf, nf, knn_k(nf, P), r - base, P);
+        else
+          knn_mutual_row(Sf, r - base);
+      }
+      __syncthreads();
+    }
+#endif
     // each side in three stages (seeds / exhaustive search / filter + cost), a CTA barrier before every stage
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {

@@ -98,81 +98,92 @@ FSD_DEV void knn_store(const KnnList &L, int k, int own, uint8_t *out) {
   out[4] = (uint8_t)(k > 4 && L.i4 >= 0 ? L.i4 : own);
 }
 
-FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
+// k of the k-NN graph of a frame with n cones (adjacency_matrix.py:60-75)
+FSD_DEV int knn_k(int n, const DevParams &P) {
   int k = n - 1 < P.max_n_neighbors ? n - 1 : P.max_n_neighbors;
-  if (k > 5) k = 5;
+  return k > 5 ? 5 : k;
+}
+
+// row i of the distance matrix -> the row's LEFT and RIGHT 5-nearest lists (S.knn)
+FSD_DEV void knn_row(SortSmem &S, int n, int k, int i, const DevParams &P) {
+  KnnList KL, KR;
+  knn_clear(KL);
+  knn_clear(KR);
+  const double xi = S.xy[i].x, yi = S.xy[i].y;
+  const int ti = S.type[i];
+  const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
+  // Edges longer than max_dist are removed after the k-NN selection in the reference (:102-107) and a longer edge can
+  // never displace a shorter one, so they are dropped before the selection.  The frame is swept in chunks of 32
+  // cones: a branch-free distance loop leaves the chunk's in-range cones as a bit mask, then the handful of set bits
+  // is offered to the row's lists in ascending j (the tie order of the selection).  Lanes stay converged through
+  // the sweep and diverge only by the number of in-range cones per chunk.
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-    KnnList KL, KR;
-    knn_clear(KL);
-    knn_clear(KR);
-    const double xi = S.xy[i].x, yi = S.xy[i].y;
-    const int ti = S.type[i];
-    const bool li = ti != FSD_CONE_RIGHT, ri = ti != FSD_CONE_LEFT;
-    // Edges longer than max_dist are removed after the k-NN selection in the reference (:102-107) and a longer edge can
-    // never displace a shorter one, so they are dropped before the selection.  The frame is swept in chunks of 32
-    // cones: a branch-free distance loop leaves the chunk's in-range cones as a bit mask, then the handful of set bits
-    // is offered to the row's lists in ascending j (the tie order of the selection).  Lanes stay converged through
-    // the sweep and diverge only by the number of in-range cones per chunk.
-#pragma unroll 1
-    for (int j0 = 0; j0 < n; j0 += 32) {
-      const int jn = n - j0 < 32 ? n - j0 : 32;
-      unsigned mask = 0;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int jn = n - j0 < 32 ? n - j0 : 32;
+    unsigned mask = 0;
 #pragma unroll 4
-      for (int jj = 0; jj < jn; ++jj) {
-        const double ddx = S.xy[j0 + jj].x - xi, ddy = S.xy[j0 + jj].y - yi;
-        mask |= (ddx * ddx + ddy * ddy <= P.max_dist2 ? 1u : 0u) << jj;
-      }
-      if ((unsigned)(i - j0) < 32u) mask &= ~(1u << (i - j0));
-      while (mask) {
-        const int jj = FSD_FFS(mask) - 1;
-        mask &= mask - 1;
-        const int j = j0 + jj;
-        const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
-        const double dd = ddx * ddx + ddy * ddy;
-        const int tj = S.type[j];
-        if (li && tj != FSD_CONE_RIGHT) knn_insert(KL, dd, j);
-        if (ri && tj != FSD_CONE_LEFT) knn_insert(KR, dd, j);
+    for (int jj = 0; jj < jn; ++jj) {
+      const double ddx = S.xy[j0 + jj].x - xi, ddy = S.xy[j0 + jj].y - yi;
+      mask |= (ddx * ddx + ddy * ddy <= P.max_dist2 ? 1u : 0u) << jj;
+    }
+    if ((unsigned)(i - j0) < 32u) mask &= ~(1u << (i - j0));
+    while (mask) {
+      const int jj = FSD_FFS(mask) - 1;
+      mask &= mask - 1;
+      const int j = j0 + jj;
+      const double ddx = S.xy[j].x - xi, ddy = S.xy[j].y - yi;
+      const double dd = ddx * ddx + ddy * ddy;
+      const int tj = S.type[j];
+      if (li && tj != FSD_CONE_RIGHT) knn_insert(KL, dd, j);
+      if (ri && tj != FSD_CONE_LEFT) knn_insert(KR, dd, j);
+    }
+  }
+  // unused slots hold the row's own index: a cone is never its own neighbour, so they match nothing below
+  knn_store(KL, k, i, S.knn[0][i]);
+  knn_store(KR, k, i, S.knn[1][i]);
+}
+
+// row i: keep edges present in both directions (:110); neighbour lists in ascending index order, the order np.where
+// gives the CSR lists of end_configurations.py:28-71.  All rows of the frame must have passed knn_row.
+FSD_DEV void knn_mutual_row(SortSmem &S, int i) {
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    int cnt = 0;
+    int t0 = 256, t1 = 256, t2 = 256, t3 = 256, t4 = 256;  // ascending, 256 = empty
+#pragma unroll 1
+    for (int q = 0; q < 5; ++q) {
+      const int j = S.knn[s][i][q];
+      if (j == i) break;  // end of the list
+      const uint8_t *kj = S.knn[s][j];
+      const bool back = (kj[0] == i) | (kj[1] == i) | (kj[2] == i) | (kj[3] == i) | (kj[4] == i);
+      if (back) {
+        ++cnt;
+        const bool c3 = j < t3, c2 = j < t2, c1 = j < t1, c0 = j < t0;
+        t4 = c3 ? t3 : j;
+        t3 = c3 ? (c2 ? t2 : j) : t3;
+        t2 = c2 ? (c1 ? t1 : j) : t2;
+        t1 = c1 ? (c0 ? t0 : j) : t1;
+        t0 = c0 ? j : t0;
       }
     }
-    // unused slots hold the row's own index: a cone is never its own neighbour, so they match nothing below
-    knn_store(KL, k, i, S.knn[0][i]);
-    knn_store(KR, k, i, S.knn[1][i]);
+    uint8_t *ni = S.nbr[s][i];
+    ni[0] = (uint8_t)t0;
+    ni[1] = (uint8_t)t1;
+    ni[2] = (uint8_t)t2;
+    ni[3] = (uint8_t)t3;
+    ni[4] = (uint8_t)t4;
+    S.deg[s][i] = (uint8_t)cnt;
   }
+}
+
+// one warp, one frame (the sort kernel pools the rows of the frames of a CTA instead, kernels.cu)
+FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
+  const int k = knn_k(n, P);
+#pragma unroll 1
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) knn_row(S, n, k, i, P);
   wsync();
-  // keep edges present in both directions (:110); neighbour lists in ascending index order, the
-  // order np.where gives the CSR lists of end_configurations.py:28-71
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-#pragma unroll 1
-    for (int s = 0; s < 2; ++s) {
-      int cnt = 0;
-      int t0 = 256, t1 = 256, t2 = 256, t3 = 256, t4 = 256;  // ascending, 256 = empty
-#pragma unroll 1
-      for (int q = 0; q < 5; ++q) {
-        const int j = S.knn[s][i][q];
-        if (j == i) break;  // end of the list
-        const uint8_t *kj = S.knn[s][j];
-        const bool back = (kj[0] == i) | (kj[1] == i) | (kj[2] == i) | (kj[3] == i) | (kj[4] == i);
-        if (back) {
-          ++cnt;
-          const bool c3 = j < t3, c2 = j < t2, c1 = j < t1, c0 = j < t0;
-          t4 = c3 ? t3 : j;
-          t3 = c3 ? (c2 ? t2 : j) : t3;
-          t2 = c2 ? (c1 ? t1 : j) : t2;
-          t1 = c1 ? (c0 ? t0 : j) : t1;
-          t0 = c0 ? j : t0;
-        }
-      }
-      uint8_t *ni = S.nbr[s][i];
-      ni[0] = (uint8_t)t0;
-      ni[1] = (uint8_t)t1;
-      ni[2] = (uint8_t)t2;
-      ni[3] = (uint8_t)t3;
-      ni[4] = (uint8_t)t4;
-      S.deg[s][i] = (uint8_t)cnt;
-    }
-  }
+  for (int i = fsd_lane(); i < n; i += FSD_LANES) knn_mutual_row(S, i);
   wsync();
 }
 
