@@ -75,6 +75,39 @@ def test_cuda_f32_batches_match_oracle(planner, gen, seed, n):
     assert ((r["status"].astype(np.uint32) & 0xFFFFFF7F) == (ref["status"] & 0xFFFFFF7F)).all()
 
 
+def test_augmented_real_frames_match_oracle(planner):
+    """SURVEY 8d "augmented-real" variant: the recorded FSG / FS-Spain frames (the golden inputs) under random rigid
+    motions plus 2 cm jitter (seed 6), stored as fp32 - FSG-shaped statistics at a few thousand frames, CUDA against the
+    oracle (sort indices, matches bit-identical; path 1e-4)."""
+    rng = np.random.default_rng(6)
+    parts = []
+    for name in ("fsg_color", "fss_color", "fsg_colorless"):
+        base, _ = load_golden(name)
+        frame_of = np.repeat(np.arange(base.n_frames), np.diff(base.offsets))
+        for _ in range(3):
+            th = rng.uniform(-np.pi, np.pi, base.n_frames)
+            tr = rng.uniform(-200, 200, (base.n_frames, 2))
+            c, s = np.cos(th), np.sin(th)
+            mv = lambda p, f: np.stack([c[f] * p[:, 0] - s[f] * p[:, 1], s[f] * p[:, 0] + c[f] * p[:, 1]], 1) + tr[f]
+            xy = mv(base.cones_xy, frame_of) + rng.normal(0, 0.02, base.cones_xy.shape)
+            parts.append(synth.FrameBatch(
+                xy.astype(np.float32), base.cones_type, base.offsets, mv(base.pos, np.arange(base.n_frames)).astype(np.float32),
+                np.stack([c * base.dir[:, 0] - s * base.dir[:, 1], s * base.dir[:, 0] + c * base.dir[:, 1]], 1).astype(np.float32)))
+    offs, tot = [np.zeros(1, np.int32)], 0
+    for p in parts:
+        offs.append((p.offsets[1:] + tot).astype(np.int32))
+        tot += p.total_cones
+    batch = synth.FrameBatch(np.concatenate([p.cones_xy for p in parts]), np.concatenate([p.cones_type for p in parts]),
+                             np.concatenate(offs), np.concatenate([p.pos for p in parts]), np.concatenate([p.dir for p in parts]))
+    assert batch.n_frames > 3000
+    ref = oracle.plan_batch(batch.astype(np.float64), threads=8)
+    r = _np(planner.plan_host(batch, force_P=ref["P"].astype(np.int16), intermediates=True))
+    assert (r["left_idx"] == ref["left_idx"]).all() and (r["right_idx"] == ref["right_idx"]).all()
+    assert (r["l2r"] == ref["l2r"]).all() and (r["r2l"] == ref["r2l"]).all()
+    assert np.abs(r["path_f64"] - ref["path"]).max() <= 1e-7 and np.abs(r["path"] - ref["path"]).max() <= 1e-4
+    assert ((r["status"].astype(np.uint32) & 0xFFFFFF7F) == (ref["status"] & 0xFFFFFF7F)).all()
+
+
 def test_full_size_properties(planner):
     """BASELINE config 3 (10 000 colourless frames): properties that need no oracle."""
     B = 10000
