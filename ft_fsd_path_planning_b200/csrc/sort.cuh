@@ -361,7 +361,8 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
     double v1x = lx - S.xy[o].x, v1y = ly - S.xy[o].y;
     double v2x = cx - S.xy[o].x, v2y = cy - S.xy[o].y;
     double d1 = v1x * v1x + v1y * v1y, d2 = v2x * v2x + v2y * v2y;
-    if (d2 < 36.0 && d1 < 36.0 && cos_between(v1x, v1y, v2x, v2y) < P.cos_150deg) return false;
+    // angle(v1, v2) > 150 deg  <=>  v1 . v2 < cos(150 deg) |v1| |v2|, without the square root
+    if (d2 < 36.0 && d1 < 36.0 && lt_scaled(v1x * v2x + v1y * v2y, P.cos_150deg, d1 * d2)) return false;
   }
   if (pos >= 1) {
     // turn angle at `last` (:173-191): difference = wrap(atan2(b) - atan2(a)) has sine cr / v and cosine dt / v with
