@@ -131,13 +131,13 @@ FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, cons
     if (ne == 1) {
       // calculate_insert_index_for_one_cone :264-282
       double dvx = cx - F.px, dvy = cy - F.py, dex = S.ex[0].x - F.px, dey = S.ex[0].y - F.py;
-      index = fsqrt(dvx * dvx + dvy * dvy) < fsqrt(dex * dex + dey * dey) ? 0 : 1;
+      index = dvx * dvx + dvy * dvy < dex * dex + dey * dey ? 0 : 1;  // distances compared squared
     } else {
       int c1 = -1, c2 = -1;
       double d1 = 0.0, d2v = 0.0;
       for (int j = 0; j < ne; ++j) {
         double ddx = S.ex[j].x - cx, ddy = S.ex[j].y - cy;
-        double d = fsqrt(ddx * ddx + ddy * ddy);
+        double d = ddx * ddx + ddy * ddy;  // only compared: squared
         if (c1 < 0 || d < d1) {
           c2 = c1;
           d2v = d1;
@@ -151,7 +151,7 @@ FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, cons
       int gap = c1 - c2;
       if (gap != 1 && gap != -1) continue;  // virtual cone skipped (:226-227)
       // angle(closest - v, second - v) > 90 deg  <=>  the cone lies between the two (:229-241)
-      bool between = cos_between(S.ex[c1].x - cx, S.ex[c1].y - cy, S.ex[c2].x - cx, S.ex[c2].y - cy) < 0.0;
+      bool between = (S.ex[c1].x - cx) * (S.ex[c2].x - cx) + (S.ex[c1].y - cy) * (S.ex[c2].y - cy) < 0.0;
       if (between)
         index = (c1 < c2 ? c1 : c2) + 1;
       else

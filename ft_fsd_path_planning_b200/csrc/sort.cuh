@@ -563,11 +563,9 @@ FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, in
 FSD_DEV void search_dir(const SortSmem &S, int a, int b, int side, double &ox, double &oy) {
   // normal of the track direction, +90 deg for RIGHT / -90 deg for LEFT (match_directions.py:7-20)
   double tx = S.xy[b].x - S.xy[a].x, ty = S.xy[b].y - S.xy[a].y;
-  double rx = side == FSD_CONE_RIGHT ? -ty : ty, ry = side == FSD_CONE_RIGHT ? tx : -tx;
-  double nrm = fsqrt(rx * rx + ry * ry);
-  double inrm = frcp(nrm);
-  ox = rx * inrm;
-  oy = ry * inrm;
+  // not normalised: only the angle to this direction is used
+  ox = side == FSD_CONE_RIGHT ? -ty : ty;
+  oy = side == FSD_CONE_RIGHT ? tx : -tx;
 }
 
 // lane-strided stream compaction of the indices i < n with flag[i] != 0 (ascending order)
@@ -659,10 +657,11 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
         }
         if (o == cj) continue;
         double vx = S.xy[o].x - x0, vy = S.xy[o].y - y0;
-        if (!(vx * vx + vy * vy < range2)) continue;
-        double cb = cos_between(vx, vy, sx, sy);
-        good += cb > 0.5;   // angle to the search direction < 60 deg
-        bad += -cb > 0.5;   // angle to the opposite direction < 60 deg
+        const double v2 = vx * vx + vy * vy;
+        if (!(v2 < range2)) continue;
+        const double dot = vx * sx + vy * sy, w2 = v2 * (sx * sx + sy * sy);
+        good += gt_scaled(dot, 0.5, w2);   // angle to the search direction < 60 deg
+        bad += lt_scaled(dot, -0.5, w2);   // angle to the opposite direction < 60 deg
       }
     }
     good = wsum_i(good);
@@ -830,7 +829,7 @@ FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
     int pl = left[li - 1], pr = right[ri - 1], ic = left[li];
     double dlx = S.xy[ic].x - S.xy[pl].x, dly = S.xy[ic].y - S.xy[pl].y;
     double drx = S.xy[ic].x - S.xy[pr].x, dry = S.xy[ic].y - S.xy[pr].y;
-    bool l_low = fsqrt(dlx * dlx + dly * dly) < 3.0, r_low = fsqrt(drx * drx + dry * dry) < 3.0;
+    bool l_low = dlx * dlx + dly * dly < 9.0, r_low = drx * drx + dry * dry < 9.0;
     if ((l_low || r_low) && !(l_low && r_low)) {
       have = true;
       if (l_low) {
