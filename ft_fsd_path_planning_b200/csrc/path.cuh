@@ -274,10 +274,13 @@ FSD_DEVFN void pm_enter_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   const int lane = fsd_lane();
   double best = INFINITY;
 #pragma unroll 1
-  for (int i = lane; i < M.nu; i += FSD_LANES) best = fmin(best, fnorm(M.F.px - S.pts[1 + i].x, M.F.py - S.pts[1 + i].y));
+  for (int i = lane; i < M.nu; i += FSD_LANES) {  // the smallest distance to the car, squared (only compared)
+    const double ddx = M.F.px - S.pts[1 + i].x, ddy = M.F.py - S.pts[1 + i].y;
+    best = fmin(best, ddx * ddx + ddy * ddy);
+  }
   best = wmin_d(best);
   wsync();
-  if (best > P.max_valid_dist) {
+  if (best > P.max_valid_dist * P.max_valid_dist) {
     M.status |= FSD_ST_PATH_TOO_FAR;
     pm_prev_to(M, S.pts + 1);
     M.nu = FSD_HORIZON;
@@ -413,7 +416,8 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
   int bi = -1;
 #pragma unroll 1
   for (int i = lane; i < n; i += FSD_LANES) {
-    const double d = fnorm(F.px - path[i].x, F.py - path[i].y);
+    const double ddx = F.px - path[i].x, ddy = F.py - path[i].y;
+    const double d = ddx * ddx + ddy * ddy;  // arg-min of the distance: squared
     if (bi < 0 || d < bv) {
       bv = d;
       bi = i;
