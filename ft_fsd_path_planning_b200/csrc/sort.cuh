@@ -258,30 +258,37 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
 // ---- reachability: common.py:36-67; only min(#reachable, max_length) is used ----------------
 
 FSD_DEVFN int reachable_count(SortSmem &S, int n, int sidx, int start, int cap) {
-  // flag2 doubles as the visited mask, idxs as the queue
+  const int lane = fsd_lane();
+  // flag2 doubles as the visited mask, idxs as the queue; breadth first, the <= 5 neighbours of a node one per lane
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) S.flag2[i] = 0;
+  for (int i = lane; i < n; i += FSD_LANES) S.flag2[i] = 0;
   wsync();
-  if (fsd_lane() == 0) {
-    int head = 0, tail = 0;
-    S.idxs[tail++] = (int16_t)start;
+  if (lane == 0) {
+    S.idxs[0] = (int16_t)start;
     S.flag2[start] = 1;
-    while (head < tail && tail < cap) {
-      int node = S.idxs[head++];
-      for (int q = 0; q < S.deg[sidx][node]; ++q) {
-        int j = S.nbr[sidx][node][q];
-        if (!S.flag2[j]) {
-          S.flag2[j] = 1;
-          S.idxs[tail++] = (int16_t)j;
-        }
-      }
-    }
-    S.scratch[0] = tail < cap ? tail : cap;
   }
   wsync();
-  int r = S.scratch[0];
-  wsync();
-  return r;
+  int head = 0, tail = 1;
+  while (head < tail && tail < cap) {
+    const int node = S.idxs[head++];
+    const int deg = S.deg[sidx][node];
+    unsigned fresh = 0;
+#pragma unroll 1
+    for (int base = 0; base < deg; base += FSD_LANES) {
+      const int q = base + lane;
+      const int j = q < deg ? (int)S.nbr[sidx][node][q] : -1;
+      const bool f = j >= 0 && !S.flag2[j];
+      const unsigned m = wballot(f);
+      if (f) {
+        S.idxs[tail + FSD_POPC(fresh) + FSD_POPC(m & ((1u << lane) - 1u))] = (int16_t)j;
+        S.flag2[j] = 1;
+      }
+      fresh |= m << base;
+    }
+    tail += FSD_POPC(fresh);
+    wsync();
+  }
+  return tail < cap ? tail : cap;
 }
 
 // ---- admissibility of one candidate: end_configurations.py:108-278 --------------------------
