@@ -39,9 +39,9 @@ FSD_DEVFN void match_directions(const d2 *c, int n, int side, d2 *out) {
     int b = i == 0 ? 1 : (i == n - 1 ? n - 1 : i + 1);
     double tx = c[b].x - c[a].x, ty = c[b].y - c[a].y;
     double rx = side == FSD_CONE_RIGHT ? -ty : ty, ry = side == FSD_CONE_RIGHT ? tx : -tx;
-    double nrm = fsqrt(rx * rx + ry * ry);
-    out[i].x = fdiv(rx, nrm);
-    out[i].y = fdiv(ry, nrm);
+    const double inv = frsqrt(rx * rx + ry * ry);  // unit vector by one reciprocal square root
+    out[i].x = rx * inv;
+    out[i].y = ry * inv;
   }
 }
 
@@ -167,9 +167,12 @@ FSD_DEVFN int insert_virtual(MatchSmem &S, const d2 *other, int no, int nv, cons
   const double cos85 = P.cos_85deg;
   bool drop[WV_CAP + 1];
   for (int i = 0; i < ne; ++i) drop[i] = false;
-  for (int i = 1; i + 1 < ne; ++i)
-    drop[i] = cos_between(S.ex[i + 1].x - S.ex[i].x, S.ex[i + 1].y - S.ex[i].y, S.ex[i - 1].x - S.ex[i].x,
-                          S.ex[i - 1].y - S.ex[i].y) > cos85;
+  for (int i = 1; i + 1 < ne; ++i) {
+    // angle < 85 deg  <=>  a . b > cos(85 deg) |a| |b|, without the square root
+    const double ax = S.ex[i + 1].x - S.ex[i].x, ay = S.ex[i + 1].y - S.ex[i].y;
+    const double bx = S.ex[i - 1].x - S.ex[i].x, by = S.ex[i - 1].y - S.ex[i].y;
+    drop[i] = gt_scaled(ax * bx + ay * by, cos85, (ax * ax + ay * ay) * (bx * bx + by * by));
+  }
   int w = 0;
   for (int i = 0; i < ne; ++i)
     if (!drop[i]) S.ex[w++] = S.ex[i];
