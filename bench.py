@@ -136,7 +136,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if distributed:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a collective that does not complete within 3 minutes aborts the run instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if distributed:
@@ -182,10 +185,12 @@ def run_ours(args):
         e1.record()
         evs.append((e0, e1))
     barrier()
+    # Same kernels, untimed, only to give nvidia-smi time to report.  Rank-local on purpose: the number of iterations
+    # differs from rank to rank, so nothing in this loop may be a collective (no all-gather, no barrier).
     t_end = time.time() + 2.0
-    while len(sampler.rows) < 5 and time.time() < t_end:  # same load, untimed, only to give nvidia-smi time to report
+    while len(sampler.rows) < 5 and time.time() < t_end:
         flush.zero_()
-        step()
+        planner.plan(xy, ty, off, pos, dr)
         torch.cuda.synchronize(dev)
     clocks = sampler.stop()
     clocks["window"] = "warm-up + timed steps (+ identical untimed steps until 5 samples)"
