@@ -22,6 +22,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FRAMES_PER_GPU = 10240  # BASELINE metric: "10k synthetic FSG cone maps"; frame shape of configs[1] (colours known)
+# Control-flow rehearsal for tests/test_bench_rehearsal.py ONLY: FSD_BENCH_REHEARSAL=<frames> runs this file's rank /
+# collective / timing control flow on CPU tensors over gloo with a planner stub that plans NOTHING (zeros), so that a
+# multi-rank deadlock in the harness shows up without a GPU.  The JSON line it prints says so and carries no value.
+REHEARSAL = int(os.environ.get("FSD_BENCH_REHEARSAL", "0"))
+if REHEARSAL:
+    FRAMES_PER_GPU = REHEARSAL
 SEED = 2
 METRIC = "frames/sec full PathPlanner on 10k synthetic FSG cone maps at 1/2/4/8 B200"
 UNIT = "frames/s"
@@ -122,40 +128,103 @@ def run_reference(args):
     }))
 
 
+class _RehearsalEvent:
+    def record(self):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return max((other.t - self.t) * 1e3, 1e-3)
+
+
+class _RehearsalSampler:
+    """Stands in for ClockSampler: reports one more "sample" every (rank + 1) polls, so that the untimed sampling loop
+    runs a different number of iterations on every rank - as it does with real nvidia-smi timing."""
+
+    def __init__(self, rank):
+        self.rank, self.polls = rank, 0
+
+    def start(self):
+        pass
+
+    @property
+    def rows(self):
+        self.polls += 1
+        return [None] * (self.polls // (self.rank + 1))
+
+    def stop(self):
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["rehearsal"], "samples": 0}
+
+
+class _RehearsalPlanner:
+    """Stands in for BatchPlanner in the CPU rehearsal: returns zeros, launches nothing."""
+
+    def __init__(self, n):
+        import torch
+        import types
+
+        self.n, self._events = n, 0
+        self.res = types.SimpleNamespace(path=torch.zeros((n, 40, 4)), status=torch.zeros((n,), dtype=torch.int32))
+        self._pinned = {"path": self.res.path}
+        self.lib = types.SimpleNamespace(fsd_plan_launches=lambda b: 4)
+
+    def plan(self, *a, kernel_events=False, **k):
+        self._events += int(kernel_events)
+        return self.res
+
+    def plan_pinned(self, *a, **k):
+        pass
+
+    def kernel_times_ms(self):
+        n, self._events = self._events, 0
+        return [(1.0, 1.0)] * max(n, 1)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from ft_fsd_path_planning_b200 import BatchPlanner, synth
+    from ft_fsd_path_planning_b200 import synth
     from ft_fsd_path_planning_b200.distributed import all_gather_frames
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    if REHEARSAL:
+        dev = torch.device("cpu")
+        new_event = _RehearsalEvent
+        sync = lambda: None
+    else:
+        from ft_fsd_path_planning_b200 import BatchPlanner
+
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        new_event = lambda: torch.cuda.Event(enable_timing=True)
+        sync = lambda: torch.cuda.synchronize(dev)
     if distributed:
         import datetime
 
         # a collective that does not complete within 3 minutes aborts the run instead of hanging the box
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        if REHEARSAL:
+            dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=180))
+        else:
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if distributed:
             dist.barrier()
-        torch.cuda.synchronize(dev)
+        sync()
 
     n_global = FRAMES_PER_GPU * world
     batch = synth.gen_autocross(SEED, FRAMES_PER_GPU, start=rank * FRAMES_PER_GPU)  # this rank's block of the global batch
     B = batch.n_frames
-    planner = BatchPlanner(dev)
+    planner = _RehearsalPlanner(B) if REHEARSAL else BatchPlanner(dev)
     xy = torch.from_numpy(batch.cones_xy).to(dev)
     ty = torch.from_numpy(batch.cones_type).to(dev)
     off = torch.from_numpy(batch.offsets).to(dev)
     pos = torch.from_numpy(batch.pos).to(dev)
     dr = torch.from_numpy(batch.dir).to(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = torch.empty(1024 if REHEARSAL else 256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(events=False):
         res = planner.plan(xy, ty, off, pos, dr, kernel_events=events)
@@ -165,7 +234,7 @@ def run_ours(args):
 
     # clocks / throttle reasons are sampled from the warm-up to the end of the timed steps (the timed region itself lasts
     # ~0.1 s, a handful of nvidia-smi periods); identical untimed steps are appended if fewer than 5 samples arrived
-    sampler = ClockSampler(local_rank)
+    sampler = _RehearsalSampler(rank) if REHEARSAL else ClockSampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
@@ -179,7 +248,7 @@ def run_ours(args):
     evs = []
     for _ in range(args.steps):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = new_event(), new_event()
         e0.record()
         step()
         e1.record()
@@ -191,7 +260,7 @@ def run_ours(args):
     while len(sampler.rows) < 5 and time.time() < t_end:
         flush.zero_()
         planner.plan(xy, ty, off, pos, dr)
-        torch.cuda.synchronize(dev)
+        sync()
     clocks = sampler.stop()
     clocks["window"] = "warm-up + timed steps (+ identical untimed steps until 5 samples)"
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
@@ -205,12 +274,12 @@ def run_ours(args):
     path_ms = float(np.mean([t[1] for t in ktimes]))
 
     # ---- end to end through the public API: pinned host buffers, H2D + plan + D2H inside the timed region -----
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)) if REHEARSAL else torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_xy, h_ty, h_off, h_pos, h_dir = pin(batch.cones_xy), pin(batch.cones_type), pin(batch.offsets), pin(batch.pos), pin(batch.dir)
-    h_path = torch.empty((B, 40, 4), dtype=torch.float32).pin_memory()
-    h_li = torch.empty((B, 12), dtype=torch.int16).pin_memory()
-    h_ri = torch.empty((B, 12), dtype=torch.int16).pin_memory()
-    h_st = torch.empty((B,), dtype=torch.int32).pin_memory()
+    h_path = pin(np.empty((B, 40, 4), dtype=np.float32))
+    h_li = pin(np.empty((B, 12), dtype=np.int16))
+    h_ri = pin(np.empty((B, 12), dtype=np.int16))
+    h_st = pin(np.empty((B,), dtype=np.int32))
 
     def e2e_step():
         # the host-to-host entry point: per chunk H2D of the inputs, the planner launches, D2H of paths / sort indices /
@@ -225,7 +294,7 @@ def run_ours(args):
     e2e_evs = []
     for _ in range(args.steps):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = new_event(), new_event()
         e0.record()
         e2e_step()
         e1.record()
@@ -243,7 +312,11 @@ def run_ours(args):
     status = planner.plan(xy, ty, off, pos, dr).status
     flagged = int(((status & 0x700) != 0).sum().item())  # overflow / reference-raises / unsupported
 
-    if rank == 0:
+    if rank == 0 and REHEARSAL:
+        # the rehearsal planned nothing: no number may leave it
+        print(json.dumps({"rehearsal": True, "value": None, "n_gpus": world, "steps": args.steps,
+                          "note": "control-flow rehearsal on CPU (gloo, planner stub): no planner work was done"}))
+    elif rank == 0:
         value = n_global / (step_ms * 1e-3)
         peak, peak_src = peaks()
         alg_bytes = batch.algorithmic_bytes()  # per launch of this rank's shard: 9 B/cone + 708 B/frame
