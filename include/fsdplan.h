@@ -21,6 +21,9 @@
  *     FSD_MAX_CONES cones per frame (more -> FSD_ST_OVERFLOW, frame planned on the first 256);
  *   - sort indices index the frame's own cone list (reference: flatten_cones_by_type_array,
  *     fsd_path_planning/sorting_cones/trace_sorter/core_trace_sorter.py:37-54);
+ *   - the library owns nothing but a few internal CUDA streams / events per device (created on first use): a large
+ *     fsd_plan_batch call runs its second half on one of them, forked from and joined back into `stream` with events,
+ *     so the call is still ONE asynchronous operation ordered on `stream` (see fsd_plan_launches);
  *   - no CPU fallback exists: without a CUDA device every entry point returns FSD_ERR_NO_DEVICE.
  */
 #ifndef FSDPLAN_H
