@@ -86,6 +86,10 @@ def lib():
                      vp, vp, sz, vp]
         L.fsd_plan_batch.argtypes = plan_args
         L.fsd_plan_batch_f64.argtypes = plan_args
+        L.fsd_plan_first_chunk.restype = i32
+        L.fsd_plan_first_chunk.argtypes = [i32]
+        L.fsd_plan_batch_ex.argtypes = [C.POINTER(Params), i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                        C.POINTER(Intermediate), vp, vp, i32, vp, vp, sz, vp, vp]
         L.fsd_sort_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.fsd_match_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, C.POINTER(Intermediate), vp, vp]
         L.fsd_sort_match_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp,

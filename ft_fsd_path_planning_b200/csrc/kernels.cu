@@ -591,6 +591,31 @@ int device_info(DeviceInfo **out) {
     cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
     D.sort_ctas = a > 0 ? a : 1;
     D.path_ctas = b > 0 ? b : 1;
+    // The constant initial path of a fresh planner with the default spline parameters, computed ONCE per device here --
+    // on a private stream with its own synchronisation -- so that no later call has to synchronise the caller's stream
+    // (the batch entry points stay asynchronous and capturable; the first call on a device must not be made under
+    // stream capture, see fsdplan.h).
+    {
+      fsd_params dp;
+      fsd_params_default(&dp);
+      double *cached = nullptr;
+      cudaStream_t st = nullptr;
+      bool ok = cudaGetSymbolAddress(reinterpret_cast<void **>(&cached), g_initial_path) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+      if (ok) {
+        initial_path_kernel<<<1, 32, INITIAL_SMEM, st>>>(make_dev_params(dp), cached);
+        ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+      }
+      if (st) cudaStreamDestroy(st);
+      if (!ok) {
+        cudaGetLastError();
+        return FSD_ERR_LAUNCH;
+      }
+      D.key[0] = dp.smoothing;
+      D.key[1] = dp.predict_every;
+      D.key[2] = dp.refit_smoothing;
+      D.initial_ready = true;
+    }
     D.sm_count = prop.multiProcessorCount;
   }
   *out = &D;
@@ -687,24 +712,18 @@ int check_launch() {
   return e == cudaSuccess ? FSD_OK : FSD_ERR_LAUNCH;
 }
 
-// the previous path used when the caller passes none: the initial path of a fresh planner
+// the previous path used when the caller passes none: the initial path of a fresh planner.  Default spline parameters:
+// the per-device constant computed in device_info; otherwise computed into `scratch` on the caller's stream
+// (asynchronous, no synchronisation).
 int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &D, double *scratch,
                       cudaStream_t stream, const double **prev) {
   const double key[3] = {params->smoothing, params->predict_every, params->refit_smoothing};
-  double *cached = nullptr;
-  if (cudaGetSymbolAddress(reinterpret_cast<void **>(&cached), g_initial_path) != cudaSuccess) {
-    cudaGetLastError();
-    return FSD_ERR_LAUNCH;
-  }
-  std::lock_guard<std::mutex> lock(g_mutex);
-  if (!D.initial_ready) {
-    initial_path_kernel<<<1, 32, INITIAL_SMEM, stream>>>(P, cached);
-    if (check_launch() != FSD_OK) return FSD_ERR_LAUNCH;
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return FSD_ERR_LAUNCH;  // once per device
-    D.initial_ready = true;
-    std::memcpy(D.key, key, sizeof(key));
-  }
-  if (std::memcmp(D.key, key, sizeof(key)) == 0) {
+  if (D.initial_ready && std::memcmp(D.key, key, sizeof(key)) == 0) {
+    double *cached = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void **>(&cached), g_initial_path) != cudaSuccess) {
+      cudaGetLastError();
+      return FSD_ERR_LAUNCH;
+    }
     *prev = cached;
     return FSD_OK;
   }
@@ -802,7 +821,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                     const int32_t *offsets, const T *pos, const T *dir, float *out_path, int16_t *out_left_idx,
                     int16_t *out_right_idx, const fsd_intermediate *inter, const int16_t *force_P,
                     const double *prev_path, int prev_path_stride, uint32_t *out_status, void *workspace,
-                    size_t workspace_bytes_given, void *stream_v) {
+                    size_t workspace_bytes_given, void *stream_v, void *chunk_ready_v = nullptr) {
   if (!params || n_frames < 0) return FSD_ERR_ARG;
   if (mission != FSD_MISSION_AUTOCROSS && mission != FSD_MISSION_TRACKDRIVE) return FSD_ERR_MISSION;
   if (n_frames == 0) return FSD_OK;
@@ -831,8 +850,13 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
     rc = sort_match_impl<T>(params, n_frames, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
                             out_status, stream);
     if (rc != FSD_OK) return rc;
-    return path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
-                        out_status, stream);
+    rc = path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
+                      out_status, stream);
+    if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
+      cudaGetLastError();
+      rc = FSD_ERR_LAUNCH;
+    }
+    return rc;
   }
   // chunk A = frames [0, na) on the caller's stream, chunk B = [na, n_frames) on the side stream; the CSR offsets are
   // absolute, so chunk B simply starts further into the same arrays
@@ -852,6 +876,12 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
     if (rc == FSD_OK)
       rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
                         stream);
+    // the outputs of frames [0, na) are final here: a caller that passed an event can start consuming them (e.g. an
+    // all-gather on a communication stream) while chunk B is still being planned
+    if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
+      cudaGetLastError();
+      rc = FSD_ERR_LAUNCH;
+    }
     if (rc == FSD_OK)
       rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
                         prev + h * (size_t)stride, stride, init_slot, scratch_b,
@@ -918,6 +948,24 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones) {
 int fsd_plan_launches(int n_frames) {
   if (n_frames <= 0) return 0;
   return first_chunk(n_frames) < n_frames ? 4 : 2;
+}
+
+int fsd_plan_first_chunk(int n_frames) { return n_frames <= 0 ? 0 : first_chunk(n_frames); }
+
+int fsd_plan_batch_ex(const fsd_params *params, int mission, int n_frames, int coords_f64, const void *cones_xy,
+                      const uint8_t *cones_type, const int32_t *offsets, const void *pos, const void *dir,
+                      float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                      const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                      void *workspace, size_t workspace_bytes_given, void *stream, void *chunk_ready_event) {
+  if (coords_f64)
+    return plan_batch_impl<double>(params, mission, n_frames, static_cast<const double *>(cones_xy), cones_type, offsets,
+                                   static_cast<const double *>(pos), static_cast<const double *>(dir), out_path,
+                                   out_left_idx, out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status,
+                                   workspace, workspace_bytes_given, stream, chunk_ready_event);
+  return plan_batch_impl<float>(params, mission, n_frames, static_cast<const float *>(cones_xy), cones_type, offsets,
+                                static_cast<const float *>(pos), static_cast<const float *>(dir), out_path, out_left_idx,
+                                out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status, workspace,
+                                workspace_bytes_given, stream, chunk_ready_event);
 }
 
 int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stream) {

@@ -26,6 +26,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _check_offsets(offsets: np.ndarray, total: int) -> None:
+    """CSR offsets seen on the host: start at >= 0, non-decreasing, end within the cone arrays."""
+    if len(offsets) and (offsets[0] < 0 or offsets[-1] > total or (np.diff(offsets) < 0).any()):
+        raise ValueError("offsets must be non-decreasing with 0 <= offsets[0] and offsets[-1] <= number of cones")
+
+
 @dataclass
 class PlanResult:
     """Device tensors produced by one batched call."""
@@ -47,8 +53,9 @@ class PlanResult:
 class BatchPlanner:
     """Plans batches of independent frames on one GPU.
 
-    Buffers (outputs, intermediates, workspace) are torch tensors owned by this object and re-used
-    across calls with the same batch size; the C library only sees raw pointers and the stream.
+    Every buffer is a torch tensor; the C library only sees raw pointers and the stream.  Outputs are fresh
+    tensors per call (or the caller's `out=` result, re-used); only the library's scratch workspace is cached
+    (one batch size resident) and calls on different streams are ordered on it with an event.
     """
 
     def __init__(self, device: Union[str, torch.device, int] = "cuda", mission: int = _lib.MISSION_TRACKDRIVE):
@@ -62,7 +69,8 @@ class BatchPlanner:
         self.lib = _lib.lib()
         self.params = _lib.default_params()
         self.mission = int(mission)
-        self._bufs = {}
+        self._ws, self._ws_key = None, None
+        self._last_stream, self._last_event = None, None
         self._prev0: Optional[torch.Tensor] = None
         self._pinned_key = None
         self._pinned: dict = {}
@@ -73,6 +81,11 @@ class BatchPlanner:
             self._prev0 = self.initial_path()
         return self._prev0
 
+    def first_chunk(self, B: int) -> int:
+        """Leading frames of a B-frame call whose outputs are final when `chunk_ready` fires (B: the call is not split)."""
+        with torch.cuda.device(self.device):
+            return int(self.lib.fsd_plan_first_chunk(B))
+
     def kernel_times_ms(self, clear: bool = True):
         """[(sort_match_ms, path_ms), ...] for the calls made with kernel_events=True (synchronize first)."""
         out = [(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) for e in self.kernel_events]
@@ -81,39 +94,65 @@ class BatchPlanner:
         return out
 
     # -- buffers -------------------------------------------------------------------------------------------
-    def _buffers(self, B: int, intermediates: bool):
-        key = (B, intermediates)
-        if key not in self._bufs:
-            dev = self.device
-            bufs = {
-                "path": torch.empty((B, HORIZON, 4), dtype=torch.float32, device=dev),
-                "left_idx": torch.empty((B, MAX_SORTED), dtype=torch.int16, device=dev),
-                "right_idx": torch.empty((B, MAX_SORTED), dtype=torch.int16, device=dev),
-                "status": torch.empty((B,), dtype=torch.int32, device=dev),
-                "workspace": torch.empty((int(self.lib.fsd_workspace_bytes(B, 0)),), dtype=torch.uint8, device=dev),
-            }
-            if intermediates:
-                bufs.update({
-                    "path_f64": torch.empty((B, HORIZON, 4), dtype=torch.float64, device=dev),
-                    "n_wv": torch.empty((B, 2), dtype=torch.int16, device=dev),
-                    "left_wv": torch.empty((B, MAX_WV, 2), dtype=torch.float64, device=dev),
-                    "right_wv": torch.empty((B, MAX_WV, 2), dtype=torch.float64, device=dev),
-                    "l2r": torch.empty((B, MAX_WV), dtype=torch.int16, device=dev),
-                    "r2l": torch.empty((B, MAX_WV), dtype=torch.int16, device=dev),
-                    "grid": torch.empty((B, 2), dtype=torch.int16, device=dev),
-                    "sort_dbg": torch.empty((B, 8), dtype=torch.int16, device=dev),
-                })
-            self._bufs = {k: v for k, v in self._bufs.items() if k[0] == B}  # one batch size resident
-            self._bufs[key] = bufs
-        return self._bufs[key]
+    def _workspace(self, B: int) -> torch.Tensor:
+        """Scratch of the C library for a batch of B frames: cached (one batch size resident), never handed out."""
+        if self._ws_key != B:
+            with torch.cuda.device(self.device):  # fsd_workspace_bytes sizes the scratch for the CURRENT device
+                nbytes = int(self.lib.fsd_workspace_bytes(B, 0))
+            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+            self._ws_key = B
+        return self._ws
+
+    def _outputs(self, B: int, intermediates: bool) -> dict:
+        """Fresh output tensors for one call: results of earlier calls are never overwritten."""
+        dev = self.device
+        bufs = {
+            "path": torch.empty((B, HORIZON, 4), dtype=torch.float32, device=dev),
+            "left_idx": torch.empty((B, MAX_SORTED), dtype=torch.int16, device=dev),
+            "right_idx": torch.empty((B, MAX_SORTED), dtype=torch.int16, device=dev),
+            "status": torch.empty((B,), dtype=torch.int32, device=dev),
+        }
+        if intermediates:
+            bufs.update({
+                "path_f64": torch.empty((B, HORIZON, 4), dtype=torch.float64, device=dev),
+                "n_wv": torch.empty((B, 2), dtype=torch.int16, device=dev),
+                "left_wv": torch.empty((B, MAX_WV, 2), dtype=torch.float64, device=dev),
+                "right_wv": torch.empty((B, MAX_WV, 2), dtype=torch.float64, device=dev),
+                "l2r": torch.empty((B, MAX_WV), dtype=torch.int16, device=dev),
+                "r2l": torch.empty((B, MAX_WV), dtype=torch.int16, device=dev),
+                "grid": torch.empty((B, 2), dtype=torch.int16, device=dev),
+                "sort_dbg": torch.empty((B, 8), dtype=torch.int16, device=dev),
+            })
+        return bufs
+
+    def _order_after_previous_call(self, stream: torch.cuda.Stream) -> None:
+        """The workspace is shared by all calls of this planner: a call on another stream than the previous one waits
+        for the previous call (calls on one stream are ordered anyway)."""
+        if self._last_stream is not None and self._last_stream != stream and self._last_event is not None:
+            stream.wait_event(self._last_event)
+
+    def _mark_call(self, stream: torch.cuda.Stream) -> None:
+        if self._last_stream is not None and self._last_stream != stream or self._last_event is None:
+            self._last_event = torch.cuda.Event()
+        self._last_stream = stream
+        self._last_event.record(stream)
 
     # -- the batched call ------------------------------------------------------------------------------------
     def plan(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
              direction: torch.Tensor, *, force_P: Optional[torch.Tensor] = None,
              prev_path: Optional[torch.Tensor] = None, intermediates: bool = False,
-             kernel_events: bool = False) -> PlanResult:
+             kernel_events: bool = False, out: Optional[PlanResult] = None,
+             chunk_ready: Optional[torch.cuda.Event] = None) -> PlanResult:
         """cones_xy [total, 2] float32|float64, cones_type [total] uint8, offsets [B+1] int32, pos/direction [B, 2]
-        (same dtype as cones_xy); all on this planner's device.  Asynchronous on the current stream.
+        (same dtype as cones_xy); all on this planner's device.  Asynchronous on the current stream.  The CSR
+        `offsets` must be non-decreasing with offsets[-1] <= total (checked for free by plan_host / plan_pinned, which
+        see them on the host; checking a device tensor here would cost a synchronisation per call).
+
+        Returns fresh tensors, or writes into `out` (a PlanResult of an earlier call with the same B and
+        `intermediates`) to avoid allocations in a loop.
+
+        chunk_ready: a CUDA event recorded as soon as the outputs of the first `first_chunk(B)` frames are final
+        (fsd_plan_batch_ex) -- the multi-GPU pipeline starts their all-gather on a side stream at that point.
 
         kernel_events=True issues the two launches through the stage entry points (fsd_sort_match_batch,
         fsd_path_batch) with CUDA events around each; the events are kept in `self.kernel_events`
@@ -130,8 +169,20 @@ class BatchPlanner:
                 raise ValueError("inputs must be contiguous tensors of the documented dtype on the planner's device")
         if cones_xy.dtype not in (torch.float32, torch.float64):
             raise ValueError("cones_xy must be float32 or float64")
+        if cones_xy.dim() != 2 or cones_xy.shape[1] != 2 or cones_type.numel() != cones_xy.shape[0]:
+            raise ValueError("cones_xy must be [total, 2] and cones_type [total]")
+        if pos.numel() != 2 * B or direction.numel() != 2 * B:
+            raise ValueError("pos and direction must be [B, 2] with B = len(offsets) - 1")
         intermediates = intermediates or kernel_events
-        bufs = self._buffers(B, intermediates)
+        if out is not None:
+            if out.path.shape[0] != B or out.path.device != self.device or (intermediates and out.path_f64 is None):
+                raise ValueError("out= must be the PlanResult of a call with the same batch size and intermediates")
+            bufs = {k: getattr(out, k) for k in ("path", "left_idx", "right_idx", "status", "path_f64", "n_wv", "left_wv",
+                                                 "right_wv", "l2r", "r2l", "grid", "sort_dbg") if getattr(out, k) is not None}
+            intermediates = intermediates or out.path_f64 is not None
+        else:
+            bufs = self._outputs(B, intermediates)
+        ws = self._workspace(B)
         inter = None
         if intermediates:
             inter = _lib.Intermediate(*[bufs[n].data_ptr() for n in
@@ -143,11 +194,14 @@ class BatchPlanner:
             stride = 0 if prev_path.numel() == HORIZON * 4 else HORIZON * 4
             if stride and prev_path.numel() != B * HORIZON * 4:
                 raise ValueError("prev_path must be [40, 4] or [B, 40, 4]")
-        if force_P is not None and (force_P.dtype != torch.int16 or force_P.numel() != B):
-            raise ValueError("force_P must be int16 [B]")
+        if force_P is not None and (force_P.dtype != torch.int16 or force_P.numel() != B or
+                                    force_P.device != self.device or not force_P.is_contiguous()):
+            raise ValueError("force_P must be a contiguous int16 [B] tensor on the planner's device")
         fn = self.lib.fsd_plan_batch_f64 if f64 else self.lib.fsd_plan_batch
         with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cur = torch.cuda.current_stream(self.device)
+            self._order_after_previous_call(cur)
+            stream = cur.cuda_stream
             if kernel_events:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 ev[0].record()
@@ -162,16 +216,27 @@ class BatchPlanner:
                 rc = self.lib.fsd_path_batch(
                     C.byref(self.params), B, int(f64), pos.data_ptr(), direction.data_ptr(), C.byref(inter),
                     _ptr(force_P), prev_path.data_ptr(), stride, bufs["path"].data_ptr(), bufs["status"].data_ptr(),
-                    bufs["workspace"].data_ptr(), bufs["workspace"].numel(), stream)
+                    ws.data_ptr(), ws.numel(), stream)
                 ev[2].record()
                 self.kernel_events.append(ev)
+            elif chunk_ready is not None:
+                chunk_ready.record(cur)  # creates the lazily-initialised CUDA event; re-recorded by the library
+                rc = self.lib.fsd_plan_batch_ex(
+                    C.byref(self.params), self.mission, B, int(f64), cones_xy.data_ptr(), cones_type.data_ptr(),
+                    offsets.data_ptr(), pos.data_ptr(), direction.data_ptr(), bufs["path"].data_ptr(),
+                    bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
+                    C.byref(inter) if inter is not None else None, _ptr(force_P), _ptr(prev_path), stride,
+                    bufs["status"].data_ptr(), ws.data_ptr(), ws.numel(), stream, chunk_ready.cuda_event)
             else:
                 rc = fn(C.byref(self.params), self.mission, B, cones_xy.data_ptr(), cones_type.data_ptr(),
                         offsets.data_ptr(), pos.data_ptr(), direction.data_ptr(), bufs["path"].data_ptr(),
                         bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
                         C.byref(inter) if inter is not None else None, _ptr(force_P), _ptr(prev_path), stride,
-                        bufs["status"].data_ptr(), bufs["workspace"].data_ptr(), bufs["workspace"].numel(), stream)
+                        bufs["status"].data_ptr(), ws.data_ptr(), ws.numel(), stream)
+            self._mark_call(cur)
         _lib.check(rc)
+        if out is not None:
+            return out
         res = PlanResult(bufs["path"], bufs["left_idx"], bufs["right_idx"], bufs["status"])
         if intermediates:
             for n in ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg"):
@@ -182,6 +247,7 @@ class BatchPlanner:
                   prev_path: Optional[np.ndarray] = None, intermediates: bool = False) -> PlanResult:
         """Convenience: host FrameBatch in, device PlanResult out (copies on the current stream)."""
         dev = self.device
+        _check_offsets(np.asarray(batch.offsets), len(batch.cones_xy))
         dt = torch.float64 if batch.cones_xy.dtype == np.float64 else torch.float32
         xy = torch.from_numpy(np.ascontiguousarray(batch.cones_xy)).to(dev, dt)
         ty = torch.from_numpy(np.ascontiguousarray(batch.cones_type, dtype=np.uint8)).to(dev)
@@ -218,6 +284,7 @@ class BatchPlanner:
                 or out_left_idx.numel() != B * MAX_SORTED or out_right_idx.numel() != B * MAX_SORTED \
                 or out_status.numel() != B:
             raise ValueError("outputs must be [B,40,4] float32, [B,12] int16, [B,12] int16, [B] int32")
+        _check_offsets(offsets.numpy(), int(cones_xy.shape[0]))
         f64 = cones_xy.dtype == torch.float64
         K = chunks if chunks is not None else max(1, min(4, B // 2500))
         K = max(1, min(int(K), B))
@@ -226,12 +293,14 @@ class BatchPlanner:
         if self._pinned_key != key:
             e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
             bounds = [B * k // K for k in range(K + 1)]
+            with torch.cuda.device(dev):  # the workspace is sized for the current device
+                ws_bytes = [int(self.lib.fsd_workspace_bytes(bounds[k + 1] - bounds[k], 0)) for k in range(K)]
             self._pinned = {
                 "xy": e((max(int(cones_xy.shape[0]), 1), 2), cones_xy.dtype), "ty": e((max(int(cones_xy.shape[0]), 1),), torch.uint8),
                 "off": e((B + 1,), torch.int32), "pos": e((B, 2), cones_xy.dtype), "dir": e((B, 2), cones_xy.dtype),
                 "path": e((B, HORIZON, 4), torch.float32), "li": e((B, MAX_SORTED), torch.int16),
                 "ri": e((B, MAX_SORTED), torch.int16), "st": e((B,), torch.int32), "bounds": bounds,
-                "ws": [e((int(self.lib.fsd_workspace_bytes(bounds[k + 1] - bounds[k], 0)),), torch.uint8) for k in range(K)],
+                "ws": [e((ws_bytes[k],), torch.uint8) for k in range(K)],
                 "streams": [torch.cuda.Stream(dev) for _ in range(K)],
             }
             self._pinned_key = key
@@ -285,11 +354,24 @@ class RelocalizationInformation:
     rotation: float
 
 
+class ReferenceRaisesError(RuntimeError):
+    """The reference raises an exception on this input (e.g. the IndexError of functional_cone_matching.py:130 when a
+    sorted side holds exactly one cone) or takes its latent-bug path (core_calculate_path.py:482-483).  The batched
+    planner flags such frames (FSD_ST_REF_RAISES / FSD_ST_UNSUPPORTED); the drop-in facade raises like the reference
+    and, like it, leaves the planner's state (the previous path) untouched."""
+
+
 class PathPlanner:
-    """Drop-in for fsd_path_planning.PathPlanner on the trackdrive / autocross path."""
+    """Drop-in for fsd_path_planning.PathPlanner on the trackdrive / autocross path.
+
+    on_reference_error: "raise" (default, the reference's behaviour: an exception, state untouched) or "previous"
+    (return the previous path instead of raising; state untouched as well)."""
 
     def __init__(self, mission: MissionTypes, experimental_performance_improvements: bool = False,
-                 device: Union[str, torch.device, int] = "cuda") -> None:
+                 device: Union[str, torch.device, int] = "cuda", on_reference_error: str = "raise") -> None:
+        if on_reference_error not in ("raise", "previous"):
+            raise ValueError('on_reference_error must be "raise" or "previous"')
+        self.on_reference_error = on_reference_error
         self.mission = MissionTypes(mission)
         if self.mission in (MissionTypes.acceleration, MissionTypes.ebs_test):
             raise NotImplementedError(
@@ -379,9 +461,15 @@ class PathPlanner:
         if self._prev_path is None:
             self._prev_path = self._planner.initial_path()
         res = self._plan_with_prev(batch)
-        path = res.path_f64[0].clone()
-        self._prev_path = path
-        out_path = path.cpu().numpy()
+        status = int(res.status[0].item())
+        if status & (_lib.STATUS_BITS["REF_RAISES"] | _lib.STATUS_BITS["UNSUPPORTED"]):
+            # the reference raises here and never reaches `self.previous_paths = ...` (core_calculate_path.py:572)
+            if self.on_reference_error == "raise":
+                raise ReferenceRaisesError(f"the reference planner raises on this input (status 0x{status:x})")
+            res.path_f64[0].copy_(self._prev_path)
+        else:
+            self._prev_path = res.path_f64[0].clone()
+        out_path = res.path_f64[0].cpu().numpy()
         if not return_intermediate_results:
             return out_path
         xy = batch.cones_xy

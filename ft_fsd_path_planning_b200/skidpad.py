@@ -20,40 +20,12 @@ _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "skidpa
 N_TRIPLES = 1140  # C(20, 3)
 
 
-def _hyper_circle_centre(pts: np.ndarray) -> np.ndarray:
-    """Centre of the algebraic (hyper) circle fit, the reference's circle_fit (utils/math_utils.py:579-646)."""
-    x, y = pts[:, 0], pts[:, 1]
-    n = len(x)
-    xi, yi = x - x.mean(), y - y.mean()
-    zi = xi * xi + yi * yi
-    mxy, mxx, myy = (xi * yi).sum() / n, (xi * xi).sum() / n, (yi * yi).sum() / n
-    mxz, myz, mzz = (xi * zi).sum() / n, (yi * zi).sum() / n, (zi * zi).sum() / n
-    mz = mxx + myy
-    cov = mxx * myy - mxy * mxy
-    var = mzz - mz * mz
-    a2 = 4 * cov - 3 * mz * mz - mzz
-    a1 = var * mz + 4.0 * cov * mz - mxz * mxz - myz * myz
-    a0 = mxz * (mxz * myy - myz * mxy) + myz * (myz * mxx - mxz * mxy) - var * cov
-    a22 = a2 + a2
-    yv, xv = a0, 0.0
-    for _ in range(99):
-        dy = a1 + xv * (a22 + 16.0 * xv * xv)
-        xn = xv - yv / dy
-        if xn == xv or not np.isfinite(xn):
-            break
-        yn = a0 + xn * (a1 + xn * (a2 + 4.0 * xn * xn))
-        if abs(yn) >= abs(yv):
-            break
-        xv, yv = xn, yn
-    det = xv * xv - xv * mz + cov
-    return np.array([(mxz * (myy - xv) - myz * mxy) / det / 2.0 + x.mean(),
-                     (myz * (mxx - xv) - mxz * mxy) / det / 2.0 + y.mean()])
-
-
 def skidpad_constants():
     """(tracked path = table[::2], reference centres [right, left], jitter)"""
     table = np.load(_DATA)
-    ref = np.stack([_hyper_circle_centre(table[table[:, 1] < -2]), _hyper_circle_centre(table[table[:, 1] > 2])])
+    # circle centres of the two loops of the canonical path (skidpad_relocalizer.py:172-183): constants of the track
+    # definition, extracted from the reference by tools/extract_skidpad_path.py like the path table itself
+    ref = np.load(os.path.join(os.path.dirname(_DATA), "skidpad_ref_centers.npy"))
     jitter = np.random.RandomState(42).randn(N_TRIPLES * 6)  # the sequence skidpad_relocalizer.py:38, 53 consumes
     return np.ascontiguousarray(table[::2]), ref, jitter
 
@@ -130,3 +102,46 @@ class SkidpadBatchPlanner:
                 self._stream()))
         out["_workspace"] = ws  # keep alive until the stream has consumed it
         return out
+
+
+def plan_skidpad_sharded(planner: SkidpadBatchPlanner, step_offsets: np.ndarray, pos: torch.Tensor,
+                         direction: torch.Tensor, reloc: torch.Tensor, index_state: torch.Tensor, *, group=None,
+                         plan_fn=None):
+    """Skidpad on several GPUs: the steps of one trajectory are sequential (`index_along_path`, the
+    previous-path fallback), trajectories are independent -> every rank plans WHOLE trajectories
+    (`distributed.shard_trajectories`, balanced by step count) and one all-gather per output tensor collects the
+    results in trajectory order.  step_offsets: host int array [T + 1]; pos / direction [S, 2], reloc [T, 8],
+    index_state [T] are the FULL tensors on every rank (each rank reads its slice; index_state is updated for the
+    rank's own trajectories and then gathered).  `plan_fn(step_offsets, pos, dir, reloc, index_state) -> dict` defaults to
+    `planner.plan`; tests pass a CPU stand-in to exercise the partition and the gathers on gloo.  Returns the gathered
+    dict (path, path_f64, internal, index, grid, status) with S rows on every rank, and the gathered index_state."""
+    import torch.distributed as dist
+
+    from .distributed import all_gather_ragged, shard_trajectories
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    off = np.asarray(step_offsets, dtype=np.int64)
+    cuts = [shard_trajectories(off, r, world) for r in range(world)]
+    t_lo, t_hi = cuts[rank]
+    s_lo, s_hi = int(off[t_lo]), int(off[t_hi])
+    dev = pos.device
+    local_off = torch.from_numpy((off[t_lo : t_hi + 1] - off[t_lo]).astype(np.int32)).to(dev)
+    local_state = index_state[t_lo:t_hi].clone()
+    fn = plan_fn if plan_fn is not None else planner.plan
+    if t_hi > t_lo:
+        out = fn(local_off, pos[s_lo:s_hi].contiguous(), direction[s_lo:s_hi].contiguous(),
+                 reloc[t_lo:t_hi].contiguous(), local_state)
+    else:
+        out = None
+    step_counts = [int(off[c[1]] - off[c[0]]) for c in cuts]
+    traj_counts = [c[1] - c[0] for c in cuts]
+    specs = {"path": ((HORIZON, 4), torch.float32), "path_f64": ((HORIZON, 4), torch.float64),
+             "internal": ((HORIZON, 4), torch.float64), "index": ((), torch.int32), "grid": ((2,), torch.int16),
+             "status": ((), torch.int32)}
+    gathered = {}
+    for k, (tail, dt) in specs.items():
+        local = out[k] if out is not None else torch.zeros((0, *tail), dtype=dt, device=dev)
+        gathered[k] = all_gather_ragged(local, step_counts, group)
+    state = all_gather_ragged(local_state, traj_counts, group)
+    index_state.copy_(state)
+    return gathered, state

@@ -113,6 +113,17 @@ def pack_frames(
     )
 
 
+def concat_batches(parts: Sequence[FrameBatch]) -> FrameBatch:
+    """Frames of several batches back to back (CSR offsets re-based)."""
+    offs, tot = [np.zeros(1, np.int32)], 0
+    for p in parts:
+        offs.append((p.offsets[1:].astype(np.int64) - int(p.offsets[0]) + tot).astype(np.int32))
+        tot += int(p.offsets[-1]) - int(p.offsets[0])
+    return FrameBatch(np.concatenate([p.cones_xy[int(p.offsets[0]):int(p.offsets[-1])] for p in parts]),
+                      np.concatenate([p.cones_type[int(p.offsets[0]):int(p.offsets[-1])] for p in parts]),
+                      np.concatenate(offs), np.concatenate([p.pos for p in parts]), np.concatenate([p.dir for p in parts]))
+
+
 def remove_color_info(batch: FrameBatch) -> FrameBatch:
     """All cones become UNKNOWN (reference: fsd_path_planning/demo/json_demo.py:266-273).
 
@@ -213,30 +224,69 @@ def gen_autocross_frame(seed: int, index: int):
     return cones_by_type, pos, direction
 
 
-def gen_autocross(seed: int, n_frames: int, start: int = 0, dtype=np.float32) -> FrameBatch:
-    """Frames start..start+n_frames-1 of the synthetic autocross stream `seed`."""
-    frames = [gen_autocross_frame(seed, start + i) for i in range(n_frames)]
-    return pack_frames(frames, dtype=dtype)
+def _mixed_frame(seed: int, index: int):
+    """Frame `index` of the mixed stream: odd frames keep their colours, even frames lose each cone's colour with
+    p = 0.5 (the frame is re-packed so UNKNOWN cones come first)."""
+    cones, pos, direction = gen_autocross_frame(seed, index)
+    if index % 2 == 0:
+        rng = np.random.default_rng([int(seed), int(index), 77])
+        unknown = [cones[UNKNOWN]]
+        new = [None] * 5
+        for t in (YELLOW, BLUE, ORANGE_SMALL, ORANGE_BIG):
+            drop = rng.random(len(cones[t])) < 0.5
+            unknown.append(cones[t][drop])
+            new[t] = cones[t][~drop]
+        new[UNKNOWN] = np.concatenate(unknown, 0)
+        cones = new
+    return cones, pos, direction
 
 
-def gen_mixed(seed: int, n_frames: int, start: int = 0, dtype=np.float32) -> FrameBatch:
+def _gen_block(args):
+    kind, seed, lo, hi = args
+    fn = _mixed_frame if kind == "mixed" else gen_autocross_frame
+    return [fn(seed, i) for i in range(lo, hi)]
+
+
+def _gen_frames(kind: str, seed: int, n_frames: int, start: int, workers: int):
+    """Frames start .. start+n_frames-1; every frame is a pure function of (seed, index), so blocks generated by
+    `workers` processes are identical to the sequential result.  The workers are plain `python -m ...synth` child
+    processes (no fork of a process that holds a CUDA context, no re-import of the caller's __main__)."""
+    if workers <= 1 or n_frames < 64 * workers:
+        return _gen_block((kind, seed, start, start + n_frames))
+    import os
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+
+    bounds = [start + n_frames * k // workers for k in range(workers + 1)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), OMP_NUM_THREADS="1",
+               OPENBLAS_NUM_THREADS="1")
+    with tempfile.TemporaryDirectory(prefix="fsd_gen_") as tmp:
+        procs = []
+        for k in range(workers):
+            out = os.path.join(tmp, f"{k}.pkl")
+            procs.append((out, subprocess.Popen([sys.executable, "-W", "ignore", "-m", "ft_fsd_path_planning_b200.synth", kind, str(seed),
+                                                 str(bounds[k]), str(bounds[k + 1]), out], env=env)))
+        frames = []
+        for out, p in procs:
+            if p.wait(timeout=1800) != 0:
+                raise RuntimeError("frame generator worker failed")
+            with open(out, "rb") as f:
+                frames.extend(pickle.load(f))
+    return frames
+
+
+def gen_autocross(seed: int, n_frames: int, start: int = 0, dtype=np.float32, workers: int = 1) -> FrameBatch:
+    """Frames start..start+n_frames-1 of the synthetic autocross stream `seed` (`workers` > 1: generated in parallel)."""
+    return pack_frames(_gen_frames("autocross", seed, n_frames, start, workers), dtype=dtype)
+
+
+def gen_mixed(seed: int, n_frames: int, start: int = 0, dtype=np.float32, workers: int = 1) -> FrameBatch:
     """BASELINE config 5: odd frames keep their colours, even frames lose each cone's colour
     with p = 0.5 (the frame is re-packed so UNKNOWN cones come first)."""
-    frames = []
-    for i in range(n_frames):
-        cones, pos, direction = gen_autocross_frame(seed, start + i)
-        if (start + i) % 2 == 0:
-            rng = np.random.default_rng([int(seed), int(start + i), 77])
-            unknown = [cones[UNKNOWN]]
-            new = [None] * 5
-            for t in (YELLOW, BLUE, ORANGE_SMALL, ORANGE_BIG):
-                drop = rng.random(len(cones[t])) < 0.5
-                unknown.append(cones[t][drop])
-                new[t] = cones[t][~drop]
-            new[UNKNOWN] = np.concatenate(unknown, 0)
-            cones = new
-        frames.append((cones, pos, direction))
-    return pack_frames(frames, dtype=dtype)
+    return pack_frames(_gen_frames("mixed", seed, n_frames, start, workers), dtype=dtype)
 
 
 # ---- skidpad (BASELINE config 4) ------------------------------------------------------------------------------------
@@ -276,3 +326,12 @@ def gen_skidpad(seed: int, n_traj: int, n_steps: int):
         ty_all.append(cones[:, 2].astype(np.uint8))
         offsets.append(offsets[-1] + len(xy))
     return (np.ascontiguousarray(np.concatenate(xy_all)), np.concatenate(ty_all), np.asarray(offsets, np.int32), pos, dirs)
+
+
+if __name__ == "__main__":  # worker of _gen_frames: kind seed lo hi out.pkl
+    import pickle
+    import sys
+
+    _kind, _seed, _lo, _hi, _out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+    with open(_out, "wb") as _f:
+        pickle.dump(_gen_block((_kind, _seed, _lo, _hi)), _f, protocol=pickle.HIGHEST_PROTOCOL)

@@ -64,7 +64,11 @@ extern "C" {
 #define FSD_ST_MPC_FAILED (1u << 6)   /* tail raised ValueError: redone with the previous path     (:561-570) */
 #define FSD_ST_TIE_P (1u << 7)        /* size of the last evaluation grid decided by the tie rule */
 #define FSD_ST_OVERFLOW (1u << 8)     /* a static bound was exceeded (cones, DFS leaves, knots, path points) */
-#define FSD_ST_REF_RAISES (1u << 9)   /* the reference raises an exception on this input; output = previous path */
+#define FSD_ST_REF_RAISES (1u << 9)   /* the reference raises an exception on this input.  Raised by the path stage: output =
+                                         previous path.  Raised by the matching stage (a sorted side with exactly one cone,
+                                         functional_cone_matching.py:130): that side is matched as all -1 and the path is
+                                         computed from what remains -- a usable path, but not one the reference produces;
+                                         the drop-in PathPlanner raises on this bit like the reference does */
 #define FSD_ST_UNSUPPORTED (1u << 10) /* reference takes a latent-bug path that is not reproduced; output = previous path */
 
 #define FSD_OK 0
@@ -121,7 +125,9 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones);
 /* Kernel launches one fsd_plan_batch call makes for n_frames frames on the current device: 2 (sort+match, path), or 4
  * when the batch is large enough to be planned as two chunks -- the second one on an internal side stream that is
  * forked from and joined back into the caller's stream with events, so the call stays asynchronous and ordered on
- * the caller's stream (and capturable in a CUDA graph). */
+ * the caller's stream (and capturable in a CUDA graph -- after one warm-up call: the FIRST call on a device initialises
+ * per-device constants, among them the initial path of a fresh planner, on a private stream with its own
+ * synchronisation, and must not be made under stream capture). */
 int fsd_plan_launches(int n_frames);
 
 /* The constant initial path of a fresh planner (core_calculate_path.py:103-107), computed on the
@@ -151,6 +157,18 @@ int fsd_plan_batch_f64(const fsd_params *params, int mission, int n_frames, cons
                        const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
                        int prev_path_stride, uint32_t *out_status, void *workspace, size_t workspace_bytes,
                        void *stream);
+
+/* fsd_plan_batch with the coordinate type as a flag (coords_f64 != 0: fp64) and an optional CUDA event:
+ * `chunk_ready_event` (cudaEvent_t, nullable) is recorded on `stream` as soon as the outputs of the first
+ * fsd_plan_first_chunk(n_frames) frames are final -- a caller can start consuming them (e.g. the all-gather of their paths
+ * on a communication stream, ft_fsd_path_planning_b200/distributed.py) while the rest of the batch is still being planned.
+ * The whole call remains ordered on `stream`. */
+int fsd_plan_first_chunk(int n_frames);
+int fsd_plan_batch_ex(const fsd_params *params, int mission, int n_frames, int coords_f64, const void *cones_xy,
+                      const uint8_t *cones_type, const int32_t *offsets, const void *pos, const void *dir,
+                      float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                      const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                      void *workspace, size_t workspace_bytes, void *stream, void *chunk_ready_event);
 
 /* Stage entry points (same conventions).  fsd_sort_batch: ConeSorting only. */
 int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy, const uint8_t *cones_type,

@@ -3,13 +3,14 @@ vectors of the unmodified reference, against the oracle on seeded synthetic batc
 full sizes -- through size-independent properties (determinism, batch-order and shard independence, rigid-motion
 equivariance).  Run on the B200 box: pytest -m gpu."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 import torch
 
 import oracle  # the checker, never the thing under test
-from conftest import GOLDEN_SETS, compare_with_golden, load_golden
+from conftest import GOLDEN_SETS, TIE_DIST_TOL, TIE_KAPPA_TOL, compare_with_golden, load_golden, tie_frame_deviation
 from ft_fsd_path_planning_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -56,6 +57,13 @@ def test_cuda_tie_normalised(planner, name):
     assert (err[ok] <= 1e-7).all()
     strict = np.abs(r["path_f64"] - g["path"]).reshape(len(ok), -1).max(1) <= 1e-4
     print(f"{name}: strict parity {int(strict[ok].sum())}/{int(ok.sum())} (reference's own P coin flip)")
+    # strict gate, made a gate: where the reference's coin flip agrees with the tie rule the default output is within
+    # 1e-4; elsewhere it is the same curve sampled one grid step apart -- bounded geometrically
+    other = ok & (g["P"] != g["tie_P"])
+    assert strict[ok & ~other].all()
+    for b in np.where(other)[0]:
+        dist, kappa = tie_frame_deviation(r["path_f64"][b], g["path"][b])
+        assert dist <= TIE_DIST_TOL and kappa <= TIE_KAPPA_TOL, (name, b, dist, kappa)
 
 
 @pytest.mark.parametrize("gen,seed,n", [("color", 11, 2048), ("colorless", 12, 2048), ("mixed", 13, 2048)])
@@ -108,10 +116,55 @@ def test_augmented_real_frames_match_oracle(planner):
     assert ((r["status"].astype(np.uint32) & 0xFFFFFF7F) == (ref["status"] & 0xFFFFFF7F)).all()
 
 
-def test_full_size_properties(planner):
-    """BASELINE config 3 (10 000 colourless frames): properties that need no oracle."""
+def _oracle_parity(planner, batch, tag, shard_of=None):
+    """CUDA (through the C-ABI) against the oracle on the same batch: sort indices, seeds / #configurations / DFS pops
+    (sort_dbg), matches and status bit-identical; with-virtual cones 1e-9; path 1e-7 (fp64) / 1e-4 (fp32 output),
+    P-conditioned (SURVEY 8d gate i).  Returns the statistics the round report quotes."""
+    ref = oracle.plan_batch(batch.astype(np.float64), threads=os.cpu_count() or 8)
+    res = planner.plan_host(batch, force_P=ref["P"].astype(np.int16), intermediates=True)
+    r = _np(res)
+    dbg = res.sort_dbg.cpu().numpy()
+    B = batch.n_frames
+    where = lambda m: f"{tag}: frames {np.where(m)[0][:8]}" + (f" of shard {shard_of}" if shard_of is not None else "")
+    bad = (r["left_idx"] != ref["left_idx"]).any(1) | (r["right_idx"] != ref["right_idx"]).any(1)
+    assert not bad.any(), "sort indices differ, " + where(bad)
+    bad = (dbg[:, :4] != ref["first_k"].reshape(B, 4)).any(1)
+    assert not bad.any(), "seeds differ, " + where(bad)
+    bad = (dbg[:, 4:6] != ref["n_configs"]).any(1) | (dbg[:, 6:8] != np.minimum(ref["n_pops"], 32767)).any(1)
+    assert not bad.any(), "number of configurations / DFS pops differ, " + where(bad)
+    bad = (r["n_wv"][:, 0] != ref["n_left_wv"]) | (r["n_wv"][:, 1] != ref["n_right_wv"]) | \
+          (r["l2r"] != ref["l2r"]).any(1) | (r["r2l"] != ref["r2l"]).any(1)
+    assert not bad.any(), "matches differ, " + where(bad)
+    assert np.abs(r["left_wv"] - ref["left_wv"]).max() <= 1e-9 and np.abs(r["right_wv"] - ref["right_wv"]).max() <= 1e-9
+    bad = (r["status"].astype(np.uint32) & 0xFFFFFF7F) != (ref["status"] & 0xFFFFFF7F)
+    assert not bad.any(), "status differs, " + where(bad)
+    assert (r["grid"][:, 1] == ref["n_trim"]).all()
+    e64 = np.abs(r["path_f64"] - ref["path"]).reshape(B, -1).max(1)
+    e32 = np.abs(r["path"] - ref["path"]).reshape(B, -1).max(1)
+    assert e64.max() <= 1e-7, f"fp64 path differs by {e64.max()}, " + where(e64 > 1e-7)
+    assert e32.max() <= 1e-4, f"fp32 path differs by {e32.max()}, " + where(e32 > 1e-4)
+    return {"frames": B, "path_max_err_f64": float(e64.max()), "path_max_err_f32": float(e32.max()),
+            "frames_with_2plus_configs": int((ref["n_configs"] >= 2).any(1).sum()),
+            "flagged": int(((ref["status"] & 0x700) != 0).sum()), "result": r}
+
+
+def test_config2_1024_coloured_frames_match_oracle(planner):
+    """BASELINE config 2, the exact batch: gen_autocross(seed=2, B=1024), colours known."""
+    batch = synth.gen_autocross(2, 1024, workers=min(os.cpu_count() or 1, 16))
+    st = _oracle_parity(planner, batch, "config 2")
+    print(f"config 2: {st['frames']} frames, fp64 path err {st['path_max_err_f64']:.2e}, fp32 {st['path_max_err_f32']:.2e}, "
+          f"{st['frames_with_2plus_configs']} frames decided by the cost function, {st['flagged']} flagged")
+    assert st["frames_with_2plus_configs"] > 0
+
+
+def test_config3_10000_colourless_frames_match_oracle(planner):
+    """BASELINE config 3 at full size: remove_color_info(gen_autocross(seed=3, B=10000)) against the oracle, plus the
+    properties that need no oracle (determinism, shard independence, well-formed outputs)."""
     B = 10000
-    batch = synth.remove_color_info(synth.gen_autocross(3, B))
+    batch = synth.remove_color_info(synth.gen_autocross(3, B, workers=min(os.cpu_count() or 1, 16)))
+    st = _oracle_parity(planner, batch, "config 3")
+    print(f"config 3: {st['frames']} frames, fp64 path err {st['path_max_err_f64']:.2e}, fp32 {st['path_max_err_f32']:.2e}, "
+          f"{st['frames_with_2plus_configs']} frames decided by the cost function, {st['flagged']} flagged")
     a = _np(planner.plan_host(batch, intermediates=True))
     b = _np(planner.plan_host(batch, intermediates=True))
     for k in ("path", "left_idx", "right_idx", "status", "path_f64"):
@@ -135,41 +188,33 @@ def test_full_size_properties(planner):
         assert ((np.diff(s, axis=1) != 0) | (s[:, 1:] < 0)).all()
 
 
-def test_config5_mixed_batch_in_eight_shards(planner):
-    """BASELINE config 5: 65 536 mixed frames block-sharded 8 192 per GPU.  On one GPU: the eight shards planned
-    separately are byte-identical to the slices of the whole batch (no state crosses frames), and every frame
-    yields a usable path.  The batch is 8 rigidly moved copies of 8 192 generated frames (generation is the slow part)."""
-    base = synth.gen_mixed(5, 8192).astype(np.float64)
-    rng = np.random.default_rng(5)
-    frame_of = np.repeat(np.arange(base.n_frames), np.diff(base.offsets))
-    parts = []
-    for _ in range(8):
-        th = rng.uniform(-np.pi, np.pi, base.n_frames)
-        tr = rng.uniform(-100, 100, (base.n_frames, 2))
-        c, s = np.cos(th), np.sin(th)
-        mv = lambda p, f: np.stack([c[f] * p[:, 0] - s[f] * p[:, 1], s[f] * p[:, 0] + c[f] * p[:, 1]], 1) + tr[f]
-        parts.append((mv(base.cones_xy, frame_of), mv(base.pos, np.arange(base.n_frames)),
-                      np.stack([c * base.dir[:, 0] - s * base.dir[:, 1], s * base.dir[:, 0] + c * base.dir[:, 1]], 1)))
-    n_c = base.total_cones
-    batch = synth.FrameBatch(
-        np.concatenate([p[0] for p in parts]).astype(np.float32), np.tile(base.cones_type, 8),
-        np.concatenate([[0]] + [base.offsets[1:] + k * n_c for k in range(8)]).astype(np.int32),
-        np.concatenate([p[1] for p in parts]).astype(np.float32), np.concatenate([p[2] for p in parts]).astype(np.float32))
+def test_config5_65536_mixed_frames_in_eight_shards_match_oracle(planner):
+    """BASELINE config 5, the exact batch: gen_mixed(seed=5, B=65536), block-sharded 8 192 frames per GPU.  On one GPU:
+    every shard against the oracle, and the eight shards planned separately are byte-identical to the slices of the
+    whole batch (no state crosses frames)."""
+    batch = synth.gen_mixed(5, 65536, workers=min(os.cpu_count() or 1, 32))
     B = batch.n_frames
     assert B == 65536
     whole = planner.plan_host(batch)
-    a = {k: getattr(whole, k).cpu().numpy() for k in ("path", "left_idx", "right_idx", "status")}
+    a = {k: getattr(whole, k).clone() for k in ("path", "left_idx", "right_idx", "status")}
+    tot = {"frames": 0, "frames_with_2plus_configs": 0, "flagged": 0, "e64": 0.0, "e32": 0.0}
     for g in range(8):
         lo, hi = g * 8192, (g + 1) * 8192
-        r = planner.plan_host(batch.slice(lo, hi))
+        shard = batch.slice(lo, hi)
+        st = _oracle_parity(planner, shard, "config 5", shard_of=g)
+        for k in ("frames", "frames_with_2plus_configs", "flagged"):
+            tot[k] += st[k]
+        tot["e64"], tot["e32"] = max(tot["e64"], st["path_max_err_f64"]), max(tot["e32"], st["path_max_err_f32"])
+        # default grid rule (no force_P): the shard alone equals its slice of the whole batch
+        r = planner.plan_host(shard)
         for k in a:
-            assert np.array_equal(getattr(r, k).cpu().numpy(), a[k][lo:hi]), f"shard {g}: {k} differs from the whole batch"
-    assert np.isfinite(a["path"]).all() and (np.diff(a["path"][:, :, 0], axis=1) > 0).all()
-    st = a["status"].astype(np.uint32)
+            assert torch.equal(getattr(r, k), a[k][lo:hi]), f"shard {g}: {k} differs from the whole batch"
+    print(f"config 5: {tot['frames']} frames in 8 shards, fp64 path err {tot['e64']:.2e}, fp32 {tot['e32']:.2e}, "
+          f"{tot['frames_with_2plus_configs']} frames decided by the cost function, {tot['flagged']} flagged "
+          f"(inputs on which the reference raises / takes its latent-bug path)")
+    st = a["status"].cpu().numpy().astype(np.uint32)
     assert ((st & 0x100) == 0).all(), "a static bound overflowed"
-    # inputs on which the reference itself raises (e.g. one side with a single cone after random colour removal) or takes
-    # its latent-bug path are flagged, not reproduced: rare
-    assert ((st & 0x600) != 0).mean() < 0.01, f"{int(((st & 0x600) != 0).sum())} frames flagged REF_RAISES / UNSUPPORTED"
+    assert ((st & 0x600) != 0).mean() < 0.01
 
 
 def test_rigid_motion_equivariance(planner):

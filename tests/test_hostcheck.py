@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 import hostcheck
-from conftest import GOLDEN_DIR, compare_with_golden
+from conftest import GOLDEN_DIR, TIE_DIST_TOL, TIE_KAPPA_TOL, compare_with_golden, tie_frame_deviation
 
 
 def test_kernel_sources_match_reference(golden):
@@ -27,6 +27,15 @@ def test_kernel_sources_tie_rule(golden):
     err = np.abs(h["path"] - g["tie_path"]).reshape(len(ok), -1).max(1)
     assert (err[ok] <= 1e-7).all(), name
     assert (h["status"][ok] & (1 << 7)).mean() > 0.9, "run-time grids are ties by construction (SURVEY Q13)"
+    # Default mode against the UNMODIFIED reference (gate iii, strict): on frames where the reference's coin flip landed
+    # on the other grid size the samples differ by up to one spacing, but they lie on the same curve -- gated
+    # geometrically so that a regression of the tie rule (or of the curve) is caught, not just printed.
+    strict = np.abs(h["path"] - g["path"]).reshape(len(ok), -1).max(1) <= 1e-4
+    other = ok & (g["P"] != g["tie_P"])
+    assert strict[ok & ~other].all(), f"{name}: default mode differs from the reference although P agrees"
+    for b in np.where(other)[0]:
+        dist, kappa = tie_frame_deviation(h["path"][b], g["path"][b])
+        assert dist <= TIE_DIST_TOL and kappa <= TIE_KAPPA_TOL, (name, b, dist, kappa)
 
 
 def test_normal_equation_spline_fit_matches_scipy():

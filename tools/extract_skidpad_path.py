@@ -34,3 +34,10 @@ known = np.array([pp.relocalizer.transform_to_known_map_frame(p, 0.0)[0] for p i
 out2 = os.path.join(os.path.dirname(out), "skidpad_cones.npy")
 np.save(out2, np.concatenate([known, ty[:, None].astype(np.float64)], axis=1))
 print(known.shape, "->", out2)
+
+# the two reference circle centres of the canonical path (calculate_reference_centers_for_skidpad_path,
+# skidpad_relocalizer.py:172-183): constants of the track definition, taken from the reference's own run-time value
+ref_centers = np.asarray(pp.relocalizer.reference_centers, dtype=np.float64)
+out3 = os.path.join(os.path.dirname(out), "skidpad_ref_centers.npy")
+np.save(out3, ref_centers)
+print(ref_centers, "->", out3)
