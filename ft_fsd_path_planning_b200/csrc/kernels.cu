@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -34,6 +35,9 @@ constexpr int WPC = FSD_WARPS_PER_CTA;
 // CTA barriers per frame in the sort kernel (phase alignment of the warps of a CTA): A/B knob
 #ifndef FSD_SORT_BARRIERS
 #define FSD_SORT_BARRIERS 4
+#endif
+#ifndef FSD_DEFAULT_PLAN_MODE
+#define FSD_DEFAULT_PLAN_MODE 29 /* 1 + 4 + 8 + 16, see plan_mode() and profiles/r2_plan_mode_ab.txt */
 #endif
 constexpr int CTA_THREADS = 32 * WPC;
 constexpr int CTAS_PER_SM = 16 / WPC;
@@ -174,10 +178,21 @@ __device__ void stage_frame(SortCta &C, const T *xy, const uint8_t *type, int n,
   __syncwarp();
 }
 
-template <typename T>
+// next frame of a free-running warp: frames are handed out in order from a counter in global memory (zeroed before the
+// launch), so a warp that finishes early simply takes more frames -- no static partition, no ragged last wave
+__device__ __forceinline__ int next_frame(int *counter) {
+  int b = 0;
+  if (fsd_lane() == 0) b = atomicAdd(counter, 1);
+  return __shfl_sync(FULL, b, 0);
+}
+
+// FREE = false: the warps of a CTA take frames in rounds and meet at phase boundaries (instruction-cache sharing for a
+// kernel that carries the whole sort + match code).  FREE = true: free-running warps with dynamic frame fetch -- used
+// when the stage is split into kernels whose code the SM's instruction cache holds (plan mode, see plan_mode()).
+template <typename T, bool FREE>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     sort_match_kernel(DevParams P, int n_frames, const T *cones_xy, const uint8_t *cones_type, const int32_t *offsets,
-                      const T *pos, const T *dir, StageOut O, int do_match) {
+                      const T *pos, const T *dir, StageOut O, int do_match, int *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   SortCta &C = *reinterpret_cast<SortCta *>(smem_raw + (size_t)warp * SORT_CTA_STRIDE);
@@ -191,14 +206,21 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   // The warps of a CTA start every frame together and meet again after the k-NN graph and after each side's search:
   // they then run the same phase (the same code) at the same time and share instruction-cache fills, like the path
   // kernel's lockstep machine.
-  for (int base = (int)blockIdx.x * WPC; base < n_frames; base += (int)gridDim.x * WPC) {
-    const int b = base + warp;
+  for (int base = (int)blockIdx.x * WPC;; base += (int)gridDim.x * WPC) {
+    int b;
+    if (FREE) {
+      b = next_frame(counter);
+      if (b >= n_frames) break;
+    } else {
+      if (base >= n_frames) break;
+      b = base + warp;
+    }
     const bool active = b < n_frames;
     int n = 0, nl = 0, nr = 0;
     unsigned st = 0;
     FramePose F = make_pose(0.0, 0.0, 1.0, 0.0);
     int16_t *dbg = nullptr;
-    if (WPC > 1 && FSD_SORT_BARRIERS >= 1) group_sync();
+    if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 1) group_sync();
     if (active) {
       const int lo = offsets[b];
       n = offsets[b + 1] - lo;
@@ -243,18 +265,18 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     for (int pass = 0; pass < 2; ++pass) {
       const int side = pass == 0 ? FSD_CONE_LEFT : FSD_CONE_RIGHT;
       SideSearch Q;
-      if (WPC > 1 && FSD_SORT_BARRIERS >= 2) group_sync();
+      if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 2) group_sync();
       if (active) side_seeds(C.S, n, F, side, P, Q);
-      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
+      if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
       if (active) side_search(C.S, n, F, side, P, Q, &st);
-      if (WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
+      if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
       if (active) (side == FSD_CONE_LEFT ? nl : nr) = side_select(C.S, n, F, side, Q, dbg);
     }
-    if (WPC > 1 && FSD_SORT_BARRIERS >= 4) group_sync();
+    if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 4) group_sync();
     if (active) {
       st |= sort_finish(C.S, nl, nr);
       store_sort(C.S, b, O);
-      if (do_match) {
+      if (!FREE && do_match) {  // the free-running variant is the sort-only kernel of the split stage
         st |= match_from_sort(C.S, F, P);
         store_match(C.S.M, b, O);
       }
@@ -264,27 +286,32 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   }
 }
 
-// matching on given sort indices (stage entry point fsd_match_batch)
+// matching on given sort indices (stage entry point fsd_match_batch; second kernel of the split sort stage): free-running
+// warps, dynamic frame fetch, the <= 24 sorted cones gathered straight from global memory
+constexpr size_t MATCH_CTA_STRIDE = (sizeof(MatchSmem) + 15) / 16 * 16;
 template <typename T>
-__global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, const T *cones_xy,
-                                                   const int32_t *offsets, const T *pos, const T *dir,
-                                                   const int16_t *left_idx, const int16_t *right_idx, StageOut O) {
-  __shared__ MatchSmem M;
-  for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+    match_kernel(DevParams P, int n_frames, const T *cones_xy, const int32_t *offsets, const T *pos, const T *dir,
+                 const int16_t *left_idx, const int16_t *right_idx, StageOut O, int or_status, int *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MatchSmem &M = *reinterpret_cast<MatchSmem *>(smem_raw + (size_t)(threadIdx.x >> 5) * MATCH_CTA_STRIDE);
+  for (;;) {
+    const int b = next_frame(counter);
+    if (b >= n_frames) break;
     const T *xy = cones_xy + 2 * (size_t)offsets[b];
     const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
     int nl = 0, nr = 0;
-    for (int q = 0; q < FSD_MAX_SORTED; ++q) {
-      nl += left_idx[(size_t)b * FSD_MAX_SORTED + q] >= 0;
-      nr += right_idx[(size_t)b * FSD_MAX_SORTED + q] >= 0;
-    }
-    for (int q = fsd_lane(); q < 2 * FSD_MAX_SORTED; q += 32) {
+    {
+      const int q = fsd_lane();
       const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
-      const int idx = (s == 0 ? left_idx : right_idx)[(size_t)b * FSD_MAX_SORTED + j];
+      const int idx = q < 2 * FSD_MAX_SORTED ? (int)(s == 0 ? left_idx : right_idx)[(size_t)b * FSD_MAX_SORTED + j] : -1;
       if (idx >= 0) {
         M.side[s][j].x = (double)xy[2 * idx];
         M.side[s][j].y = (double)xy[2 * idx + 1];
       }
+      const unsigned have = __ballot_sync(FULL, idx >= 0);
+      nl = __popc(have & ((1u << FSD_MAX_SORTED) - 1u));
+      nr = __popc(have >> FSD_MAX_SORTED);
     }
     if (fsd_lane() == 0) {
       M.nside[0] = nl;
@@ -293,7 +320,7 @@ __global__ void __launch_bounds__(32) match_kernel(DevParams P, int n_frames, co
     __syncwarp();
     unsigned st = match_frame(M, F, P);
     store_match(M, b, O);
-    if (fsd_lane() == 0) O.status[b] = st;
+    if (fsd_lane() == 0) O.status[b] = or_status ? (O.status[b] | st) : st;
     __syncwarp();
   }
 }
@@ -308,9 +335,10 @@ template <typename T>
 __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
-                unsigned char *scratch) {
+                unsigned char *scratch, int *counter, int flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_state[WPC];
+  __shared__ int s_base;
 #ifdef FSD_ALIGN_SLACK
   __shared__ volatile int s_prog[WPC];
   int round = 0;
@@ -325,9 +353,21 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
   }
   __syncwarp();
-  for (int base = (int)blockIdx.x * WPC; base < n_frames; base += (int)gridDim.x * WPC) {
+  for (int base = (int)blockIdx.x * WPC;; base += (int)gridDim.x * WPC) {
+    if (counter) {
+      // rounds of WPC frames handed out to the CTAs from a counter (zeroed before the launch): a CTA whose frames were
+      // cheap takes more rounds, so the kernel ends when the WORK ends, not when the unluckiest static share ends
+      __syncthreads();
+      if (threadIdx.x == 0) s_base = atomicAdd(counter, WPC);
+      __syncthreads();
+      base = s_base;
+    }
+    if (base >= n_frames) break;
     const int b = base + warp;
     const bool active = b < n_frames;
+#ifdef FSD_FRAME_CYCLES
+    const long long fsd_t0 = clock64();
+#endif
 #ifdef FSD_MACHINE_IN_SMEM
     // one copy of the machine state per warp in shared memory (every lane reads it, every lane writes the same values)
     // instead of 32 identical per-lane copies in local memory
@@ -339,7 +379,9 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     M.state = PS_DONE;
     M.status = 0;
     M.P_grid = M.n_trim = 0;
-    double *out = out_f64 + (size_t)(active ? b : 0) * FSD_HORIZON * 4;
+    // the frame's 40 x 4 result is assembled in shared memory (the fits' factor storage is dead by the time it is written)
+    static_assert(sizeof(S.W.G) >= FSD_HORIZON * 4 * sizeof(double), "the result aliases SplineWork::G");
+    double *out = &S.W.G[0][0];
     if (active) {
       const FramePose F =
           make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
@@ -370,6 +412,9 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     ++round;
 #elif defined(FSD_NO_LOCKSTEP)
     while (M.state != PS_DONE) pm_step(S, M, P);  // A/B only: free-running warps
+#ifdef FSD_FRAME_CYCLES
+    const long long fsd_t1 = clock64();
+#endif
     __syncthreads();
 #else
     for (;;) {
@@ -390,15 +435,31 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
 #endif
     if (active) {
       __syncwarp();
-      if (out_f32)
-        for (int i = lane; i < FSD_HORIZON * 4; i += 32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)out[i];
+      for (int i = lane; i < FSD_HORIZON * 4; i += 32) {
+        const double v = out[i];
+        if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
+        if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;  // only when the caller asked for the fp64 path
+      }
       if (lane == 0) {
         O.status[b] |= M.status;
         if (grid_out) {
           grid_out[2 * (size_t)b] = (int16_t)M.P_grid;
           grid_out[2 * (size_t)b + 1] = (int16_t)M.n_trim;
+#ifdef FSD_FRAME_CYCLES
+          // measurement build only: this frame's own path-machine time in units of 256 cycles instead of n_trim
+          grid_out[2 * (size_t)b + 1] = (int16_t)min((fsd_t1 - fsd_t0) >> 8, 32767ll);
+#endif
         }
       }
+    }
+    if (flags & 1) {
+      // the frame's points are dead: drop the buffer's lines from L2 now, before the cache gets round to writing the
+      // dirty data back to HBM (5 discards per lane; the next frame re-allocates the lines by writing them)
+      __syncwarp();
+      unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+      if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)
+        for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
     }
   }
 #ifdef FSD_ALIGN_SLACK
@@ -412,6 +473,148 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     static_assert(PATH_SCRATCH_BYTES % 128 == 0, "per-warp point buffers must be whole L2 lines");
     unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
     if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)  // never touch a line shared with a neighbour's buffer
+      for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
+  }
+}
+
+// ---- path stage, split into three free-running kernels ------------------------------------------------------------------
+// The path pipeline is cut at the end of its first two spline fits: phase 1 = centre line + fit #1, phase 2 = evaluation,
+// validity / connect / extend / cut + fit #2, phase 3 = evaluation, trim, fit #3, curvature, 40 samples.  Each kernel's hot
+// code is a fraction of the whole pipeline's, so its warps need not be kept in lockstep to share the instruction cache:
+// they run free, take frames from a counter, and nobody waits for the slowest frame of a CTA.  What crosses a cut is the
+// fitted spline (knots, coefficients) and a few machine flags per frame (PathCarry, ~0.3 KB written / read per frame and
+// cut); the point buffers do not cross (the next phase starts by evaluating the spline).  Rare backward transitions of the
+// machine (previous-path fallbacks) are completed inside the kernel in which they occur.
+struct PathCarry {
+  int32_t state, n, k, ier;
+  uint32_t status, tail_status;
+  int32_t flags, pad;
+  double max_u;
+  double t[NCAP];
+  double c[NCAP][2];
+};
+
+__device__ void carry_save(PathCarry &C, const PathSmem &S, const PathMachine &M) {
+  const int lane = fsd_lane();
+  const bool have = M.state != PS_DONE && M.fit.ier != 10;
+  const int n = have ? S.W.n : 0, k = have ? S.W.k : 0;
+  if (lane == 0) {
+    C.state = M.state;
+    C.n = n;
+    C.k = k;
+    C.ier = M.fit.ier;
+    C.status = M.status;
+    C.tail_status = M.tail_status;
+    C.flags = (M.fit1_retry ? 1 : 0) | (M.tail_retry ? 2 : 0);
+    C.max_u = have ? S.W.max_u : 0.0;
+  }
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) C.t[i] = S.W.t[i];
+#pragma unroll 1
+  for (int i = lane; i < 2 * (n - k - 1); i += 32) (&C.c[0][0])[i] = (&S.W.c[0][0])[i];
+}
+
+// the machine of frame b at the cut it was saved at (every lane gets the same copy); false: the frame is finished
+__device__ bool carry_restore(const PathCarry &C, PathSmem &S, PathMachine &M, const FramePose &F, int force_P,
+                              const double *prev, double *out) {
+  const int lane = fsd_lane();
+  pm_init(S, M, 0, F, force_P, prev, out);
+  M.state = C.state;
+  if (M.state == PS_DONE) return false;
+  M.status = C.status;
+  M.tail_status = C.tail_status;
+  M.fit1_retry = (C.flags & 1) != 0;
+  M.tail_retry = (C.flags & 2) != 0;
+  M.fit.ier = C.ier;
+  M.fit.phase = FIT_DONE;
+  const int n = C.n, k = C.k;
+  __syncwarp();
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) S.W.t[i] = C.t[i];
+#pragma unroll 1
+  for (int i = lane; i < 2 * (n - k - 1); i += 32) (&S.W.c[0][0])[i] = (&C.c[0][0])[i];
+  if (lane == 0) {
+    S.W.n = n;
+    S.W.k = k;
+    S.W.max_u = C.max_u;
+  }
+  __syncwarp();
+  if (n > 0) knot_reciprocals(S.W, n, k);  // the evaluation's table of reciprocal knot differences (same values as in the fit)
+  return true;
+}
+
+constexpr int P1_PTS = FSD_HORIZON;  // phase 1 only ever holds the <= 40 centre-line / previous-path points: shared memory
+constexpr size_t PATH_P1_STRIDE = PATH_CTA_STRIDE + (size_t)P1_PTS * (sizeof(d2) + sizeof(double));
+
+template <typename T, int PHASE>
+__global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
+    path_phase_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
+                      const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
+                      unsigned char *scratch, PathCarry *carry, int *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = fsd_lane();
+  constexpr size_t STRIDE = PHASE == 1 ? PATH_P1_STRIDE : PATH_CTA_STRIDE;
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * STRIDE);
+  if (lane == 0) {
+    unsigned char *mine = PHASE == 1 ? smem_raw + (size_t)warp * STRIDE + PATH_CTA_STRIDE
+                                     : scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)(PHASE == 1 ? P1_PTS : PCAP) * sizeof(d2));
+  }
+  __syncwarp();
+  for (;;) {
+    const int b = next_frame(counter);
+    if (b >= n_frames) break;
+    PathMachine M;
+    double *out = &S.W.G[0][0];  // assembled in shared memory, see path_kernel
+    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
+    const int fp = force_P ? (int)force_P[b] : 0;
+    const double *pv = prev + (size_t)b * prev_stride;
+    if (PHASE == 1) {
+      const int nl = O.n_wv[2 * (size_t)b], nr = O.n_wv[2 * (size_t)b + 1];
+      const d2 *left = reinterpret_cast<const d2 *>(O.left_wv + (size_t)b * WV_CAP * 2);
+      const d2 *right = reinterpret_cast<const d2 *>(O.right_wv + (size_t)b * WV_CAP * 2);
+      pm_begin_frame(S, M, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F, fp, pv, P, out);
+      if (M.state == PS_FIT1) {  // pm_step's PS_FIT1 case, without linking the later stages into this kernel
+        if (M.fit.phase != FIT_DONE) fit_run(S.W, M.fit, &M.status);
+        if (M.fit.phase == FIT_DONE) M.state = PS_FIT1_DONE;
+      }
+    } else {
+      if (!carry_restore(carry[b], S, M, F, fp, pv, out)) continue;  // finished in an earlier phase
+      const int stop = PHASE == 2 ? PS_FIT2_DONE : PS_DONE;
+      // phase 2 ends when fit #2 is finished for the first time; phase 3 runs the machine to the end (including a rare
+      // re-entry into the tail with the previous path)
+#pragma unroll 1
+      do {
+        pm_step(S, M, P);
+      } while (M.state != PS_DONE && M.state != stop);
+    }
+    __syncwarp();
+    if (M.state == PS_DONE) {
+      if (PHASE != 3 && lane == 0) carry[b].state = PS_DONE;
+      for (int i = lane; i < FSD_HORIZON * 4; i += 32) {
+        const double v = out[i];
+        if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
+        if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;
+      }
+      if (lane == 0) {
+        O.status[b] |= M.status;
+        if (grid_out) {
+          grid_out[2 * (size_t)b] = (int16_t)M.P_grid;
+          grid_out[2 * (size_t)b + 1] = (int16_t)M.n_trim;
+        }
+      }
+    } else {
+      carry_save(carry[b], S, M);
+    }
+    __syncwarp();
+  }
+  if (PHASE != 1) {
+    // the point buffers are dead now: drop their lines from L2 instead of writing them back (see path_kernel)
+    __syncwarp();
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+    if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)
       for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
   }
@@ -560,11 +763,34 @@ struct DeviceInfo {
   bool initial_ready = false;
   double key[3] = {0, 0, 0};
   SideStream side[SIDE_STREAMS];
+  int *counter_ring = nullptr;  // COUNTER_SLOTS x 8 ints of device memory: frame counters of the free-running kernels
+  unsigned counter_next = 0;
 };
+constexpr int COUNTER_SLOTS = 128;
 DeviceInfo g_dev[MAX_DEVICES];
 std::mutex g_mutex;
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename K>
+void set_smem(K kernel, size_t bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// How a batch is planned (FSD_PLAN_MODE in the environment, read once; a measurement knob, not an API):
+//   bit 0: the sort stage as two free-running kernels (sort | match) instead of one lockstep kernel
+//   bit 1: the path stage as three free-running kernels (path_phase_kernel) instead of one lockstep kernel
+//   bit 2: the lockstep path kernel takes its rounds of frames from a counter instead of a static stride
+//   bit 3: fsd_plan_batch never splits a batch into two chunks on two streams
+//   bit 4: the path kernel discards a frame's point-buffer lines from L2 when the frame ends
+//   bit 5: the path kernel's point buffers as a persisting L2 access-policy window
+int plan_mode() {
+  static const int mode = [] {
+    const char *e = std::getenv("FSD_PLAN_MODE");
+    return e ? std::atoi(e) : FSD_DEFAULT_PLAN_MODE;
+  }();
+  return mode;
+}
 
 int device_info(DeviceInfo **out) {
   int dev = -1;
@@ -581,12 +807,22 @@ int device_info(DeviceInfo **out) {
       return FSD_ERR_NO_DEVICE;
     }
     int a = 0, b = 0;
-    cudaFuncSetAttribute(sort_match_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
-    cudaFuncSetAttribute(sort_match_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * SORT_CTA_STRIDE));
+    set_smem(sort_match_kernel<float, false>, WPC * SORT_CTA_STRIDE);
+    set_smem(sort_match_kernel<double, false>, WPC * SORT_CTA_STRIDE);
+    set_smem(sort_match_kernel<float, true>, WPC * SORT_CTA_STRIDE);
+    set_smem(sort_match_kernel<double, true>, WPC * SORT_CTA_STRIDE);
+    set_smem(match_kernel<float>, WPC * MATCH_CTA_STRIDE);
+    set_smem(match_kernel<double>, WPC * MATCH_CTA_STRIDE);
+    set_smem(path_phase_kernel<float, 1>, WPC * PATH_P1_STRIDE);
+    set_smem(path_phase_kernel<double, 1>, WPC * PATH_P1_STRIDE);
+    set_smem(path_phase_kernel<float, 2>, WPC * PATH_CTA_STRIDE);
+    set_smem(path_phase_kernel<double, 2>, WPC * PATH_CTA_STRIDE);
+    set_smem(path_phase_kernel<float, 3>, WPC * PATH_CTA_STRIDE);
+    set_smem(path_phase_kernel<double, 3>, WPC * PATH_CTA_STRIDE);
     cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(skid_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float, false>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
     D.sort_ctas = a > 0 ? a : 1;
@@ -616,10 +852,37 @@ int device_info(DeviceInfo **out) {
       D.key[2] = dp.refit_smoothing;
       D.initial_ready = true;
     }
+    if (plan_mode() & 32) {
+      size_t want = (size_t)prop.persistingL2CacheMaxSize;
+      if (want > (size_t)64 << 20) want = (size_t)64 << 20;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaGetLastError();
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&D.counter_ring), COUNTER_SLOTS * 8 * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError();
+      D.counter_ring = nullptr;  // the free-running kernels are not used without it
+    }
     D.sm_count = prop.multiProcessorCount;
   }
   *out = &D;
   return FSD_OK;
+}
+
+// Eight zeroed frame counters for one sequence of free-running kernels on `stream` (a slot of the per-device ring; a slot
+// comes round again after COUNTER_SLOTS sequences, far more than can be in flight).  nullptr: not available.
+int *take_counters(DeviceInfo &D, cudaStream_t stream) {
+  if (!D.counter_ring) return nullptr;
+  unsigned slot;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    slot = D.counter_next++ % COUNTER_SLOTS;
+  }
+  int *p = D.counter_ring + 8 * slot;
+  if (cudaMemsetAsync(p, 0, 8 * sizeof(int), stream) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
 }
 
 int grid_for(int n_frames, int sm_count, int ctas_per_sm) {
@@ -654,7 +917,7 @@ size_t path_grid_bound(int n_frames) {
 // idle (persistent CTAs stride statically over their chunk).  Returns the size of the first chunk (n_frames: no split).
 int first_chunk(int n_frames) {
   DeviceInfo *D = nullptr;
-  if (device_info(&D) != FSD_OK) return n_frames;
+  if (device_info(&D) != FSD_OK || (plan_mode() & 8)) return n_frames;
   const long wave = (long)D->sm_count * (D->path_ctas < D->sort_ctas ? D->path_ctas : D->sort_ctas) * WPC;
   if ((long)n_frames < 2 * wave) return n_frames;
   return (n_frames / 2 + WPC - 1) / WPC * WPC;
@@ -668,18 +931,24 @@ size_t path_scratch_bytes(int n_frames) {
 size_t workspace_bytes(int n_frames) {
   const size_t B = (size_t)(n_frames > 0 ? n_frames : 0);
   size_t total = align_up(path_scratch_bytes(n_frames), 256);
-  total += align_up(B * FSD_HORIZON * 4 * sizeof(double), 256);         // path_f64
   total += align_up(B * 2 * sizeof(int16_t), 256);                      // n_wv
   total += 2 * align_up(B * FSD_MAX_WV * 2 * sizeof(double), 256);      // left_wv, right_wv
   total += 2 * align_up(B * FSD_MAX_WV * sizeof(int16_t), 256);         // l2r, r2l
   total += align_up(B * 2 * sizeof(int16_t), 256);                      // grid
   total += align_up(FSD_HORIZON * 4 * sizeof(double), 256);             // initial path (non-default params)
+  total += align_up(B * sizeof(PathCarry), 256);                        // splines carried between the path phases
+  total += align_up(B * 2 * FSD_MAX_SORTED * sizeof(int16_t), 256);     // sort indices when the caller wants none
   return total;
 }
 
 // resolve every intermediate tensor to user memory or workspace
+struct Extra {
+  PathCarry *carry = nullptr;
+  int16_t *idx = nullptr;
+};
+
 int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t workspace_bytes_given,
-            fsd_intermediate *out, double **initial_slot, unsigned char **path_scratch) {
+            fsd_intermediate *out, double **initial_slot, unsigned char **path_scratch, Extra *extra = nullptr) {
   fsd_intermediate r;
   std::memset(&r, 0, sizeof(r));
   if (inter) r = *inter;
@@ -687,7 +956,6 @@ int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t
   Carve cv = {static_cast<unsigned char *>(workspace), 0, workspace_bytes_given};
   const size_t B = (size_t)n_frames;
   *path_scratch = cv.take<unsigned char>(path_scratch_bytes(n_frames));
-  double *w_path = cv.take<double>(B * FSD_HORIZON * 4);
   int16_t *w_nwv = cv.take<int16_t>(B * 2);
   double *w_lwv = cv.take<double>(B * FSD_MAX_WV * 2);
   double *w_rwv = cv.take<double>(B * FSD_MAX_WV * 2);
@@ -695,7 +963,12 @@ int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t
   int16_t *w_r2l = cv.take<int16_t>(B * FSD_MAX_WV);
   int16_t *w_grid = cv.take<int16_t>(B * 2);
   double *w_init = cv.take<double>(FSD_HORIZON * 4);
-  if (!r.path_f64) r.path_f64 = w_path;
+  PathCarry *w_carry = cv.take<PathCarry>(B);
+  int16_t *w_idx = cv.take<int16_t>(B * 2 * FSD_MAX_SORTED);
+  if (extra) {
+    extra->carry = w_carry;
+    extra->idx = w_idx;
+  }
   if (!r.n_wv) r.n_wv = w_nwv;
   if (!r.left_wv) r.left_wv = w_lwv;
   if (!r.right_wv) r.right_wv = w_rwv;
@@ -733,10 +1006,12 @@ int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &
   return check_launch();
 }
 
+// idx_scratch: room for the sort indices (2 x n_frames x 12) when the caller passes no output tensors for them
 template <typename T>
 int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, const uint8_t *cones_type,
                     const int32_t *offsets, const T *pos, const T *dir, int16_t *out_left_idx, int16_t *out_right_idx,
-                    const fsd_intermediate *inter, uint32_t *out_status, cudaStream_t stream) {
+                    const fsd_intermediate *inter, uint32_t *out_status, cudaStream_t stream,
+                    int16_t *idx_scratch = nullptr) {
   if (!params || n_frames < 0 || !offsets || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
   if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
   if (n_frames == 0) return FSD_OK;
@@ -746,19 +1021,38 @@ int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, c
   if (rc != FSD_OK) return rc;
   StageOut O = {out_left_idx, out_right_idx, inter->sort_dbg, inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r,   inter->r2l,    out_status};
-  sort_match_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
-      make_dev_params(*params), n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1);
+  const int grid = grid_for(n_frames, D->sm_count, D->sort_ctas);
+  int *counters = nullptr;
+  if ((plan_mode() & 1) && (out_left_idx || idx_scratch) && (out_right_idx || idx_scratch))
+    counters = take_counters(*D, stream);
+  if (!counters) {
+    sort_match_kernel<T, false><<<grid, CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
+        make_dev_params(*params), n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1, nullptr);
+    return check_launch();
+  }
+  // two free-running kernels: sorting (writes the sort indices), then matching on them
+  if (!O.left_idx) O.left_idx = idx_scratch;
+  if (!O.right_idx) O.right_idx = idx_scratch + (size_t)n_frames * FSD_MAX_SORTED;
+  const DevParams P = make_dev_params(*params);
+  sort_match_kernel<T, true><<<grid, CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
+      P, n_frames, cones_xy, cones_type, offsets, pos, dir, O, 0, counters);
+  rc = check_launch();
+  if (rc != FSD_OK) return rc;
+  match_kernel<T><<<grid_for(n_frames, D->sm_count, CTAS_PER_SM), CTA_THREADS, WPC * MATCH_CTA_STRIDE, stream>>>(
+      P, n_frames, cones_xy, offsets, pos, dir, O.left_idx, O.right_idx, O, 1, counters + 1);
   return check_launch();
 }
 
+// `carry`: room for n_frames PathCarry records (split mode only)
 template <typename T>
 int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
               const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
-              unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream) {
+              unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream,
+              PathCarry *carry = nullptr) {
   if (!path_scratch) return FSD_ERR_WORKSPACE;
   if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
-  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l || !inter->path_f64)
-    return FSD_ERR_ARG;
+  if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
+  if (!inter->path_f64 && !out_path) return FSD_ERR_ARG;  // at least one of the two path outputs
   if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
   if (n_frames == 0) return FSD_OK;
   DeviceInfo *D = nullptr;
@@ -774,8 +1068,51 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   }
   StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r, inter->r2l, out_status};
-  path_kernel<T><<<grid_for(n_frames, D->sm_count, D->path_ctas), CTA_THREADS, PATH_KERNEL_SMEM, stream>>>(
-      P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch);
+  const int grid = grid_for(n_frames, D->sm_count, D->path_ctas);
+  int *counters = ((plan_mode() & 2) && carry) ? take_counters(*D, stream) : nullptr;
+  if (counters) {
+    path_phase_kernel<T, 1><<<grid, CTA_THREADS, WPC * PATH_P1_STRIDE, stream>>>(
+        P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch, carry,
+        counters);
+    path_phase_kernel<T, 2><<<grid, CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
+        P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch, carry,
+        counters + 1);
+    path_phase_kernel<T, 3><<<grid, CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
+        P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch, carry,
+        counters + 2);
+    return check_launch();
+  }
+  int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
+  const int flags = (plan_mode() & 16) ? 1 : 0;
+  if (plan_mode() & 32) {
+    // the point buffers as a persisting L2 window: their lines are not chosen for eviction while the kernel runs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(CTA_THREADS);
+    cfg.dynamicSmemBytes = PATH_KERNEL_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = path_scratch;
+    attr[0].val.accessPolicyWindow.num_bytes = (size_t)grid * WPC * PATH_SCRATCH_BYTES;
+    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int16_t *fp = force_P;
+    double *o64 = inter->path_f64;
+    int16_t *gr = inter->grid;
+    if (cudaLaunchKernelEx(&cfg, path_kernel<T>, P, n_frames, pos, dir, O, fp, prev, stride, o64, out_path, gr,
+                           path_scratch, round_counter, flags) != cudaSuccess) {
+      cudaGetLastError();
+      return FSD_ERR_LAUNCH;
+    }
+    return FSD_OK;
+  }
+  path_kernel<T><<<grid, CTA_THREADS, PATH_KERNEL_SMEM, stream>>>(
+      P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
+      round_counter, flags);
   return check_launch();
 }
 
@@ -831,7 +1168,8 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
   fsd_intermediate R;
   double *init_slot = nullptr;
   unsigned char *path_scratch = nullptr;
-  int rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot, &path_scratch);
+  Extra X;
+  int rc = resolve(inter, n_frames, workspace, workspace_bytes_given, &R, &init_slot, &path_scratch, &X);
   if (rc != FSD_OK) return rc;
   DeviceInfo *D = nullptr;
   rc = device_info(&D);
@@ -848,10 +1186,10 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
   SideStream *side = nb > 0 ? acquire_side(*D) : nullptr;
   if (!side) {
     rc = sort_match_impl<T>(params, n_frames, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
-                            out_status, stream);
+                            out_status, stream, X.idx);
     if (rc != FSD_OK) return rc;
     rc = path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
-                      out_status, stream);
+                      out_status, stream, X.carry);
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
       cudaGetLastError();
       rc = FSD_ERR_LAUNCH;
@@ -866,16 +1204,17 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
   bool ok = cudaEventRecord(side->fork, stream) == cudaSuccess &&
             cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess;
   if (ok) {
+    // (the sort-index scratch of chunk A is [0, 2 na x 12), chunk B's follows it)
     rc = sort_match_impl<T>(params, na, cones_xy, cones_type, offsets, pos, dir, out_left_idx, out_right_idx, &R,
-                            out_status, stream);
+                            out_status, stream, X.idx);
     if (rc == FSD_OK)
       rc = sort_match_impl<T>(params, nb, cones_xy, cones_type, offsets + h, pos + 2 * h, dir + 2 * h,
                               out_left_idx ? out_left_idx + h * FSD_MAX_SORTED : nullptr,
                               out_right_idx ? out_right_idx + h * FSD_MAX_SORTED : nullptr, &RB, out_status + h,
-                              side->stream);
+                              side->stream, X.idx + 2 * h * FSD_MAX_SORTED);
     if (rc == FSD_OK)
       rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
-                        stream);
+                        stream, X.carry);
     // the outputs of frames [0, na) are final here: a caller that passed an event can start consuming them (e.g. an
     // all-gather on a communication stream) while chunk B is still being planned
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
@@ -885,7 +1224,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
     if (rc == FSD_OK)
       rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
                         prev + h * (size_t)stride, stride, init_slot, scratch_b,
-                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream);
+                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.carry + h);
   }
   // always join, so that the caller's stream never runs ahead of work queued on the side stream
   ok = cudaEventRecord(side->join, side->stream) == cudaSuccess && ok;
@@ -947,7 +1286,8 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones) {
 
 int fsd_plan_launches(int n_frames) {
   if (n_frames <= 0) return 0;
-  return first_chunk(n_frames) < n_frames ? 4 : 2;
+  const int per_chunk = ((plan_mode() & 1) ? 2 : 1) + ((plan_mode() & 2) ? 3 : 1);
+  return first_chunk(n_frames) < n_frames ? 2 * per_chunk : per_chunk;
 }
 
 int fsd_plan_first_chunk(int n_frames) { return n_frames <= 0 ? 0 : first_chunk(n_frames); }
@@ -1010,9 +1350,15 @@ int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy
   int rc = device_info(&D);
   if (rc != FSD_OK) return rc;
   StageOut O = {out_left_idx, out_right_idx, sort_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, out_status};
-  sort_match_kernel<float><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
-                             static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
-                                                                  cones_type, offsets, pos, dir, O, 0);
+  int *counters = (plan_mode() & 1) ? take_counters(*D, static_cast<cudaStream_t>(stream)) : nullptr;
+  if (counters)
+    sort_match_kernel<float, true><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
+                                     static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
+                                                                          cones_type, offsets, pos, dir, O, 0, counters);
+  else
+    sort_match_kernel<float, false><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
+                                      static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
+                                                                           cones_type, offsets, pos, dir, O, 0, nullptr);
   return check_launch();
 }
 
@@ -1029,9 +1375,11 @@ int fsd_match_batch(const fsd_params *params, int n_frames, const float *cones_x
   if (rc != FSD_OK) return rc;
   StageOut O = {nullptr,        nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r,     inter->r2l, out_status};
-  const int match_grid = n_frames < D->sm_count * 16 ? n_frames : D->sm_count * 16;
-  match_kernel<float><<<match_grid, 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      make_dev_params(*params), n_frames, cones_xy, offsets, pos, dir, left_idx, right_idx, O);
+  int *counters = take_counters(*D, static_cast<cudaStream_t>(stream));
+  if (!counters) return FSD_ERR_LAUNCH;
+  match_kernel<float><<<grid_for(n_frames, D->sm_count, CTAS_PER_SM), CTA_THREADS, WPC * MATCH_CTA_STRIDE,
+                        static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy, offsets, pos,
+                                                             dir, left_idx, right_idx, O, 0, counters);
   return check_launch();
 }
 
@@ -1057,11 +1405,17 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
   if (n_frames > 0 && (!workspace || workspace_bytes_given < path_grid_bound(n_frames) * PATH_SCRATCH_BYTES))
     return FSD_ERR_WORKSPACE;
   unsigned char *scratch = static_cast<unsigned char *>(workspace);
+  // the splines carried between the path phases sit behind the point buffers when the workspace has room for them (a
+  // workspace of fsd_workspace_bytes() always has); otherwise the stage runs as one kernel
+  PathCarry *carry = nullptr;
+  const size_t carry_at = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
+  if (n_frames > 0 && workspace_bytes_given >= carry_at + (size_t)n_frames * sizeof(PathCarry))
+    carry = reinterpret_cast<PathCarry *>(scratch + carry_at);
   if (coords_f64)
     return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
-                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st);
+                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
-                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st);
+                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry);
 }
 
 size_t fsd_skidpad_workspace_bytes(int n_steps) {

@@ -19,6 +19,15 @@
 
 namespace fsd {
 
+// Loops of the serial (lane 0) and rarely executed parts of the sort stage are kept ROLLED: fully unrolled they were 60 KB
+// of straight-line code that every frame streams through the instruction cache once (the free-running sort kernel spent
+// 41 % of its stall samples waiting for instructions, profiles/r2_e_sort_kernel_ncu_raw.txt).
+#ifdef FSD_SORT_UNROLL_COLD
+#define FSD_ROLLED
+#else
+#define FSD_ROLLED _Pragma("unroll 1")
+#endif
+
 constexpr int MAX_LEAVES = 64;
 constexpr int STACK_CAP = 64;  // depth <= 12, <= 5 pushes per level
 
@@ -490,13 +499,20 @@ FSD_DEVFN int find_leaves(SortSmem &S, int n, const FramePose &F, int side, int 
 
 // ---- post-filter: end_configurations.py:484-518 (lane 0; a handful of rows) -------------------
 
-FSD_DEV int row_len(const int16_t *row) {
+#ifdef FSD_SORT_UNROLL_COLD
+#define FSD_ROWFN FSD_DEV
+#else
+#define FSD_ROWFN FSD_DEVFN
+#endif
+FSD_ROWFN int row_len(const int16_t *row) {
   int n = 0;
+  FSD_ROLLED
   for (int q = 0; q < FSD_MAX_SORTED; ++q) n += row[q] != -1;
   return n;
 }
 
-FSD_DEV int row_cmp(const int16_t *a, const int16_t *b) {
+FSD_ROWFN int row_cmp(const int16_t *a, const int16_t *b) {
+  FSD_ROLLED
   for (int q = 0; q < FSD_MAX_SORTED; ++q)
     if (a[q] != b[q]) return a[q] < b[q] ? -1 : 1;
   return 0;
@@ -505,12 +521,14 @@ FSD_DEV int row_cmp(const int16_t *a, const int16_t *b) {
 FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, int nfk) {
   if (fsd_lane() == 0) {
     int kept = 0;
+    FSD_ROLLED
     for (int r = 0; r < n_leaves; ++r) {
       int16_t *row = S.leaves[r];
       int len = row_len(row);
       if (len <= 2) continue;
       bool ok = true;
       if (nfk > 1)
+        FSD_ROLLED
         for (int q = 0; q < nfk; ++q) ok &= row[q] == fk[q];
       if (!ok) continue;
       // a trailing cone that does not have the side's colour is dropped (:492-500)
@@ -523,7 +541,9 @@ FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, in
       int p = kept;
       bool dup = false;
       int16_t tmp[FSD_MAX_SORTED];
+      FSD_ROLLED
       for (int q = 0; q < FSD_MAX_SORTED; ++q) tmp[q] = row[q];
+      FSD_ROLLED
       while (p > 0) {
         int c = row_cmp(S.leaves[p - 1], tmp);
         if (c == 0) dup = true;
@@ -531,25 +551,33 @@ FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, in
         --p;
       }
       if (dup) continue;
+      FSD_ROLLED
       for (int m = kept; m > p; --m)
+        FSD_ROLLED
         for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[m][q] = S.leaves[m - 1][q];
+      FSD_ROLLED
       for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[p][q] = tmp[q];
       ++kept;
     }
     // rows that are a strict prefix of another row are removed (:509-515)
     int out = 0;
+    FSD_ROLLED
     for (int j = 0; j < kept; ++j) {
       int covered = 0;
+      FSD_ROLLED
       for (int i = 0; i < kept; ++i) {
         bool all = true;
+        FSD_ROLLED
         for (int q = 0; q < FSD_MAX_SORTED; ++q) all &= (S.leaves[i][q] == S.leaves[j][q]) || (S.leaves[j][q] == -1);
         covered += all;
       }
       S.flag2[j] = covered > 1 ? 1 : 0;
     }
+    FSD_ROLLED
     for (int j = 0; j < kept; ++j)
       if (!S.flag2[j]) {
         if (out != j)
+          FSD_ROLLED
           for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[out][q] = S.leaves[j][q];
         ++out;
       }
@@ -579,6 +607,7 @@ FSD_DEV void search_dir(const SortSmem &S, int a, int b, int side, double &ox, d
 FSD_DEVFN int compact_flags(const uint8_t *flag, int n, int16_t *out) {
   int count = 0;
   const int lane = fsd_lane();
+  FSD_ROLLED
   for (int base = 0; base < n; base += FSD_LANES) {
     int i = base + lane;
     bool p = i < n && flag[i];
@@ -598,7 +627,9 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
   for (int i = lane; i < n; i += FSD_LANES) S.flag[i] = 0;
   wsync();
   if (lane == 0)
+    FSD_ROLLED
     for (int r = 0; r < C; ++r)
+      FSD_ROLLED
       for (int q = 0; q < FSD_MAX_SORTED; ++q)
         if (S.leaves[r][q] != -1) S.flag[S.leaves[r][q]] = 1;
   wsync();
@@ -607,6 +638,7 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
 #pragma unroll 1
   for (int j = lane; j < n; j += FSD_LANES) {
     bool near = false;
+    FSD_ROLLED
     for (int q = 0; q < nidx && !near; ++q) {
       int i = S.idxs[q];
       if (i == j) continue;
@@ -625,6 +657,7 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
 #pragma unroll 1
   for (int q = lane; q < nidx; q += FSD_LANES) {
     int v = S.idxs[q], lo = 0, hi = nall;
+    FSD_ROLLED
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
       if (S.close[mid] < v)
@@ -635,10 +668,12 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
     if (lo < nall) S.flag2[S.close[lo]] = 1;  // removed
   }
   wsync();
+  FSD_ROLLED
   for (int r = 0; r < C; ++r) {
     const int16_t *c = S.leaves[r];
     int len = row_len(c);
     int good = 0, bad = 0;
+    FSD_ROLLED
     for (int j = 0; j < len; ++j) {
       double sx, sy;
       if (j == 0)
@@ -659,6 +694,7 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
         } else {
           o = S.idxs[q - nall];
           bool member = false;
+          FSD_ROLLED
           for (int w = 0; w < len; ++w) member |= c[w] == o;
           if (member) continue;
         }
@@ -684,9 +720,9 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
 FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const FramePose &F) {
   if (C == 1) return 0;
   cones_on_either_side(S, n, C, side);
-  const double w[7] = {1000.0, 200.0, 5000.0, 1000.0, 0.0, 1000.0, 1000.0};
   const double wsum_ = 9200.0;
   int mn = 0;
+  FSD_ROLLED
   for (int r = 0; r < C; ++r) {
     int d = S.n_good[r] - S.n_bad[r];
     if (r == 0 || d < mn) mn = d;
@@ -695,50 +731,60 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
   for (int r = fsd_lane(); r < C; r += FSD_LANES) {
     const int16_t *c = S.leaves[r];
     const int len = row_len(c);
-    double px[FSD_MAX_SORTED], py[FSD_MAX_SORTED];
-    for (int q = 0; q < len; ++q) {
-      px[q] = S.xy[c[q]].x;
-      py[q] = S.xy[c[q]].y;
-    }
+#define px(q) S.xy[c[q]].x
+#define py(q) S.xy[c[q]].y
     // angle cost (:41-79): mean of (pi - theta)/pi over interior angles, times (1 + #{theta < 40 deg})
     double asum = 0.0;
     int under = 0;
+    FSD_ROLLED
     for (int q = 0; q + 2 < len; ++q) {
-      double th = fsd_acos(cos_between(px[q + 1] - px[q + 2], py[q + 1] - py[q + 2], px[q + 1] - px[q], py[q + 1] - py[q]));
+      double th = fsd_acos(cos_between(px(q + 1) - px(q + 2), py(q + 1) - py(q + 2), px(q + 1) - px(q), py(q + 1) - py(q)));
       asum += (PI - th) / PI;
       under += th < 40.0 * PI / 180.0;
     }
     double angle_cost = asum / (double)(len - 2) * (double)(under + 1);
     // residual distance (cone_distance_cost.py:14-32)
     double resid = 0.0;
+    FSD_ROLLED
     for (int q = 0; q + 1 < len; ++q) {
-      double ddx = px[q + 1] - px[q], ddy = py[q + 1] - py[q];
+      double ddx = px(q + 1) - px(q), ddy = py(q + 1) - py(q);
       double d = fsqrt(ddx * ddx + ddy * ddy) - 3.0;
       resid += d > 0.0 ? d : 0.0;
     }
     double ncones = 1.0 / (double)len;
-    double init_dir = fsd_acos(cos_between(px[1] - px[0], py[1] - py[0], F.dx, F.dy));
+    double init_dir = fsd_acos(cos_between(px(1) - px(0), py(1) - py(0), F.dx, F.dy));
     double either = 1.0 / (double)(S.n_good[r] - S.n_bad[r] + (mn < 0 ? -mn : mn) + 1);
     // wrong direction (:149-188)
     double wrong = 0.0;
     if (len != 3) {
       double unwanted = side == FSD_CONE_LEFT ? 1.0 : -1.0, sum = 0.0;
-      double prev = fsd_atan2(py[1] - py[0], px[1] - px[0]);
+      double prev = fsd_atan2(py(1) - py(0), px(1) - px(0));
+      FSD_ROLLED
       for (int q = 1; q + 1 < len; ++q) {
-        double cur = fsd_atan2(py[q + 1] - py[q], px[q + 1] - px[q]);
+        double cur = fsd_atan2(py(q + 1) - py(q), px(q + 1) - px(q));
         double d = angle_difference(prev, cur);
         if (sgn(d) == unwanted && fabs(d) > 40.0 * PI / 180.0) sum += d;
         prev = cur;
       }
       wrong = fabs(sum);
     }
-    double terms[7] = {angle_cost, resid, ncones, init_dir, 0.0, either, wrong};
+    // sum of w_i term_i / sum(w) in the reference's order (weights 1000, 200, 5000, 1000, 0, 1000, 1000; the
+    // change-of-direction term has weight 0)
     double total = 0.0;
-    for (int q = 0; q < 7; ++q) total += terms[q] * (w[q] / wsum_);
+    total += angle_cost * (1000.0 / wsum_);
+    total += resid * (200.0 / wsum_);
+    total += ncones * (5000.0 / wsum_);
+    total += init_dir * (1000.0 / wsum_);
+    total += 0.0 * (0.0 / wsum_);
+    total += either * (1000.0 / wsum_);
+    total += wrong * (1000.0 / wsum_);
     S.costs[r] = total;
+#undef px
+#undef py
   }
   wsync();
   int arg = 0;
+  FSD_ROLLED
   for (int r = 1; r < C; ++r)
     if (S.costs[r] < S.costs[arg]) arg = r;
   wsync();
@@ -783,6 +829,7 @@ FSD_DEVFN int side_select(SortSmem &S, int n, const FramePose &F, int side, cons
       const int arg = best_configuration(S, n, n_cfg, side, F);
       len = row_len(S.leaves[arg]);
       if (fsd_lane() == 0)
+        FSD_ROLLED
         for (int q = 0; q < FSD_MAX_SORTED; ++q) S.best[sidx][q] = S.leaves[arg][q];
       wsync();
     }
@@ -822,8 +869,10 @@ FSD_DEVFN void combine_sides(const SortSmem &S, int &nl, int &nr) {
     const int e = base + fsd_lane();
     bool hl = false, hr = false;
     if (e < nl)
+      FSD_ROLLED
       for (int b = 0; b < nr; ++b) hl |= left[e] == right[b];
     if (e < nr)
+      FSD_ROLLED
       for (int a = 0; a < nl; ++a) hr |= right[e] == left[a];
     ml |= wballot(hl) << base;
     mr |= wballot(hr) << base;
@@ -904,7 +953,9 @@ FSD_DEVFN unsigned sort_finish(SortSmem &S, int nl, int nr) {
   if (nr == 0) status |= FSD_ST_NO_RIGHT;
   if (nl > 0 && nr > 0) combine_sides(S, nl, nr);
   if (fsd_lane() == 0) {
+    FSD_ROLLED
     for (int q = nl; q < FSD_MAX_SORTED; ++q) S.best[0][q] = -1;
+    FSD_ROLLED
     for (int q = nr; q < FSD_MAX_SORTED; ++q) S.best[1][q] = -1;
     S.nbest[0] = nl;
     S.nbest[1] = nr;

@@ -8,7 +8,9 @@ from ft_fsd_path_planning_b200 import BatchPlanner, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10240
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-batch = synth.gen_autocross(2, n)
+import os
+
+batch = synth.gen_autocross(2, n, workers=min(os.cpu_count() or 1, 16))
 bp = BatchPlanner("cuda:0")
 dev = bp.device
 xy, ty, off = (torch.from_numpy(a).to(dev) for a in (batch.cones_xy, batch.cones_type, batch.offsets))
