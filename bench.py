@@ -333,17 +333,18 @@ def run_ours(args):
                     return planner.plan(*self.dev_args, kernel_events=True).path
                 self.res = planner.plan(*self.dev_args, out=self.res)
                 return self.res.path
-            if events or len(self.sizes) == 1:
-                res = planner.plan(*self.dev_args, kernel_events=events)
-                off = 0
-                for p, sz in enumerate(self.sizes):
-                    self.pipe.gather(p, res.path[off:off + sz])
-                    off += sz
+            if events:
+                res = planner.plan(*self.dev_args, kernel_events=True)
+            elif len(self.sizes) == 1:
+                self.res = res = planner.plan(*self.dev_args, out=self.res)
             else:
                 self.res = res = planner.plan(*self.dev_args, out=self.res, chunk_ready=self.ready)
-                na = self.sizes[0]
-                self.pipe.gather(0, res.path[:na], after=self.ready)  # starts while the second chunk is being planned
-                self.pipe.gather(1, res.path[na:])
+            off = 0
+            for p, sz in enumerate(self.sizes):
+                # the first chunk's gather starts when the planner's chunk-ready event fires (the second chunk is still
+                # being planned); a single-chunk plan is gathered when it is finished
+                self.pipe.gather(p, res.path[off:off + sz], after=self.ready if (p == 0 and not events and len(self.sizes) > 1) else None)
+                off += sz
             return self.pipe.finish()
 
     main = Workload("autocross", SEED, FRAMES_PER_GPU)
@@ -401,6 +402,20 @@ def run_ours(args):
     ktimes = planner.kernel_times_ms()
     sort_ms = float(np.mean([t[0] for t in ktimes]))
     path_ms = float(np.mean([t[1] for t in ktimes]))
+    # ---- the cost-matrix step in isolation: fsd_knn_batch over the whole batch, events per launch ---------------
+    knn_ms = 0.0
+    if not REHEARSAL:
+        knn_out = planner.knn(*main.dev_args[:3])
+        kev = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = new_event(), new_event()
+            e0.record()
+            planner.knn(*main.dev_args[:3], out=knn_out)
+            e1.record()
+            kev.append((e0, e1))
+        sync()
+        knn_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     # ---- communication detail (N > 1): the same steps again with a sync per step to read the gather events -------------
     comm = None
     if distributed:
@@ -460,7 +475,7 @@ def run_ours(args):
 
     # ---- max over ranks; per-rank numbers for the comm block ----------------------------------------------------------
     mine = [step_ms, e2e_ms, sort_ms, path_ms, c5_ms, comm["gather_ms"] or 0.0 if comm else 0.0,
-            comm["step_ms_with_sync_per_step"] if comm else 0.0]
+            comm["step_ms_with_sync_per_step"] if comm else 0.0, knn_ms]
     per_rank = None
     if distributed:
         t = torch.tensor(mine, dtype=torch.float64, device=dev)
@@ -468,6 +483,7 @@ def run_ours(args):
         dist.all_gather_into_tensor(allr, t)
         per_rank = allr.cpu().numpy().reshape(world, len(mine))
         step_ms, e2e_ms, sort_ms, path_ms, c5_ms = (float(v) for v in per_rank[:, :5].max(0))
+        knn_ms = float(per_rank[:, 7].max())
         if parity is not None:
             keys = [k for k, v in parity.items() if isinstance(v, int) and not isinstance(v, bool)]
             for par in (parity, parity5):
@@ -505,11 +521,22 @@ def run_ours(args):
                     issue = {"warp_inst_per_launch": t["warp_inst"], "warp_inst_per_frame": t["warp_inst"] / B,
                              "achieved_ipc_per_sm": ipc, "peak_ipc_per_sm": 4.0, "frac": ipc / 4.0,
                              "source": "profiles/ncu_traffic.json (ncu inst_executed) / live kernel time"}
+        # the cost-matrix step: SURVEY 8d's B_cm = 19.25 N + 16 bytes per frame (9 N + 16 read, 10 N of k-NN lists + two
+        # N/8-byte masks written); the kernel actually writes 12 N (adjacency lists + degrees)
+        cm_bytes = 19.25 * batch.total_cones + 16 * B
+        cm_gbs = cm_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else None
+        cm_ncu = (json.load(open(tpath)).get("knn_kernel") or {}) if os.path.exists(tpath) else {}
+        cost_matrix = {"kernel": "knn_kernel (fsd_knn_batch)", "ms": knn_ms, "frames_per_s": B / (knn_ms * 1e-3) if knn_ms > 0 else None,
+                       "algorithmic_bytes_per_launch": cm_bytes, "achieved": cm_gbs, "unit": "GB/s",
+                       "frac": cm_gbs / peak if cm_gbs else None,
+                       "fp64_pipe_pct": cm_ncu.get("fp64_pipe_pct"), "issue_active_pct": cm_ncu.get("issue_active_pct"),
+                       "bound": "CUDA-core pipe, not HBM: ~N^2 x 2 sides x ~10 instructions per frame against 19.25 N bytes "
+                                "(~100 flop/B, ridge ~12); SURVEY 8d puts the pipe bound at ~12 % of HBM for N ~ 80"}
         cfg = bench_config(world)
         cfg.update({"cones_per_frame_mean": batch.total_cones / B,
-                    "parallelism": (f"frames partitioned over {world} GPU(s): every rank plans the planner's two chunks of "
-                                    f"{main.sizes} frames; the all-gather of the first chunk's paths runs on a "
-                                    "communication stream while the second chunk is planned, one more all-gather for the rest")
+                    "parallelism": (f"frames partitioned over {world} GPU(s), {main.sizes} frames per rank and planner chunk; "
+                                    "the paths are all-gathered on a communication stream (the first chunk's gather "
+                                    "starts at the planner's chunk-ready event when the planner splits the batch)")
                     if distributed else "single GPU"})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -518,7 +545,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "issue": issue, "kernel": dom_name, "kernel_ms": dom_ms,
                          "other_kernel_ms": sort_ms if dom_name == "path_kernel" else path_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "cost_matrix": cost_matrix,
                          "note": "latency/issue-bound integer+fp64 work: the HBM fraction is reported as required, "
                                  "see DESIGN.md"},
             "parity": parity,
@@ -532,17 +559,16 @@ def run_ours(args):
         }
         if distributed:
             names = ["step_ms", "e2e_ms", "sort_kernel_ms", "path_kernel_ms", "config5_step_ms", "gather_ms",
-                     "step_ms_with_sync_per_step"]
+                     "step_ms_with_sync_per_step", "knn_kernel_ms"]
             out["comm"] = {
-                "collective": "2 x all_gather_into_tensor of the fp32 paths per step (NCCL), "
-                              f"{4 * 160 * main.sizes[0]} + {4 * 160 * (B - main.sizes[0])} bytes per rank",
+                "collective": f"{len(main.sizes)} x all_gather_into_tensor of the fp32 paths per step (NCCL), "
+                              + " + ".join(str(4 * 160 * sz) for sz in main.sizes) + " bytes per rank",
                 "gather_ms_max_over_ranks": float(per_rank[:, 5].max()),
                 "gather_share_of_step": float(per_rank[:, 5].max() / step_ms),
                 "per_rank": {n: [float(v) for v in per_rank[:, i]] for i, n in enumerate(names)},
                 "step_ms_min_median_max": [float(per_rank[:, 0].min()), float(np.median(per_rank[:, 0])), float(per_rank[:, 0].max())],
-                "note": "gather_ms = device time of the two gathers on the communication stream (events), measured in "
-                        "a separate pass with one synchronisation per step; the gather of the first chunk overlaps the "
-                        "planning of the second, so only part of it is exposed in step_ms",
+                "note": "gather_ms = device time of the gathers on the communication stream (events), measured in a "
+                        "separate pass with one synchronisation per step",
             }
         else:
             # ---- the CPU beside it (rank 0, N = 1 only): the oracle port on all host threads, and the real reference ---

@@ -10,7 +10,7 @@ from .synth import FrameBatch, gen_autocross, gen_mixed, pack_frames, remove_col
 
 __all__ = ["ConeTypes", "MissionTypes", "FrameBatch", "gen_autocross", "gen_mixed", "pack_frames",
            "remove_color_info", "PathPlanner", "BatchPlanner", "SkidpadBatchPlanner", "PlanResult",
-           "RelocalizationInformation", "ReferenceRaisesError", "build"]
+           "RelocalizationInformation", "ReferenceRaisesError", "CpuBatchPlanner", "build"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -22,7 +22,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def __getattr__(name):
     # torch is imported lazily so that the host-side helpers (synth, enums) stay importable without it
-    if name in ("PathPlanner", "BatchPlanner", "PlanResult", "RelocalizationInformation", "ReferenceRaisesError"):
+    if name in ("PathPlanner", "BatchPlanner", "PlanResult", "RelocalizationInformation", "ReferenceRaisesError",
+                "CpuBatchPlanner"):
         from . import planner
 
         return getattr(planner, name)

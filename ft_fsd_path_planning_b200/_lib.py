@@ -1,5 +1,7 @@
-"""ctypes binding of libfsdplan.so (include/fsdplan.h).  There is no CPU path: loading fails loudly when the
-CUDA library has not been built, and every entry point returns FSD_ERR_NO_DEVICE without a GPU."""
+"""ctypes binding of libfsdplan.so (include/fsdplan.h).  Loading fails loudly when the library has not been built, and
+every CUDA entry point returns FSD_ERR_NO_DEVICE without a GPU -- nothing falls back to the host.  The one host entry
+point, fsd_plan_batch_cpu (the kernels' own per-frame sources compiled for the host), is used only when the caller asks
+for device="cpu" explicitly."""
 from __future__ import annotations
 
 import ctypes as C
@@ -44,7 +46,7 @@ class Intermediate(C.Structure):
 
 
 def sources():
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh")) or f == "cpu_backend.cpp"]
     return files + [INCLUDE]
 
 
@@ -53,7 +55,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in sources())
     if stale:
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "kernels.cu")]
+        # kernels.cu: the CUDA kernels and the C-ABI; cpu_backend.cpp: the same per-frame sources compiled for the host
+        # (fsd_plan_batch_cpu, an explicit entry point -- the CUDA entry points never fall back to it)
+        cmd = ["nvcc", *NVCC_FLAGS, "-Xcompiler", "-Wno-unknown-pragmas", "-o", LIB_PATH, os.path.join(CSRC, "kernels.cu"),
+               os.path.join(CSRC, "cpu_backend.cpp")]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
@@ -90,6 +95,10 @@ def lib():
         L.fsd_plan_first_chunk.argtypes = [i32]
         L.fsd_plan_batch_ex.argtypes = [C.POINTER(Params), i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                         C.POINTER(Intermediate), vp, vp, i32, vp, vp, sz, vp, vp]
+        L.fsd_plan_batch_cpu.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                         C.POINTER(Intermediate), vp, vp, i32, vp, i32]
+        L.fsd_initial_path_cpu.argtypes = [C.POINTER(Params), vp]
+        L.fsd_knn_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp]
         L.fsd_sort_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.fsd_match_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, C.POINTER(Intermediate), vp, vp]
         L.fsd_sort_match_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp,

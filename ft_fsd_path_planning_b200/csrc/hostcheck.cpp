@@ -69,6 +69,27 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
   return 0;
 }
 
+// the cost-matrix step alone (layout of fsd_knn_batch)
+extern "C" int fsd_hostcheck_knn(const fsd_params *params, int n_frames, const double *xy, const uint8_t *type,
+                                 const int32_t *offsets, uint8_t *out_nbr, uint8_t *out_deg) {
+  DevParams P = make_dev_params(*params);
+  SortSmem *S = new SortSmem();
+  for (int b = 0; b < n_frames; ++b) {
+    const int lo = offsets[b];
+    int n = offsets[b + 1] - lo;
+    if (n > FSD_MAX_CONES) n = FSD_MAX_CONES;
+    load_frame_plain(*S, xy + 2 * (size_t)lo, type + lo, n);
+    if (n >= 3) build_knn(*S, n, P);
+    for (int i = 0; i < n; ++i)
+      for (int s = 0; s < 2; ++s) {
+        for (int q = 0; q < 5; ++q) out_nbr[((size_t)lo + i) * 10 + s * 5 + q] = n >= 3 ? S->nbr[s][i][q] : 0;
+        out_deg[((size_t)lo + i) * 2 + s] = n >= 3 ? S->deg[s][i] : 0;
+      }
+  }
+  delete S;
+  return 0;
+}
+
 extern "C" int fsd_hostcheck_params_default(fsd_params *p) {
   std::memset(p, 0, sizeof(*p));
   p->max_n_neighbors = 5;

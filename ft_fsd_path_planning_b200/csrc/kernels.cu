@@ -286,6 +286,37 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   }
 }
 
+// The cost-matrix step in isolation (stage entry point fsd_knn_batch): stage the frame, build both sides' k-NN graphs and
+// write the mutual-edge adjacency lists.  Free-running warps, dynamic frame fetch; 6 KB of code, the N x N distances
+// never leave registers.
+template <typename T>
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+    knn_kernel(DevParams P, int n_frames, const T *cones_xy, const uint8_t *cones_type, const int32_t *offsets,
+               uint8_t *out_nbr, uint8_t *out_deg, int *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortCta &C = *reinterpret_cast<SortCta *>(smem_raw + (size_t)(threadIdx.x >> 5) * SORT_CTA_STRIDE);
+  const int lane = fsd_lane();
+  if (lane == 0) mbar_init(&C.mbar, 1);
+  __syncwarp();
+  uint32_t phase = 0;
+  for (;;) {
+    const int b = next_frame(counter);
+    if (b >= n_frames) break;
+    const int lo = offsets[b];
+    int n = offsets[b + 1] - lo;
+    n = n > FSD_MAX_CONES ? FSD_MAX_CONES : (n < 0 ? 0 : n);
+    stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
+    if (n >= 3) build_knn(C.S, n, P);
+    // [cone][side][5] neighbour indices (ascending, frame-local; entries >= degree are unspecified) and [cone][side] degrees
+    for (int e = lane; e < n * 10; e += 32) {
+      const int i = e / 10, s = (e % 10) / 5, q = e % 5;
+      out_nbr[(size_t)lo * 10 + e] = n >= 3 ? C.S.nbr[s][i][q] : (uint8_t)0;
+    }
+    for (int e = lane; e < n * 2; e += 32) out_deg[(size_t)lo * 2 + e] = n >= 3 ? C.S.deg[e & 1][e >> 1] : (uint8_t)0;
+    __syncwarp();
+  }
+}
+
 // matching on given sort indices (stage entry point fsd_match_batch; second kernel of the split sort stage): free-running
 // warps, dynamic frame fetch, the <= 24 sorted cones gathered straight from global memory
 constexpr size_t MATCH_CTA_STRIDE = (sizeof(MatchSmem) + 15) / 16 * 16;
@@ -811,6 +842,8 @@ int device_info(DeviceInfo **out) {
     set_smem(sort_match_kernel<double, false>, WPC * SORT_CTA_STRIDE);
     set_smem(sort_match_kernel<float, true>, WPC * SORT_CTA_STRIDE);
     set_smem(sort_match_kernel<double, true>, WPC * SORT_CTA_STRIDE);
+    set_smem(knn_kernel<float>, WPC * SORT_CTA_STRIDE);
+    set_smem(knn_kernel<double>, WPC * SORT_CTA_STRIDE);
     set_smem(match_kernel<float>, WPC * MATCH_CTA_STRIDE);
     set_smem(match_kernel<double>, WPC * MATCH_CTA_STRIDE);
     set_smem(path_phase_kernel<float, 1>, WPC * PATH_P1_STRIDE);
@@ -1359,6 +1392,28 @@ int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy
     sort_match_kernel<float, false><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
                                       static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
                                                                            cones_type, offsets, pos, dir, O, 0, nullptr);
+  return check_launch();
+}
+
+int fsd_knn_batch(const fsd_params *params, int n_frames, int coords_f64, const void *cones_xy,
+                  const uint8_t *cones_type, const int32_t *offsets, uint8_t *out_nbr, uint8_t *out_deg, void *stream) {
+  if (!params || n_frames < 0 || !offsets || !out_nbr || !out_deg) return FSD_ERR_ARG;
+  if (n_frames == 0) return FSD_OK;
+  if (!cones_xy || !cones_type) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int *counters = take_counters(*D, st);
+  if (!counters) return FSD_ERR_LAUNCH;
+  const int grid = grid_for(n_frames, D->sm_count, D->sort_ctas);
+  const DevParams P = make_dev_params(*params);
+  if (coords_f64)
+    knn_kernel<double><<<grid, CTA_THREADS, WPC * SORT_CTA_STRIDE, st>>>(
+        P, n_frames, static_cast<const double *>(cones_xy), cones_type, offsets, out_nbr, out_deg, counters);
+  else
+    knn_kernel<float><<<grid, CTA_THREADS, WPC * SORT_CTA_STRIDE, st>>>(
+        P, n_frames, static_cast<const float *>(cones_xy), cones_type, offsets, out_nbr, out_deg, counters);
   return check_launch();
 }
 

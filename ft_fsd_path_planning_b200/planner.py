@@ -60,7 +60,8 @@ class BatchPlanner:
 
     def __init__(self, device: Union[str, torch.device, int] = "cuda", mission: int = _lib.MISSION_TRACKDRIVE):
         if not torch.cuda.is_available():
-            raise RuntimeError("ft_fsd_path_planning_b200 needs a CUDA device: the planner has no CPU implementation")
+            raise RuntimeError("BatchPlanner needs a CUDA device and never falls back to the host (the host build of the "
+                               "kernel sources is a separate, explicit choice: CpuBatchPlanner / PathPlanner(device='cpu'))")
         self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if self.device.type != "cuda":
             raise RuntimeError("BatchPlanner runs on CUDA devices only")
@@ -243,6 +244,22 @@ class BatchPlanner:
                 setattr(res, n, bufs[n])
         return res
 
+    def knn(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor,
+            out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The cost-matrix step in isolation (fsd_knn_batch): both sides' k-NN graphs of every frame as adjacency lists.
+        Returns (nbr [total, 2, 5] uint8, deg [total, 2] uint8), frame-local indices, ascending; asynchronous."""
+        B = offsets.numel() - 1
+        total = int(cones_xy.shape[0])
+        if out is None:
+            out = (torch.empty((total, 2, 5), dtype=torch.uint8, device=self.device),
+                   torch.empty((total, 2), dtype=torch.uint8, device=self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fsd_knn_batch(
+                C.byref(self.params), B, int(cones_xy.dtype == torch.float64), cones_xy.data_ptr(), cones_type.data_ptr(),
+                offsets.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
     def plan_host(self, batch: FrameBatch, *, force_P: Optional[np.ndarray] = None,
                   prev_path: Optional[np.ndarray] = None, intermediates: bool = False) -> PlanResult:
         """Convenience: host FrameBatch in, device PlanResult out (copies on the current stream)."""
@@ -346,6 +363,65 @@ class BatchPlanner:
         return out
 
 
+class CpuBatchPlanner:
+    """The planner on the host: fsd_plan_batch_cpu, i.e. the kernels' own per-frame sources compiled for the CPU
+    (csrc/cpu_backend.cpp).  BASELINE config 1 ("CPU plumbing, no GPU") and machines without a GPU; chosen EXPLICITLY with
+    device="cpu" -- the CUDA planner never falls back to it.  Same results as the CUDA path up to fp64 rounding."""
+
+    def __init__(self, mission: int = _lib.MISSION_TRACKDRIVE, threads: Optional[int] = None):
+        import os
+
+        self.lib = _lib.lib()
+        self.params = _lib.default_params()
+        self.mission = int(mission)
+        self.threads = int(threads or os.cpu_count() or 1)
+        self.device = torch.device("cpu")
+
+    def initial_path(self) -> torch.Tensor:
+        out = np.zeros((HORIZON, 4))
+        _lib.check(self.lib.fsd_initial_path_cpu(C.byref(self.params), out.ctypes.data))
+        return torch.from_numpy(out)
+
+    def plan_host(self, batch: FrameBatch, *, force_P: Optional[np.ndarray] = None,
+                  prev_path: Optional[np.ndarray] = None, intermediates: bool = False) -> PlanResult:
+        """Host FrameBatch in, PlanResult of CPU tensors out (synchronous)."""
+        _check_offsets(np.asarray(batch.offsets), len(batch.cones_xy))
+        B = batch.n_frames
+        xy = np.ascontiguousarray(batch.cones_xy, dtype=np.float64).reshape(-1, 2)
+        ty = np.ascontiguousarray(batch.cones_type, dtype=np.uint8)
+        off = np.ascontiguousarray(batch.offsets, dtype=np.int32)
+        pos = np.ascontiguousarray(batch.pos, dtype=np.float64)
+        dr = np.ascontiguousarray(batch.dir, dtype=np.float64)
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt)
+        res = PlanResult(z((B, HORIZON, 4), torch.float32), z((B, MAX_SORTED), torch.int16), z((B, MAX_SORTED), torch.int16),
+                         z((B,), torch.int32))
+        inter = None
+        if intermediates:
+            res.path_f64, res.n_wv = z((B, HORIZON, 4), torch.float64), z((B, 2), torch.int16)
+            res.left_wv, res.right_wv = z((B, MAX_WV, 2), torch.float64), z((B, MAX_WV, 2), torch.float64)
+            res.l2r, res.r2l = z((B, MAX_WV), torch.int16), z((B, MAX_WV), torch.int16)
+            res.grid, res.sort_dbg = z((B, 2), torch.int16), z((B, 8), torch.int16)
+            inter = _lib.Intermediate(*[getattr(res, n).data_ptr() for n in
+                                        ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg")])
+        fp = None if force_P is None else np.ascontiguousarray(force_P, dtype=np.int16)
+        if fp is not None and fp.size != B:
+            raise ValueError("force_P must be int16 [B]")
+        pv = None if prev_path is None else np.ascontiguousarray(prev_path, dtype=np.float64)
+        stride = 0
+        if pv is not None:
+            stride = 0 if pv.size == HORIZON * 4 else HORIZON * 4
+            if stride and pv.size != B * HORIZON * 4:
+                raise ValueError("prev_path must be [40, 4] or [B, 40, 4]")
+        if B:
+            _lib.check(self.lib.fsd_plan_batch_cpu(
+                C.byref(self.params), self.mission, B, xy.ctypes.data if xy.size else None, ty.ctypes.data if ty.size else None,
+                off.ctypes.data, pos.ctypes.data, dr.ctypes.data, res.path.data_ptr(), res.left_idx.data_ptr(),
+                res.right_idx.data_ptr(), C.byref(inter) if inter is not None else None,
+                None if fp is None else fp.ctypes.data, None if pv is None else pv.ctypes.data, stride,
+                res.status.data_ptr(), self.threads))
+        return res
+
+
 @dataclass
 class RelocalizationInformation:
     """fsd_path_planning/relocalization/relocalization_information.py:13-35"""
@@ -379,7 +455,12 @@ class PathPlanner:
                 "and is out of scope (SURVEY.md section 2); use trackdrive / autocross / skidpad")
         # the experimental sorting cache of the reference changes results and is not reproduced
         self.experimental_performance_improvements = experimental_performance_improvements
-        self._planner = BatchPlanner(device, mission=_lib.MISSION_TRACKDRIVE)
+        self._cpu = str(device) == "cpu"
+        if self._cpu and self.mission == MissionTypes.skidpad:
+            raise NotImplementedError("the host planner (device='cpu') covers trackdrive / autocross only")
+        # device="cpu" selects the host build of the kernels' sources (fsd_plan_batch_cpu) EXPLICITLY; the default
+        # (CUDA) never falls back to it and raises without a GPU
+        self._planner = CpuBatchPlanner(threads=1) if self._cpu else BatchPlanner(device, mission=_lib.MISSION_TRACKDRIVE)
         self.global_path = None
         self._prev_path: Optional[torch.Tensor] = None  # previous_paths[-1] of the reference
         self._skid = None
@@ -488,6 +569,8 @@ class PathPlanner:
         )
 
     def _plan_with_prev(self, batch: FrameBatch) -> PlanResult:
+        if self._cpu:
+            return self._planner.plan_host(batch, prev_path=self._prev_path.numpy(), intermediates=True)
         dev = self._planner.device
         xy = torch.from_numpy(batch.cones_xy).to(dev)
         ty = torch.from_numpy(batch.cones_type).to(dev)

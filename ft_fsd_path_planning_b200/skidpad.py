@@ -43,7 +43,7 @@ class SkidpadBatchPlanner:
 
     def __init__(self, device="cuda"):
         if not torch.cuda.is_available():
-            raise RuntimeError("ft_fsd_path_planning_b200 needs a CUDA device: the planner has no CPU implementation")
+            raise RuntimeError("SkidpadBatchPlanner needs a CUDA device and never falls back to the host")
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())

@@ -21,10 +21,13 @@
  *     FSD_MAX_CONES cones per frame (more -> FSD_ST_OVERFLOW, frame planned on the first 256);
  *   - sort indices index the frame's own cone list (reference: flatten_cones_by_type_array,
  *     fsd_path_planning/sorting_cones/trace_sorter/core_trace_sorter.py:37-54);
- *   - the library owns nothing but a few internal CUDA streams / events per device (created on first use): a large
- *     fsd_plan_batch call runs its second half on one of them, forked from and joined back into `stream` with events,
- *     so the call is still ONE asynchronous operation ordered on `stream` (see fsd_plan_launches);
- *   - no CPU fallback exists: without a CUDA device every entry point returns FSD_ERR_NO_DEVICE.
+ *   - the library owns a few internal CUDA streams / events per device (created on first use): a large fsd_plan_batch
+ *     call may run its second half on one of them, forked from and joined back into `stream` with events, so the call
+ *     is still ONE asynchronous operation ordered on `stream` (see fsd_plan_launches);
+ *   - no CPU fallback exists: without a CUDA device every CUDA entry point returns FSD_ERR_NO_DEVICE (the host planner
+ *     fsd_plan_batch_cpu is a separate, explicit entry point);
+ *   - besides its internal streams / events the library owns 4 KB of device memory per device (frame counters of its
+ *     free-running kernels, allocated on first use).
  */
 #ifndef FSDPLAN_H
 #define FSDPLAN_H
@@ -158,6 +161,21 @@ int fsd_plan_batch_f64(const fsd_params *params, int mission, int n_frames, cons
                        int prev_path_stride, uint32_t *out_status, void *workspace, size_t workspace_bytes,
                        void *stream);
 
+/*
+ * fsd_plan_batch_cpu: the same planner on the HOST (BASELINE config 1, "CPU plumbing"; machines without a GPU).  All
+ * pointers are HOST pointers, coordinates are fp64, no workspace, synchronous; n_threads worker threads share the batch.
+ * It is compiled from the very sources the CUDA kernels are compiled from (csrc/sort.cuh, match.cuh, spline.cuh,
+ * path.cuh as a warp of one lane, csrc/cpu_backend.cpp) -- not from the test oracle -- and it is an explicit entry point:
+ * no CUDA entry point ever falls back to it.  inter (nullable) holds HOST pointers; at least one of out_path /
+ * inter->path_f64 must be given.
+ */
+int fsd_plan_batch_cpu(const fsd_params *params, int mission, int n_frames, const double *cones_xy,
+                       const uint8_t *cones_type, const int32_t *offsets, const double *pos, const double *dir,
+                       float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                       const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                       int n_threads);
+int fsd_initial_path_cpu(const fsd_params *params, double *out_prev_path /* host, [40][4] */);
+
 /* fsd_plan_batch with the coordinate type as a flag (coords_f64 != 0: fp64) and an optional CUDA event:
  * `chunk_ready_event` (cudaEvent_t, nullable) is recorded on `stream` as soon as the outputs of the first
  * fsd_plan_first_chunk(n_frames) frames are final -- a caller can start consuming them (e.g. the all-gather of their paths
@@ -174,6 +192,17 @@ int fsd_plan_batch_ex(const fsd_params *params, int mission, int n_frames, int c
 int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy, const uint8_t *cones_type,
                    const int32_t *offsets, const float *pos, const float *dir, int16_t *out_left_idx,
                    int16_t *out_right_idx, int16_t *sort_dbg, uint32_t *out_status, void *stream);
+
+/* fsd_knn_batch: the cost-matrix step in isolation (SURVEY.md 8a row S3, 8d "cost-matrix step"): both sides' k-NN graphs
+ * of create_adjacency_matrix, fsd_path_planning/sorting_cones/trace_sorter/adjacency_matrix.py:60-128 (squared distances,
+ * opposite colour excluded per side, k = min(5, N-1) nearest, edges longer than max_dist cut, A & A^T).  Per cone (packed
+ * order, frame-local indices): out_nbr [total][2][5] uint8 = the cone's neighbours in the LEFT / RIGHT graph in ascending
+ * index order (the CSR order of end_configurations.py:28-71; entries past the degree are unspecified),
+ * out_deg [total][2] uint8 = the degrees.  Frames with fewer than 3 cones get degree 0 (the sorter does not build a
+ * graph for them).  Algorithmic bytes per frame: 9 N + 16 read, 12 N written (SURVEY's B_cm = 19.25 N + 16 counts the
+ * 10 N bytes of lists + two N/8-byte masks). */
+int fsd_knn_batch(const fsd_params *params, int n_frames, int coords_f64, const void *cones_xy,
+                  const uint8_t *cones_type, const int32_t *offsets, uint8_t *out_nbr, uint8_t *out_deg, void *stream);
 
 /* fsd_match_batch: ConeMatching on given sort indices; writes n_wv, left_wv, right_wv, l2r, r2l of `inter`
  * (all five must be non-NULL). */

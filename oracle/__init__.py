@@ -74,6 +74,7 @@ def lib():
         L.fsd_oracle_sort.argtypes = [dp, up, C.c_int, dp, dp, C.POINTER(Result)]
         L.fsd_oracle_match.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, C.POINTER(Result)]
         L.fsd_oracle_path.argtypes = [dp, C.c_int, dp, C.c_int, ip, ip, dp, dp, C.c_int, dp, C.POINTER(Result)]
+        L.fsd_oracle_adjacency.argtypes = [dp, up, C.c_int, C.c_int, ip, ip]
         _lib = L
     return _lib
 
@@ -99,6 +100,30 @@ def plan_batch(batch, force_P=None, threads: int = 1) -> np.ndarray:
                                 off.ctypes.data_as(C.POINTER(C.c_int)), B, _dp(pos), _dp(dr), fp,
                                 int(threads), res.ctypes.data)
     return res
+
+
+def adjacency(batch):
+    """Both sides' k-NN graphs of every frame (create_adjacency_matrix): (nbr [total, 2, 5] int, deg [total, 2] int) in
+    the layout of fsd_knn_batch (side 0 = left graph, 1 = right graph; frames with fewer than 3 cones: degree 0)."""
+    xy = np.ascontiguousarray(batch.cones_xy, dtype=np.float64)
+    ty = np.ascontiguousarray(batch.cones_type, dtype=np.uint8)
+    off = np.asarray(batch.offsets)
+    total = len(xy)
+    nbr = np.zeros((total, 2, 5), dtype=np.int32)
+    deg = np.zeros((total, 2), dtype=np.int32)
+    L = lib()
+    for b in range(len(off) - 1):
+        lo, n = int(off[b]), int(off[b + 1] - off[b])
+        if n < 3:
+            continue
+        for s, side in enumerate((2, 1)):
+            nb = np.zeros((n, 5), dtype=np.int32)
+            dg = np.zeros(n, dtype=np.int32)
+            L.fsd_oracle_adjacency(_dp(xy[lo:lo + n]), ty[lo:lo + n].ctypes.data_as(C.POINTER(C.c_ubyte)), n, side,
+                                   nb.ctypes.data_as(C.POINTER(C.c_int)), dg.ctypes.data_as(C.POINTER(C.c_int)))
+            nbr[lo:lo + n, s] = nb
+            deg[lo:lo + n, s] = dg
+    return nbr, deg
 
 
 def initial_path() -> np.ndarray:

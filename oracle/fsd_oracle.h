@@ -68,6 +68,9 @@ int fsd_oracle_parcur(const double *x, const double *u, int m, int k, double s, 
 void fsd_oracle_splev(const double *t, int n, const double *c, int k, const double *xs, int mx, double *ys);
 
 /* stage entry points for stage-level checks */
+/* create_adjacency_matrix (sorting_cones/trace_sorter/adjacency_matrix.py:60-128) for one side (1 = right / yellow,
+ * 2 = left / blue): neighbour lists nbr [n][5] in ascending index order, degrees deg [n] */
+int fsd_oracle_adjacency(const double *cones_xy, const unsigned char *cones_type, int n, int side, int *nbr, int *deg);
 int fsd_oracle_sort(const double *cones_xy, const unsigned char *cones_type, int n, const double *pos,
                     const double *dir, fsd_oracle_result *out);
 int fsd_oracle_match(const double *left, int nl, const double *right, int nr, const double *pos, const double *dir,

@@ -266,6 +266,15 @@ static void build_graph(const fsd_o_frame *f, int side, int start, fsd_o_graph *
   free(kcnt);
 }
 
+/* stage wrapper for the adjacency parity test: neighbour lists (n x 5, ascending) and degrees of one side's graph */
+int fsd_oracle_adjacency(const double *cones_xy, const unsigned char *cones_type, int n, int side, int *nbr, int *deg) {
+  if (n < 1) return 0;
+  fsd_o_frame f = {cones_xy, cones_type, n, {0.0, 0.0}, {1.0, 0.0}};
+  fsd_o_graph g = {nbr, deg, 0};
+  build_graph(&f, side, 0, &g);
+  return g.reachable;
+}
+
 /* ---- S5: admissibility (sorting_cones/trace_sorter/end_configurations.py:108-278) ------ */
 
 static void can_be_added(const fsd_o_frame *f, int side, const int *attempt, int pos, const int *nb, int nnb,

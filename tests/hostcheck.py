@@ -104,6 +104,19 @@ def plan_batch(batch, force_P=None, prev=None):
     return out
 
 
+def knn(batch):
+    """(nbr [total, 2, 5] uint8, deg [total, 2] uint8) of the kernels' k-NN graph code (layout of fsd_knn_batch)."""
+    xy = np.ascontiguousarray(batch.cones_xy, dtype=np.float64)
+    ty = np.ascontiguousarray(batch.cones_type, dtype=np.uint8)
+    off = np.ascontiguousarray(batch.offsets, dtype=np.int32)
+    nbr = np.zeros((len(xy), 2, 5), np.uint8)
+    deg = np.zeros((len(xy), 2), np.uint8)
+    p = default_params()
+    lib().fsd_hostcheck_knn(C.byref(p), len(off) - 1, _p(xy, C.c_double), _p(ty, C.c_uint8), _p(off, C.c_int32),
+                            _p(nbr, C.c_uint8), _p(deg, C.c_uint8))
+    return nbr, deg
+
+
 def fit(points: np.ndarray, s: float):
     pts = np.ascontiguousarray(points, dtype=np.float64)
     m = len(pts)

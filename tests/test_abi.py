@@ -65,17 +65,17 @@ def test_argument_errors_do_not_need_a_device(lib):
     assert rc == -5
 
 
-def test_product_has_no_cpu_path():
+def test_cuda_planner_never_falls_back_to_the_host():
     import torch
 
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     from ft_fsd_path_planning_b200 import BatchPlanner, MissionTypes, PathPlanner
 
-    with pytest.raises(RuntimeError, match="no CPU implementation"):
+    with pytest.raises(RuntimeError, match="never falls back to the host"):
         BatchPlanner()
-    with pytest.raises(RuntimeError, match="no CPU implementation"):
-        PathPlanner(MissionTypes.trackdrive)
+    with pytest.raises(RuntimeError, match="never falls back to the host"):
+        PathPlanner(MissionTypes.trackdrive)  # default device: CUDA.  The host planner needs device="cpu"
 
 
 def test_product_never_imports_the_oracle():

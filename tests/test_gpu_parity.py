@@ -221,6 +221,26 @@ def test_config5_65536_mixed_frames_in_eight_shards_match_oracle(planner):
     assert ((st & 0x600) != 0).mean() < 0.01
 
 
+@pytest.mark.parametrize("kind", ["color", "colorless", "mixed"])
+def test_knn_stage_adjacency_is_bit_exact(planner, kind):
+    """fsd_knn_batch (the cost-matrix step in isolation) against the oracle's create_adjacency_matrix on 4 096 synthetic
+    frames per colour mode and on the recorded FSG / FS-Spain frames: degrees and neighbour lists identical."""
+    from test_hostcheck import adjacency_equal
+
+    batches = [synth.gen_mixed(33, 4096, workers=16) if kind == "mixed" else synth.gen_autocross(32, 4096, workers=16)]
+    if kind == "colorless":
+        batches[0] = synth.remove_color_info(batches[0])
+    batches.append(load_golden("fsg_" + ("colorless" if kind == "colorless" else "color"))[0])
+    batches.append(load_golden("fss_" + ("colorless" if kind == "colorless" else "color"))[0])
+    dev = planner.device
+    for batch in batches:
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        nbr, deg = planner.knn(t(batch.cones_xy), t(batch.cones_type), t(batch.offsets))
+        torch.cuda.synchronize()
+        ref_nbr, ref_deg = oracle.adjacency(batch)
+        assert adjacency_equal(nbr.cpu().numpy(), deg.cpu().numpy(), ref_nbr, ref_deg)
+
+
 def test_rigid_motion_equivariance(planner):
     """Planning a rotated + translated copy of a frame gives the same sort indices and the transformed path."""
     B = 1024

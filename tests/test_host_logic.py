@@ -99,3 +99,35 @@ def test_json_loader_reads_reference_log_format():
     batch, _ = load_golden("fsg_color")
     loaded = load_data_json(path)
     assert np.array_equal(loaded.cones_xy, batch.cones_xy) and np.array_equal(loaded.offsets, batch.offsets)
+
+
+def test_host_planner_is_explicit_and_matches_goldens():
+    """fsd_plan_batch_cpu (the kernels' per-frame sources compiled for the host, BASELINE config 1 "CPU plumbing"): all 440
+    recorded FSG frames against the reference's goldens, through the batched entry point and through the drop-in facade
+    with device="cpu".  The default device stays CUDA-only: nothing falls back to the host planner."""
+    import pytest
+    import torch
+
+    from conftest import compare_with_golden, load_golden
+    from ft_fsd_path_planning_b200 import BatchPlanner, CpuBatchPlanner, MissionTypes, PathPlanner
+
+    batch, g = load_golden("fsg_color")
+    r = CpuBatchPlanner(threads=4).plan_host(batch, force_P=g["P"], intermediates=True)
+    n = lambda t: t.numpy()
+    compare_with_golden("fsg_color", g, n(r.left_idx), n(r.right_idx), n(r.n_wv), n(r.left_wv), n(r.right_wv), n(r.l2r),
+                        n(r.r2l), n(r.path_f64), path_tol=1e-7)
+    compare_with_golden("fsg_color", g, n(r.left_idx), n(r.right_idx), n(r.n_wv), n(r.left_wv), n(r.right_wv), n(r.l2r),
+                        n(r.r2l), n(r.path), path_tol=1e-4)
+    pp = PathPlanner(MissionTypes.trackdrive, device="cpu")
+    worst = 0.0
+    for b in range(0, 440, 11):
+        cones, pos, direction = batch.frame(b)
+        path, sl, sr, lwv, rwv, l2r, r2l = pp.calculate_path_in_global_frame(cones, pos, direction, return_intermediate_results=True)
+        worst = max(worst, float(np.abs(path - g["tie_path"][b]).max()))
+        assert (l2r == g["l2r"][b][: len(l2r)]).all()
+    assert worst < 1e-7
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="needs a CUDA device"):
+            BatchPlanner("cuda")
+        with pytest.raises(RuntimeError):
+            PathPlanner(MissionTypes.trackdrive)  # the default device is CUDA: no silent fallback to the host planner

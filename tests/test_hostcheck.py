@@ -4,6 +4,7 @@ of the kernel logic, not a product path."""
 import os
 
 import numpy as np
+import pytest
 
 import hostcheck
 from conftest import GOLDEN_DIR, TIE_DIST_TOL, TIE_KAPPA_TOL, compare_with_golden, tie_frame_deviation
@@ -59,3 +60,26 @@ def test_initial_path_matches_oracle():
     import oracle
 
     assert np.abs(hostcheck.initial_path() - oracle.initial_path()).max() < 1e-9
+
+
+def adjacency_equal(nbr, deg, ref_nbr, ref_deg):
+    """Degrees equal and the first `degree` entries of every neighbour list equal (entries past the degree are unspecified)."""
+    if not np.array_equal(np.asarray(deg, dtype=np.int32), ref_deg):
+        return False
+    live = np.arange(5)[None, None, :] < ref_deg[:, :, None]
+    return bool((np.asarray(nbr, dtype=np.int32)[live] == ref_nbr[live]).all())
+
+
+def test_knn_graph_sources_match_oracle_adjacency(golden):
+    """the cost-matrix step (create_adjacency_matrix, adjacency_matrix.py:60-128) bit-exact on every golden
+    frame -- kernel sources (host-check build) against the oracle's restatement of the reference's dense formulation."""
+    import oracle
+
+    name, batch, g = golden
+    if name == "fixtures":
+        # hand-made frames on an exact lattice: equal distances everywhere, and the k-th neighbour among equals is
+        # unspecified in the reference itself (np.argsort's default sort is unstable, SURVEY Q3)
+        pytest.skip("lattice-exact coordinates: k-NN ties are unspecified in the reference")
+    nbr, deg = hostcheck.knn(batch)
+    ref_nbr, ref_deg = oracle.adjacency(batch)
+    assert adjacency_equal(nbr, deg, ref_nbr, ref_deg), name
