@@ -46,7 +46,7 @@ class Intermediate(C.Structure):
 
 
 def sources():
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh")) or f == "cpu_backend.cpp"]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h")) or f == "cpu_backend.cpp"]
     return files + [INCLUDE]
 
 
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         # kernels.cu: the CUDA kernels and the C-ABI; cpu_backend.cpp: the same per-frame sources compiled for the host
         # (fsd_plan_batch_cpu, an explicit entry point -- the CUDA entry points never fall back to it)
         cmd = ["nvcc", *NVCC_FLAGS, "-Xcompiler", "-Wno-unknown-pragmas", "-o", LIB_PATH, os.path.join(CSRC, "kernels.cu"),
-               os.path.join(CSRC, "cpu_backend.cpp")]
+               os.path.join(CSRC, "kernels_big.cu"), os.path.join(CSRC, "cpu_backend.cpp")]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
@@ -105,6 +105,9 @@ def lib():
                                            C.POINTER(Intermediate), vp, vp]
         L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp,
                                      vp, sz, vp]
+        L.fsd_global_path_workspace_bytes.restype = sz
+        L.fsd_global_path_workspace_bytes.argtypes = [i32]
+        L.fsd_global_path_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]
         L.fsd_skidpad_workspace_bytes.restype = sz
         L.fsd_skidpad_workspace_bytes.argtypes = [i32]
         L.fsd_skidpad_relocalize_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]

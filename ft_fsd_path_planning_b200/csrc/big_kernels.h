@@ -1,0 +1,17 @@
+// Launchers of the kernels built with LARGE static bounds (kernels_big.cu: 2 048 path points, 64 knots per fit).  They
+// serve the inputs the planner kernels' own bounds do not cover -- a centre line taken from a global path is several times
+// longer than one built from <= 12 matched cones -- and are not on the batched hot path.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/fsdplan.h"
+
+size_t fsd_big_global_path_scratch_bytes(int n_poses, int sm_count);
+int fsd_big_global_path(const fsd_params *params, int n_poses, const double *pos, const double *dir, const double *gpath,
+                        int n_points, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
+                        float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, int *counter,
+                        int sm_count, cudaStream_t stream);

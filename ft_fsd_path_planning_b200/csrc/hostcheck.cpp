@@ -69,6 +69,30 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
   return 0;
 }
 
+// path calculation along a global path (fsd_global_path_batch)
+extern "C" int fsd_hostcheck_global_path(const fsd_params *params, int n_poses, const double *pos, const double *dir,
+                                         const double *gpath, int n_points, const int16_t *force_P, const double *prev,
+                                         int prev_stride, double *out, int16_t *grid, uint32_t *status) {
+  DevParams P = make_dev_params(*params);
+  PathSmem *Q = new_path_smem();
+  double initial[FSD_HORIZON * 4];
+  if (!prev) {
+    initial_path_frame(*Q, P, initial);
+    prev = initial;
+    prev_stride = 0;
+  }
+  for (int b = 0; b < n_poses; ++b) {
+    const FramePose F = make_pose(pos[2 * b], pos[2 * b + 1], dir[2 * b], dir[2 * b + 1]);
+    int g[2] = {0, 0};
+    status[b] = path_global(*Q, gpath, n_points, F, force_P ? force_P[b] : 0, prev + (size_t)b * prev_stride, P,
+                            out + 160 * (size_t)b, g);
+    grid[2 * b] = (int16_t)g[0];
+    grid[2 * b + 1] = (int16_t)g[1];
+  }
+  free_path_smem(Q);
+  return 0;
+}
+
 // the cost-matrix step alone (layout of fsd_knn_batch)
 extern "C" int fsd_hostcheck_knn(const fsd_params *params, int n_frames, const double *xy, const uint8_t *type,
                                  const int32_t *offsets, uint8_t *out_nbr, uint8_t *out_deg) {

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "big_kernels.h"
 #include "frame.cuh"
 #include "skidpad.cuh"
 
@@ -1471,6 +1472,38 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
                              force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
                           force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry);
+}
+
+size_t fsd_global_path_workspace_bytes(int n_poses) {
+  DeviceInfo *D = nullptr;
+  const int sms = device_info(&D) == FSD_OK ? D->sm_count : 160;
+  return fsd_big_global_path_scratch_bytes(n_poses, sms);
+}
+
+int fsd_global_path_batch(const fsd_params *params, int n_poses, const double *pos, const double *dir,
+                          const double *global_path, int n_points, const int16_t *force_P, const double *prev_path,
+                          int prev_path_stride, float *out_path, double *out_path_f64, int16_t *out_grid,
+                          uint32_t *out_status, void *workspace, size_t workspace_bytes_given, void *stream_v) {
+  if (!params || n_poses < 0) return FSD_ERR_ARG;
+  if (n_poses == 0) return FSD_OK;
+  if (!pos || !dir || !global_path || n_points < 1 || !out_status || (!out_path && !out_path_f64)) return FSD_ERR_ARG;
+  if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
+  DeviceInfo *D = nullptr;
+  int rc = device_info(&D);
+  if (rc != FSD_OK) return rc;
+  if (!workspace || workspace_bytes_given < fsd_big_global_path_scratch_bytes(n_poses, D->sm_count)) return FSD_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const double *prev = prev_path;
+  int stride = prev_path_stride;
+  if (!prev) {
+    rc = default_prev_path(params, make_dev_params(*params), *D, nullptr, stream, &prev);
+    if (rc != FSD_OK) return rc;
+    stride = 0;
+  }
+  int *counters = take_counters(*D, stream);
+  if (!counters) return FSD_ERR_LAUNCH;
+  return fsd_big_global_path(params, n_poses, pos, dir, global_path, n_points, force_P, prev, stride, out_path_f64, out_path,
+                             out_grid, out_status, static_cast<unsigned char *>(workspace), counters, D->sm_count, stream);
 }
 
 size_t fsd_skidpad_workspace_bytes(int n_steps) {

@@ -1,0 +1,83 @@
+// Kernels built with LARGE static bounds: the per-frame sources (spline.cuh, path.cuh) compiled a second time, in a
+// namespace of their own, with room for 2 048 path points and 64 knots per fit.  A centre line taken from a GLOBAL PATH
+// (PathPlanner.set_global_path, the acceleration mission's map; core_calculate_path.py:516-528) spans up to 60 m + 60 m of
+// path -- 1 250 evaluation points at 0.1 m -- where the planner kernels of kernels.cu are sized for the <= 45 m a centre
+// line of <= 12 matched cones can have.  Not on the batched hot path: one warp per pose, 4 warps per CTA.
+#define FSD_PCAP 2048
+#define FSD_NCAP 64
+#define fsd fsd_big  // the same sources, a second namespace (distinct symbols next to kernels.cu's instantiation)
+#include "big_kernels.h"
+#include "path.cuh"
+
+using namespace fsd_big;
+
+namespace {
+
+constexpr int BIG_WPC = 4;
+constexpr size_t BIG_STRIDE = (sizeof(PathSmem) + 15) / 16 * 16;
+
+__global__ void __launch_bounds__(32 * BIG_WPC)
+    global_path_kernel(DevParams P, int n_poses, const double *pos, const double *dir, const double *gpath, int n_points,
+                       const int16_t *force_P, const double *prev, int prev_stride, double *out_f64, float *out_f32,
+                       int16_t *grid_out, uint32_t *status, unsigned char *scratch, int *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = fsd_lane();
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * BIG_STRIDE);
+  if (lane == 0) {
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * BIG_WPC + warp) * PATH_SCRATCH_BYTES;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
+  }
+  __syncwarp();
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= n_poses) break;
+    const FramePose F = make_pose(pos[2 * b], pos[2 * b + 1], dir[2 * b], dir[2 * b + 1]);
+    int grid[2] = {0, 0};
+    double *out = &S.W.G[0][0];  // the 40 x 4 result is assembled in shared memory (the fits' factor storage is dead)
+    const unsigned st = path_global(S, gpath, n_points, F, force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P,
+                                    out, grid);
+    for (int i = lane; i < FSD_HORIZON * 4; i += 32) {
+      const double v = out[i];
+      if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
+      if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;
+    }
+    if (lane == 0) {
+      status[b] = st;
+      if (grid_out) {
+        grid_out[2 * (size_t)b] = (int16_t)grid[0];
+        grid_out[2 * (size_t)b + 1] = (int16_t)grid[1];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int big_grid(int n_poses, int sm_count) {
+  const long need = ((long)n_poses + BIG_WPC - 1) / BIG_WPC, cap = (long)sm_count * 2;
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace
+
+size_t fsd_big_global_path_scratch_bytes(int n_poses, int sm_count) {
+  return (size_t)big_grid(n_poses > 0 ? n_poses : 1, sm_count) * BIG_WPC * PATH_SCRATCH_BYTES;
+}
+
+int fsd_big_global_path(const fsd_params *params, int n_poses, const double *pos, const double *dir, const double *gpath,
+                        int n_points, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
+                        float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, int *counter,
+                        int sm_count, cudaStream_t stream) {
+  static_assert(sizeof(SplineWork::G) >= FSD_HORIZON * 4 * sizeof(double), "the result aliases SplineWork::G");
+  const size_t smem = BIG_WPC * BIG_STRIDE;
+  if (cudaFuncSetAttribute(global_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return FSD_ERR_LAUNCH;
+  }
+  global_path_kernel<<<big_grid(n_poses, sm_count), 32 * BIG_WPC, smem, stream>>>(
+      make_dev_params(*params), n_poses, pos, dir, gpath, n_points, force_P, prev, prev_stride, out_f64, out_f32, grid_out,
+      status, scratch, counter);
+  return cudaGetLastError() == cudaSuccess ? FSD_OK : FSD_ERR_LAUNCH;
+}

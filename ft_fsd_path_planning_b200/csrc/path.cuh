@@ -15,7 +15,10 @@
 
 namespace fsd {
 
-constexpr int PCAP = 704;   // path points held per frame (fallback path: 62.8 m / 0.1 m + extension)
+#ifndef FSD_PCAP
+#define FSD_PCAP 704
+#endif
+constexpr int PCAP = FSD_PCAP;  // path points held per frame (fallback path: 62.8 m / 0.1 m + extension)
 constexpr int GRID_CAP = 128;  // size of the last evaluation grid (P = 120 or 121 at run time)
 
 enum { RC_OK = 0, RC_VALUE_ERROR = 1, RC_RAISES = 2, RC_UNSUPPORTED = 3 };
@@ -686,6 +689,61 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
   pm_start_fit1(S, M, S.pts, ncl, P);
 }
 
+// run_path_calculation with a GLOBAL PATH (core_calculate_path.py:516-528; PathPlanner.set_global_path, and the
+// acceleration mission's known map): the centre line is the part of the global path within 30 m of the car, in the order
+// of np.roll(path, -argmin + M / 3), i.e. starting M / 3 points before the closest one.  Distances lane-strided, the
+// closest point by a warp arg-min (first minimum, like np.argmin), the kept points compacted by ballot in rolled order.
+FSD_DEVFN void pm_begin_global(PathSmem &S, PathMachine &M, const double *gpath, int Mn, const FramePose &F, int force_P,
+                               const double *prev, const DevParams &P, double *out) {
+  const int lane = fsd_lane();
+  pm_init(S, M, 0, F, force_P, prev, out);
+  double bv = 0.0;
+  int bi = -1;
+#pragma unroll 1
+  for (int i = lane; i < Mn; i += FSD_LANES) {
+    const double d = fnorm(F.px - gpath[2 * i], F.py - gpath[2 * i + 1]);
+    if (bi < 0 || d < bv) {
+      bv = d;
+      bi = i;
+    }
+  }
+  wargmin(bv, bi);
+  int ncl = 0;
+  bool overflow = false;
+  const int third = Mn / 3;
+#pragma unroll 1
+  for (int base = 0; base < Mn; base += FSD_LANES) {
+    const int i = base + lane;
+    bool keep = false;
+    double x = 0.0, y = 0.0;
+    if (i < Mn) {
+      int src = (i + bi - third) % Mn;
+      if (src < 0) src += Mn;
+      x = gpath[2 * src];
+      y = gpath[2 * src + 1];
+      keep = fnorm(F.px - x, F.py - y) < 30.0;
+    }
+    const unsigned mask = wballot(keep);
+    const int slot = ncl + FSD_POPC(mask & ((1u << lane) - 1u));
+    if (keep) {
+      if (slot < PCAP) {
+        S.pts[slot].x = x;
+        S.pts[slot].y = y;
+      } else {
+        overflow = true;
+      }
+    }
+    ncl += FSD_POPC(mask);
+  }
+  if (wany(overflow)) {
+    // more points within 30 m than the point buffer holds: flagged, planned with the previous path
+    pm_finish_with_prev(M, FSD_ST_OVERFLOW | FSD_ST_UNSUPPORTED);
+    return;
+  }
+  wsync();
+  pm_start_fit1(S, M, S.pts, ncl, P);
+}
+
 // second half of run_path_calculation only: the path update already sits in S.pts[1 .. 1+nu) (skidpad)
 FSD_DEVFN void pm_begin_update(PathSmem &S, PathMachine &M, int nu, const FramePose &F, int force_P, const double *prev,
                                const DevParams &P, double *out) {
@@ -724,6 +782,19 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
                               const DevParams &P, double *out, int *grid) {
   PathMachine M;
   pm_begin_frame(S, M, left, nl, right, nr, l2r, r2l, F, force_P, prev, P, out);
+  pm_run(S, M, P);
+  if (grid && fsd_lane() == 0) {
+    grid[0] = M.P_grid;
+    grid[1] = M.n_trim;
+  }
+  wsync();
+  return M.status;
+}
+
+FSD_DEVFN unsigned path_global(PathSmem &S, const double *gpath, int Mn, const FramePose &F, int force_P,
+                               const double *prev, const DevParams &P, double *out, int *grid) {
+  PathMachine M;
+  pm_begin_global(S, M, gpath, Mn, F, force_P, prev, P, out);
   pm_run(S, M, P);
   if (grid && fsd_lane() == 0) {
     grid[0] = M.P_grid;

@@ -260,6 +260,33 @@ class BatchPlanner:
                 torch.cuda.current_stream(self.device).cuda_stream))
         return out
 
+    def plan_global_path(self, global_path: torch.Tensor, pos: torch.Tensor, direction: torch.Tensor, *,
+                         force_P: Optional[torch.Tensor] = None, prev_path: Optional[torch.Tensor] = None) -> dict:
+        """Path calculation along a GLOBAL PATH (fsd_global_path_batch; core_calculate_path.py:516-528): `global_path`
+        [M, 2] float64 shared by all poses, pos / direction [n, 2] float64, all on this planner's device.  Returns a dict of
+        device tensors: path [n, 40, 4] float32, path_f64, grid [n, 2] int16, status [n] int32.  Asynchronous."""
+        n = pos.shape[0]
+        dev = self.device
+        for t in (global_path, pos, direction):
+            if t.device != dev or t.dtype != torch.float64 or not t.is_contiguous():
+                raise ValueError("global_path, pos and direction must be contiguous float64 tensors on the planner's device")
+        out = {"path": torch.empty((n, HORIZON, 4), dtype=torch.float32, device=dev),
+               "path_f64": torch.empty((n, HORIZON, 4), dtype=torch.float64, device=dev),
+               "grid": torch.empty((n, 2), dtype=torch.int16, device=dev),
+               "status": torch.empty((n,), dtype=torch.int32, device=dev)}
+        stride = 0
+        if prev_path is not None:
+            stride = 0 if prev_path.numel() == HORIZON * 4 else HORIZON * 4
+        with torch.cuda.device(dev):
+            ws = torch.empty((int(self.lib.fsd_global_path_workspace_bytes(n)),), dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.fsd_global_path_batch(
+                C.byref(self.params), n, pos.data_ptr(), direction.data_ptr(), global_path.data_ptr(), global_path.shape[0],
+                _ptr(force_P), _ptr(prev_path), stride, out["path"].data_ptr(), out["path_f64"].data_ptr(),
+                out["grid"].data_ptr(), out["status"].data_ptr(), ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream(dev).cuda_stream))
+        out["_workspace"] = ws  # keep alive until the stream has consumed it
+        return out
+
     def plan_host(self, batch: FrameBatch, *, force_P: Optional[np.ndarray] = None,
                   prev_path: Optional[np.ndarray] = None, intermediates: bool = False) -> PlanResult:
         """Convenience: host FrameBatch in, device PlanResult out (copies on the current stream)."""
@@ -430,6 +457,59 @@ class RelocalizationInformation:
     rotation: float
 
 
+class _AccelerationRelocalization:
+    """Relocalization of the acceleration / EBS missions (AccelerationRelocalizer,
+    fsd_path_planning/relocalization/acceleration/acceleration_relocalization.py:120-172): the cones 0 .. 2 m to the left of
+    the car are taken for the left boundary; of 100 random 3-cone subsets the straight line with the smallest squared
+    error gives the track direction, and the map frame is the first pose's position turned by that direction.  A
+    one-off, ~100 tiny line fits: host code (numpy), like the constants of the skidpad mission.  The reference draws the
+    subsets from numpy's GLOBAL unseeded RNG; `seed` (None = the same global RNG) makes the draw reproducible --
+    np.random.seed(seed) before the reference's first call gives the same subsets."""
+
+    def __init__(self, seed: Optional[int] = None):
+        self._rng = np.random if seed is None else np.random.RandomState(seed)
+        self.origin: Optional[np.ndarray] = None
+        self.angle: Optional[float] = None
+
+    @property
+    def done(self) -> bool:
+        return self.angle is not None
+
+    @staticmethod
+    def _turn(points: np.ndarray, theta: float) -> np.ndarray:
+        c, s = np.cos(theta), np.sin(theta)
+        return np.dot(points, np.array(((c, -s), (s, c))).T)
+
+    def attempt(self, cones: Sequence[np.ndarray], position: np.ndarray, direction: np.ndarray) -> None:
+        if self.done:
+            return
+        if self.origin is None:
+            self.origin = np.array(position, dtype=np.float64)
+        pts = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in cones])
+        if len(pts) < 3:
+            return
+        yaw = np.arctan2(direction[1], direction[0])
+        local = self._turn(pts - position, -yaw)
+        left = local[(local[:, 1] > 0) & (local[:, 1] < 2)]
+        left = left[left[:, 0].argsort()]
+        if len(left) < 4:
+            return
+        best, best_err = None, np.inf
+        for _ in range(100):  # the draws must be consumed one by one, in this order
+            sub = left[self._rng.choice(left.shape[0], 3, replace=False)]
+            coeff = np.polyfit(sub[:, 0], sub[:, 1], 1)
+            err = float(np.sum((sub[:, 1] - np.polyval(coeff, sub[:, 0])) ** 2))
+            if err < best_err:
+                best, best_err = coeff, err
+        self.angle = float(np.arctan(best[0]) + yaw)
+
+    def to_map(self, position: np.ndarray, yaw: float):
+        return self._turn(np.asarray(position, dtype=np.float64) - self.origin, -self.angle), yaw - self.angle
+
+    def to_world(self, points: np.ndarray) -> np.ndarray:
+        return self._turn(points, self.angle) + self.origin
+
+
 class ReferenceRaisesError(RuntimeError):
     """The reference raises an exception on this input (e.g. the IndexError of functional_cone_matching.py:130 when a
     sorted side holds exactly one cone) or takes its latent-bug path (core_calculate_path.py:482-483).  The batched
@@ -444,15 +524,17 @@ class PathPlanner:
     (return the previous path instead of raising; state untouched as well)."""
 
     def __init__(self, mission: MissionTypes, experimental_performance_improvements: bool = False,
-                 device: Union[str, torch.device, int] = "cuda", on_reference_error: str = "raise") -> None:
+                 device: Union[str, torch.device, int] = "cuda", on_reference_error: str = "raise",
+                 relocalization_seed: Optional[int] = None) -> None:
         if on_reference_error not in ("raise", "previous"):
             raise ValueError('on_reference_error must be "raise" or "previous"')
         self.on_reference_error = on_reference_error
         self.mission = MissionTypes(mission)
+        self._accel: Optional[_AccelerationRelocalization] = None
         if self.mission in (MissionTypes.acceleration, MissionTypes.ebs_test):
-            raise NotImplementedError(
-                f"mission {self.mission.name}: the acceleration relocalizer draws from an unseeded RNG in the reference "
-                "and is out of scope (SURVEY.md section 2); use trackdrive / autocross / skidpad")
+            if str(device) == "cpu":
+                raise NotImplementedError("the host planner (device='cpu') covers trackdrive / autocross only")
+            self._accel = _AccelerationRelocalization(relocalization_seed)
         # the experimental sorting cache of the reference changes results and is not reproduced
         self.experimental_performance_improvements = experimental_performance_improvements
         self._cpu = str(device) == "cpu"
@@ -485,11 +567,65 @@ class PathPlanner:
         raise ValueError("direction must be a float or a 2 element array")
 
     def set_global_path(self, global_path):
-        self.global_path = global_path
+        """full_pipeline.py:81: from now on the path is calculated along this (M, 2) line (core_calculate_path.py:516-528)."""
+        self.global_path = None if global_path is None else np.ascontiguousarray(global_path, dtype=np.float64).reshape(-1, 2)
+        self._global_path_dev = None
+
+    def _global_path_step(self, position: np.ndarray, direction: np.ndarray) -> np.ndarray:
+        """One call with a global path set: fsd_global_path_batch on one pose, stateful like the reference."""
+        if self._cpu:
+            raise NotImplementedError("global-path planning is not part of the host planner (device='cpu')")
+        dev = self._planner.device
+        if getattr(self, "_global_path_dev", None) is None:
+            self._global_path_dev = torch.from_numpy(self.global_path).to(dev)
+        if self._prev_path is None:
+            self._prev_path = self._planner.initial_path()
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(1, 2)).to(dev)
+        res = self._planner.plan_global_path(self._global_path_dev, t(position), t(direction), prev_path=self._prev_path)
+        status = int(res["status"][0].item())
+        if status & (_lib.STATUS_BITS["REF_RAISES"] | _lib.STATUS_BITS["UNSUPPORTED"]):
+            if self.on_reference_error == "raise":
+                raise ReferenceRaisesError(f"the reference planner raises on this input (status 0x{status:x})")
+            return self._prev_path.cpu().numpy()
+        self._prev_path = res["path_f64"][0].clone()
+        return self._prev_path.cpu().numpy()
+
+    def _acceleration_step(self, cones, position, direction, return_intermediate_results):
+        """full_pipeline.py:122-194 for the acceleration / EBS missions: relocalize once, then follow the known map."""
+        self._accel.attempt(cones, position, direction)
+        e2, ei = np.zeros((0, 2)), np.zeros(0, dtype=int)
+        if self._accel.done:
+            yaw = float(np.arctan2(direction[1], direction[0]))
+            pos_map, yaw_map = self._accel.to_map(position, yaw)
+            if self.global_path is None:
+                import os
+
+                self.set_global_path(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data",
+                                                         "acceleration_path.npy")))
+            path = self._global_path_step(pos_map, np.array([np.cos(yaw_map), np.sin(yaw_map)])).copy()
+            path[:, 1:3] = self._accel.to_world(path[:, 1:3])
+        else:
+            # not relocalized yet: no sorting / matching in these missions, so both sides are empty and the planner
+            # returns the path of the previous call (core_calculate_path.py:531-536)
+            batch = pack_frames([([e2] * 5, position, direction)], dtype=np.float64)
+            if self._prev_path is None:
+                self._prev_path = self._planner.initial_path()
+            res = self._plan_with_prev(batch)
+            self._prev_path = res.path_f64[0].clone()
+            path = self._prev_path.cpu().numpy()
+        if not return_intermediate_results:
+            return path
+        return path, e2, e2, e2, e2, ei, ei
 
     @property
     def relocalization_info(self) -> Optional[RelocalizationInformation]:
         """relocalization_information.py:13-35: where the SLAM origin and the x axis land in the map frame."""
+        if self._accel is not None:
+            if not self._accel.done:
+                return None
+            o, _ = self._accel.to_map(np.zeros(2), 0.0)
+            e, _ = self._accel.to_map(np.array([1.0, 0.0]), 0.0)
+            return RelocalizationInformation(o, float(np.arctan2(e[1] - o[1], e[0] - o[0])))
         if self._skid is None or self._reloc_host[7] == 0.0:
             return None
         from .skidpad import to_known_frame
@@ -535,12 +671,20 @@ class PathPlanner:
         if self._skid is not None:
             return self._skidpad_step(cones, np.asarray(vehicle_position, dtype=np.float64).reshape(2), direction,
                                       return_intermediate_results)
-        if self.global_path is not None:
-            raise NotImplementedError("global-path tracking belongs to the skidpad mission")
-        batch = pack_frames([(cones, np.asarray(vehicle_position, dtype=np.float64).reshape(2), direction)],
-                            dtype=np.float64)
+        position = np.asarray(vehicle_position, dtype=np.float64).reshape(2)
+        if self._accel is not None:
+            return self._acceleration_step(cones, position, direction, return_intermediate_results)
+        batch = pack_frames([(cones, position, direction)], dtype=np.float64)
         if self._prev_path is None:
             self._prev_path = self._planner.initial_path()
+        if self.global_path is not None:
+            # set_global_path: sorting and matching still run (their results are returned as intermediates), the path
+            # follows the global line (core_calculate_path.py:516-528)
+            out_path = self._global_path_step(position, direction)
+            if not return_intermediate_results:
+                return out_path
+            res = self._plan_with_prev(batch)
+            return (out_path, *self._intermediates(batch, res))
         res = self._plan_with_prev(batch)
         status = int(res.status[0].item())
         if status & (_lib.STATUS_BITS["REF_RAISES"] | _lib.STATUS_BITS["UNSUPPORTED"]):
@@ -553,13 +697,17 @@ class PathPlanner:
         out_path = res.path_f64[0].cpu().numpy()
         if not return_intermediate_results:
             return out_path
+        return (out_path, *self._intermediates(batch, res))
+
+    @staticmethod
+    def _intermediates(batch: FrameBatch, res: PlanResult):
+        """(sorted_left, sorted_right, left_with_virtual, right_with_virtual, l2r, r2l) of a one-frame result."""
         xy = batch.cones_xy
         li = res.left_idx[0].cpu().numpy()
         ri = res.right_idx[0].cpu().numpy()
         n_wv = res.n_wv[0].cpu().numpy()
         nl, nr = int(n_wv[0]), int(n_wv[1])
         return (
-            out_path,
             xy[li[li >= 0]],
             xy[ri[ri >= 0]],
             res.left_wv[0, :nl].cpu().numpy(),

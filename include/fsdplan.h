@@ -229,6 +229,21 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
                    size_t workspace_bytes, void *stream);
 
 /*
+ * fsd_global_path_batch: CalculatePath.run_path_calculation with a GLOBAL PATH
+ * (fsd_path_planning/calculate_path/core_calculate_path.py:516-528): what PathPlanner does after set_global_path(path)
+ * (full_pipeline.py:81) and what the acceleration / EBS missions do with their known map once relocalized
+ * (acceleration_relocalization.py:168-169).  For each of n_poses poses: the points of global_path [n_points][2] (fp64,
+ * shared by all poses) within 30 m of the position, starting n_points / 3 points before the closest one, are the centre
+ * line; then fit, validity check, MPC tail as in fsd_path_batch.  More than 704 such points: FSD_ST_OVERFLOW, the previous
+ * path is returned.  prev_path / force_P / outputs as for fsd_path_batch; poses are fp64.
+ */
+size_t fsd_global_path_workspace_bytes(int n_poses);
+int fsd_global_path_batch(const fsd_params *params, int n_poses, const double *pos, const double *dir,
+                          const double *global_path, int n_points, const int16_t *force_P, const double *prev_path,
+                          int prev_path_stride, float *out_path, double *out_path_f64, int16_t *out_grid,
+                          uint32_t *out_status, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Skidpad mission (MissionTypes.skidpad): relocalization + stateful tracking of the canonical skidpad path.
  *   SkidpadRelocalizer.do_relocalization_once   fsd_path_planning/relocalization/skidpad/skidpad_relocalizer.py:198-240
  *   SkidpadCalculatePath.fit_matches_as_spline  fsd_path_planning/calculate_path/skidpad_calculate_path.py:49-71

@@ -74,6 +74,7 @@ def lib():
         L.fsd_oracle_sort.argtypes = [dp, up, C.c_int, dp, dp, C.POINTER(Result)]
         L.fsd_oracle_match.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, C.POINTER(Result)]
         L.fsd_oracle_path.argtypes = [dp, C.c_int, dp, C.c_int, ip, ip, dp, dp, C.c_int, dp, C.POINTER(Result)]
+        L.fsd_oracle_path_global.argtypes = [dp, C.c_int, dp, dp, C.c_int, dp, C.POINTER(Result)]
         L.fsd_oracle_adjacency.argtypes = [dp, up, C.c_int, C.c_int, ip, ip]
         _lib = L
     return _lib
@@ -124,6 +125,18 @@ def adjacency(batch):
             nbr[lo:lo + n, s] = nb
             deg[lo:lo + n, s] = dg
     return nbr, deg
+
+
+def path_global(global_path, pos, direction, force_P=0, prev_path=None) -> Result:
+    """run_path_calculation with a global path for one pose; returns the Result struct (path, P, n_trim, status)."""
+    gp = np.ascontiguousarray(global_path, dtype=np.float64)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    dr = np.ascontiguousarray(direction, dtype=np.float64)
+    pv = None if prev_path is None else np.ascontiguousarray(prev_path, dtype=np.float64)
+    res = Result()
+    lib().fsd_oracle_path_global(_dp(gp), len(gp), _dp(pos), _dp(dr), int(force_P), None if pv is None else _dp(pv),
+                                 C.byref(res))
+    return res
 
 
 def initial_path() -> np.ndarray:

@@ -39,6 +39,13 @@ int fsd_oracle_path(const double *left_wv, int nl, const double *right_wv, int n
   return fsd_o_path(left_wv, nl, right_wv, nr, l2r, r2l, pos, dir, force_P, prev_path, out);
 }
 
+/* run_path_calculation with a global path (set_global_path / the acceleration mission), core_calculate_path.py:516-528 */
+int fsd_oracle_path_global(const double *global_path, int n_points, const double *pos, const double *dir, int force_P,
+                           const double *prev_path, fsd_oracle_result *out) {
+  result_init(out);
+  return fsd_o_path_global(global_path, n_points, pos, dir, force_P, prev_path, out);
+}
+
 int fsd_oracle_plan_frame(const double *cones_xy, const unsigned char *cones_type, int n, const double *pos,
                           const double *dir, int force_P, const double *prev_path, fsd_oracle_result *out) {
   result_init(out);

@@ -67,6 +67,10 @@ int fsd_oracle_parcur(const double *x, const double *u, int m, int k, double s, 
                       double *fp_out);
 void fsd_oracle_splev(const double *t, int n, const double *c, int k, const double *xs, int mx, double *ys);
 
+/* CalculatePath.run_path_calculation with a global path (core_calculate_path.py:516-528) */
+int fsd_oracle_path_global(const double *global_path, int n_points, const double *pos, const double *dir, int force_P,
+                           const double *prev_path, fsd_oracle_result *out);
+
 /* stage entry points for stage-level checks */
 /* create_adjacency_matrix (sorting_cones/trace_sorter/adjacency_matrix.py:60-128) for one side (1 = right / yellow,
  * 2 = left / blue): neighbour lists nbr [n][5] in ascending index order, degrees deg [n] */

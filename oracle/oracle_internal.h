@@ -40,6 +40,8 @@ int fsd_o_match(const double *left, int nl, const double *right, int nr, const d
                 fsd_oracle_result *out);
 int fsd_o_path(const double *left_wv, int nl, const double *right_wv, int nr, const int *l2r, const int *r2l,
                const double *pos, const double *dir, int force_P, const double *prev_path, fsd_oracle_result *out);
+int fsd_o_path_global(const double *gpath, int M, const double *pos, const double *dir, int force_P,
+                      const double *prev_path, fsd_oracle_result *out);
 
 int fsd_o_path_from_update(double *update, int nu, const double *pos, const double *dir, int force_P,
                            const double *prev_path, fsd_oracle_result *out);

@@ -488,6 +488,65 @@ int fsd_o_path_from_update(double *update, int nu, const double *pos, const doub
   return 0;
 }
 
+/* fit_matches_as_spline :207-223 and everything after it, on a given centre line */
+static int path_from_centerline(const double *cl, int ncl, double prev[HORIZON][4], const double *prev_xy,
+                                const double *pos, const double *dir, int force_P, fsd_oracle_result *out) {
+  double *update = (double *)malloc(sizeof(double) * 2 * MAXP);
+  int nu = 0;
+  int rc = fit_predict(cl, ncl, 0.2, 0.1, -1.0, update, &nu);
+  if (rc == VALUE_ERROR) {
+    out->status |= FSD_O_FIT1_FAILED;
+    rc = fit_predict(prev_xy, HORIZON, 0.2, 0.1, -1.0, update, &nu);
+  }
+  if (rc != OK || nu < 1) {
+    out->status |= rc == UNSUPPORTED ? (FSD_O_UNSUPPORTED | FSD_O_OVERFLOW) : FSD_O_REF_RAISES;
+    memcpy(out->path, prev, sizeof(double) * HORIZON * 4);
+    free(update);
+    return 0;
+  }
+  fsd_o_path_from_update(update, nu, pos, dir, force_P, &prev[0][0], out);
+  free(update);
+  return 0;
+}
+
+/* ---- run_path_calculation with a global path (core_calculate_path.py:516-528): the centre line is the part of the
+ * global path within 30 m of the car, rolled so that the closest point sits at index M / 3 ------------------------ */
+int fsd_o_path_global(const double *gpath, int M, const double *pos, const double *dir, int force_P,
+                      const double *prev_path, fsd_oracle_result *out) {
+  double prev[HORIZON][4];
+  if (prev_path)
+    memcpy(prev, prev_path, sizeof(prev));
+  else
+    fsd_oracle_initial_path(&prev[0][0]);
+  double prev_xy[2 * HORIZON];
+  for (int i = 0; i < HORIZON; ++i) {
+    prev_xy[2 * i] = prev[i][1];
+    prev_xy[2 * i + 1] = prev[i][2];
+  }
+  double *dist = (double *)malloc(sizeof(double) * (M > 0 ? M : 1));
+  double *cl = (double *)malloc(sizeof(double) * 2 * (M > 0 ? M : 1));
+  int best = 0;
+  for (int i = 0; i < M; ++i) {
+    double dx = pos[0] - gpath[2 * i], dy = pos[1] - gpath[2 * i + 1];
+    dist[i] = sqrt(dx * dx + dy * dy);
+    if (dist[i] < dist[best]) best = i; /* np.argmin: first minimum */
+  }
+  /* np.roll(a, r)[i] = a[(i - r) mod M] with r = -best + M / 3 */
+  int ncl = 0;
+  for (int i = 0; i < M; ++i) {
+    int src = ((i + best - M / 3) % M + M) % M;
+    if (dist[src] < 30.0) {
+      cl[2 * ncl] = gpath[2 * src];
+      cl[2 * ncl + 1] = gpath[2 * src + 1];
+      ncl++;
+    }
+  }
+  int rc = path_from_centerline(cl, ncl, prev, prev_xy, pos, dir, force_P, out);
+  free(dist);
+  free(cl);
+  return rc;
+}
+
 /* ---- CalculatePath.run_path_calculation (core_calculate_path.py:514-575), global_path None ---- */
 
 int fsd_o_path(const double *left, int nl, const double *right, int nr, const int *l2r, const int *r2l,
@@ -540,21 +599,5 @@ int fsd_o_path(const double *left, int nl, const double *right, int nr, const in
       ncl = nc;
     }
   }
-  /* fit_matches_as_spline :207-223 */
-  double *update = (double *)malloc(sizeof(double) * 2 * MAXP);
-  int nu = 0;
-  int rc = fit_predict(cl, ncl, 0.2, 0.1, -1.0, update, &nu);
-  if (rc == VALUE_ERROR) {
-    out->status |= FSD_O_FIT1_FAILED;
-    rc = fit_predict(prev_xy, HORIZON, 0.2, 0.1, -1.0, update, &nu);
-  }
-  if (rc != OK || nu < 1) {
-    out->status |= rc == UNSUPPORTED ? (FSD_O_UNSUPPORTED | FSD_O_OVERFLOW) : FSD_O_REF_RAISES;
-    memcpy(out->path, prev, sizeof(prev));
-    free(update);
-    return 0;
-  }
-  fsd_o_path_from_update(update, nu, pos, dir, force_P, &prev[0][0], out);
-  free(update);
-  return 0;
+  return path_from_centerline(cl, ncl, prev, prev_xy, pos, dir, force_P, out);
 }

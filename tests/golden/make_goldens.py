@@ -187,6 +187,75 @@ def skidpad_goldens():
     print("[skidpad] log", len(log), "frames; synthetic", T, "x", S)
 
 
+def global_path_goldens():
+    """Reference runs of the GLOBAL-PATH branch of run_path_calculation (core_calculate_path.py:516-528):
+    (a) PathPlanner(trackdrive).set_global_path(line) on poses along a synthetic closed racing line, fresh planner per pose
+        and one sequential (stateful) run;
+    (b) MissionTypes.acceleration, sequential, on a synthetic acceleration track (two straight cone rows under a rigid
+        motion); the relocalizer's unseeded np.random.choice (acceleration_relocalization.py:32) is pinned by seeding
+        numpy's global RNG at run time -- no source edit."""
+    mod = rh.load_reference()
+    rec = rh._state["rec"]
+    rng = np.random.default_rng(7)
+    centre, tangent = synth._track(np.random.default_rng([7, 0]))
+    line = centre[::2].copy()  # ~0.3 m spacing, closed
+    idx = rng.integers(0, len(centre), 48)
+    nrm = np.stack([-tangent[idx, 1], tangent[idx, 0]], 1)
+    pos = centre[idx] + nrm * rng.normal(0, 0.4, (48, 1))
+    yaw = np.arctan2(tangent[idx, 1], tangent[idx, 0]) + rng.normal(0, np.deg2rad(6), 48)
+    dirs = np.stack([np.cos(yaw), np.sin(yaw)], 1)
+    empty = [np.zeros((0, 2)) for _ in range(5)]
+    fresh, fresh_P = [], []
+    for i in range(48):
+        pp = mod.PathPlanner(mod.MissionTypes.trackdrive)
+        pp.set_global_path(line)
+        rec.clear()
+        fresh.append(pp.calculate_path_in_global_frame(empty, pos[i], dirs[i]))
+        fresh_P.append(int(rec.get("P", 0)))
+    order = np.argsort(idx)  # one lap in driving order, one planner
+    pp = mod.PathPlanner(mod.MissionTypes.trackdrive)
+    pp.set_global_path(line)
+    seq, seq_P = [], []
+    for i in order:
+        rec.clear()
+        seq.append(pp.calculate_path_in_global_frame(empty, pos[i], dirs[i]))
+        seq_P.append(int(rec.get("P", 0)))
+    out = {"line": line, "pos": pos, "dir": dirs, "fresh_path": np.array(fresh), "fresh_P": np.array(fresh_P, np.int16),
+           "seq_order": order, "seq_path": np.array(seq), "seq_P": np.array(seq_P, np.int16)}
+    # (b) acceleration: cones every 5 m on both sides of a 75 m straight, 3 m wide, under a rigid motion + 3 cm noise
+    from fsd_path_planning.relocalization.acceleration.acceleration_relocalization import BASE_ACCELERATION_PATH
+
+    th, tr = 0.7, np.array([12.0, -30.0])
+    rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    xs = np.arange(0.0, 80.0, 5.0)
+    blue = np.stack([xs, np.full_like(xs, 1.5)], 1) + rng.normal(0, 0.03, (len(xs), 2))
+    yellow = np.stack([xs, np.full_like(xs, -1.5)], 1) + rng.normal(0, 0.03, (len(xs), 2))
+    cones = [np.zeros((0, 2)), yellow @ rot.T + tr, blue @ rot.T + tr, np.zeros((0, 2)), np.zeros((0, 2))]
+    S = 40
+    px = np.linspace(-2.0, 70.0, S)
+    ppos = np.stack([px, rng.normal(0, 0.1, S)], 1) @ rot.T + tr
+    pyaw = th + rng.normal(0, np.deg2rad(2), S)
+    pdir = np.stack([np.cos(pyaw), np.sin(pyaw)], 1)
+    seed = 1234
+    np.random.seed(seed)
+    pa = mod.PathPlanner(mod.MissionTypes.acceleration)
+    acc, acc_P, acc_flag = [], [], []
+    for s in range(S):
+        rec.clear()
+        acc.append(pa.calculate_path_in_global_frame(cones, ppos[s], pdir[s]))
+        acc_P.append(int(rec.get("P", 0)))
+        acc_flag.append(bool(pa.relocalizer.is_relocalized))
+    info = pa.relocalization_info
+    out.update({"acc_map": np.asarray(BASE_ACCELERATION_PATH, dtype=np.float64), "acc_seed": seed,
+                "acc_cones_xy": np.concatenate(cones), "acc_cones_type": np.concatenate([np.full(len(c), t, np.uint8) for t, c in enumerate(cones)]),
+                "acc_pos": ppos, "acc_dir": pdir, "acc_path": np.array(acc), "acc_P": np.array(acc_P, np.int16),
+                "acc_relocalized": np.array(acc_flag),
+                "acc_info": np.array([info.translation[0], info.translation[1], info.rotation])})
+    np.savez_compressed(os.path.join(HERE, "global_path.npz"), **out)
+    print("[global_path] trackdrive", len(fresh), "poses; acceleration", S, "steps, relocalized at",
+          int(np.argmax(acc_flag)) if any(acc_flag) else -1)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:] or None
     fsg = synth.pack_frames(rh.load_demo_log("fsg_19_2_laps.json"))
@@ -202,6 +271,7 @@ if __name__ == "__main__":
         "synth_mixed": lambda: save("synth_mixed", synth.gen_mixed(5, 256).astype(np.float64)),
         "fitpack": fitpack_goldens,
         "skidpad": skidpad_goldens,
+        "global_path": global_path_goldens,
     }
     for name, fn in jobs.items():
         if only is None or name in only:

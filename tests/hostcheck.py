@@ -41,6 +41,23 @@ def build(force: bool = False) -> str:
     return _LIB
 
 
+_LIB_BIG = os.path.join(_CSRC, "libfsdplan_hostcheck_big.so")
+_lib_big = None
+
+
+def lib_big():
+    """The same sources with the large static bounds of csrc/kernels_big.cu (2 048 path points, 64 knots per fit)."""
+    global _lib_big
+    if _lib_big is None:
+        srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".cpp"))]
+        if not os.path.exists(_LIB_BIG) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_BIG) for s in srcs):
+            subprocess.check_call(
+                ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
+                 "-DFSD_PCAP=2048", "-DFSD_NCAP=64", "-o", _LIB_BIG, os.path.join(_CSRC, "hostcheck.cpp")])
+        _lib_big = C.CDLL(_LIB_BIG)
+    return _lib_big
+
+
 _lib = None
 
 
@@ -102,6 +119,29 @@ def plan_batch(batch, force_P=None, prev=None):
         _p(out["right_wv"], C.c_double), _p(out["l2r"], i16), _p(out["r2l"], i16), _p(out["grid"], i16),
         _p(out["sort_dbg"], i16), _p(out["status"], C.c_uint32))
     return out
+
+
+def global_path(gpath, pos, direction, force_P=None, prev=None):
+    """Poses [n, 2] along a global path [M, 2] through the kernels' path code; returns dict(path, grid, status)."""
+    gp = np.ascontiguousarray(gpath, dtype=np.float64)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    dr = np.ascontiguousarray(direction, dtype=np.float64).reshape(-1, 2)
+    n = len(pos)
+    out = np.zeros((n, HORIZON, 4))
+    grid = np.zeros((n, 2), np.int16)
+    status = np.zeros(n, np.uint32)
+    fp = None
+    if force_P is not None:
+        fpa = np.ascontiguousarray(force_P, dtype=np.int16)
+        fp = _p(fpa, C.c_int16)
+    pv, stride = None, 0
+    if prev is not None:
+        pva = np.ascontiguousarray(prev, dtype=np.float64)
+        pv, stride = _p(pva, C.c_double), (0 if pva.size == HORIZON * 4 else HORIZON * 4)
+    p = default_params()
+    lib_big().fsd_hostcheck_global_path(C.byref(p), n, _p(pos, C.c_double), _p(dr, C.c_double), _p(gp, C.c_double), len(gp),
+                                    fp, pv, stride, _p(out, C.c_double), _p(grid, C.c_int16), _p(status, C.c_uint32))
+    return {"path": out, "grid": grid, "status": status}
 
 
 def knn(batch):

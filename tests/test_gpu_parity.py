@@ -448,8 +448,6 @@ def test_drop_in_path_planner_sequential():
     assert np.abs(p2 - PathPlanner(MissionTypes.trackdrive).calculate_path_in_global_frame(cones, pos, direction / np.linalg.norm(direction))).max() < 1e-6
     with pytest.raises(ValueError, match="direction must be a float or a 2 element array"):
         pp.calculate_path_in_global_frame(cones, pos, [1.0, 0.0, 0.0])
-    with pytest.raises(NotImplementedError):
-        PathPlanner(MissionTypes.acceleration)
 
 
 # ---- skidpad mission (BASELINE config 4) --------------------------------------------------------

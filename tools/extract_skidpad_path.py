@@ -41,3 +41,11 @@ ref_centers = np.asarray(pp.relocalizer.reference_centers, dtype=np.float64)
 out3 = os.path.join(os.path.dirname(out), "skidpad_ref_centers.npy")
 np.save(out3, ref_centers)
 print(ref_centers, "->", out3)
+
+# the known map of the acceleration / EBS missions (BASE_ACCELERATION_PATH, acceleration_relocalization.py:175-211: a
+# 160 m x 4.8 m loop at 0.2 m spacing with 1 cm of seeded noise) -- track-definition DATA like the skidpad table
+from fsd_path_planning.relocalization.acceleration.acceleration_relocalization import BASE_ACCELERATION_PATH  # noqa: E402
+
+out4 = os.path.join(os.path.dirname(out), "acceleration_path.npy")
+np.save(out4, np.asarray(BASE_ACCELERATION_PATH, dtype=np.float64))
+print(BASE_ACCELERATION_PATH.shape, "->", out4)
