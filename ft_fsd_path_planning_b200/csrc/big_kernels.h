@@ -15,3 +15,10 @@ int fsd_big_global_path(const fsd_params *params, int n_poses, const double *pos
                         int n_points, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
                         float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, int *counter,
                         int sm_count, cudaStream_t stream);
+
+// second chance for the frames path_kernel marked (status bit 31): the path stage with the large bounds
+size_t fsd_big_path_fixup_scratch_bytes();
+int fsd_big_path_fixup(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
+                       const int16_t *n_wv, const double *left_wv, const double *right_wv, const int16_t *l2r,
+                       const int16_t *r2l, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
+                       float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, cudaStream_t stream);

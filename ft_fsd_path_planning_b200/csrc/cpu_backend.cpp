@@ -6,6 +6,9 @@
 // is an EXPLICIT entry point: nothing in the CUDA path falls back to it, the Python host layer uses it only when the
 // caller asks for device="cpu".  It never touches oracle/ (test infrastructure).
 #define FSD_HOSTCHECK 1
+// no shared-memory budget on the host: the large static bounds of kernels_big.cu from the start
+#define FSD_PCAP 2048
+#define FSD_NCAP 64
 #include <cstring>
 #include <thread>
 #include <vector>

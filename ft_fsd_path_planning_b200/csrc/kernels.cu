@@ -473,7 +473,12 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
         if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;  // only when the caller asked for the fp64 path
       }
       if (lane == 0) {
-        O.status[b] |= M.status;
+        const unsigned before = O.status[b];
+        unsigned after = before | M.status;
+        // a static bound overflowed in this stage: marked for the large-bounds second chance (kernels_big.cu), the earlier
+        // stages' bits parked in bits 16-30 meanwhile
+        if ((flags & 2) && (M.status & FSD_ST_OVERFLOW)) after |= 0x80000000u | ((before & 0x7fffu) << 16);
+        O.status[b] = after;
         if (grid_out) {
           grid_out[2 * (size_t)b] = (int16_t)M.P_grid;
           grid_out[2 * (size_t)b + 1] = (int16_t)M.n_trim;
@@ -815,7 +820,7 @@ void set_smem(K kernel, size_t bytes) {
 //   bit 2: the lockstep path kernel takes its rounds of frames from a counter instead of a static stride
 //   bit 3: fsd_plan_batch never splits a batch into two chunks on two streams
 //   bit 4: the path kernel discards a frame's point-buffer lines from L2 when the frame ends
-//   bit 5: the path kernel's point buffers as a persisting L2 access-policy window
+//   (bit 5, the point buffers as a persisting L2 access-policy window, was measured and removed: 4x MORE write-back)
 int plan_mode() {
   static const int mode = [] {
     const char *e = std::getenv("FSD_PLAN_MODE");
@@ -885,12 +890,6 @@ int device_info(DeviceInfo **out) {
       D.key[1] = dp.predict_every;
       D.key[2] = dp.refit_smoothing;
       D.initial_ready = true;
-    }
-    if (plan_mode() & 32) {
-      size_t want = (size_t)prop.persistingL2CacheMaxSize;
-      if (want > (size_t)64 << 20) want = (size_t)64 << 20;
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-      cudaGetLastError();
     }
     if (cudaMalloc(reinterpret_cast<void **>(&D.counter_ring), COUNTER_SLOTS * 8 * sizeof(int)) != cudaSuccess) {
       cudaGetLastError();
@@ -972,6 +971,7 @@ size_t workspace_bytes(int n_frames) {
   total += align_up(FSD_HORIZON * 4 * sizeof(double), 256);             // initial path (non-default params)
   total += align_up(B * sizeof(PathCarry), 256);                        // splines carried between the path phases
   total += align_up(B * 2 * FSD_MAX_SORTED * sizeof(int16_t), 256);     // sort indices when the caller wants none
+  total += 2 * align_up(fsd_big_path_fixup_scratch_bytes(), 256);       // point buffers of the large-bounds second chance
   return total;
 }
 
@@ -979,6 +979,7 @@ size_t workspace_bytes(int n_frames) {
 struct Extra {
   PathCarry *carry = nullptr;
   int16_t *idx = nullptr;
+  unsigned char *fixup[2] = {nullptr, nullptr};
 };
 
 int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t workspace_bytes_given,
@@ -999,9 +1000,13 @@ int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t
   double *w_init = cv.take<double>(FSD_HORIZON * 4);
   PathCarry *w_carry = cv.take<PathCarry>(B);
   int16_t *w_idx = cv.take<int16_t>(B * 2 * FSD_MAX_SORTED);
+  unsigned char *w_fix0 = cv.take<unsigned char>(fsd_big_path_fixup_scratch_bytes());
+  unsigned char *w_fix1 = cv.take<unsigned char>(fsd_big_path_fixup_scratch_bytes());
   if (extra) {
     extra->carry = w_carry;
     extra->idx = w_idx;
+    extra->fixup[0] = w_fix0;
+    extra->fixup[1] = w_fix1;
   }
   if (!r.n_wv) r.n_wv = w_nwv;
   if (!r.left_wv) r.left_wv = w_lwv;
@@ -1082,7 +1087,7 @@ template <typename T>
 int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
               const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
               unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream,
-              PathCarry *carry = nullptr) {
+              PathCarry *carry = nullptr, unsigned char *fixup_scratch = nullptr) {
   if (!path_scratch) return FSD_ERR_WORKSPACE;
   if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
   if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
@@ -1117,37 +1122,16 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
     return check_launch();
   }
   int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
-  const int flags = (plan_mode() & 16) ? 1 : 0;
-  if (plan_mode() & 32) {
-    // the point buffers as a persisting L2 window: their lines are not chosen for eviction while the kernel runs
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(CTA_THREADS);
-    cfg.dynamicSmemBytes = PATH_KERNEL_SMEM;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-    attr[0].val.accessPolicyWindow.base_ptr = path_scratch;
-    attr[0].val.accessPolicyWindow.num_bytes = (size_t)grid * WPC * PATH_SCRATCH_BYTES;
-    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const int16_t *fp = force_P;
-    double *o64 = inter->path_f64;
-    int16_t *gr = inter->grid;
-    if (cudaLaunchKernelEx(&cfg, path_kernel<T>, P, n_frames, pos, dir, O, fp, prev, stride, o64, out_path, gr,
-                           path_scratch, round_counter, flags) != cudaSuccess) {
-      cudaGetLastError();
-      return FSD_ERR_LAUNCH;
-    }
-    return FSD_OK;
-  }
+  const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0);
   path_kernel<T><<<grid, CTA_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
       round_counter, flags);
-  return check_launch();
+  rc = check_launch();
+  if (rc != FSD_OK || !fixup_scratch) return rc;
+  // frames on which a static bound of path_kernel overflowed get a second chance with the large bounds (kernels_big.cu)
+  return fsd_big_path_fixup(params, n_frames, sizeof(T) == 8, pos, dir, inter->n_wv, inter->left_wv, inter->right_wv,
+                            inter->l2r, inter->r2l, force_P, prev, stride, inter->path_f64, out_path, inter->grid,
+                            out_status, fixup_scratch, stream);
 }
 
 // take / return a side stream of the current device (created on first use)
@@ -1223,7 +1207,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                             out_status, stream, X.idx);
     if (rc != FSD_OK) return rc;
     rc = path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
-                      out_status, stream, X.carry);
+                      out_status, stream, X.carry, X.fixup[0]);
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
       cudaGetLastError();
       rc = FSD_ERR_LAUNCH;
@@ -1248,7 +1232,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                               side->stream, X.idx + 2 * h * FSD_MAX_SORTED);
     if (rc == FSD_OK)
       rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
-                        stream, X.carry);
+                        stream, X.carry, X.fixup[0]);
     // the outputs of frames [0, na) are final here: a caller that passed an event can start consuming them (e.g. an
     // all-gather on a communication stream) while chunk B is still being planned
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
@@ -1258,7 +1242,8 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
     if (rc == FSD_OK)
       rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
                         prev + h * (size_t)stride, stride, init_slot, scratch_b,
-                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.carry + h);
+                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.carry + h,
+                        X.fixup[1]);
   }
   // always join, so that the caller's stream never runs ahead of work queued on the side stream
   ok = cudaEventRecord(side->join, side->stream) == cudaSuccess && ok;
@@ -1320,7 +1305,8 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones) {
 
 int fsd_plan_launches(int n_frames) {
   if (n_frames <= 0) return 0;
-  const int per_chunk = ((plan_mode() & 1) ? 2 : 1) + ((plan_mode() & 2) ? 3 : 1);
+  // sort (+ match as a kernel of its own), path (or its three phases), the large-bounds second chance of the path stage
+  const int per_chunk = ((plan_mode() & 1) ? 2 : 1) + ((plan_mode() & 2) ? 3 : 2);
   return first_chunk(n_frames) < n_frames ? 2 * per_chunk : per_chunk;
 }
 
@@ -1465,13 +1451,18 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
   // workspace of fsd_workspace_bytes() always has); otherwise the stage runs as one kernel
   PathCarry *carry = nullptr;
   const size_t carry_at = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
-  if (n_frames > 0 && workspace_bytes_given >= carry_at + (size_t)n_frames * sizeof(PathCarry))
+  unsigned char *fixup = nullptr;
+  if (n_frames > 0 && workspace_bytes_given >= carry_at + (size_t)n_frames * sizeof(PathCarry)) {
     carry = reinterpret_cast<PathCarry *>(scratch + carry_at);
+    const size_t fix_at = align_up(carry_at + (size_t)n_frames * sizeof(PathCarry), 256);
+    if (workspace_bytes_given >= fix_at + fsd_big_path_fixup_scratch_bytes()) fixup = scratch + fix_at;
+  }
   if (coords_f64)
     return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
-                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry);
+                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry,
+                             fixup);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
-                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry);
+                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry, fixup);
 }
 
 size_t fsd_global_path_workspace_bytes(int n_poses) {

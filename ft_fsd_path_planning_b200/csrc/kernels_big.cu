@@ -55,12 +55,89 @@ __global__ void __launch_bounds__(32 * BIG_WPC)
   }
 }
 
+// Second chance for frames on which a static bound of the batched path kernel overflowed (more than 32 knots in one fit,
+// more than 704 path points): the path stage again, with the large bounds.  path_kernel marks such frames (bit 31 of the
+// status word, the sort / match stage's own status bits parked in bits 16-30); every warp of this kernel scans its share
+// of the batch and re-plans the marked frames.  Almost always there is nothing to do.
+__global__ void __launch_bounds__(32 * BIG_WPC)
+    path_fixup_kernel(DevParams P, int n_frames, int coords_f64, const void *pos_v, const void *dir_v, const int16_t *n_wv,
+                      const double *left_wv, const double *right_wv, const int16_t *l2r, const int16_t *r2l,
+                      const int16_t *force_P, const double *prev, int prev_stride, double *out_f64, float *out_f32,
+                      int16_t *grid_out, uint32_t *status, unsigned char *scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = fsd_lane();
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * BIG_STRIDE);
+  if (lane == 0) {
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * BIG_WPC + warp) * PATH_SCRATCH_BYTES;
+    S.pts = reinterpret_cast<d2 *>(mine);
+    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
+  }
+  __syncwarp();
+  const int n_warps = (int)gridDim.x * BIG_WPC, w = (int)blockIdx.x * BIG_WPC + warp;
+  for (int base = w * 32; base < n_frames; base += n_warps * 32) {
+    const int mine = base + lane;
+    unsigned marked = __ballot_sync(0xffffffffu, mine < n_frames && (status[mine] >> 31) != 0u);
+    while (marked) {
+      const int b = base + __ffs((int)marked) - 1;
+      marked &= marked - 1;
+      double px, py, dx, dy;
+      if (coords_f64) {
+        const double *pos = static_cast<const double *>(pos_v), *dir = static_cast<const double *>(dir_v);
+        px = pos[2 * b], py = pos[2 * b + 1], dx = dir[2 * b], dy = dir[2 * b + 1];
+      } else {
+        const float *pos = static_cast<const float *>(pos_v), *dir = static_cast<const float *>(dir_v);
+        px = pos[2 * b], py = pos[2 * b + 1], dx = dir[2 * b], dy = dir[2 * b + 1];
+      }
+      const FramePose F = make_pose(px, py, dx, dy);
+      int grid[2] = {0, 0};
+      double *out = &S.W.G[0][0];
+      const unsigned st = path_frame(S, reinterpret_cast<const d2 *>(left_wv + (size_t)b * FSD_MAX_WV * 2), n_wv[2 * (size_t)b],
+                                     reinterpret_cast<const d2 *>(right_wv + (size_t)b * FSD_MAX_WV * 2), n_wv[2 * (size_t)b + 1],
+                                     l2r + (size_t)b * FSD_MAX_WV, r2l + (size_t)b * FSD_MAX_WV, F,
+                                     force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out, grid);
+      for (int i = lane; i < FSD_HORIZON * 4; i += 32) {
+        const double v = out[i];
+        if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
+        if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;
+      }
+      if (lane == 0) {
+        status[b] = ((status[b] >> 16) & 0x7fffu) | st;  // the sort / match stage's bits + this run's
+        if (grid_out) {
+          grid_out[2 * (size_t)b] = (int16_t)grid[0];
+          grid_out[2 * (size_t)b + 1] = (int16_t)grid[1];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+constexpr int FIXUP_CTAS = 32;
+
 int big_grid(int n_poses, int sm_count) {
   const long need = ((long)n_poses + BIG_WPC - 1) / BIG_WPC, cap = (long)sm_count * 2;
   return (int)(need < cap ? need : cap);
 }
 
 }  // namespace
+
+size_t fsd_big_path_fixup_scratch_bytes() { return (size_t)FIXUP_CTAS * BIG_WPC * PATH_SCRATCH_BYTES; }
+
+int fsd_big_path_fixup(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
+                       const int16_t *n_wv, const double *left_wv, const double *right_wv, const int16_t *l2r,
+                       const int16_t *r2l, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
+                       float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, cudaStream_t stream) {
+  const size_t smem = BIG_WPC * BIG_STRIDE;
+  if (cudaFuncSetAttribute(path_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return FSD_ERR_LAUNCH;
+  }
+  const int need = (n_frames + 32 * BIG_WPC - 1) / (32 * BIG_WPC);
+  path_fixup_kernel<<<need < FIXUP_CTAS ? need : FIXUP_CTAS, 32 * BIG_WPC, smem, stream>>>(
+      make_dev_params(*params), n_frames, coords_f64, pos, dir, n_wv, left_wv, right_wv, l2r, r2l, force_P, prev,
+      prev_stride, out_f64, out_f32, grid_out, status, scratch);
+  return cudaGetLastError() == cudaSuccess ? FSD_OK : FSD_ERR_LAUNCH;
+}
 
 size_t fsd_big_global_path_scratch_bytes(int n_poses, int sm_count) {
   return (size_t)big_grid(n_poses > 0 ? n_poses : 1, sm_count) * BIG_WPC * PATH_SCRATCH_BYTES;

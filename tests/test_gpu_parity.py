@@ -136,10 +136,12 @@ def _oracle_parity(planner, batch, tag, shard_of=None):
           (r["l2r"] != ref["l2r"]).any(1) | (r["r2l"] != ref["r2l"]).any(1)
     assert not bad.any(), "matches differ, " + where(bad)
     assert np.abs(r["left_wv"] - ref["left_wv"]).max() <= 1e-9 and np.abs(r["right_wv"] - ref["right_wv"]).max() <= 1e-9
-    # A frame on which a STATIC bound of the kernels overflowed (here: more than 32 knots in one spline fit) carries
-    # FSD_ST_OVERFLOW and is excluded from the path comparison -- flagged, never silent; at most 1 frame in 10 000.
+    # A frame on which a static bound of the batched path kernel overflows (more than 32 knots in one spline fit: 1 frame
+    # of the 65 536 of config 5) is re-planned by the large-bounds kernel (csrc/kernels_big.cu) and must match as well;
+    # only a frame that exceeds even those bounds stays flagged FSD_ST_OVERFLOW (none is expected).
     over = (r["status"].astype(np.uint32) & 0x100) != 0
-    assert over.sum() <= max(1, B // 10000), f"{int(over.sum())} frames overflowed a static bound, " + where(over)
+    assert over.sum() == 0, f"{int(over.sum())} frames overflowed a static bound, " + where(over)
+    assert not (r["status"].astype(np.uint32) >> 16).any(), "internal marker bits leaked into out_status"
     bad = ~over & ((r["status"].astype(np.uint32) & 0xFFFFFF7F) != (ref["status"] & 0xFFFFFF7F))
     assert not bad.any(), "status differs, " + where(bad)
     assert (r["grid"][~over, 1] == ref["n_trim"][~over]).all()
@@ -217,7 +219,7 @@ def test_config5_65536_mixed_frames_in_eight_shards_match_oracle(planner):
           f"{tot['frames_with_2plus_configs']} frames decided by the cost function, {tot['flagged']} flagged "
           f"(inputs on which the reference raises / takes its latent-bug path), {tot['overflowed']} overflowed a static bound")
     st = a["status"].cpu().numpy().astype(np.uint32)
-    assert ((st & 0x100) != 0).sum() <= 6, "static bounds overflowed"
+    assert ((st & 0x100) != 0).sum() == 0, "static bounds overflowed"
     assert ((st & 0x600) != 0).mean() < 0.01
 
 
