@@ -30,6 +30,7 @@ void plan_range(const DevParams &P, int lo_frame, int hi_frame, const double *xy
                 int16_t *out_ri, const fsd_intermediate *inter, const int16_t *force_P, const double *prev, int stride,
                 uint32_t *out_status) {
   SortSmem *S = new SortSmem();
+  MatchSmem *MS = new MatchSmem();
   PathSmem *Q = new PathSmem();
   Q->pts = new d2[PCAP];
   Q->u = new double[PCAP];
@@ -48,8 +49,8 @@ void plan_range(const DevParams &P, int lo_frame, int hi_frame, const double *xy
     load_frame_plain(*S, xy + 2 * (size_t)lo, type + lo, n);
     st |= sort_frame(*S, n, F, P, F0.dbg);
     store_sort(*S, 0, O);
-    st |= match_from_sort(*S, F, P);
-    store_match(S->M, 0, O);
+    st |= match_from_sort(*S, *MS, F, P);
+    store_match(*MS, 0, O);
     F0.status = st;
     F0.grid[0] = F0.grid[1] = 0;
     path_from_tensors(*Q, 0, O, F, force_P ? force_P[b] : 0, prev + (size_t)b * stride, P, F0.path, nullptr, F0.grid);
@@ -74,6 +75,7 @@ void plan_range(const DevParams &P, int lo_frame, int hi_frame, const double *xy
   delete[] Q->pts;
   delete[] Q->u;
   delete Q;
+  delete MS;
   delete S;
 }
 

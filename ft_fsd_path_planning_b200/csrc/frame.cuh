@@ -42,10 +42,9 @@ FSD_DEVFN void store_sort(const SortSmem &S, int b, const StageOut &O) {
   }
 }
 
-// S holds the sorted frame; M is filled from it
-// the sorted cones are read from S.xy into registers first: M overlays the sorting scratch of S
-FSD_DEVFN unsigned match_from_sort(SortSmem &S, const FramePose &F, const DevParams &P) {
-  MatchSmem &M = S.M;
+// S holds the sorted frame; the matching state M is filled from it (host builds: the CUDA path matches in a kernel of
+// its own, which gathers the sorted cones from global memory)
+FSD_DEVFN unsigned match_from_sort(const SortSmem &S, MatchSmem &M, const FramePose &F, const DevParams &P) {
   wsync();
 #pragma unroll 1
   for (int q = fsd_lane(); q < 2 * FSD_MAX_SORTED; q += FSD_LANES) {

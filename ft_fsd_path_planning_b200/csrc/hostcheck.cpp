@@ -41,6 +41,7 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
                                   int16_t *r2l, int16_t *grid, int16_t *sort_dbg, uint32_t *status) {
   DevParams P = make_dev_params(*params);
   SortSmem *S = new SortSmem();
+  MatchSmem *MS = new MatchSmem();
   PathSmem *Q = new_path_smem();
   double initial[FSD_HORIZON * 4];
   if (!prev) {
@@ -59,12 +60,13 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
     load_frame_plain(*S, xy + 2 * (size_t)lo, type + lo, n);
     st |= sort_frame(*S, n, F, P, sort_dbg + 8 * (size_t)b);
     store_sort(*S, b, O);
-    st |= match_from_sort(*S, F, P);
-    store_match(S->M, b, O);
+    st |= match_from_sort(*S, *MS, F, P);
+    store_match(*MS, b, O);
     status[b] = st;
     path_from_tensors(*Q, b, O, F, force_P ? force_P[b] : 0, prev, P, out_path, nullptr, grid);
   }
   delete S;
+  delete MS;
   free_path_smem(Q);
   return 0;
 }

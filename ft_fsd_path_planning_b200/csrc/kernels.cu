@@ -1,12 +1,15 @@
 // libfsdplan.so: CUDA kernels (sm_100a) and the C-ABI of include/fsdplan.h.
 //
-// Execution model: ONE WARP PLANS ONE FRAME.  Every kernel is launched with 32-thread CTAs (one warp, its
-// frame state in that CTA's shared memory) and a grid of  min(B, #SM x resident CTAs per SM)  CTAs that
-// stride over the frame batch, so the grid is an exact multiple of the SM count whenever B allows.
+// Execution model: ONE WARP PLANS ONE FRAME.  CTAs hold 8 warps, each with its frame's state in its slice of the CTA's
+// shared memory; grids are  min(ceil(B / 8), #SM x resident CTAs per SM)  persistent CTAs -- a multiple of the SM count
+// whenever B allows -- whose warps (sort / match / k-NN) or CTAs (path) take frames from a counter in global memory.
 //
-//   sort_match_kernel   S1-S8 + M1-M6.  The frame's cone coordinates are staged global -> shared with a
-//                       TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx, SASS: UBLKCP) and widened to
-//                       fp64 in shared memory; the k-NN cost matrix never leaves registers/shared memory.
+//   sort_kernel         S1-S8.  The frame's cone coordinates are staged global -> shared with a TMA bulk copy
+//                       (cp.async.bulk ... mbarrier::complete_tx, SASS: UBLKCP) and widened to fp64 in shared
+//                       memory; the k-NN cost matrix never leaves registers/shared memory; the two sides are
+//                       searched at the same time on the two half-warps.  Free-running warps, dynamic frame fetch.
+//   match_kernel        M1-M6 on the sort indices.  Free-running warps, dynamic frame fetch.
+//   knn_kernel          the cost-matrix step alone (stage entry point fsd_knn_batch).
 //   path_kernel         P1-P4: three smoothing-spline fits, extension, curvature, 40 samples.
 //   initial_path_kernel the constant path of a fresh planner, one warp.
 //
@@ -26,17 +29,11 @@ using namespace fsd;
 
 namespace {
 
-// Warps (= frames in flight) per CTA.  The warps of a CTA start every frame together (one __syncthreads per
-// frame): frames walk through the same phases at roughly the same time, so the SM's instruction cache serves
-// all of them from one copy of the phase's code (the kernels are instruction-fetch bound).
+// Warps (= frames in flight) per CTA.
 #ifndef FSD_WARPS_PER_CTA
 #define FSD_WARPS_PER_CTA 8
 #endif
 constexpr int WPC = FSD_WARPS_PER_CTA;
-// CTA barriers per frame in the sort kernel (phase alignment of the warps of a CTA): A/B knob
-#ifndef FSD_SORT_BARRIERS
-#define FSD_SORT_BARRIERS 4
-#endif
 #ifndef FSD_DEFAULT_PLAN_MODE
 #define FSD_DEFAULT_PLAN_MODE 29 /* 1 + 4 + 8 + 16, see plan_mode() and profiles/r2_plan_mode_ab.txt */
 #endif
@@ -110,7 +107,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 // shared-memory image of one sort/match CTA
 struct SortCta {
-  SortSmem S;  // includes the fp32 staging area of the bulk copy (S.raw) and the matching state (S.M)
+  SortSmem S;  // includes the fp32 staging area of the bulk copy (S.raw)
   alignas(8) uint64_t mbar;
 };
 constexpr size_t SORT_CTA_STRIDE = (sizeof(SortCta) + 15) / 16 * 16;
@@ -187,103 +184,40 @@ __device__ __forceinline__ int next_frame(int *counter) {
   return __shfl_sync(FULL, b, 0);
 }
 
-// FREE = false: the warps of a CTA take frames in rounds and meet at phase boundaries (instruction-cache sharing for a
-// kernel that carries the whole sort + match code).  FREE = true: free-running warps with dynamic frame fetch -- used
-// when the stage is split into kernels whose code the SM's instruction cache holds (plan mode, see plan_mode()).
-template <typename T, bool FREE>
+// Cone sorting: free-running warps, dynamic frame fetch.  Per frame: TMA staging, the k-NN graph of both sides by the
+// whole warp, then the LEFT and the RIGHT search at the same time on the two half-warps (sort.cuh: sort_sides), conflict
+// resolution, the sort indices to global memory.  Matching is a kernel of its own (match_kernel): with its code out of
+// this kernel the SM's instruction cache holds the sorting code, and the warps need not be kept in lockstep to share it.
+template <typename T>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
-    sort_match_kernel(DevParams P, int n_frames, const T *cones_xy, const uint8_t *cones_type, const int32_t *offsets,
-                      const T *pos, const T *dir, StageOut O, int do_match, int *counter) {
+    sort_kernel(DevParams P, int n_frames, const T *cones_xy, const uint8_t *cones_type, const int32_t *offsets,
+                const T *pos, const T *dir, StageOut O, int *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  SortCta &C = *reinterpret_cast<SortCta *>(smem_raw + (size_t)warp * SORT_CTA_STRIDE);
-#ifdef FSD_POOLED_KNN
-  __shared__ int s_n[WPC];
-  const int lane = fsd_lane();
-#endif
+  SortCta &C = *reinterpret_cast<SortCta *>(smem_raw + (size_t)(threadIdx.x >> 5) * SORT_CTA_STRIDE);
   if (fsd_lane() == 0) mbar_init(&C.mbar, 1);
   __syncwarp();
   uint32_t phase = 0;
-  // The warps of a CTA start every frame together and meet again after the k-NN graph and after each side's search:
-  // they then run the same phase (the same code) at the same time and share instruction-cache fills, like the path
-  // kernel's lockstep machine.
-  for (int base = (int)blockIdx.x * WPC;; base += (int)gridDim.x * WPC) {
-    int b;
-    if (FREE) {
-      b = next_frame(counter);
-      if (b >= n_frames) break;
-    } else {
-      if (base >= n_frames) break;
-      b = base + warp;
-    }
-    const bool active = b < n_frames;
-    int n = 0, nl = 0, nr = 0;
+  for (;;) {
+    const int b = next_frame(counter);
+    if (b >= n_frames) break;
     unsigned st = 0;
-    FramePose F = make_pose(0.0, 0.0, 1.0, 0.0);
-    int16_t *dbg = nullptr;
-    if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 1) group_sync();
-    if (active) {
-      const int lo = offsets[b];
-      n = offsets[b + 1] - lo;
-      if (n > FSD_MAX_CONES) {
-        n = FSD_MAX_CONES;
-        st |= FSD_ST_OVERFLOW;
-      }
-      if (n < 0) n = 0;
-      F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
-      dbg = O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr;
-      stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
-#ifndef FSD_POOLED_KNN
-      if (n >= 3) build_knn(C.S, n, P);
-#endif
+    const int lo = offsets[b];
+    int n = offsets[b + 1] - lo;
+    if (n > FSD_MAX_CONES) {
+      n = FSD_MAX_CONES;
+      st |= FSD_ST_OVERFLOW;
     }
-#ifdef FSD_POOLED_KNN
-    // The k-NN graph costs N^2 per frame and N varies 3x inside a batch: the rows of all frames of the CTA are pooled and
-    // dealt out evenly to its threads (a thread may work on another warp's frame - every slice is in this CTA's shared
-    // memory), so no warp waits for the frame with the most cones.
-    if (lane == 0) s_n[warp] = (active && n >= 3) ? n : 0;
-    __syncthreads();
-    for (int stage = 0; stage < 2; ++stage) {
-      int total = 0;
-#pragma unroll
-      for (int w = 0; w < WPC; ++w) total += s_n[w];
-#pragma unroll 1
-      for (int r = (int)threadIdx.x; r < total; r += CTA_THREADS) {
-        int f = 0, base = 0;
-        while (r >= base + s_n[f]) base += s_n[f++];
-        SortSmem &Sf = reinterpret_cast<SortCta *>(smem_raw + (size_t)f * SORT_CTA_STRIDE)->S;
-        const int nf = s_n[f];
-        if (stage == 0)
-          knn_row(Sf, nf, knn_k(nf, P), r - base, P);
-        else
-          knn_mutual_row(Sf, r - base);
-      }
-      __syncthreads();
-    }
-#endif
-    // each side in three stages (seeds / exhaustive search / filter + cost), a CTA barrier before every stage
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int side = pass == 0 ? FSD_CONE_LEFT : FSD_CONE_RIGHT;
-      SideSearch Q;
-      if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 2) group_sync();
-      if (active) side_seeds(C.S, n, F, side, P, Q);
-      if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
-      if (active) side_search(C.S, n, F, side, P, Q, &st);
-      if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 5) group_sync();
-      if (active) (side == FSD_CONE_LEFT ? nl : nr) = side_select(C.S, n, F, side, Q, dbg);
-    }
-    if (!FREE && WPC > 1 && FSD_SORT_BARRIERS >= 4) group_sync();
-    if (active) {
-      st |= sort_finish(C.S, nl, nr);
-      store_sort(C.S, b, O);
-      if (!FREE && do_match) {  // the free-running variant is the sort-only kernel of the split stage
-        st |= match_from_sort(C.S, F, P);
-        store_match(C.S.M, b, O);
-      }
-      if (fsd_lane() == 0) O.status[b] = st;
-      __syncwarp();
-    }
+    if (n < 0) n = 0;
+    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
+    int16_t *dbg = O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr;
+    stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
+    if (n >= 3) build_knn(C.S, n, P);
+    int nl = 0, nr = 0;
+    sort_sides(C.S, n, F, P, dbg, &st, nl, nr);
+    st |= sort_finish(C.S, nl, nr);
+    store_sort(C.S, b, O);
+    if (fsd_lane() == 0) O.status[b] = st;
+    __syncwarp();
   }
 }
 
@@ -815,7 +749,7 @@ void set_smem(K kernel, size_t bytes) {
 }
 
 // How a batch is planned (FSD_PLAN_MODE in the environment, read once; a measurement knob, not an API):
-//   bit 0: the sort stage as two free-running kernels (sort | match) instead of one lockstep kernel
+//   (bit 0, the sort stage as two free-running kernels instead of one lockstep kernel, is always on since r2_h)
 //   bit 1: the path stage as three free-running kernels (path_phase_kernel) instead of one lockstep kernel
 //   bit 2: the lockstep path kernel takes its rounds of frames from a counter instead of a static stride
 //   bit 3: fsd_plan_batch never splits a batch into two chunks on two streams
@@ -844,10 +778,8 @@ int device_info(DeviceInfo **out) {
       return FSD_ERR_NO_DEVICE;
     }
     int a = 0, b = 0;
-    set_smem(sort_match_kernel<float, false>, WPC * SORT_CTA_STRIDE);
-    set_smem(sort_match_kernel<double, false>, WPC * SORT_CTA_STRIDE);
-    set_smem(sort_match_kernel<float, true>, WPC * SORT_CTA_STRIDE);
-    set_smem(sort_match_kernel<double, true>, WPC * SORT_CTA_STRIDE);
+    set_smem(sort_kernel<float>, WPC * SORT_CTA_STRIDE);
+    set_smem(sort_kernel<double>, WPC * SORT_CTA_STRIDE);
     set_smem(knn_kernel<float>, WPC * SORT_CTA_STRIDE);
     set_smem(knn_kernel<double>, WPC * SORT_CTA_STRIDE);
     set_smem(match_kernel<float>, WPC * MATCH_CTA_STRIDE);
@@ -861,7 +793,7 @@ int device_info(DeviceInfo **out) {
     cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(skid_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_match_kernel<float, false>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_kernel<float>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
     D.sort_ctas = a > 0 ? a : 1;
@@ -1060,21 +992,15 @@ int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, c
   if (rc != FSD_OK) return rc;
   StageOut O = {out_left_idx, out_right_idx, inter->sort_dbg, inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r,   inter->r2l,    out_status};
-  const int grid = grid_for(n_frames, D->sm_count, D->sort_ctas);
-  int *counters = nullptr;
-  if ((plan_mode() & 1) && (out_left_idx || idx_scratch) && (out_right_idx || idx_scratch))
-    counters = take_counters(*D, stream);
-  if (!counters) {
-    sort_match_kernel<T, false><<<grid, CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
-        make_dev_params(*params), n_frames, cones_xy, cones_type, offsets, pos, dir, O, 1, nullptr);
-    return check_launch();
-  }
   // two free-running kernels: sorting (writes the sort indices), then matching on them
+  if (!(out_left_idx || idx_scratch) || !(out_right_idx || idx_scratch)) return FSD_ERR_ARG;
+  int *counters = take_counters(*D, stream);
+  if (!counters) return FSD_ERR_LAUNCH;
   if (!O.left_idx) O.left_idx = idx_scratch;
   if (!O.right_idx) O.right_idx = idx_scratch + (size_t)n_frames * FSD_MAX_SORTED;
   const DevParams P = make_dev_params(*params);
-  sort_match_kernel<T, true><<<grid, CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
-      P, n_frames, cones_xy, cones_type, offsets, pos, dir, O, 0, counters);
+  sort_kernel<T><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE, stream>>>(
+      P, n_frames, cones_xy, cones_type, offsets, pos, dir, O, counters);
   rc = check_launch();
   if (rc != FSD_OK) return rc;
   match_kernel<T><<<grid_for(n_frames, D->sm_count, CTAS_PER_SM), CTA_THREADS, WPC * MATCH_CTA_STRIDE, stream>>>(
@@ -1306,7 +1232,7 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones) {
 int fsd_plan_launches(int n_frames) {
   if (n_frames <= 0) return 0;
   // sort (+ match as a kernel of its own), path (or its three phases), the large-bounds second chance of the path stage
-  const int per_chunk = ((plan_mode() & 1) ? 2 : 1) + ((plan_mode() & 2) ? 3 : 2);
+  const int per_chunk = 2 + ((plan_mode() & 2) ? 3 : 2);
   return first_chunk(n_frames) < n_frames ? 2 * per_chunk : per_chunk;
 }
 
@@ -1370,15 +1296,11 @@ int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy
   int rc = device_info(&D);
   if (rc != FSD_OK) return rc;
   StageOut O = {out_left_idx, out_right_idx, sort_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, out_status};
-  int *counters = (plan_mode() & 1) ? take_counters(*D, static_cast<cudaStream_t>(stream)) : nullptr;
-  if (counters)
-    sort_match_kernel<float, true><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
-                                     static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
-                                                                          cones_type, offsets, pos, dir, O, 0, counters);
-  else
-    sort_match_kernel<float, false><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
-                                      static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy,
-                                                                           cones_type, offsets, pos, dir, O, 0, nullptr);
+  int *counters = take_counters(*D, static_cast<cudaStream_t>(stream));
+  if (!counters) return FSD_ERR_LAUNCH;
+  sort_kernel<float><<<grid_for(n_frames, D->sm_count, D->sort_ctas), CTA_THREADS, WPC * SORT_CTA_STRIDE,
+                       static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params), n_frames, cones_xy, cones_type,
+                                                            offsets, pos, dir, O, counters);
   return check_launch();
 }
 

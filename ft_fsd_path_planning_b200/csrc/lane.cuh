@@ -111,7 +111,49 @@ FSD_DEV void wsum16_transposed(double (&v)[16]) {
   v[0] += __shfl_xor_sync(FULL, v[0], 1);
 }
 
+// Lane GROUPS: G consecutive lanes (G = 32, 16 or 8, aligned) that work on one task while the other groups of the warp work
+// on other tasks -- the sort stage runs the LEFT and the RIGHT search of a frame on the two half-warps at the same time.
+// All collectives name the group's own lanes in their member mask, so the groups may diverge (different trip counts,
+// different branches); where their control flow coincides the hardware executes them together.
+template <int G>
+struct Grp {
+  static_assert(G == 32 || G == 16 || G == 8, "lane groups are aligned powers of two");
+  static constexpr int N = G;
+  FSD_DEV static int lane() { return (int)(threadIdx.x & (unsigned)(G - 1)); }
+  FSD_DEV static int index() { return (int)((threadIdx.x & 31u) / (unsigned)G); }  // which group of the warp
+  FSD_DEV static unsigned base() { return threadIdx.x & 31u & ~(unsigned)(G - 1); }
+  FSD_DEV static unsigned mask() { return G == 32 ? FULL : (((1u << (G & 31)) - 1u) << base()); }
+  FSD_DEV static void sync() { __syncwarp(mask()); }
+  FSD_DEV static unsigned ballot(bool p) { return __ballot_sync(mask(), p) >> base(); }  // bit i = lane i of the group
+  FSD_DEV static int sum_i(int v) { return __reduce_add_sync(mask(), v); }
+  // argmin with ties -> smallest index; lanes with idx < 0 do not take part; the result reaches every lane of the group
+  FSD_DEV static void argmin(double &v, int &idx) {
+    const unsigned m = mask();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(m, v, o);
+      const int oi = __shfl_xor_sync(m, idx, o);
+      const bool take = (oi >= 0) && (idx < 0 || ov < v || (ov == v && oi < idx));
+      if (take) {
+        v = ov;
+        idx = oi;
+      }
+    }
+  }
+};
+
 #else  // host-check build: a warp of one lane
+
+template <int G>
+struct Grp {
+  static constexpr int N = 1;
+  static inline int lane() { return 0; }
+  static inline int index() { return 0; }
+  static inline void sync() {}
+  static inline unsigned ballot(bool p) { return p ? 1u : 0u; }
+  static inline int sum_i(int v) { return v; }
+  static inline void argmin(double &, int &) {}
+};
 
 constexpr int FSD_LANES = 1;
 #define FSD_FOR_TASKS(e, count) for (int e = 0; e < (count); ++e)

@@ -14,7 +14,6 @@
 #pragma once
 
 #include "lane.cuh"
-#include "match.cuh"
 #include "plan_types.cuh"
 
 namespace fsd {
@@ -28,42 +27,44 @@ namespace fsd {
 #define FSD_ROLLED _Pragma("unroll 1")
 #endif
 
-constexpr int MAX_LEAVES = 64;
-constexpr int STACK_CAP = 64;  // depth <= 12, <= 5 pushes per level
+constexpr int MAX_LEAVES = 24;  // raw leaves of one side's search (the reference's own data: <= 12); more -> FSD_ST_OVERFLOW
+constexpr int STACK_CAP = 64;   // depth <= 12, <= 5 pushes per level
 
-// Shared-memory image of one frame.  Phase-local arrays are overlaid so that 16 frames fit one SM:
-//   region A: fp32 staging of the TMA copy -> k-NN lists (build_knn) -> search / cost scratch (both sides)
-//   region B: adjacency lists + configurations (sorting) -> MatchSmem (matching, after sorting is finished)
+// The two sides of a frame are searched at the same time by the two half-warps (lanes 0-15: LEFT, lanes 16-31: RIGHT;
+// the host-check build runs them one after the other on its single lane): every lane group has its own scratch.
+#ifdef FSD_DEVICE_BUILD
+using SG = Grp<16>;
+#else
+using SG = Grp<1>;
+#endif
+
+// per-side scratch of the search (seeds, reachability, exhaustive search, filter, cost)
+struct SideScratch {
+  uint8_t idxs[FSD_MAX_CONES];   // cone indices used by any configuration (cost term) / BFS queue
+  uint8_t close[FSD_MAX_CONES];  // nearby cones (cost term)
+  int16_t n_good[MAX_LEAVES], n_bad[MAX_LEAVES];
+  uint8_t flag[FSD_MAX_CONES];  // seed mask / in-configuration mask
+  uint8_t flag2[FSD_MAX_CONES];
+  uint8_t stack_node[STACK_CAP], stack_pos[STACK_CAP];
+  int16_t attempt[16];
+  int16_t leaves[MAX_LEAVES][FSD_MAX_SORTED];
+  double costs[MAX_LEAVES];
+  int32_t scratch[4];
+};
+
+// Shared-memory image of one frame.  The fp32 staging area of the TMA copy, the k-NN lists (build_knn) and the two sides'
+// search scratch are overlaid: each is dead when the next is first written.
 struct SortSmem {
   d2 xy[FSD_MAX_CONES];
   uint8_t type[FSD_MAX_CONES];
   int16_t best[2][FSD_MAX_SORTED];
   int32_t nbest[2];
-  int32_t scratch[8];
+  uint8_t nbr[2][FSD_MAX_CONES][5];  // mutual-edge adjacency lists, ascending
+  uint8_t deg[2][FSD_MAX_CONES];
   union {
     alignas(16) float raw[2 * (FSD_MAX_CONES + 2)];
-    struct {
-      uint8_t knn[2][FSD_MAX_CONES][5];  // unused slots hold the row's own index
-    };
-    struct {
-      int16_t idxs[FSD_MAX_CONES];   // cone indices used by any configuration (cost term) / BFS queue
-      int16_t close[FSD_MAX_CONES];  // nearby cones (cost term)
-      int32_t n_good[MAX_LEAVES], n_bad[MAX_LEAVES];
-      uint8_t flag[FSD_MAX_CONES];  // seed mask / in-configuration mask
-      uint8_t flag2[FSD_MAX_CONES];
-      uint8_t stack_node[STACK_CAP], stack_pos[STACK_CAP];
-      int16_t attempt[16];
-      uint8_t can[8];
-    };
-  };
-  union {
-    struct {
-      uint8_t nbr[2][FSD_MAX_CONES][5];
-      uint8_t deg[2][FSD_MAX_CONES];
-      int16_t leaves[MAX_LEAVES][FSD_MAX_SORTED];
-      double costs[MAX_LEAVES];
-    };
-    MatchSmem M;
+    uint8_t knn[2][FSD_MAX_CONES][5];  // unused slots hold the row's own index
+    SideScratch side[2];
   };
 };
 
@@ -198,14 +199,14 @@ FSD_DEVFN void build_knn(SortSmem &S, int n, const DevParams &P) {
 
 // ---- seeds: core_trace_sorter.py:344-465 ----------------------------------------------------
 
-FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int *fk) {
+FSD_DEVFN int select_first_k(SortSmem &S, SideScratch &Q, int n, const FramePose &F, int side, const DevParams &P, int *fk) {
   const int opp = side == FSD_CONE_LEFT ? FSD_CONE_RIGHT : FSD_CONE_LEFT;
   const double c = F.ux, s = F.uy;  // rotation by -yaw
   const double cos_max = P.cos_seed_max, cos_min = P.cos_seed_min, max_first2 = P.max_dist_to_first * P.max_dist_to_first;
   double bv = 0.0;
   int bi = -1;
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+  for (int i = SG::lane(); i < n; i += SG::N) {
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
     double rx = px * c + py * s, ry = -px * s + py * c;
     // distances to the car are compared squared (monotone, no square root)
@@ -216,22 +217,22 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
     bool ang_ok = gt_scaled(rx, cos_max, r) && lt_scaled(rx, cos_min, r);
     int t = S.type[i];
     bool valid = in_ellipse && ((side_ok && ang_ok) || t == side) && t != opp;
-    S.flag[i] = valid ? 1 : 0;
-    S.flag2[i] = rx > 0.0 ? 1 : 0;  // in front of the car: |angle to heading| < pi/2 (:433)
+    Q.flag[i] = valid ? 1 : 0;
+    Q.flag2[i] = rx > 0.0 ? 1 : 0;  // in front of the car: |angle to heading| < pi/2 (:433)
     if (valid && (bi < 0 || r < bv)) {
       bv = r;
       bi = i;
     }
   }
-  wargmin(bv, bi);
-  wsync();
+  SG::argmin(bv, bi);
+  SG::sync();
   if (bi < 0 || bv > max_first2) return 0;
   int i1 = bi;
   bv = 0.0;
   bi = -1;
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
-    if (!S.flag[i] || S.flag2[i] || i == i1) continue;
+  for (int i = SG::lane(); i < n; i += SG::N) {
+    if (!Q.flag[i] || Q.flag2[i] || i == i1) continue;
     double px = S.xy[i].x - F.px, py = S.xy[i].y - F.py;
     double rx = px * c + py * s, ry = -px * s + py * c;
     double r = rx * rx + ry * ry;
@@ -240,8 +241,8 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
       bi = i;
     }
   }
-  wargmin(bv, bi);
-  wsync();
+  SG::argmin(bv, bi);
+  SG::sync();
   if (bi < 0 || bv > max_first2) {
     fk[0] = i1;
     return 1;
@@ -266,36 +267,36 @@ FSD_DEVFN int select_first_k(SortSmem &S, int n, const FramePose &F, int side, c
 
 // ---- reachability: common.py:36-67; only min(#reachable, max_length) is used ----------------
 
-FSD_DEVFN int reachable_count(SortSmem &S, int n, int sidx, int start, int cap) {
-  const int lane = fsd_lane();
+FSD_DEVFN int reachable_count(SortSmem &S, SideScratch &Q, int n, int sidx, int start, int cap) {
+  const int lane = SG::lane();
   // flag2 doubles as the visited mask, idxs as the queue; breadth first, the <= 5 neighbours of a node one per lane
 #pragma unroll 1
-  for (int i = lane; i < n; i += FSD_LANES) S.flag2[i] = 0;
-  wsync();
+  for (int i = lane; i < n; i += SG::N) Q.flag2[i] = 0;
+  SG::sync();
   if (lane == 0) {
-    S.idxs[0] = (int16_t)start;
-    S.flag2[start] = 1;
+    Q.idxs[0] = (uint8_t)start;
+    Q.flag2[start] = 1;
   }
-  wsync();
+  SG::sync();
   int head = 0, tail = 1;
   while (head < tail && tail < cap) {
-    const int node = S.idxs[head++];
+    const int node = Q.idxs[head++];
     const int deg = S.deg[sidx][node];
     unsigned fresh = 0;
 #pragma unroll 1
-    for (int base = 0; base < deg; base += FSD_LANES) {
+    for (int base = 0; base < deg; base += SG::N) {
       const int q = base + lane;
       const int j = q < deg ? (int)S.nbr[sidx][node][q] : -1;
-      const bool f = j >= 0 && !S.flag2[j];
-      const unsigned m = wballot(f);
+      const bool f = j >= 0 && !Q.flag2[j];
+      const unsigned m = SG::ballot(f);
       if (f) {
-        S.idxs[tail + FSD_POPC(fresh) + FSD_POPC(m & ((1u << lane) - 1u))] = (int16_t)j;
-        S.flag2[j] = 1;
+        Q.idxs[tail + FSD_POPC(fresh) + FSD_POPC(m & ((1u << lane) - 1u))] = (uint8_t)j;
+        Q.flag2[j] = 1;
       }
       fresh |= m << base;
     }
     tail += FSD_POPC(fresh);
-    wsync();
+    SG::sync();
   }
   return tail < cap ? tail : cap;
 }
@@ -344,19 +345,19 @@ FSD_DEV bool segments_intersect(double a0x, double a0y, double a1x, double a1y, 
          (fmin(b0y, b1y) - eps <= y && y <= fmax(b0y, b1y) + eps);
 }
 
-FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int sidx, int pos, int i,
+FSD_DEVFN bool can_be_added(const SortSmem &S, const SideScratch &Q, const FramePose &F, int side, int sidx, int pos, int i,
                             const DevParams &P) {
-  const int last = S.attempt[pos];
+  const int last = Q.attempt[pos];
   const uint8_t *nb = S.nbr[sidx][last];
   const int nnb = S.deg[sidx][last];
   const int cand = nb[i];
-  if (S.flag[cand]) return false;  // already in the attempt (:126); find_leaves keeps the membership flags
+  if (Q.flag[cand]) return false;  // already in the attempt (:126); find_leaves keeps the membership flags
   const double lx = S.xy[last].x, ly = S.xy[last].y;
   const double cx = S.xy[cand].x, cy = S.xy[cand].y;
   const double bx = cx - lx, by = cy - ly;  // last -> candidate
   double ax = 0.0, ay = 0.0;                // previous -> last
   if (pos >= 1) {
-    const int prev = S.attempt[pos - 1];
+    const int prev = Q.attempt[pos - 1];
     ax = lx - S.xy[prev].x;
     ay = ly - S.xy[prev].y;
     // ellipse around `last`, major axis 6 m along (last - previous), minor 3 m (:281-300):
@@ -393,7 +394,7 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
     if (pos >= 2) {
       // change of turning direction (:193-205): sign(difference) != sign(difference_2) and |difference -
       // difference_2| = |difference| + |difference_2| > 1.3, on the sine and cosine of the sum of the two magnitudes
-      const int prev = S.attempt[pos - 1], pp = S.attempt[pos - 2];
+      const int prev = Q.attempt[pos - 1], pp = Q.attempt[pos - 2];
       const double zx = S.xy[prev].x - S.xy[pp].x, zy = S.xy[prev].y - S.xy[pp].y;
       const double cr2 = zx * ay - zy * ax, dt2 = zx * ax + zy * ay, w2 = cr2 * cr2 + dt2 * dt2;
       if (isgn(cr) != isgn(cr2)) {
@@ -405,7 +406,7 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
   }
   if (pos == 1) {
     // angle(heading, candidate - first) < pi/2 (:207-211)
-    const int first = S.attempt[0];
+    const int first = Q.attempt[0];
     if (!(F.dx * (cx - S.xy[first].x) + F.dy * (cy - S.xy[first].y) > 0.0)) return false;
   }
   // the new edge must not cross the car (:213-221)
@@ -415,66 +416,66 @@ FSD_DEVFN bool can_be_added(const SortSmem &S, const FramePose &F, int side, int
 }
 
 // ---- exhaustive search: end_configurations.py:320-431 ----------------------------------------
-// returns the number of raw leaves in S.leaves (rows padded with -1 up to FSD_MAX_SORTED)
+// returns the number of raw leaves in Q.leaves (rows padded with -1 up to FSD_MAX_SORTED)
 
-FSD_DEVFN int find_leaves(SortSmem &S, int n, const FramePose &F, int side, int sidx, const int *fk, int nfk, int L,
+FSD_DEVFN int find_leaves(SortSmem &S, SideScratch &Q, int n, const FramePose &F, int side, int sidx, const int *fk, int nfk, int L,
                           const DevParams &P, int *pops_out, unsigned *status) {
-  const int lane = fsd_lane();
+  const int lane = SG::lane();
   int sp = 0, n_leaves = 0, pops = 0;
-  // S.flag[c] == 1 <=> cone c is in the current attempt
+  // Q.flag[c] == 1 <=> cone c is in the current attempt
 #pragma unroll 1
-  for (int i = lane; i < n; i += FSD_LANES) S.flag[i] = 0;
-  wsync();
+  for (int i = lane; i < n; i += SG::N) Q.flag[i] = 0;
+  SG::sync();
   if (lane == 0) {
-    for (int q = 0; q < 16; ++q) S.attempt[q] = -1;
+    for (int q = 0; q < 16; ++q) Q.attempt[q] = -1;
     if (nfk > 1) {
-      S.attempt[0] = (int16_t)fk[0];
-      S.flag[fk[0]] = 1;
-      S.stack_node[0] = (uint8_t)fk[1];
-      S.stack_pos[0] = 1;
+      Q.attempt[0] = (int16_t)fk[0];
+      Q.flag[fk[0]] = 1;
+      Q.stack_node[0] = (uint8_t)fk[1];
+      Q.stack_pos[0] = 1;
     } else {
-      S.stack_node[0] = (uint8_t)fk[0];
-      S.stack_pos[0] = 0;
+      Q.stack_node[0] = (uint8_t)fk[0];
+      Q.stack_pos[0] = 0;
     }
   }
-  wsync();
+  SG::sync();
   while (sp >= 0) {
     if (++pops > P.max_dfs_pops) {
       *status |= FSD_ST_OVERFLOW;
       break;
     }
-    const int node = S.stack_node[sp], pos = S.stack_pos[sp];
+    const int node = Q.stack_node[sp], pos = Q.stack_pos[sp];
     --sp;
-    wsync();
+    SG::sync();
     // the popped node becomes entry `pos` of the attempt, everything behind it is cleared (one entry per lane)
 #pragma unroll 1
-    for (int q = pos + lane; q < L; q += FSD_LANES) {
-      const int old = S.attempt[q];
-      if (old >= 0) S.flag[old] = 0;
-      S.attempt[q] = (int16_t)(q == pos ? node : -1);
+    for (int q = pos + lane; q < L; q += SG::N) {
+      const int old = Q.attempt[q];
+      if (old >= 0) Q.flag[old] = 0;
+      Q.attempt[q] = (int16_t)(q == pos ? node : -1);
     }
-    wsync();
-    if (lane == 0) S.flag[node] = 1;
-    wsync();
+    SG::sync();
+    if (lane == 0) Q.flag[node] = 1;
+    SG::sync();
     // one candidate neighbour per lane; the admissible ones as a bit mask
     const int nnb = S.deg[sidx][node];
     unsigned ok_mask = 0;
 #pragma unroll 1
-    for (int base = 0; base < nnb; base += FSD_LANES) {
+    for (int base = 0; base < nnb; base += SG::N) {
       const int i = base + lane;
-      const bool ok = i < nnb && can_be_added(S, F, side, sidx, pos, i, P);
-      ok_mask |= wballot(ok) << base;
+      const bool ok = i < nnb && can_be_added(S, Q, F, side, sidx, pos, i, P);
+      ok_mask |= SG::ballot(ok) << base;
     }
     const int n_ok = FSD_POPC(ok_mask);
     if (pos < L - 1 && n_ok > 0) {
       // push the admissible neighbours in list order (each lane writes its own slot)
 #pragma unroll 1
-      for (int i = lane; i < nnb; i += FSD_LANES)
+      for (int i = lane; i < nnb; i += SG::N)
         if ((ok_mask >> i) & 1u) {
           const int w = sp + 1 + FSD_POPC(ok_mask & ((1u << i) - 1u));
           if (w < STACK_CAP) {
-            S.stack_node[w] = S.nbr[sidx][node][i];
-            S.stack_pos[w] = (uint8_t)(pos + 1);
+            Q.stack_node[w] = S.nbr[sidx][node][i];
+            Q.stack_pos[w] = (uint8_t)(pos + 1);
           }
         }
       sp += n_ok;
@@ -485,13 +486,13 @@ FSD_DEVFN int find_leaves(SortSmem &S, int n, const FramePose &F, int side, int 
     } else {
       if (n_leaves < MAX_LEAVES) {
 #pragma unroll 1
-        for (int q = lane; q < FSD_MAX_SORTED; q += FSD_LANES) S.leaves[n_leaves][q] = q < L ? S.attempt[q] : (int16_t)-1;
+        for (int q = lane; q < FSD_MAX_SORTED; q += SG::N) Q.leaves[n_leaves][q] = q < L ? Q.attempt[q] : (int16_t)-1;
         ++n_leaves;
       } else {
         *status |= FSD_ST_OVERFLOW;
       }
     }
-    wsync();
+    SG::sync();
   }
   *pops_out = pops;
   return n_leaves;
@@ -518,12 +519,12 @@ FSD_ROWFN int row_cmp(const int16_t *a, const int16_t *b) {
   return 0;
 }
 
-FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, int nfk) {
-  if (fsd_lane() == 0) {
+FSD_DEVFN int post_filter(SortSmem &S, SideScratch &Q, int n_leaves, int side, const int *fk, int nfk) {
+  if (SG::lane() == 0) {
     int kept = 0;
     FSD_ROLLED
     for (int r = 0; r < n_leaves; ++r) {
-      int16_t *row = S.leaves[r];
+      int16_t *row = Q.leaves[r];
       int len = row_len(row);
       if (len <= 2) continue;
       bool ok = true;
@@ -545,7 +546,7 @@ FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, in
       for (int q = 0; q < FSD_MAX_SORTED; ++q) tmp[q] = row[q];
       FSD_ROLLED
       while (p > 0) {
-        int c = row_cmp(S.leaves[p - 1], tmp);
+        int c = row_cmp(Q.leaves[p - 1], tmp);
         if (c == 0) dup = true;
         if (c <= 0) break;
         --p;
@@ -554,9 +555,9 @@ FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, in
       FSD_ROLLED
       for (int m = kept; m > p; --m)
         FSD_ROLLED
-        for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[m][q] = S.leaves[m - 1][q];
+        for (int q = 0; q < FSD_MAX_SORTED; ++q) Q.leaves[m][q] = Q.leaves[m - 1][q];
       FSD_ROLLED
-      for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[p][q] = tmp[q];
+      for (int q = 0; q < FSD_MAX_SORTED; ++q) Q.leaves[p][q] = tmp[q];
       ++kept;
     }
     // rows that are a strict prefix of another row are removed (:509-515)
@@ -568,24 +569,24 @@ FSD_DEVFN int post_filter(SortSmem &S, int n_leaves, int side, const int *fk, in
       for (int i = 0; i < kept; ++i) {
         bool all = true;
         FSD_ROLLED
-        for (int q = 0; q < FSD_MAX_SORTED; ++q) all &= (S.leaves[i][q] == S.leaves[j][q]) || (S.leaves[j][q] == -1);
+        for (int q = 0; q < FSD_MAX_SORTED; ++q) all &= (Q.leaves[i][q] == Q.leaves[j][q]) || (Q.leaves[j][q] == -1);
         covered += all;
       }
-      S.flag2[j] = covered > 1 ? 1 : 0;
+      Q.flag2[j] = covered > 1 ? 1 : 0;
     }
     FSD_ROLLED
     for (int j = 0; j < kept; ++j)
-      if (!S.flag2[j]) {
+      if (!Q.flag2[j]) {
         if (out != j)
           FSD_ROLLED
-          for (int q = 0; q < FSD_MAX_SORTED; ++q) S.leaves[out][q] = S.leaves[j][q];
+          for (int q = 0; q < FSD_MAX_SORTED; ++q) Q.leaves[out][q] = Q.leaves[j][q];
         ++out;
       }
-    S.scratch[0] = out;
+    Q.scratch[0] = out;
   }
-  wsync();
-  int c = S.scratch[0];
-  wsync();
+  SG::sync();
+  int c = Q.scratch[0];
+  SG::sync();
   return c;
 }
 
@@ -604,73 +605,73 @@ FSD_DEV void search_dir(const SortSmem &S, int a, int b, int side, double &ox, d
 }
 
 // lane-strided stream compaction of the indices i < n with flag[i] != 0 (ascending order)
-FSD_DEVFN int compact_flags(const uint8_t *flag, int n, int16_t *out) {
+FSD_DEVFN int compact_flags(const uint8_t *flag, int n, uint8_t *out) {
   int count = 0;
-  const int lane = fsd_lane();
+  const int lane = SG::lane();
   FSD_ROLLED
-  for (int base = 0; base < n; base += FSD_LANES) {
+  for (int base = 0; base < n; base += SG::N) {
     int i = base + lane;
     bool p = i < n && flag[i];
-    unsigned m = wballot(p);
-    if (p) out[count + FSD_POPC(m & ((1u << lane) - 1u))] = (int16_t)i;
+    unsigned m = SG::ballot(p);
+    if (p) out[count + FSD_POPC(m & ((1u << lane) - 1u))] = (uint8_t)i;
     count += FSD_POPC(m);
   }
-  wsync();
+  SG::sync();
   return count;
 }
 
-FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
+FSD_DEVFN void cones_on_either_side(SortSmem &S, SideScratch &Q, int n, int C, int side) {
   // nearby_cone_search.py:212-297, search distance 6 m, search angle 120 deg
-  const int lane = fsd_lane();
+  const int lane = SG::lane();
   const double range2 = 36.0;
 #pragma unroll 1
-  for (int i = lane; i < n; i += FSD_LANES) S.flag[i] = 0;
-  wsync();
+  for (int i = lane; i < n; i += SG::N) Q.flag[i] = 0;
+  SG::sync();
   if (lane == 0)
     FSD_ROLLED
     for (int r = 0; r < C; ++r)
       FSD_ROLLED
       for (int q = 0; q < FSD_MAX_SORTED; ++q)
-        if (S.leaves[r][q] != -1) S.flag[S.leaves[r][q]] = 1;
-  wsync();
-  int nidx = compact_flags(S.flag, n, S.idxs);
+        if (Q.leaves[r][q] != -1) Q.flag[Q.leaves[r][q]] = 1;
+  SG::sync();
+  int nidx = compact_flags(Q.flag, n, Q.idxs);
   // cones within 6 m of any configuration cone (:97-103)
 #pragma unroll 1
-  for (int j = lane; j < n; j += FSD_LANES) {
+  for (int j = lane; j < n; j += SG::N) {
     bool near = false;
     FSD_ROLLED
     for (int q = 0; q < nidx && !near; ++q) {
-      int i = S.idxs[q];
+      int i = Q.idxs[q];
       if (i == j) continue;
       double ddx = S.xy[i].x - S.xy[j].x, ddy = S.xy[i].y - S.xy[j].y;
       near = ddx * ddx + ddy * ddy < range2;
     }
-    S.flag2[j] = near ? 1 : 0;
+    Q.flag2[j] = near ? 1 : 0;
   }
-  wsync();
+  SG::sync();
   // `close` first holds all nearby cones, then loses the entries hit by the reference's
   // sorted_set_diff (:88-94): mask[searchsorted(all, idxs)] = False, no membership test
-  int nall = compact_flags(S.flag2, n, S.close);
+  int nall = compact_flags(Q.flag2, n, Q.close);
 #pragma unroll 1
-  for (int j = lane; j < n; j += FSD_LANES) S.flag2[j] = 0;
-  wsync();
+  for (int j = lane; j < n; j += SG::N) Q.flag2[j] = 0;
+  SG::sync();
 #pragma unroll 1
-  for (int q = lane; q < nidx; q += FSD_LANES) {
-    int v = S.idxs[q], lo = 0, hi = nall;
+  for (int q = lane; q < nidx; q += SG::N) {
+    int v = Q.idxs[q], lo = 0, hi = nall;
     FSD_ROLLED
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (S.close[mid] < v)
+      if (Q.close[mid] < v)
         lo = mid + 1;
       else
         hi = mid;
     }
-    if (lo < nall) S.flag2[S.close[lo]] = 1;  // removed
+    if (lo < nall) Q.flag2[Q.close[lo]] = 1;  // removed
   }
-  wsync();
+  SG::sync();
   FSD_ROLLED
   for (int r = 0; r < C; ++r) {
-    const int16_t *c = S.leaves[r];
+    const int16_t *c = Q.leaves[r];
     int len = row_len(c);
     int good = 0, bad = 0;
     FSD_ROLLED
@@ -686,13 +687,13 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
       const double x0 = S.xy[cj].x, y0 = S.xy[cj].y;
       // other = close (minus removed) ++ configuration cones of OTHER configurations
 #pragma unroll 1
-      for (int q = lane; q < nall + nidx; q += FSD_LANES) {
+      for (int q = lane; q < nall + nidx; q += SG::N) {
         int o;
         if (q < nall) {
-          o = S.close[q];
-          if (S.flag2[o]) continue;
+          o = Q.close[q];
+          if (Q.flag2[o]) continue;
         } else {
-          o = S.idxs[q - nall];
+          o = Q.idxs[q - nall];
           bool member = false;
           FSD_ROLLED
           for (int w = 0; w < len; ++w) member |= c[w] == o;
@@ -707,29 +708,29 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, int n, int C, int side) {
         bad += lt_scaled(dot, -0.5, w2);   // angle to the opposite direction < 60 deg
       }
     }
-    good = wsum_i(good);
-    bad = wsum_i(bad);
+    good = SG::sum_i(good);
+    bad = SG::sum_i(bad);
     if (lane == 0) {
-      S.n_good[r] = good;
-      S.n_bad[r] = bad;
+      Q.n_good[r] = good;
+      Q.n_bad[r] = bad;
     }
   }
-  wsync();
+  SG::sync();
 }
 
-FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const FramePose &F) {
+FSD_DEVFN int best_configuration(SortSmem &S, SideScratch &Q, int n, int C, int side, const FramePose &F) {
   if (C == 1) return 0;
-  cones_on_either_side(S, n, C, side);
+  cones_on_either_side(S, Q, n, C, side);
   const double wsum_ = 9200.0;
   int mn = 0;
   FSD_ROLLED
   for (int r = 0; r < C; ++r) {
-    int d = S.n_good[r] - S.n_bad[r];
+    int d = Q.n_good[r] - Q.n_bad[r];
     if (r == 0 || d < mn) mn = d;
   }
 #pragma unroll 1
-  for (int r = fsd_lane(); r < C; r += FSD_LANES) {
-    const int16_t *c = S.leaves[r];
+  for (int r = SG::lane(); r < C; r += SG::N) {
+    const int16_t *c = Q.leaves[r];
     const int len = row_len(c);
 #define px(q) S.xy[c[q]].x
 #define py(q) S.xy[c[q]].y
@@ -753,7 +754,7 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
     }
     double ncones = 1.0 / (double)len;
     double init_dir = fsd_acos(cos_between(px(1) - px(0), py(1) - py(0), F.dx, F.dy));
-    double either = 1.0 / (double)(S.n_good[r] - S.n_bad[r] + (mn < 0 ? -mn : mn) + 1);
+    double either = 1.0 / (double)(Q.n_good[r] - Q.n_bad[r] + (mn < 0 ? -mn : mn) + 1);
     // wrong direction (:149-188)
     double wrong = 0.0;
     if (len != 3) {
@@ -778,77 +779,71 @@ FSD_DEVFN int best_configuration(SortSmem &S, int n, int C, int side, const Fram
     total += 0.0 * (0.0 / wsum_);
     total += either * (1000.0 / wsum_);
     total += wrong * (1000.0 / wsum_);
-    S.costs[r] = total;
+    Q.costs[r] = total;
 #undef px
 #undef py
   }
-  wsync();
+  SG::sync();
   int arg = 0;
   FSD_ROLLED
   for (int r = 1; r < C; ++r)
-    if (S.costs[r] < S.costs[arg]) arg = r;
-  wsync();
+    if (Q.costs[r] < Q.costs[arg]) arg = r;
+  SG::sync();
   return arg;
 }
 
 // ---- one side: core_trace_sorter.py:252-327 -----------------------------------------------------
 
-// The side's search in three stages, so that the sort kernel can align the warps of a CTA between them (they then run
-// the same stage -- the same code -- at the same time).  `SideSearch` carries the state from stage to stage; every lane
-// holds an identical copy.
-struct SideSearch {
-  int fk[2], nfk, L, n_leaves, pops;
-};
-
-// stage 1: seeds and search depth
-FSD_DEVFN void side_seeds(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, SideSearch &Q) {
+// One side's search by one lane group: seeds and search depth, exhaustive search, filter + cost; the side's result goes
+// to S.best[sidx], its length is returned (0: no configuration).  Every lane of the group holds the same values.
+FSD_DEVFN int sort_one_side(SortSmem &S, SideScratch &Q, int n, const FramePose &F, int side, const DevParams &P,
+                            int16_t *dbg, unsigned *status) {
   const int sidx = side == FSD_CONE_LEFT ? 0 : 1;
-  Q.fk[0] = Q.fk[1] = -1;
-  Q.L = Q.n_leaves = Q.pops = 0;
-  Q.nfk = n < 3 ? 0 : select_first_k(S, n, F, side, P, Q.fk);
-  if (Q.nfk > 0) {
-    const int R = reachable_count(S, n, sidx, Q.fk[0], P.max_length);
-    Q.L = R < P.max_length ? R : P.max_length;  // find_configs_and_scores.py:76
+  int fk[2] = {-1, -1}, L = 0, n_leaves = 0, pops = 0, len = 0, n_cfg = 0;
+  const int nfk = n < 3 ? 0 : select_first_k(S, Q, n, F, side, P, fk);
+  if (nfk > 0) {
+    const int R = reachable_count(S, Q, n, sidx, fk[0], P.max_length);
+    L = R < P.max_length ? R : P.max_length;  // find_configs_and_scores.py:76
   }
-}
-
-// stage 2: exhaustive search
-FSD_DEVFN void side_search(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, SideSearch &Q,
-                           unsigned *status) {
-  if (Q.nfk > 0 && Q.L >= 3)
-    Q.n_leaves = find_leaves(S, n, F, side, side == FSD_CONE_LEFT ? 0 : 1, Q.fk, Q.nfk, Q.L, P, &Q.pops, status);
-}
-
-// stage 3: filter, cost, the side's result in S.best; returns its length
-FSD_DEVFN int side_select(SortSmem &S, int n, const FramePose &F, int side, const SideSearch &Q, int16_t *dbg) {
-  const int sidx = side == FSD_CONE_LEFT ? 0 : 1;
-  int len = 0, n_cfg = 0;
-  if (Q.nfk > 0 && Q.L >= 3) {
-    n_cfg = post_filter(S, Q.n_leaves, side, Q.fk, Q.nfk);
+  if (nfk > 0 && L >= 3) {
+    n_leaves = find_leaves(S, Q, n, F, side, sidx, fk, nfk, L, P, &pops, status);
+    n_cfg = post_filter(S, Q, n_leaves, side, fk, nfk);
     if (n_cfg > 0) {
-      const int arg = best_configuration(S, n, n_cfg, side, F);
-      len = row_len(S.leaves[arg]);
-      if (fsd_lane() == 0)
+      const int arg = best_configuration(S, Q, n, n_cfg, side, F);
+      len = row_len(Q.leaves[arg]);
+      if (SG::lane() == 0)
         FSD_ROLLED
-        for (int q = 0; q < FSD_MAX_SORTED; ++q) S.best[sidx][q] = S.leaves[arg][q];
-      wsync();
+        for (int q = 0; q < FSD_MAX_SORTED; ++q) S.best[sidx][q] = Q.leaves[arg][q];
+      SG::sync();
     }
   }
-  if (dbg && fsd_lane() == 0) {
-    dbg[2 * sidx] = (int16_t)Q.fk[0];
-    dbg[2 * sidx + 1] = (int16_t)(Q.nfk > 1 ? Q.fk[1] : -1);
+  if (dbg && SG::lane() == 0) {
+    dbg[2 * sidx] = (int16_t)fk[0];
+    dbg[2 * sidx + 1] = (int16_t)(nfk > 1 ? fk[1] : -1);
     dbg[4 + sidx] = (int16_t)n_cfg;
-    dbg[6 + sidx] = (int16_t)(Q.pops > 32767 ? 32767 : Q.pops);
+    dbg[6 + sidx] = (int16_t)(pops > 32767 ? 32767 : pops);
   }
   return len;
 }
 
-FSD_DEVFN int sort_one_side(SortSmem &S, int n, const FramePose &F, int side, const DevParams &P, int16_t *dbg,
-                            unsigned *status) {
-  SideSearch Q;
-  side_seeds(S, n, F, side, P, Q);
-  side_search(S, n, F, side, P, Q, status);
-  return side_select(S, n, F, side, Q, dbg);
+// Both sides of a frame.  Device: the LEFT search on lanes 0-15, the RIGHT search on lanes 16-31, at the same time (the
+// two searches share nothing but the read-only frame: coordinates, types, adjacency lists); the half-warps meet again
+// at the end and exchange their results.  Host-check build: one after the other.
+FSD_DEVFN void sort_sides(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg, unsigned *status,
+                          int &nl, int &nr) {
+#ifdef FSD_DEVICE_BUILD
+  __syncwarp();
+  const int sidx = SG::index();
+  unsigned st = 0;
+  const int len = sort_one_side(S, S.side[sidx], n, F, sidx == 0 ? FSD_CONE_LEFT : FSD_CONE_RIGHT, P, dbg, &st);
+  __syncwarp();
+  nl = __shfl_sync(FULL, len, 0);
+  nr = __shfl_sync(FULL, len, 16);
+  *status |= __shfl_sync(FULL, st, 0) | __shfl_sync(FULL, st, 16);
+#else
+  nl = sort_one_side(S, S.side[0], n, F, FSD_CONE_LEFT, P, dbg, status);
+  nr = sort_one_side(S, S.side[1], n, F, FSD_CONE_RIGHT, P, dbg, status);
+#endif
 }
 
 // ---- left/right conflict: combine_traces.py:115-257 (lane 0) --------------------------------------
@@ -967,8 +962,8 @@ FSD_DEVFN unsigned sort_finish(SortSmem &S, int nl, int nr) {
 FSD_DEVFN unsigned sort_frame(SortSmem &S, int n, const FramePose &F, const DevParams &P, int16_t *dbg) {
   unsigned status = 0;
   if (n >= 3) build_knn(S, n, P);
-  int nl = sort_one_side(S, n, F, FSD_CONE_LEFT, P, dbg, &status);
-  int nr = sort_one_side(S, n, F, FSD_CONE_RIGHT, P, dbg, &status);
+  int nl = 0, nr = 0;
+  sort_sides(S, n, F, P, dbg, &status, nl, nr);
   return status | sort_finish(S, nl, nr);
 }
 
