@@ -126,6 +126,64 @@ struct Grp {
   FSD_DEV static void sync() { __syncwarp(mask()); }
   FSD_DEV static unsigned ballot(bool p) { return __ballot_sync(mask(), p) >> base(); }  // bit i = lane i of the group
   FSD_DEV static int sum_i(int v) { return __reduce_add_sync(mask(), v); }
+  FSD_DEV static int min_i(int v) { return __reduce_min_sync(mask(), v); }
+  FSD_DEV static bool any(bool p) { return __any_sync(mask(), p); }
+  __device__ __noinline__ static double sum(double v) {
+    const unsigned m = mask();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+  }
+  __device__ __noinline__ static double min_d(double v) {
+    const unsigned m = mask();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(m, v, o));
+    return v;
+  }
+  // inclusive prefix sum across the lanes of the group
+  __device__ __noinline__ static double scan_incl(double v) {
+    const unsigned m = mask();
+    const int l = lane();
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      const double t = __shfl_up_sync(m, v, o, G);
+      if (l >= o) v += t;
+    }
+    return v;
+  }
+  FSD_DEV static double last(double v) { return __shfl_sync(mask(), v, G - 1, G); }  // value of the group's last lane
+  // N sums at once, butterfly steps interleaved across the N values
+  template <int N>
+  FSD_DEV static void sum_vec(double (&v)[N]) {
+    const unsigned m = mask();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) v[e] += __shfl_xor_sync(m, v[e], o);
+    }
+  }
+  // Group totals of 16 values with 15 (G = 16) / 16 (G = 32) shuffles instead of 64 / 80: in every butterfly step a lane
+  // hands over the half of the values its partner becomes responsible for and adds the partner's copy of its own half.
+  // On return v[0] of lane L holds the total of value `owned16()`.
+  FSD_DEV static void sum16_transposed(double (&v)[16]) {
+    static_assert(G == 32 || G == 16, "16 values need at least 16 lanes");
+    const unsigned m = mask();
+    const int l = lane();
+#pragma unroll
+    for (int h = 8, o = G / 2; h >= 1; h >>= 1, o >>= 1) {
+      const bool up = (l & o) != 0;
+#pragma unroll
+      for (int j = 0; j < h; ++j) {
+        const double send = up ? v[j] : v[j + h];
+        const double keep = up ? v[j + h] : v[j];
+        v[j] = keep + __shfl_xor_sync(m, send, o);
+      }
+    }
+    if (G == 32) v[0] += __shfl_xor_sync(m, v[0], 1);
+  }
+  // which of the 16 values this lane owns after sum16_transposed, and whether it is the lane that adds it to memory
+  FSD_DEV static int owned16() { return G == 32 ? (lane() >> 1) : lane(); }
+  FSD_DEV static bool owner16() { return G == 32 ? (lane() & 1) == 0 : true; }
   // argmin with ties -> smallest index; lanes with idx < 0 do not take part; the result reaches every lane of the group
   FSD_DEV static void argmin(double &v, int &idx) {
     const unsigned m = mask();
@@ -152,6 +210,14 @@ struct Grp {
   static inline void sync() {}
   static inline unsigned ballot(bool p) { return p ? 1u : 0u; }
   static inline int sum_i(int v) { return v; }
+  static inline int min_i(int v) { return v; }
+  static inline bool any(bool p) { return p; }
+  static inline double sum(double v) { return v; }
+  static inline double min_d(double v) { return v; }
+  static inline double scan_incl(double v) { return v; }
+  static inline double last(double v) { return v; }
+  template <int N>
+  static inline void sum_vec(double (&)[N]) {}
   static inline void argmin(double &, int &) {}
 };
 
@@ -173,6 +239,24 @@ FSD_DEV double wlast(double v) { return v; }
 template <int N>
 FSD_DEV void wsum_vec(double (&)[N]) {}
 
+#endif
+
+// The path stage (spline.cuh, path.cuh) runs one frame per lane group: TWO frames per warp on the device (the kernels
+// are bound by instruction delivery, and most of the path code keeps 16 lanes or fewer busy: the banded solve has 18
+// tasks, the reductions and the control flow are shared by both frames of the warp), one lane on the host.
+#ifndef FSD_PATH_LANES
+#define FSD_PATH_LANES 16
+#endif
+#ifdef FSD_DEVICE_BUILD
+using PG = Grp<FSD_PATH_LANES>;
+#else
+using PG = Grp<1>;
+#endif
+// `count` independent tasks, at most one per lane of the path lane group and round
+#ifdef FSD_DEVICE_BUILD
+#define FSD_FOR_PTASKS(e, count) for (int e = PG::lane(); e < (count); e += PG::N)
+#else
+#define FSD_FOR_PTASKS(e, count) for (int e = 0; e < (count); ++e)
 #endif
 
 constexpr double PI = 3.14159265358979323846;

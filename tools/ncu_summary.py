@@ -6,6 +6,7 @@ kfilter = ["--kernel-name", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []
 raw = subprocess.run(["ncu", "-i", rep, *kfilter, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[-1]
+n_launches = max(len(rows) - 2, 1)  # the source page below aggregates every captured launch of the kernel
 keep = ["gpu__time_duration.sum", "launch__", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__pcsamp_warps_issue_stalled",
         "sm__pipe_fp64_cycles_active", "sm__inst_executed.sum", "sm__icc_request", "gcc__cache_requests_type_instruction", "gcc__average_cache_request_hit_rate",
@@ -44,7 +45,7 @@ for r in rows:
         inst[(cur_file, fn)] += n
         samp[(cur_file, fn)] += s
 tot, ts = sum(inst.values()), sum(samp.values())
-frames = int(sys.argv[3]) if len(sys.argv) > 3 else 10240
+frames = (int(sys.argv[3]) if len(sys.argv) > 3 else 10240) * n_launches
 with open(f"profiles/{tag}_by_function.txt", "w") as f:
     f.write(f"warp instructions per frame: {tot / frames:.0f}\n")
     for k, v in inst.most_common(24):
