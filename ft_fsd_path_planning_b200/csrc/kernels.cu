@@ -39,36 +39,6 @@ constexpr int WPC = FSD_WARPS_PER_CTA;
 #endif
 constexpr int CTA_THREADS = 32 * WPC;
 constexpr int CTAS_PER_SM = 16 / WPC;
-#ifndef FSD_PATH_CTAS_PER_SM
-#define FSD_PATH_CTAS_PER_SM CTAS_PER_SM
-#endif
-
-// Frame scheduling inside a kernel: the warps of a CTA take frames in rounds of WPC (CTA-strided over the batch) with
-// one __syncthreads per round, so that the frames of a round walk through the same phases together and share the
-// instruction cache.  Measured alternatives (profiles/r1_scheduling_ab.txt): one contiguous block of frames per CTA
-// (-7 %) and per-warp dynamic fetch from a shared counter without the barrier (-9 %).
-#define FSD_FRAME_LOOP(b, n_frames)                                                                          \
-  for (int fsd_base = (int)blockIdx.x * WPC, b = 0; fsd_base < (n_frames); fsd_base += (int)gridDim.x * WPC) \
-    if ((WPC > 1 ? (__syncthreads(), 0) : 0), (b = fsd_base + (int)(threadIdx.x >> 5)) >= (n_frames))         \
-      continue;                                                                                              \
-    else
-
-// Alignment group: the warps of a CTA that wait for each other at the phase boundaries.  Default: the whole CTA.
-// Smaller groups (A/B knob) keep the warps that share an SM sub-partition together: warp w sits on sub-partition w % 4,
-// so a group is the set of warps with the same index modulo WPC / FSD_ALIGN_GROUP.
-#ifndef FSD_ALIGN_GROUP
-#define FSD_ALIGN_GROUP FSD_WARPS_PER_CTA
-#endif
-constexpr int AG = FSD_ALIGN_GROUP;
-__device__ __forceinline__ void group_sync() {
-  if (AG == WPC) {
-    __syncthreads();
-  } else {
-    const unsigned id = 1u + ((threadIdx.x >> 5) % (WPC / AG));
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(AG * 32) : "memory");
-  }
-}
-
 // ---- TMA bulk copy helpers (raw PTX) ------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,12 +82,6 @@ struct SortCta {
 };
 constexpr size_t SORT_CTA_STRIDE = (sizeof(SortCta) + 15) / 16 * 16;
 constexpr size_t PATH_CTA_STRIDE = (sizeof(PathSmem) + 15) / 16 * 16;
-constexpr size_t PATH_MACHINE_STRIDE = (sizeof(PathMachine) + 15) / 16 * 16;
-#ifdef FSD_MACHINE_IN_SMEM
-constexpr size_t PATH_KERNEL_SMEM = WPC * (PATH_CTA_STRIDE + PATH_MACHINE_STRIDE);
-#else
-constexpr size_t PATH_KERNEL_SMEM = WPC * PATH_CTA_STRIDE;
-#endif
 
 // Stage the frame's coordinates into S.xy (fp64).  The 16-byte aligned interior of the frame's slice goes
 // through the TMA bulk copy; a leading / trailing cone that is not 16-byte aligned (fp32 input, odd offset)
@@ -291,57 +255,67 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   }
 }
 
-// Path stage.  The WPC warps of a CTA run their frames' path machines (path.cuh) in LOCKSTEP: one machine step per
-// loop iteration (a pass of a spline fit, or one stage between fits), a CTA barrier per iteration, and a warp that
-// reaches an alignment state (a fit is finished) waits there until no other warp of the CTA is behind it.  The warps
-// therefore execute the same few kilobytes of code at the same time and share every instruction-cache fill; measured
-// with 16 identical frames per CTA (perfect sharing) the kernel is 1.7x faster than with free-running warps
-// (profiles/r1_lockstep_probe.txt).
+// Path stage.  One frame per lane group (PG, lane.cuh: the whole warp by default; two frames per warp is a build option
+// that lost its A/B).  The PATH_FPC frames of a CTA
+// run their path machines (path.cuh) in LOCKSTEP at the granularity of a spline fit: a group that finishes a fit waits
+// (CTA barrier + vote in shared memory) until no group of the CTA is behind it, so all of them are inside the same fit --
+// the same ~40 KB of code -- at the same time and share every instruction-cache fill (identical frames per CTA run 1.7x
+// faster than distinct ones, profiles/r1_lockstep_probe.txt; waiting itself is free, profiles/r2_plan_mode_ab.txt).
+// Rounds of PATH_FPC frames are handed out to the CTAs from a counter in global memory.
+#ifndef FSD_PATH_WPC
+#define FSD_PATH_WPC 8
+#endif
+#ifndef FSD_PATH_CTAS_PER_SM
+#define FSD_PATH_CTAS_PER_SM 2
+#endif
+constexpr int PATH_WPC = FSD_PATH_WPC;             // warps per path CTA
+constexpr int PATH_FPW = 32 / PG::N;               // frames per warp
+constexpr int PATH_FPC = PATH_WPC * PATH_FPW;      // frames per CTA and round
+constexpr int PATH_THREADS = 32 * PATH_WPC;
+constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE;
+
+// drop a frame's point-buffer lines from L2 (they are dead; written back they were 5x the algorithmic bytes of the step)
+__device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned) {
+  static_assert(PATH_SCRATCH_BYTES % 128 == 0, "point buffers must be whole L2 lines");
+  if (aligned)
+    for (size_t o = (size_t)PG::lane() * 128; o + 128 <= PATH_SCRATCH_BYTES; o += (size_t)PG::N * 128)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
+}
+
 template <typename T>
-__global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
+__global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
                 unsigned char *scratch, int *counter, int flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_state[WPC];
+  __shared__ int s_state[PATH_FPC];
   __shared__ int s_base;
-#ifdef FSD_ALIGN_SLACK
-  __shared__ volatile int s_prog[WPC];
-  int round = 0;
-  if (threadIdx.x < WPC) s_prog[threadIdx.x] = 0;
-  __syncthreads();
-#endif
-  const int warp = threadIdx.x >> 5, lane = fsd_lane();
-  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * PATH_CTA_STRIDE);
+  const int grp = (int)threadIdx.x / PG::N, lane = PG::lane();  // this frame's slot in the CTA, lane within the frame
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)grp * PATH_CTA_STRIDE);
+  unsigned char *mine = scratch + ((size_t)blockIdx.x * PATH_FPC + grp) * PATH_SCRATCH_BYTES;
+  const bool aligned = (reinterpret_cast<uintptr_t>(scratch) & 127u) == 0;  // never touch a line shared with a neighbour
   if (lane == 0) {
-    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
     S.pts = reinterpret_cast<d2 *>(mine);
     S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
   }
-  __syncwarp();
-  for (int base = (int)blockIdx.x * WPC;; base += (int)gridDim.x * WPC) {
+  PG::sync();
+  for (int base = (int)blockIdx.x * PATH_FPC;; base += (int)gridDim.x * PATH_FPC) {
     if (counter) {
-      // rounds of WPC frames handed out to the CTAs from a counter (zeroed before the launch): a CTA whose frames were
-      // cheap takes more rounds, so the kernel ends when the WORK ends, not when the unluckiest static share ends
+      // rounds handed out from a counter (zeroed before the launch): a CTA whose frames were cheap takes more rounds, so
+      // the kernel ends when the WORK ends, not when the unluckiest static share ends
       __syncthreads();
-      if (threadIdx.x == 0) s_base = atomicAdd(counter, WPC);
+      if (threadIdx.x == 0) s_base = atomicAdd(counter, PATH_FPC);
       __syncthreads();
       base = s_base;
     }
     if (base >= n_frames) break;
-    const int b = base + warp;
+    const int b = base + grp;
     const bool active = b < n_frames;
 #ifdef FSD_FRAME_CYCLES
     const long long fsd_t0 = clock64();
+    long long fsd_t1 = fsd_t0;
 #endif
-#ifdef FSD_MACHINE_IN_SMEM
-    // one copy of the machine state per warp in shared memory (every lane reads it, every lane writes the same values)
-    // instead of 32 identical per-lane copies in local memory
-    PathMachine &M = *reinterpret_cast<PathMachine *>(smem_raw + (size_t)WPC * PATH_CTA_STRIDE + (size_t)warp * PATH_MACHINE_STRIDE);
-    __syncwarp();
-#else
     PathMachine M;
-#endif
     M.state = PS_DONE;
     M.status = 0;
     M.P_grid = M.n_trim = 0;
@@ -357,51 +331,30 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
       pm_begin_frame(S, M, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F,
                      force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out);
     }
-#if defined(FSD_ALIGN_SLACK)
-    // Elastic lockstep (A/B): no CTA barrier; a warp that reaches an alignment state publishes its progress and waits
-    // there only while more than FSD_ALIGN_SLACK warps of the CTA are behind it
-    for (;;) {
-      while (M.state != PS_DONE && !pm_is_alignment_state(M.state)) pm_step(S, M, P);
-      const int my = M.state == PS_DONE ? round * 256 + 255 : round * 256 + M.state;
-      if (lane == 0) s_prog[warp] = my;
-      __syncwarp();
-      if (M.state == PS_DONE) break;
-      for (;;) {
-        int behind = 0;
-#pragma unroll
-        for (int w = 0; w < WPC; ++w) behind += s_prog[w] < my;
-        if (behind <= FSD_ALIGN_SLACK) break;
-        __nanosleep(200);
-      }
-      pm_step(S, M, P);
-    }
-    ++round;
-#elif defined(FSD_NO_LOCKSTEP)
-    while (M.state != PS_DONE) pm_step(S, M, P);  // A/B only: free-running warps
+#if defined(FSD_NO_LOCKSTEP)
+    while (M.state != PS_DONE) pm_step(S, M, P);  // A/B and measurement builds only: free-running groups
 #ifdef FSD_FRAME_CYCLES
-    const long long fsd_t1 = clock64();
+    fsd_t1 = clock64();
 #endif
     __syncthreads();
 #else
     for (;;) {
-#ifndef FSD_LOCKSTEP_PER_STEP
-      // free-run to the next alignment point (the end of a spline fit): the warps of the CTA are then inside the same
-      // fit at the same time -- the same ~40 KB of code -- without waiting for each other after every pass
+      // free-run to the next alignment point (the end of a spline fit): the groups of the CTA are then inside the same
+      // fit at the same time without waiting for each other after every pass
       while (M.state != PS_DONE && !pm_is_alignment_state(M.state)) pm_step(S, M, P);
-#endif
-      if (lane == 0) s_state[warp] = M.state;
-      group_sync();
+      if (lane == 0) s_state[grp] = M.state;
+      __syncthreads();
       int behind = PS_DONE;
 #pragma unroll
-      for (int w = warp % (WPC / AG); w < WPC; w += WPC / AG) behind = min(behind, s_state[w]);
-      group_sync();
+      for (int g = 0; g < PATH_FPC; ++g) behind = min(behind, s_state[g]);
+      __syncthreads();
       if (behind == PS_DONE) break;
       if (M.state != PS_DONE && !(pm_is_alignment_state(M.state) && behind < M.state)) pm_step(S, M, P);
     }
 #endif
     if (active) {
-      __syncwarp();
-      for (int i = lane; i < FSD_HORIZON * 4; i += 32) {
+      PG::sync();
+      for (int i = lane; i < FSD_HORIZON * 4; i += PG::N) {
         const double v = out[i];
         if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
         if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;  // only when the caller asked for the fp64 path
@@ -425,182 +378,26 @@ __global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
     }
     if (flags & 1) {
       // the frame's points are dead: drop the buffer's lines from L2 now, before the cache gets round to writing the
-      // dirty data back to HBM (5 discards per lane; the next frame re-allocates the lines by writing them)
-      __syncwarp();
-      unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
-      if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)
-        for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
-          asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
+      // dirty data back to HBM (the next frame re-allocates the lines by writing them)
+      PG::sync();
+      discard_points(mine, aligned);
     }
   }
-#ifdef FSD_ALIGN_SLACK
-  if (lane == 0) s_prog[warp] = 0x7fffffff;  // retired: nobody waits for this warp any more
-#endif
-  // The point buffers are dead now: drop their lines from L2 instead of letting the dirty data be written back to HBM
-  // (scratch traffic was 5x the algorithmic bytes of the whole step).  discard.L2 works on whole 128-byte lines; the
-  // buffers are 256-byte aligned and a multiple of 128 bytes long.
-  {
-    __syncwarp();
-    static_assert(PATH_SCRATCH_BYTES % 128 == 0, "per-warp point buffers must be whole L2 lines");
-    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
-    if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)  // never touch a line shared with a neighbour's buffer
-      for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
-  }
-}
-
-// ---- path stage, split into three free-running kernels ------------------------------------------------------------------
-// The path pipeline is cut at the end of its first two spline fits: phase 1 = centre line + fit #1, phase 2 = evaluation,
-// validity / connect / extend / cut + fit #2, phase 3 = evaluation, trim, fit #3, curvature, 40 samples.  Each kernel's hot
-// code is a fraction of the whole pipeline's, so its warps need not be kept in lockstep to share the instruction cache:
-// they run free, take frames from a counter, and nobody waits for the slowest frame of a CTA.  What crosses a cut is the
-// fitted spline (knots, coefficients) and a few machine flags per frame (PathCarry, ~0.3 KB written / read per frame and
-// cut); the point buffers do not cross (the next phase starts by evaluating the spline).  Rare backward transitions of the
-// machine (previous-path fallbacks) are completed inside the kernel in which they occur.
-struct PathCarry {
-  int32_t state, n, k, ier;
-  uint32_t status, tail_status;
-  int32_t flags, pad;
-  double max_u;
-  double t[NCAP];
-  double c[NCAP][2];
-};
-
-__device__ void carry_save(PathCarry &C, const PathSmem &S, const PathMachine &M) {
-  const int lane = fsd_lane();
-  const bool have = M.state != PS_DONE && M.fit.ier != 10;
-  const int n = have ? S.W.n : 0, k = have ? S.W.k : 0;
-  if (lane == 0) {
-    C.state = M.state;
-    C.n = n;
-    C.k = k;
-    C.ier = M.fit.ier;
-    C.status = M.status;
-    C.tail_status = M.tail_status;
-    C.flags = (M.fit1_retry ? 1 : 0) | (M.tail_retry ? 2 : 0);
-    C.max_u = have ? S.W.max_u : 0.0;
-  }
-#pragma unroll 1
-  for (int i = lane; i < n; i += 32) C.t[i] = S.W.t[i];
-#pragma unroll 1
-  for (int i = lane; i < 2 * (n - k - 1); i += 32) (&C.c[0][0])[i] = (&S.W.c[0][0])[i];
-}
-
-// the machine of frame b at the cut it was saved at (every lane gets the same copy); false: the frame is finished
-__device__ bool carry_restore(const PathCarry &C, PathSmem &S, PathMachine &M, const FramePose &F, int force_P,
-                              const double *prev, double *out) {
-  const int lane = fsd_lane();
-  pm_init(S, M, 0, F, force_P, prev, out);
-  M.state = C.state;
-  if (M.state == PS_DONE) return false;
-  M.status = C.status;
-  M.tail_status = C.tail_status;
-  M.fit1_retry = (C.flags & 1) != 0;
-  M.tail_retry = (C.flags & 2) != 0;
-  M.fit.ier = C.ier;
-  M.fit.phase = FIT_DONE;
-  const int n = C.n, k = C.k;
-  __syncwarp();
-#pragma unroll 1
-  for (int i = lane; i < n; i += 32) S.W.t[i] = C.t[i];
-#pragma unroll 1
-  for (int i = lane; i < 2 * (n - k - 1); i += 32) (&S.W.c[0][0])[i] = (&C.c[0][0])[i];
-  if (lane == 0) {
-    S.W.n = n;
-    S.W.k = k;
-    S.W.max_u = C.max_u;
-  }
-  __syncwarp();
-  if (n > 0) knot_reciprocals(S.W, n, k);  // the evaluation's table of reciprocal knot differences (same values as in the fit)
-  return true;
-}
-
-constexpr int P1_PTS = FSD_HORIZON;  // phase 1 only ever holds the <= 40 centre-line / previous-path points: shared memory
-constexpr size_t PATH_P1_STRIDE = PATH_CTA_STRIDE + (size_t)P1_PTS * (sizeof(d2) + sizeof(double));
-
-template <typename T, int PHASE>
-__global__ void __launch_bounds__(CTA_THREADS, FSD_PATH_CTAS_PER_SM)
-    path_phase_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
-                      const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
-                      unsigned char *scratch, PathCarry *carry, int *counter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = fsd_lane();
-  constexpr size_t STRIDE = PHASE == 1 ? PATH_P1_STRIDE : PATH_CTA_STRIDE;
-  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * STRIDE);
-  if (lane == 0) {
-    unsigned char *mine = PHASE == 1 ? smem_raw + (size_t)warp * STRIDE + PATH_CTA_STRIDE
-                                     : scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
-    S.pts = reinterpret_cast<d2 *>(mine);
-    S.u = reinterpret_cast<double *>(mine + (size_t)(PHASE == 1 ? P1_PTS : PCAP) * sizeof(d2));
-  }
-  __syncwarp();
-  for (;;) {
-    const int b = next_frame(counter);
-    if (b >= n_frames) break;
-    PathMachine M;
-    double *out = &S.W.G[0][0];  // assembled in shared memory, see path_kernel
-    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
-    const int fp = force_P ? (int)force_P[b] : 0;
-    const double *pv = prev + (size_t)b * prev_stride;
-    if (PHASE == 1) {
-      const int nl = O.n_wv[2 * (size_t)b], nr = O.n_wv[2 * (size_t)b + 1];
-      const d2 *left = reinterpret_cast<const d2 *>(O.left_wv + (size_t)b * WV_CAP * 2);
-      const d2 *right = reinterpret_cast<const d2 *>(O.right_wv + (size_t)b * WV_CAP * 2);
-      pm_begin_frame(S, M, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F, fp, pv, P, out);
-      if (M.state == PS_FIT1) {  // pm_step's PS_FIT1 case, without linking the later stages into this kernel
-        if (M.fit.phase != FIT_DONE) fit_run(S.W, M.fit, &M.status);
-        if (M.fit.phase == FIT_DONE) M.state = PS_FIT1_DONE;
-      }
-    } else {
-      if (!carry_restore(carry[b], S, M, F, fp, pv, out)) continue;  // finished in an earlier phase
-      const int stop = PHASE == 2 ? PS_FIT2_DONE : PS_DONE;
-      // phase 2 ends when fit #2 is finished for the first time; phase 3 runs the machine to the end (including a rare
-      // re-entry into the tail with the previous path)
-#pragma unroll 1
-      do {
-        pm_step(S, M, P);
-      } while (M.state != PS_DONE && M.state != stop);
-    }
-    __syncwarp();
-    if (M.state == PS_DONE) {
-      if (PHASE != 3 && lane == 0) carry[b].state = PS_DONE;
-      for (int i = lane; i < FSD_HORIZON * 4; i += 32) {
-        const double v = out[i];
-        if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
-        if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;
-      }
-      if (lane == 0) {
-        O.status[b] |= M.status;
-        if (grid_out) {
-          grid_out[2 * (size_t)b] = (int16_t)M.P_grid;
-          grid_out[2 * (size_t)b + 1] = (int16_t)M.n_trim;
-        }
-      }
-    } else {
-      carry_save(carry[b], S, M);
-    }
-    __syncwarp();
-  }
-  if (PHASE != 1) {
-    // the point buffers are dead now: drop their lines from L2 instead of writing them back (see path_kernel)
-    __syncwarp();
-    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
-    if ((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0)
-      for (size_t o = (size_t)lane * 128; o + 128 <= PATH_SCRATCH_BYTES; o += 32 * 128)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
-  }
+  PG::sync();
+  discard_points(mine, aligned);
 }
 
 __global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *out) {
-  // one warp, once per device: the point buffers sit in shared memory behind the PathSmem image
+  // one lane group (launched with PG::N threads), once per device: the point buffers sit in shared memory behind the
+  // PathSmem image
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
-  if (fsd_lane() == 0) {
+  if (PG::lane() == 0) {
     unsigned char *mine = smem_raw + ((sizeof(PathSmem) + 15) / 16) * 16;
     S.pts = reinterpret_cast<d2 *>(mine);
     S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
   }
-  __syncwarp();
+  PG::sync();
   initial_path_frame(S, P, out);
 }
 
@@ -639,42 +436,44 @@ __global__ void __launch_bounds__(32) skid_track_kernel(int n_traj, const int32_
   }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
+// one lane group per pose step (two steps per warp), all steps of all trajectories in parallel, free-running
+__global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     skid_step_kernel(DevParams P, int n_steps, const double *reloc, const int32_t *traj_of_step, const double *table,
                      int n_table, const int32_t *index, const double *known, const int16_t *force_P,
                      const double *prev, int prev_stride, double *out_f64, double *out_internal, float *out_f32,
                      int16_t *grid_out, uint32_t *status, unsigned char *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)warp * PATH_CTA_STRIDE);
-  if (fsd_lane() == 0) {
-    unsigned char *mine = scratch + ((size_t)blockIdx.x * WPC + warp) * PATH_SCRATCH_BYTES;
+  const int grp = (int)threadIdx.x / PG::N;
+  PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)grp * PATH_CTA_STRIDE);
+  if (PG::lane() == 0) {
+    unsigned char *mine = scratch + ((size_t)blockIdx.x * PATH_FPC + grp) * PATH_SCRATCH_BYTES;
     S.pts = reinterpret_cast<d2 *>(mine);
     S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
   }
-  __syncwarp();
-  FSD_FRAME_LOOP(s, n_steps) {
+  PG::sync();
+  for (int s = (int)blockIdx.x * PATH_FPC + grp; s < n_steps; s += (int)gridDim.x * PATH_FPC) {
     const SkidReloc R = *reinterpret_cast<const SkidReloc *>(reloc + 8 * (size_t)traj_of_step[s]);
     int grid[2] = {0, 0};
     double *out = out_f64 + (size_t)s * FSD_HORIZON * 4;
     unsigned st = skidpad_step(S, R, table, n_table, index[s], known + 4 * (size_t)s, force_P ? (int)force_P[s] : 0,
                                prev + (size_t)s * prev_stride, P, out, out_internal + (size_t)s * FSD_HORIZON * 4, grid);
     if (out_f32)
-      for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += 32) out_f32[(size_t)s * FSD_HORIZON * 4 + i] = (float)out[i];
-    if (fsd_lane() == 0) {
+      for (int i = PG::lane(); i < FSD_HORIZON * 4; i += PG::N) out_f32[(size_t)s * FSD_HORIZON * 4 + i] = (float)out[i];
+    if (PG::lane() == 0) {
       status[s] = st;
       if (grid_out) {
         grid_out[2 * (size_t)s] = (int16_t)grid[0];
         grid_out[2 * (size_t)s + 1] = (int16_t)grid[1];
       }
     }
-    __syncwarp();
+    PG::sync();
   }
 }
 
 // Sequential semantics inside a trajectory: a step whose previous-path fallback fired (path too far from the car,
 // failed tail, ...) must see the PREVIOUS STEP's path (core_calculate_path.py:573), which the step-parallel launch
-// cannot know.  One warp per trajectory walks its steps in order and recomputes only the flagged ones.
+// cannot know.  One lane group per trajectory (CTAs of PG::N threads) walks its steps in order and recomputes only the
+// flagged ones.
 __global__ void __launch_bounds__(32) skid_fixup_kernel(DevParams P, int n_traj, const int32_t *step_offsets,
                                                         const double *reloc, const double *table, int n_table,
                                                         const int32_t *index, const double *known,
@@ -683,12 +482,12 @@ __global__ void __launch_bounds__(32) skid_fixup_kernel(DevParams P, int n_traj,
                                                         unsigned char *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
-  if (fsd_lane() == 0) {
+  if (PG::lane() == 0) {
     unsigned char *mine = scratch + (size_t)blockIdx.x * PATH_SCRATCH_BYTES;
     S.pts = reinterpret_cast<d2 *>(mine);
     S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
   }
-  __syncwarp();
+  PG::sync();
   const unsigned uses_prev = FSD_ST_FEW_CONES | FSD_ST_FEW_MATCHES | FSD_ST_FIT1_FAILED | FSD_ST_PATH_TOO_FAR |
                              FSD_ST_MPC_FAILED | FSD_ST_REF_RAISES | FSD_ST_UNSUPPORTED;
   for (int t = blockIdx.x; t < n_traj; t += gridDim.x) {
@@ -701,15 +500,15 @@ __global__ void __launch_bounds__(32) skid_fixup_kernel(DevParams P, int n_traj,
                                  out_internal + (size_t)(s - 1) * FSD_HORIZON * 4, P, out,
                                  out_internal + (size_t)s * FSD_HORIZON * 4, grid);
       if (out_f32)
-        for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += 32) out_f32[(size_t)s * FSD_HORIZON * 4 + i] = (float)out[i];
-      if (fsd_lane() == 0) {
+        for (int i = PG::lane(); i < FSD_HORIZON * 4; i += PG::N) out_f32[(size_t)s * FSD_HORIZON * 4 + i] = (float)out[i];
+      if (PG::lane() == 0) {
         status[s] = st;
         if (grid_out) {
           grid_out[2 * (size_t)s] = (int16_t)grid[0];
           grid_out[2 * (size_t)s + 1] = (int16_t)grid[1];
         }
       }
-      __syncwarp();
+      PG::sync();
     }
   }
 }
@@ -750,7 +549,7 @@ void set_smem(K kernel, size_t bytes) {
 
 // How a batch is planned (FSD_PLAN_MODE in the environment, read once; a measurement knob, not an API):
 //   (bit 0, the sort stage as two free-running kernels instead of one lockstep kernel, is always on since r2_h)
-//   bit 1: the path stage as three free-running kernels (path_phase_kernel) instead of one lockstep kernel
+//   (bit 1, the path stage as three free-running kernels cut at the fit boundaries, lost its A/B by 8 % and was removed)
 //   bit 2: the lockstep path kernel takes its rounds of frames from a counter instead of a static stride
 //   bit 3: fsd_plan_batch never splits a batch into two chunks on two streams
 //   bit 4: the path kernel discards a frame's point-buffer lines from L2 when the frame ends
@@ -784,17 +583,11 @@ int device_info(DeviceInfo **out) {
     set_smem(knn_kernel<double>, WPC * SORT_CTA_STRIDE);
     set_smem(match_kernel<float>, WPC * MATCH_CTA_STRIDE);
     set_smem(match_kernel<double>, WPC * MATCH_CTA_STRIDE);
-    set_smem(path_phase_kernel<float, 1>, WPC * PATH_P1_STRIDE);
-    set_smem(path_phase_kernel<double, 1>, WPC * PATH_P1_STRIDE);
-    set_smem(path_phase_kernel<float, 2>, WPC * PATH_CTA_STRIDE);
-    set_smem(path_phase_kernel<double, 2>, WPC * PATH_CTA_STRIDE);
-    set_smem(path_phase_kernel<float, 3>, WPC * PATH_CTA_STRIDE);
-    set_smem(path_phase_kernel<double, 3>, WPC * PATH_CTA_STRIDE);
     cudaFuncSetAttribute(path_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(path_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
-    cudaFuncSetAttribute(skid_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPC * PATH_CTA_STRIDE));
+    cudaFuncSetAttribute(skid_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATH_KERNEL_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sort_kernel<float>, CTA_THREADS, WPC * SORT_CTA_STRIDE);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, CTA_THREADS, PATH_KERNEL_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, path_kernel<float>, PATH_THREADS, PATH_KERNEL_SMEM);
     cudaFuncSetAttribute(initial_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INITIAL_SMEM);
     D.sort_ctas = a > 0 ? a : 1;
     D.path_ctas = b > 0 ? b : 1;
@@ -810,7 +603,7 @@ int device_info(DeviceInfo **out) {
       bool ok = cudaGetSymbolAddress(reinterpret_cast<void **>(&cached), g_initial_path) == cudaSuccess &&
                 cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
       if (ok) {
-        initial_path_kernel<<<1, 32, INITIAL_SMEM, st>>>(make_dev_params(dp), cached);
+        initial_path_kernel<<<1, PG::N, INITIAL_SMEM, st>>>(make_dev_params(dp), cached);
         ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
       }
       if (st) cudaStreamDestroy(st);
@@ -850,9 +643,9 @@ int *take_counters(DeviceInfo &D, cudaStream_t stream) {
   return p;
 }
 
-int grid_for(int n_frames, int sm_count, int ctas_per_sm) {
+int grid_for(int n_frames, int sm_count, int ctas_per_sm, int frames_per_cta = WPC) {
   long cap = (long)sm_count * ctas_per_sm;
-  long need = ((long)n_frames + WPC - 1) / WPC;
+  long need = ((long)n_frames + frames_per_cta - 1) / frames_per_cta;
   return (int)(need < cap ? need : cap);
 }
 
@@ -870,10 +663,10 @@ struct Carve {
 
 // upper bound of resident path CTAs (each owns PATH_SCRATCH_BYTES of point buffers in the workspace)
 size_t path_grid_bound(int n_frames) {
-  size_t cap = 160 * 16;  // no device visible: any current part
+  size_t cap = 160 * 32;  // no device visible: any current part
   DeviceInfo *D = nullptr;
-  if (device_info(&D) == FSD_OK) cap = (size_t)D->sm_count * D->path_ctas * WPC;
-  const size_t B = ((size_t)(n_frames > 0 ? n_frames : 0) + WPC - 1) / WPC * WPC;
+  if (device_info(&D) == FSD_OK) cap = (size_t)D->sm_count * D->path_ctas * PATH_FPC;
+  const size_t B = ((size_t)(n_frames > 0 ? n_frames : 0) + PATH_FPC - 1) / PATH_FPC * PATH_FPC;
   return B < cap ? B : cap;
 }
 
@@ -883,9 +676,9 @@ size_t path_grid_bound(int n_frames) {
 int first_chunk(int n_frames) {
   DeviceInfo *D = nullptr;
   if (device_info(&D) != FSD_OK || (plan_mode() & 8)) return n_frames;
-  const long wave = (long)D->sm_count * (D->path_ctas < D->sort_ctas ? D->path_ctas : D->sort_ctas) * WPC;
+  const long wave = (long)D->sm_count * D->path_ctas * PATH_FPC;
   if ((long)n_frames < 2 * wave) return n_frames;
-  return (n_frames / 2 + WPC - 1) / WPC * WPC;
+  return (n_frames / 2 + PATH_FPC - 1) / PATH_FPC * PATH_FPC;
 }
 
 size_t path_scratch_bytes(int n_frames) {
@@ -901,7 +694,6 @@ size_t workspace_bytes(int n_frames) {
   total += 2 * align_up(B * FSD_MAX_WV * sizeof(int16_t), 256);         // l2r, r2l
   total += align_up(B * 2 * sizeof(int16_t), 256);                      // grid
   total += align_up(FSD_HORIZON * 4 * sizeof(double), 256);             // initial path (non-default params)
-  total += align_up(B * sizeof(PathCarry), 256);                        // splines carried between the path phases
   total += align_up(B * 2 * FSD_MAX_SORTED * sizeof(int16_t), 256);     // sort indices when the caller wants none
   total += 2 * align_up(fsd_big_path_fixup_scratch_bytes(), 256);       // point buffers of the large-bounds second chance
   return total;
@@ -909,7 +701,6 @@ size_t workspace_bytes(int n_frames) {
 
 // resolve every intermediate tensor to user memory or workspace
 struct Extra {
-  PathCarry *carry = nullptr;
   int16_t *idx = nullptr;
   unsigned char *fixup[2] = {nullptr, nullptr};
 };
@@ -930,12 +721,10 @@ int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t
   int16_t *w_r2l = cv.take<int16_t>(B * FSD_MAX_WV);
   int16_t *w_grid = cv.take<int16_t>(B * 2);
   double *w_init = cv.take<double>(FSD_HORIZON * 4);
-  PathCarry *w_carry = cv.take<PathCarry>(B);
   int16_t *w_idx = cv.take<int16_t>(B * 2 * FSD_MAX_SORTED);
   unsigned char *w_fix0 = cv.take<unsigned char>(fsd_big_path_fixup_scratch_bytes());
   unsigned char *w_fix1 = cv.take<unsigned char>(fsd_big_path_fixup_scratch_bytes());
   if (extra) {
-    extra->carry = w_carry;
     extra->idx = w_idx;
     extra->fixup[0] = w_fix0;
     extra->fixup[1] = w_fix1;
@@ -972,7 +761,7 @@ int default_prev_path(const fsd_params *params, const DevParams &P, DeviceInfo &
     return FSD_OK;
   }
   if (!scratch) return FSD_ERR_ARG;  // non-default spline parameters: the caller must pass prev_path
-  initial_path_kernel<<<1, 32, INITIAL_SMEM, stream>>>(P, scratch);
+  initial_path_kernel<<<1, PG::N, INITIAL_SMEM, stream>>>(P, scratch);
   *prev = scratch;
   return check_launch();
 }
@@ -1008,12 +797,11 @@ int sort_match_impl(const fsd_params *params, int n_frames, const T *cones_xy, c
   return check_launch();
 }
 
-// `carry`: room for n_frames PathCarry records (split mode only)
 template <typename T>
 int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
               const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
               unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream,
-              PathCarry *carry = nullptr, unsigned char *fixup_scratch = nullptr) {
+              unsigned char *fixup_scratch = nullptr) {
   if (!path_scratch) return FSD_ERR_WORKSPACE;
   if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
   if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
@@ -1033,23 +821,10 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   }
   StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r, inter->r2l, out_status};
-  const int grid = grid_for(n_frames, D->sm_count, D->path_ctas);
-  int *counters = ((plan_mode() & 2) && carry) ? take_counters(*D, stream) : nullptr;
-  if (counters) {
-    path_phase_kernel<T, 1><<<grid, CTA_THREADS, WPC * PATH_P1_STRIDE, stream>>>(
-        P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch, carry,
-        counters);
-    path_phase_kernel<T, 2><<<grid, CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
-        P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch, carry,
-        counters + 1);
-    path_phase_kernel<T, 3><<<grid, CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
-        P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch, carry,
-        counters + 2);
-    return check_launch();
-  }
+  const int grid = grid_for(n_frames, D->sm_count, D->path_ctas, PATH_FPC);
   int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
   const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0);
-  path_kernel<T><<<grid, CTA_THREADS, PATH_KERNEL_SMEM, stream>>>(
+  path_kernel<T><<<grid, PATH_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
       round_counter, flags);
   rc = check_launch();
@@ -1133,7 +908,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                             out_status, stream, X.idx);
     if (rc != FSD_OK) return rc;
     rc = path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
-                      out_status, stream, X.carry, X.fixup[0]);
+                      out_status, stream, X.fixup[0]);
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
       cudaGetLastError();
       rc = FSD_ERR_LAUNCH;
@@ -1158,7 +933,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                               side->stream, X.idx + 2 * h * FSD_MAX_SORTED);
     if (rc == FSD_OK)
       rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
-                        stream, X.carry, X.fixup[0]);
+                        stream, X.fixup[0]);
     // the outputs of frames [0, na) are final here: a caller that passed an event can start consuming them (e.g. an
     // all-gather on a communication stream) while chunk B is still being planned
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
@@ -1168,8 +943,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
     if (rc == FSD_OK)
       rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
                         prev + h * (size_t)stride, stride, init_slot, scratch_b,
-                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.carry + h,
-                        X.fixup[1]);
+                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.fixup[1]);
   }
   // always join, so that the caller's stream never runs ahead of work queued on the side stream
   ok = cudaEventRecord(side->join, side->stream) == cudaSuccess && ok;
@@ -1232,7 +1006,7 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones) {
 int fsd_plan_launches(int n_frames) {
   if (n_frames <= 0) return 0;
   // sort (+ match as a kernel of its own), path (or its three phases), the large-bounds second chance of the path stage
-  const int per_chunk = 2 + ((plan_mode() & 2) ? 3 : 2);
+  const int per_chunk = 4;
   return first_chunk(n_frames) < n_frames ? 2 * per_chunk : per_chunk;
 }
 
@@ -1259,7 +1033,7 @@ int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stre
   DeviceInfo *D = nullptr;
   int rc = device_info(&D);
   if (rc != FSD_OK) return rc;
-  initial_path_kernel<<<1, 32, INITIAL_SMEM, static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params),
+  initial_path_kernel<<<1, PG::N, INITIAL_SMEM, static_cast<cudaStream_t>(stream)>>>(make_dev_params(*params),
                                                                                       out_prev_path);
   return check_launch();
 }
@@ -1369,22 +1143,16 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
   if (n_frames > 0 && (!workspace || workspace_bytes_given < path_grid_bound(n_frames) * PATH_SCRATCH_BYTES))
     return FSD_ERR_WORKSPACE;
   unsigned char *scratch = static_cast<unsigned char *>(workspace);
-  // the splines carried between the path phases sit behind the point buffers when the workspace has room for them (a
-  // workspace of fsd_workspace_bytes() always has); otherwise the stage runs as one kernel
-  PathCarry *carry = nullptr;
-  const size_t carry_at = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
+  // the point buffers of the large-bounds second chance sit behind the kernel's own when the workspace has room for them
+  // (a workspace of fsd_workspace_bytes() always has)
   unsigned char *fixup = nullptr;
-  if (n_frames > 0 && workspace_bytes_given >= carry_at + (size_t)n_frames * sizeof(PathCarry)) {
-    carry = reinterpret_cast<PathCarry *>(scratch + carry_at);
-    const size_t fix_at = align_up(carry_at + (size_t)n_frames * sizeof(PathCarry), 256);
-    if (workspace_bytes_given >= fix_at + fsd_big_path_fixup_scratch_bytes()) fixup = scratch + fix_at;
-  }
+  const size_t fix_at = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
+  if (n_frames > 0 && workspace_bytes_given >= fix_at + fsd_big_path_fixup_scratch_bytes()) fixup = scratch + fix_at;
   if (coords_f64)
     return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
-                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry,
-                             fixup);
+                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
-                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, carry, fixup);
+                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup);
 }
 
 size_t fsd_global_path_workspace_bytes(int n_poses) {
@@ -1475,14 +1243,14 @@ int fsd_skidpad_plan_batch(const fsd_params *params, int n_traj, int n_steps, co
                                               known, out_index, traj_of_step);
   rc = check_launch();
   if (rc != FSD_OK) return rc;
-  skid_step_kernel<<<grid_for(n_steps, D->sm_count, D->path_ctas), CTA_THREADS, WPC * PATH_CTA_STRIDE, stream>>>(
+  skid_step_kernel<<<grid_for(n_steps, D->sm_count, D->path_ctas, PATH_FPC), PATH_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_steps, reloc, traj_of_step, path_table, n_table, out_index, known, force_P, prev, stride, out_path_f64,
       out_internal_f64, out_path, out_grid, out_status, scratch);
   rc = check_launch();
   if (rc != FSD_OK || stride != 0) return rc;  // per-step previous paths given: the caller owns the chaining
   const long bound = (long)path_grid_bound(n_steps);
   const int fgrid = (int)(n_traj < bound ? n_traj : bound);
-  skid_fixup_kernel<<<fgrid, 32, PATH_CTA_STRIDE, stream>>>(P, n_traj, step_offsets, reloc, path_table, n_table,
+  skid_fixup_kernel<<<fgrid, PG::N, PATH_CTA_STRIDE, stream>>>(P, n_traj, step_offsets, reloc, path_table, n_table,
                                                             out_index, known, force_P, out_path_f64, out_internal_f64,
                                                             out_path, out_grid, out_status, scratch);
   return check_launch();

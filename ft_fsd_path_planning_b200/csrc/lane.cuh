@@ -127,6 +127,7 @@ struct Grp {
   FSD_DEV static unsigned ballot(bool p) { return __ballot_sync(mask(), p) >> base(); }  // bit i = lane i of the group
   FSD_DEV static int sum_i(int v) { return __reduce_add_sync(mask(), v); }
   FSD_DEV static int min_i(int v) { return __reduce_min_sync(mask(), v); }
+  FSD_DEV static int bcast0(int v) { return __shfl_sync(mask(), v, 0, G); }  // the value of the group's lane 0
   FSD_DEV static bool any(bool p) { return __any_sync(mask(), p); }
   __device__ __noinline__ static double sum(double v) {
     const unsigned m = mask();
@@ -185,7 +186,7 @@ struct Grp {
   FSD_DEV static int owned16() { return G == 32 ? (lane() >> 1) : lane(); }
   FSD_DEV static bool owner16() { return G == 32 ? (lane() & 1) == 0 : true; }
   // argmin with ties -> smallest index; lanes with idx < 0 do not take part; the result reaches every lane of the group
-  FSD_DEV static void argmin(double &v, int &idx) {
+  __device__ __noinline__ static void argmin(double &v, int &idx) {
     const unsigned m = mask();
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
@@ -211,6 +212,7 @@ struct Grp {
   static inline unsigned ballot(bool p) { return p ? 1u : 0u; }
   static inline int sum_i(int v) { return v; }
   static inline int min_i(int v) { return v; }
+  static inline int bcast0(int v) { return v; }
   static inline bool any(bool p) { return p; }
   static inline double sum(double v) { return v; }
   static inline double min_d(double v) { return v; }
@@ -241,19 +243,23 @@ FSD_DEV void wsum_vec(double (&)[N]) {}
 
 #endif
 
-// The path stage (spline.cuh, path.cuh) runs one frame per lane group: TWO frames per warp on the device (the kernels
-// are bound by instruction delivery, and most of the path code keeps 16 lanes or fewer busy: the banded solve has 18
-// tasks, the reductions and the control flow are shared by both frames of the warp), one lane on the host.
+// The path stage (spline.cuh, path.cuh) runs one frame per lane group of FSD_PATH_LANES lanes: the whole warp by default,
+// one lane on the host.  (-DFSD_PATH_LANES=16 plans TWO frames per warp.  Measured, profiles/r2_plan_mode_ab.txt: the two
+// half-warps run diverged almost all the time -- warp instructions per frame fall by only 7 %, not the ~30 % their shared
+// control flow and 18-task solves promise -- while the doubled shared-memory footprint costs a quarter of the resident
+// warps and half of L1: 1.68 ms against 1.39 ms.  Kept as a build option, off.)
 #ifndef FSD_PATH_LANES
-#define FSD_PATH_LANES 16
+#define FSD_PATH_LANES 32
 #endif
 #ifdef FSD_DEVICE_BUILD
 using PG = Grp<FSD_PATH_LANES>;
 #else
 using PG = Grp<1>;
 #endif
-// `count` independent tasks, at most one per lane of the path lane group and round
-#ifdef FSD_DEVICE_BUILD
+// `count` (<= 32) independent tasks, one per lane of the path lane group (in rounds when the group is narrower)
+#if defined(FSD_DEVICE_BUILD) && FSD_PATH_LANES >= 32
+#define FSD_FOR_PTASKS(e, count) if (const int e = PG::lane(); e < (count))
+#elif defined(FSD_DEVICE_BUILD)
 #define FSD_FOR_PTASKS(e, count) for (int e = PG::lane(); e < (count); e += PG::N)
 #else
 #define FSD_FOR_PTASKS(e, count) for (int e = 0; e < (count); ++e)

@@ -72,8 +72,8 @@ FSD_DEV double orient(const d2 &p0, const d2 &p1, const d2 &p2) {
 // shift to the window mean below cancels a few digits at most) instead of re-reading 25 points per window: 31 point
 // visits per lane instead of 100.  curv[i] = sign / clamp(radius, 1, 3000).
 FSD_DEVFN void curvature_windows(const d2 *p, int Pn, int hw, double *curv) {
-  const int per = (Pn + FSD_LANES - 1) / FSD_LANES;
-  const int i0 = fsd_lane() * per, i1 = i0 + per < Pn ? i0 + per : Pn;
+  const int per = (Pn + PG::N - 1) / PG::N;
+  const int i0 = PG::lane() * per, i1 = i0 + per < Pn ? i0 + per : Pn;
   if (i0 >= i1) return;
   const double ox = p[i0].x, oy = p[i0].y;
   double s1x = 0, s1y = 0, sxx = 0, sxy = 0, syy = 0, sxxx = 0, sxxy = 0, sxyy = 0, syyy = 0, sz2 = 0;
@@ -127,15 +127,15 @@ FSD_DEVFN void curvature_windows(const d2 *p, int Pn, int hw, double *curv) {
 FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, double &r) {
   double sx = 0.0, sy = 0.0;
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+  for (int i = PG::lane(); i < n; i += PG::N) {
     sx += p[i].x;
     sy += p[i].y;
   }
   const double inv_n = frcp((double)n);
-  const double mx = wsum(sx) * inv_n, my = wsum(sy) * inv_n;
+  const double mx = PG::sum(sx) * inv_n, my = PG::sum(sy) * inv_n;
   double Mxy = 0, Mxx = 0, Myy = 0, Mxz = 0, Myz = 0, Mzz = 0;
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+  for (int i = PG::lane(); i < n; i += PG::N) {
     double xi = p[i].x - mx, yi = p[i].y - my, zi = xi * xi + yi * yi;
     Mxy += xi * yi;
     Mxx += xi * xi;
@@ -144,34 +144,34 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
     Myz += yi * zi;
     Mzz += zi * zi;
   }
-  Mxy = wsum(Mxy) * inv_n;
-  Mxx = wsum(Mxx) * inv_n;
-  Myy = wsum(Myy) * inv_n;
-  Mxz = wsum(Mxz) * inv_n;
-  Myz = wsum(Myz) * inv_n;
-  Mzz = wsum(Mzz) * inv_n;
+  Mxy = PG::sum(Mxy) * inv_n;
+  Mxx = PG::sum(Mxx) * inv_n;
+  Myy = PG::sum(Myy) * inv_n;
+  Mxz = PG::sum(Mxz) * inv_n;
+  Myz = PG::sum(Myz) * inv_n;
+  Mzz = PG::sum(Mzz) * inv_n;
   hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, cx, cy, r);
 }
 
 // ---- chord-length parameters: u[0] = 0, u[i] = u[i-1] + |p_i - p_{i-1}| (np.cumsum) -------------------
 
 FSD_DEVFN void chord_params(const d2 *p, int m, double *u) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   double carry = 0.0;
   if (lane == 0) u[0] = 0.0;
 #pragma unroll 1
-  for (int base = 1; base < m; base += FSD_LANES) {
+  for (int base = 1; base < m; base += PG::N) {
     const int i = base + lane;
     double d = 0.0;
     if (i < m) {
       double ddx = p[i].x - p[i - 1].x, ddy = p[i].y - p[i - 1].y;
       d = fsqrt(ddx * ddx + ddy * ddy);
     }
-    double incl = wscan_incl(d) + carry;
+    double incl = PG::scan_incl(d) + carry;
     if (i < m) u[i] = incl;
-    carry = wlast(incl);
+    carry = PG::last(incl);
   }
-  wsync();
+  PG::sync();
 }
 
 // ---- the path pipeline as a resumable state machine -----------------------------------------------------------------
@@ -210,13 +210,13 @@ FSD_DEV bool pm_is_alignment_state(int st) { return st == PS_FIT1_DONE || st == 
 // x, y of the previous path (40 x 4, global memory) into dst[0 .. 40): only the fallbacks need them, so they are read
 // when a fallback fires instead of being kept in shared memory
 FSD_DEVFN void pm_prev_to(const PathMachine &M, d2 *dst) {
-  wsync();
+  PG::sync();
 #pragma unroll 1
-  for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
+  for (int i = PG::lane(); i < FSD_HORIZON; i += PG::N) {
     dst[i].x = M.prev[4 * i + 1];
     dst[i].y = M.prev[4 * i + 2];
   }
-  wsync();
+  PG::sync();
 }
 
 // evaluate the fitted spline every `step` up to max_u into dst (len(np.arange(0, max_u, step)) points)
@@ -224,27 +224,27 @@ FSD_DEVFN int pm_evaluate(PathSmem &S, double max_u, double step, d2 *dst, int d
   const double q = ceil(fdiv(max_u, step));
   const int n = q > 0.0 ? (q > 1e6 ? 1000000 : (int)q) : 0;
   if (n > dst_cap) return -1;
-  wsync();
+  PG::sync();
 #pragma unroll 1
-  for (int i = fsd_lane(); i < n; i += FSD_LANES) {
+  for (int i = PG::lane(); i < n; i += PG::N) {
     double x, y;
     spline_point(S.W, (double)i * step, x, y);
     dst[i].x = x;
     dst[i].y = y;
   }
-  wsync();
+  PG::sync();
   return n;
 }
 
 FSD_DEVFN void pm_finish_with_prev(PathMachine &M, unsigned bits) {
   M.status |= bits;
-  wsync();
+  PG::sync();
 #pragma unroll 1
-  for (int i = fsd_lane(); i < FSD_HORIZON * 4; i += FSD_LANES) M.out[i] = M.prev[i];
+  for (int i = PG::lane(); i < FSD_HORIZON * 4; i += PG::N) M.out[i] = M.prev[i];
   M.P_grid = 0;
   M.n_trim = 0;
   M.state = PS_DONE;
-  wsync();
+  PG::sync();
 }
 
 // the tail failed with return code rc: ValueError -> once more with the previous path (:561-570), else give up
@@ -274,15 +274,15 @@ FSD_DEVFN void pm_start_fit1(PathSmem &S, PathMachine &M, const d2 *src, int m, 
 
 // overwrite_path_if_it_is_too_far_away :225-237 on the path update S.pts[1 .. 1+nu), then the tail
 FSD_DEVFN void pm_enter_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   double best = INFINITY;
 #pragma unroll 1
-  for (int i = lane; i < M.nu; i += FSD_LANES) {  // the smallest distance to the car, squared (only compared)
+  for (int i = lane; i < M.nu; i += PG::N) {  // the smallest distance to the car, squared (only compared)
     const double ddx = M.F.px - S.pts[1 + i].x, ddy = M.F.py - S.pts[1 + i].y;
     best = fmin(best, ddx * ddx + ddy * ddy);
   }
-  best = wmin_d(best);
-  wsync();
+  best = PG::min_d(best);
+  PG::sync();
   if (best > P.max_valid_dist * P.max_valid_dist) {
     M.status |= FSD_ST_PATH_TOO_FAR;
     pm_prev_to(M, S.pts + 1);
@@ -294,31 +294,31 @@ FSD_DEVFN void pm_enter_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
 
 // _refit_spline :125-161 on S.pts[0..n): path length, sub-sampling, start of fit #3
 FSD_DEVFN void pm_start_fit3(PathSmem &S, PathMachine &M, int n, const DevParams &P) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   if (n < 2) {
     pm_tail_failed(S, M, RC_RAISES);
     return;
   }
   double len = 0.0, first10 = 0.0;
 #pragma unroll 1
-  for (int i = lane; i + 1 < n; i += FSD_LANES) {
+  for (int i = lane; i + 1 < n; i += PG::N) {
     const double d = fnorm(S.pts[i + 1].x - S.pts[i].x, S.pts[i + 1].y - S.pts[i].y);
     len += d;
     if (i < 10) first10 += d;
   }
-  const double path_length = wsum(len);
+  const double path_length = PG::sum(len);
   const int nm = n - 1 < 10 ? n - 1 : 10;
-  const double mean_dist = fdiv(wsum(first10), (double)nm);
+  const double mean_dist = fdiv(PG::sum(first10), (double)nm);
   M.predict_every = fdiv(fdiv(path_length, (double)FSD_HORIZON), 3.0);
   const double ratio = fdiv(M.predict_every, mean_dist);
   int skip = 1;
   if (isfinite(ratio) && ratio < 1e6 && (int)ratio > 1) skip = (int)ratio;
   const int ms = (n + skip - 1) / skip;
-  wsync();
+  PG::sync();
   if (skip > 1) {
     if (lane == 0)
       for (int i = 1; i < ms; ++i) S.pts[i] = S.pts[i * skip];  // path[::skip]
-    wsync();
+    PG::sync();
   }
   chord_params(S.pts, ms, S.u);
   fit_init(S.W, M.fit, S.pts, S.u, ms, P.refit_smoothing);
@@ -327,7 +327,7 @@ FSD_DEVFN void pm_start_fit3(PathSmem &S, PathMachine &M, int n, const DevParams
 
 // connect_path_to_car, extend_path, remove_path_behind_car (core_calculate_path.py:430-465, 261-334), start of fit #2
 FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const FramePose &F = M.F;
   if (M.nu < 1) {
     pm_tail_failed(S, M, RC_RAISES);
@@ -339,7 +339,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
     const double fx = path[0].x - F.px, fy = path[0].y - F.py;
     const double d = fnorm(fx, fy);
     const bool behind = cos_between(fx, fy, F.dx, F.dy) < 0.0;  // angle > pi/2
-    wsync();
+    PG::sync();
     if (!(d < 0.5 || behind)) {
       if (lane == 0) {
         S.pts[0].x = F.px + fdiv(fx, d) * 0.2;
@@ -348,17 +348,17 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
       path = S.pts;
       n = M.nu + 1;
     }
-    wsync();
+    PG::sync();
   }
   {
     int first = n;
 #pragma unroll 1
-    for (int i = lane; i < n; i += FSD_LANES)
+    for (int i = lane; i < n; i += PG::N)
       if ((path[i].x - F.px) * F.dx + (path[i].y - F.py) * F.dy > 0.0) {
         first = i;
         break;
       }
-    first = wmin_i(first);
+    first = PG::min_i(first);
     int start = n - 20 < 0 ? 0 : n - 20;
     if (first < start) start = first;
     const int nf = n - start;
@@ -368,8 +368,8 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
     }
     double part = 0.0;
 #pragma unroll 1
-    for (int i = start + lane; i + 1 < n; i += FSD_LANES) part += fnorm(path[i + 1].x - path[i].x, path[i + 1].y - path[i].y);
-    const double plen = wsum(part);
+    for (int i = start + lane; i + 1 < n; i += PG::N) part += fnorm(path[i + 1].x - path[i].x, path[i + 1].y - path[i].y);
+    const double plen = PG::sum(part);
     if (!(plen > P.mpc_len)) {
       const int nr = nf < 20 ? nf : 20;
       const d2 *rel = path + (n - nr);
@@ -390,9 +390,9 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
         const double a0 = fsd_atan2(p0.y, p0.x), a1 = a0 + sg * PI;
         const double stepa = fdiv(a1 - a0, 49.0);  // np.linspace(a0, a1) has 50 samples; the first is dropped
         const double r0x = fsd_cos(a0) * r_use, r0y = fsd_sin(a0) * r_use;
-        wsync();
+        PG::sync();
 #pragma unroll 1
-        for (int i = 1 + lane; i < 50; i += FSD_LANES) {
+        for (int i = 1 + lane; i < 50; i += PG::N) {
           const double ang = i == 49 ? a1 : (double)i * stepa + a0;
           path[n + i - 1].x = fsd_cos(ang) * r_use - r0x + lastx;
           path[n + i - 1].y = fsd_sin(ang) * r_use - r0y + lasty;
@@ -403,22 +403,22 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
         const double nrm = fnorm(ddx, ddy);
         ddx = fdiv(ddx, nrm);
         ddy = fdiv(ddy, nrm);
-        wsync();
+        PG::sync();
 #pragma unroll 1
-        for (int i = 1 + lane; i < 30; i += FSD_LANES) {
+        for (int i = 1 + lane; i < 30; i += PG::N) {
           path[n + i - 1].x = lastx + ddx * (double)i;
           path[n + i - 1].y = lasty + ddy * (double)i;
         }
         n += 29;
       }
-      wsync();
+      PG::sync();
     }
   }
   // first point of minimal distance to the car
   double bv = 0.0;
   int bi = -1;
 #pragma unroll 1
-  for (int i = lane; i < n; i += FSD_LANES) {
+  for (int i = lane; i < n; i += PG::N) {
     const double ddx = F.px - path[i].x, ddy = F.py - path[i].y;
     const double d = ddx * ddx + ddy * ddy;  // arg-min of the distance: squared
     if (bi < 0 || d < bv) {
@@ -426,7 +426,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
       bi = i;
     }
   }
-  wargmin(bv, bi);
+  PG::argmin(bv, bi);
   // refit_path_for_mpc_with_safety_factor :239-259
   const int off = (int)(path - S.pts) + bi, m2 = n - bi;
   if (m2 < 2) {
@@ -440,7 +440,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
 
 // fit #2 is done: evaluate up to 1.5 x the MPC length, keep the first mpc_path_length metres (:467-499), start fit #3
 FSD_DEVFN void pm_stage_after_fit2(PathSmem &S, PathMachine &M, const DevParams &P) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   if (M.fit.ier == 10) {
     pm_tail_failed(S, M, (M.tail_status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR);
     return;
@@ -454,22 +454,22 @@ FSD_DEVFN void pm_stage_after_fit2(PathSmem &S, PathMachine &M, const DevParams 
   int first_over = nfix;
   double carry = 0.0;
 #pragma unroll 1
-  for (int base = 0; base < nfix - 1; base += FSD_LANES) {
+  for (int base = 0; base < nfix - 1; base += PG::N) {
     const int i = base + lane;
     double d = 0.0;
     if (i < nfix - 1) d = fnorm(S.pts[i + 1].x - S.pts[i].x, S.pts[i + 1].y - S.pts[i].y);
-    const double incl = wscan_incl(d) + carry;
+    const double incl = PG::scan_incl(d) + carry;
     if (i < nfix - 1 && incl > P.mpc_len && i < first_over) first_over = i;
-    carry = wlast(incl);
+    carry = PG::last(incl);
   }
-  first_over = wmin_i(first_over);
+  first_over = PG::min_i(first_over);
   M.n_trim = first_over >= nfix ? nfix - 1 : first_over;
   pm_start_fit3(S, M, M.n_trim, P);
 }
 
 // fit #3 is done: evaluation grid, curvature, 40 samples (path_parameterization.py:163-295)
 FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams &P) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   if (M.fit.ier == 10) {
     pm_tail_failed(S, M, (M.tail_status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR);
     return;
@@ -499,15 +499,15 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
     pm_tail_failed(S, M, RC_UNSUPPORTED);
     return;
   }
-  wsync();
+  PG::sync();
 #pragma unroll 1
-  for (int i = lane; i < Pn; i += FSD_LANES) {
+  for (int i = lane; i < Pn; i += PG::N) {
     double x, y;
     spline_point(S.W, (double)i * predict_every, x, y);
     S.pts[i].x = x;
     S.pts[i].y = y;
   }
-  wsync();
+  PG::sync();
   // _calculate_path_curvature :163-193 / calculate_path_curvature :49-93 (open path).  The curvature samples live in the
   // fit's normal-equation storage: the fits are over, only knots and coefficients of the last one are still needed.
   static_assert(sizeof(S.W.N) >= GRID_CAP * sizeof(double), "curvature samples alias SplineWork::N");
@@ -516,13 +516,13 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   if (window % 2 == 0) window += 1;
   const int hw = window / 2;
   curvature_windows(S.pts, Pn, hw, curv);
-  wsync();
+  PG::sync();
   // uniform_filter1d(size, mode="nearest") evaluated at the 40 sampled indices only;
   // indices np.linspace(0, P-1, 40, dtype=int) (:277-282)
   const int fs = window / 2 > 2 ? window / 2 : 2;
   const double stp = fdiv((double)(Pn - 1), (double)(FSD_HORIZON - 1));
 #pragma unroll 1
-  for (int j = lane; j < FSD_HORIZON; j += FSD_LANES) {
+  for (int j = lane; j < FSD_HORIZON; j += PG::N) {
     const int idx = j == FSD_HORIZON - 1 ? Pn - 1 : (int)floor((double)j * stp);
     double acc = 0.0;
 #pragma unroll 1
@@ -535,7 +535,7 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
     M.out[4 * j + 2] = S.pts[idx].y;
     M.out[4 * j + 3] = fdiv(acc, (double)fs);
   }
-  wsync();
+  PG::sync();
   M.status |= M.tail_status;
   M.state = PS_DONE;
 }
@@ -638,7 +638,7 @@ FSD_DEVFN void pm_init(PathSmem &S, PathMachine &M, int mode, const FramePose &F
 FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int nl, const d2 *right, int nr,
                               const int16_t *l2r, const int16_t *r2l, const FramePose &F, int force_P,
                               const double *prev, const DevParams &P, double *out) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   pm_init(S, M, 0, F, force_P, prev, out);
   // the data of fit #1 (centre line of the matches, or the previous path) lives at the start of the point buffer, which
   // is free until the fit has been evaluated
@@ -649,13 +649,13 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
     // select_side_to_use :165-183: max over (number of matches, sum of match indices), ties -> left; one cone per lane
     int nml = 0, nmr = 0, sl = 0, sr = 0;
 #pragma unroll 1
-    for (int base = 0; base < nl || base < nr; base += FSD_LANES) {
+    for (int base = 0; base < nl || base < nr; base += PG::N) {
       const int i = base + lane;
       const int ml = i < nl ? (int)l2r[i] : -1, mr = i < nr ? (int)r2l[i] : -1;
-      nml += FSD_POPC(wballot(ml != -1));
-      nmr += FSD_POPC(wballot(mr != -1));
-      sl += wsum_i(ml != -1 ? ml : 0);
-      sr += wsum_i(mr != -1 ? mr : 0);
+      nml += FSD_POPC(PG::ballot(ml != -1));
+      nmr += FSD_POPC(PG::ballot(mr != -1));
+      sl += PG::sum_i(ml != -1 ? ml : 0);
+      sr += PG::sum_i(mr != -1 ? mr : 0);
     }
     const bool use_left = !(nmr > nml || (nmr == nml && sr > sl));
     const d2 *a = use_left ? left : right, *b = use_left ? right : left;
@@ -664,10 +664,10 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
     // calculate_centerline_points_of_matches :185-205: the matched cones in order, compacted by ballot
     int nc = 0;
 #pragma unroll 1
-    for (int base = 0; base < ns; base += FSD_LANES) {
+    for (int base = 0; base < ns; base += PG::N) {
       const int i = base + lane;
       const int m = i < ns ? (int)mt[i] : -1;
-      const unsigned mask = wballot(m != -1);
+      const unsigned mask = PG::ballot(m != -1);
       const int slot = nc + FSD_POPC(mask & ((1u << lane) - 1u));
       if (m != -1 && slot < FSD_HORIZON) {
         S.pts[slot].x = (a[i].x + b[m].x) / 2.0;
@@ -676,7 +676,7 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
       nc += FSD_POPC(mask);
     }
     if (nc > FSD_HORIZON) nc = FSD_HORIZON;
-    wsync();
+    PG::sync();
     if (nc < 2)
       M.status |= FSD_ST_FEW_MATCHES;
     else
@@ -695,24 +695,24 @@ FSD_DEVFN void pm_begin_frame(PathSmem &S, PathMachine &M, const d2 *left, int n
 // closest point by a warp arg-min (first minimum, like np.argmin), the kept points compacted by ballot in rolled order.
 FSD_DEVFN void pm_begin_global(PathSmem &S, PathMachine &M, const double *gpath, int Mn, const FramePose &F, int force_P,
                                const double *prev, const DevParams &P, double *out) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   pm_init(S, M, 0, F, force_P, prev, out);
   double bv = 0.0;
   int bi = -1;
 #pragma unroll 1
-  for (int i = lane; i < Mn; i += FSD_LANES) {
+  for (int i = lane; i < Mn; i += PG::N) {
     const double d = fnorm(F.px - gpath[2 * i], F.py - gpath[2 * i + 1]);
     if (bi < 0 || d < bv) {
       bv = d;
       bi = i;
     }
   }
-  wargmin(bv, bi);
+  PG::argmin(bv, bi);
   int ncl = 0;
   bool overflow = false;
   const int third = Mn / 3;
 #pragma unroll 1
-  for (int base = 0; base < Mn; base += FSD_LANES) {
+  for (int base = 0; base < Mn; base += PG::N) {
     const int i = base + lane;
     bool keep = false;
     double x = 0.0, y = 0.0;
@@ -723,7 +723,7 @@ FSD_DEVFN void pm_begin_global(PathSmem &S, PathMachine &M, const double *gpath,
       y = gpath[2 * src + 1];
       keep = fnorm(F.px - x, F.py - y) < 30.0;
     }
-    const unsigned mask = wballot(keep);
+    const unsigned mask = PG::ballot(keep);
     const int slot = ncl + FSD_POPC(mask & ((1u << lane) - 1u));
     if (keep) {
       if (slot < PCAP) {
@@ -735,12 +735,12 @@ FSD_DEVFN void pm_begin_global(PathSmem &S, PathMachine &M, const double *gpath,
     }
     ncl += FSD_POPC(mask);
   }
-  if (wany(overflow)) {
+  if (PG::any(overflow)) {
     // more points within 30 m than the point buffer holds: flagged, planned with the previous path
     pm_finish_with_prev(M, FSD_ST_OVERFLOW | FSD_ST_UNSUPPORTED);
     return;
   }
-  wsync();
+  PG::sync();
   pm_start_fit1(S, M, S.pts, ncl, P);
 }
 
@@ -760,13 +760,13 @@ FSD_DEVFN void pm_begin_initial(PathSmem &S, PathMachine &M, const DevParams &P,
   const double max_angle = PI / 50.0, radius = 1000.0, stp = max_angle / (FSD_HORIZON - 1);
   const double c = fsd_cos(-PI / 2.0), s = fsd_sin(-PI / 2.0);
 #pragma unroll 1
-  for (int i = fsd_lane(); i < FSD_HORIZON; i += FSD_LANES) {
+  for (int i = PG::lane(); i < FSD_HORIZON; i += PG::N) {
     const double a = i == FSD_HORIZON - 1 ? max_angle : (double)i * stp;
     const double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;
     S.pts[i].x = px * c - py * s;
     S.pts[i].y = px * s + py * c;
   }
-  wsync();
+  PG::sync();
   pm_start_fit1(S, M, S.pts, FSD_HORIZON, P);
 }
 
@@ -783,11 +783,11 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
   PathMachine M;
   pm_begin_frame(S, M, left, nl, right, nr, l2r, r2l, F, force_P, prev, P, out);
   pm_run(S, M, P);
-  if (grid && fsd_lane() == 0) {
+  if (grid && PG::lane() == 0) {
     grid[0] = M.P_grid;
     grid[1] = M.n_trim;
   }
-  wsync();
+  PG::sync();
   return M.status;
 }
 
@@ -796,11 +796,11 @@ FSD_DEVFN unsigned path_global(PathSmem &S, const double *gpath, int Mn, const F
   PathMachine M;
   pm_begin_global(S, M, gpath, Mn, F, force_P, prev, P, out);
   pm_run(S, M, P);
-  if (grid && fsd_lane() == 0) {
+  if (grid && PG::lane() == 0) {
     grid[0] = M.P_grid;
     grid[1] = M.n_trim;
   }
-  wsync();
+  PG::sync();
   return M.status;
 }
 
@@ -809,11 +809,11 @@ FSD_DEVFN unsigned path_from_update(PathSmem &S, int nu, const FramePose &F, int
   PathMachine M;
   pm_begin_update(S, M, nu, F, force_P, prev, P, out);
   pm_run(S, M, P);
-  if (grid && fsd_lane() == 0) {
+  if (grid && PG::lane() == 0) {
     grid[0] = M.P_grid;
     grid[1] = M.n_trim;
   }
-  wsync();
+  PG::sync();
   return M.status;
 }
 

@@ -323,7 +323,7 @@ FSD_DEVFN void skidpad_track(const SkidReloc &R, const double *table, int n_tabl
 FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *table, int n_table, int index,
                                 const double *known, int force_P, const double *prev, const DevParams &P, double *out,
                                 double *out_internal, int *grid) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const FramePose F = make_pose(known[0], known[1], known[2], known[3]);
   int nu;
   if (index >= 0) {
@@ -335,7 +335,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     nu = fin - index;
     if (nu > PCAP - 64) nu = PCAP - 64;
 #pragma unroll 1
-    for (int i = lane; i < nu; i += FSD_LANES) {
+    for (int i = lane; i < nu; i += PG::N) {
       S.pts[1 + i].x = table[2 * (index + i)];
       S.pts[1 + i].y = table[2 * (index + i) + 1];
     }
@@ -346,7 +346,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     const double yaw = fsd_atan2(F.dy, F.dx), cy = fsd_cos(yaw), sy = fsd_sin(yaw);
     nu = FSD_HORIZON - 1;
 #pragma unroll 1
-    for (int i = lane; i < nu; i += FSD_LANES) {
+    for (int i = lane; i < nu; i += PG::N) {
       const int k = i + 1;
       const double a = k == FSD_HORIZON - 1 ? max_angle : (double)k * stp;
       const double px = (fsd_cos(a) - 1.0) * radius, py = fsd_sin(a) * radius;
@@ -355,11 +355,11 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
       S.pts[1 + i].y = qx * sy + qy * cy + F.py;
     }
   }
-  wsync();
+  PG::sync();
   unsigned status = path_from_update(S, nu, F, force_P, prev, P, out_internal, grid);
-  wsync();
+  PG::sync();
 #pragma unroll 1
-  for (int i = lane; i < FSD_HORIZON; i += FSD_LANES) {
+  for (int i = lane; i < FSD_HORIZON; i += PG::N) {
     double x = out_internal[4 * i + 1], y = out_internal[4 * i + 2];
     if (index >= 0) skid_to_original(R, x, y, x, y);
     out[4 * i] = out_internal[4 * i];
@@ -367,7 +367,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     out[4 * i + 2] = y;
     out[4 * i + 3] = out_internal[4 * i + 3];
   }
-  wsync();
+  PG::sync();
   return status;
 }
 

@@ -60,7 +60,7 @@ struct SplineWork {
 FSD_DEVFN void knot_reciprocals(SplineWork &W, int n, int k) {
   const int nrint = n - 2 * k - 1;
 #pragma unroll 1
-  for (int e = fsd_lane(); e < nrint * 6; e += FSD_LANES) {
+  for (int e = PG::lane(); e < nrint * 6; e += PG::N) {
     const int ii = e / 6, q = e % 6;
     const int j = q == 0 ? 1 : (q < 3 ? 2 : 3);
     const int i = q == 0 ? 1 : (q < 3 ? q : q - 2);
@@ -72,7 +72,7 @@ FSD_DEVFN void knot_reciprocals(SplineWork &W, int n, int k) {
     }
     W.rk[ii][q] = r;
   }
-  wsync();
+  PG::sync();
 }
 
 // B-spline basis values of degree k at x for knot interval ii (t[k+ii] <= x < t[k+ii+1]); fully unrolled,
@@ -175,12 +175,13 @@ FSD_DEV void chol_task(int e, int kbm, int npairs, int &ta, int &tb) {
 // All lanes return the same flag: false on a non-positive pivot.
 FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[2], double (*z)[2], double (*c)[2],
                           double *rpiv) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const int kbm = kb - 1, npairs = kbm * (kbm + 1) / 2, ntasks = npairs + 2 * kbm;
 #pragma unroll 1
-  for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&z[0][0])[e] = (&rhs[0][0])[e];
+  for (int e = lane; e < nk1 * 2; e += PG::N) (&z[0][0])[e] = (&rhs[0][0])[e];
 #ifdef FSD_DEVICE_BUILD
-  // this lane's task as three running pointers (factor, multiplier, target) and the first row without a target
+  // this lane's tasks as running pointers (factor, multiplier, target) and the first row without a target; a group of 16
+  // lanes has up to 18 tasks, so lanes 0 and 1 carry a second one
   int ta = 0, tb = 0;
   chol_task(lane, kbm, npairs, ta, tb);
   const bool is_pair = lane < npairs, has_task = lane < ntasks;
@@ -189,21 +190,40 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
   double *pt = is_pair ? &M[ta][tb - ta] : &z[ta][tb & 1];
   const int sb = is_pair ? BW : 2;
   const int ilim = has_task ? nk1 - (is_pair ? tb : ta) : 0;
-  wsync();
+#if FSD_PATH_LANES < 18
+  // second task of lanes 0 and 1 (groups narrower than the task list)
+  const int e2 = lane + PG::N;
+  const bool has2 = e2 < ntasks;
+  int ta2 = 1, tb2 = 0;
+  if (has2) chol_task(e2, kbm, npairs, ta2, tb2);
+  const bool is_pair2 = e2 < npairs;
+  const double *pa2 = &M[0][has2 ? ta2 : 0];
+  const double *pb2 = is_pair2 ? &M[0][tb2] : &z[0][tb2 & 1];
+  double *pt2 = is_pair2 ? &M[ta2][tb2 - ta2] : &z[ta2][tb2 & 1];
+  const int sb2 = is_pair2 ? BW : 2;
+  const int ilim2 = has2 ? nk1 - (is_pair2 ? tb2 : ta2) : 0;
+#endif
+  PG::sync();
 #pragma unroll 1
   for (int i = 0; i < nk1; ++i) {
     const double s = M[i][0];
     if (!(s > 0.0)) return false;
     const double rs = frcp(s);
     if (i < ilim) *pt -= *pa * rs * *pb;
+#if FSD_PATH_LANES < 18
+    if (i < ilim2) *pt2 -= *pa2 * rs * *pb2;
+    pa2 += BW;
+    pb2 += sb2;
+    pt2 += sb2;
+#endif
     if (lane == 0) rpiv[i] = rs;
     pa += BW;
     pb += sb;
     pt += sb;
-    wsync();
+    PG::sync();
   }
 #else
-  wsync();
+  PG::sync();
 #pragma unroll 1
   for (int i = 0; i < nk1; ++i) {
     const double s = M[i][0];
@@ -226,7 +246,7 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
   const int nback = 2 * kb;
 #pragma unroll 1
   for (int i = nk1 - 1; i >= 0; --i) {
-    FSD_FOR_TASKS(e, nback) {
+    FSD_FOR_PTASKS(e, nback) {
       const int l = e >> 1, col = e & 1;
       const double ci = z[i][col] * rpiv[i];
       if (l == 0)
@@ -234,7 +254,7 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
       else if (i - l >= 0)
         z[i - l][col] -= M[i - l][l] * ci;
     }
-    wsync();
+    PG::sync();
   }
   return true;
 }
@@ -244,7 +264,7 @@ FSD_DEVFN bool chol_solve(double (*M)[BW], int nk1, int kb, const double (*rhs)[
 // -- no search over the data.
 FSD_DEVFN void interval_starts(SplineWork &W, int m, int n, int k) {
   const int nrint = n - 2 * k - 1;
-  if (fsd_lane() == 0) {
+  if (PG::lane() == 0) {
     int s = 0;
     W.start[0] = 0;
 #pragma unroll 1
@@ -254,24 +274,24 @@ FSD_DEVFN void interval_starts(SplineWork &W, int m, int n, int k) {
     }
     W.start[nrint] = m;
   }
-  wsync();
+  PG::sync();
 }
 
 // N = B^T B and r = B^T x for the current knots (k == 3 uses all 4 x 4 entries; lower degrees fewer)
 FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, int n, int k) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const int nk1 = n - k - 1, nrint = n - 2 * k - 1, k1 = k + 1;
 #pragma unroll 1
-  for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.N[0][0])[i] = 0.0;
+  for (int i = lane; i < nk1 * BW; i += PG::N) (&W.N[0][0])[i] = 0.0;
 #pragma unroll 1
-  for (int i = lane; i < nk1 * 2; i += FSD_LANES) (&W.rhs[0][0])[i] = 0.0;
+  for (int i = lane; i < nk1 * 2; i += PG::N) (&W.rhs[0][0])[i] = 0.0;
 #ifdef FSD_DEVICE_BUILD
   // the sum this lane owns after the transposed reduction below and where it goes (relative to knot interval 0)
   double *own_base = &W.N[0][0];
   int own_stride = BW;
-  bool own_ok = (lane & 1) == 0;
+  bool own_ok = PG::owner16();
   {
-    const int e = lane >> 1;
+    const int e = PG::owned16();
     if (e < 10) {
       int a = 0, rem = e;
 #pragma unroll 1
@@ -289,14 +309,14 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
     }
   }
 #endif
-  wsync();
+  PG::sync();
 #pragma unroll 1
   for (int ii = 0; ii < nrint; ++ii) {
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double rx[4] = {0, 0, 0, 0}, ry[4] = {0, 0, 0, 0};
     const int lo = W.start[ii], hi = W.start[ii + 1];
 #pragma unroll 1
-    for (int i = lo + lane; i < hi; i += FSD_LANES) {
+    for (int i = lo + lane; i < hi; i += PG::N) {
       double h[4] = {0, 0, 0, 0};
       bspl(W, k, u[i], ii, h);
       const double x = pts[i].x, y = pts[i].y;
@@ -319,10 +339,10 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
     for (int a = 0; a < 4; ++a) red[10 + a] = rx[a];
     red[14] = ry[0];
     red[15] = ry[1];
-    wsum16_transposed(red);
-    wsum_vec(tail);
+    PG::sum16_transposed(red);
+    PG::sum_vec(tail);
     if (own_ok) own_base[ii * own_stride] += red[0];
-    if (lane == 1 && 2 < k1) W.rhs[ii + 2][1] += tail[0];
+    if (lane == 1 && 2 < k1) W.rhs[ii + 2][1] += tail[0];  // (every lane holds the totals; any two distinct lanes do)
     if (lane == 3 && 3 < k1) W.rhs[ii + 3][1] += tail[1];
 #else
     double red[18];
@@ -349,14 +369,14 @@ FSD_DEVFN void assemble_normal(SplineWork &W, const d2 *pts, const double *u, in
       }
     }
 #endif
-    wsync();
+    PG::sync();
   }
 }
 
 // squared residuals: fp (returned) and, when `per_interval`, fpint[] with FITPACK's half/half split
 // of a data point that coincides with a knot (fppara's residual walk)
 FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n, int k, bool per_interval) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const int nrint = n - 2 * k - 1;
   double fp = 0.0;
 #pragma unroll 1
@@ -365,7 +385,7 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
     const int last = ii < nrint - 1 ? hi : hi - 1;  // the next interval's first point is shared
     double part = 0.0, full = 0.0;
 #pragma unroll 1
-    for (int i = lo + lane; i <= last; i += FSD_LANES) {
+    for (int i = lo + lane; i <= last; i += PG::N) {
       const int li = i >= hi ? ii + 1 : ii;
       double h[4] = {0, 0, 0, 0};
       bspl(W, k, u[i], li, h);
@@ -383,11 +403,11 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
       if (i < hi) full += term;
     }
     double red[2] = {part, full};
-    wsum_vec(red);
+    PG::sum_vec(red);
     fp += red[1];
     if (per_interval && lane == 0) W.fpint[ii] = red[0];
   }
-  wsync();
+  PG::sync();
   return fp;
 }
 
@@ -396,13 +416,13 @@ FSD_DEVFN double residuals(SplineWork &W, const d2 *pts, const double *u, int n,
 //     sum |B c - x|^2 = sum |B c0 - x|^2 + (c - c0)^T N (c - c0),      N = B^T B (already assembled, banded)
 // -- a sum of two non-negative terms, no cancellation.  One row of N per lane; z is free after chol_solve.
 FSD_DEVFN double smoothing_excess(SplineWork &W, int nk1, int k) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
 #pragma unroll 1
-  for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.z[0][0])[e] = (&W.c[0][0])[e] - (&W.c0[0][0])[e];
-  wsync();
+  for (int e = lane; e < nk1 * 2; e += PG::N) (&W.z[0][0])[e] = (&W.c[0][0])[e] - (&W.c0[0][0])[e];
+  PG::sync();
   double part = 0.0;
 #pragma unroll 1
-  for (int i = lane; i < nk1; i += FSD_LANES) {
+  for (int i = lane; i < nk1; i += PG::N) {
     const double dx = W.z[i][0], dy = W.z[i][1];
     double ax = W.N[i][0] * dx, ay = W.N[i][0] * dy;
 #pragma unroll 1
@@ -414,8 +434,8 @@ FSD_DEVFN double smoothing_excess(SplineWork &W, int nk1, int k) {
       }
     part += dx * ax + dy * ay;
   }
-  wsync();
-  return wsum(part);
+  PG::sync();
+  return PG::sum(part);
 }
 
 // fpknot: split the interval with the largest residual at its middle data point (lane 0)
@@ -454,7 +474,7 @@ FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
   const int k1 = k + 1, k2 = k + 2, nk1 = n - k1, nrint = nk1 - k;
   const double fac = fdiv((double)nrint, W.t[nk1] - W.t[k]);
 #pragma unroll 1
-  for (int l = k2 + fsd_lane(); l <= nk1; l += FSD_LANES) {  // 1-based row index of FITPACK
+  for (int l = k2 + PG::lane(); l <= nk1; l += PG::N) {  // 1-based row index of FITPACK
     const int lmk = l - k1;
     double h[10];
 #pragma unroll 1
@@ -476,7 +496,7 @@ FSD_DEVFN void disc_jumps(SplineWork &W, int n, int k) {
       ++lp;
     }
   }
-  wsync();
+  PG::sync();
 }
 
 // ---- the fit as a resumable state machine -----------------------------------------------------------------------
@@ -498,7 +518,7 @@ struct FitState {
 // pts/u: m data points and their (strictly increasing) parameters.  ier = 10 (phase FIT_DONE) on invalid input,
 // the reference's ValueError.
 FSD_DEVFN void fit_init(SplineWork &W, FitState &F, const d2 *pts, const double *u, int m, double s) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   F.pts = pts;
   F.u = u;
   F.m = m;
@@ -512,8 +532,8 @@ FSD_DEVFN void fit_init(SplineWork &W, FitState &F, const d2 *pts, const double 
   // u strictly increasing (parcur's input check)
   int bad = 0;
 #pragma unroll 1
-  for (int i = 1 + lane; i < m; i += FSD_LANES) bad |= !(u[i - 1] < u[i]);
-  if (wany(bad != 0)) return;
+  for (int i = 1 + lane; i < m; i += PG::N) bad |= !(u[i - 1] < u[i]);
+  if (PG::any(bad != 0)) return;
   F.acc = 1e-3 * s;
   F.nest = m + 2 * k;
   F.capped = false;
@@ -534,19 +554,19 @@ FSD_DEVFN void fit_init(SplineWork &W, FitState &F, const d2 *pts, const double 
     W.k = k;
     W.max_u = u[m - 1];
   }
-  wsync();
+  PG::sync();
 }
 
 FSD_DEVFN void fit_finish(SplineWork &W, FitState &F, int ier) {
   F.ier = ier;
   F.phase = FIT_DONE;
-  if (fsd_lane() == 0) W.n = F.n;
-  wsync();
+  if (PG::lane() == 0) W.n = F.n;
+  PG::sync();
 }
 
 // one least-squares pass for the current knots + FITPACK's decision what to do next
 FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const int k = F.k, k1 = k + 1, k2 = k + 2, nmin = 2 * k1, m = F.m;
   const double *u = F.u;
   int n = F.n;
@@ -558,13 +578,13 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
       W.t[j] = u[0];
       W.t[n - 1 - j] = u[m - 1];
     }
-  wsync();
+  PG::sync();
   interval_starts(W, m, n, k);
   knot_reciprocals(W, n, k);
   assemble_normal(W, F.pts, u, n, k);
 #pragma unroll 1
-  for (int e = lane; e < F.nk1 * BW; e += FSD_LANES) (&W.G[0][0])[e] = (&W.N[0][0])[e];
-  wsync();
+  for (int e = lane; e < F.nk1 * BW; e += PG::N) (&W.G[0][0])[e] = (&W.N[0][0])[e];
+  PG::sync();
   if (!chol_solve(W.G, F.nk1, k1, W.rhs, W.z, W.c, W.rpiv)) {
     *status |= FSD_ST_UNSUPPORTED;
     fit_finish(W, F, 10);
@@ -610,7 +630,7 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
     F.ier = 0;
   }
   F.fpold = F.fp;
-  wsync();
+  PG::sync();
 #pragma unroll 1
   for (int l = 1; l <= F.nplus; ++l) {
     if (lane == 0) add_knot(W, u, n, nrint);
@@ -641,28 +661,28 @@ FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
   }
   F.n = n;
   if (++F.iter >= m) fit_finish(W, F, F.ier);  // fppara's outer loop bound (never reached in practice)
-  wsync();
+  PG::sync();
 }
 
 // smoothing phase, set-up: discontinuity jumps, D^T D, initial p
 FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const int k = F.k, k2 = k + 2, nmin = 2 * (k + 1), n = F.n, nk1 = F.nk1;
   // p0 = nk1 / trace of the Cholesky factor of N (chol_solve leaves the pivots d_i = G_ii^2 on the diagonal); read
   // before the jump matrix overwrites G (they share storage)
 #pragma unroll 1
-  for (int i = lane; i < nk1; i += FSD_LANES) W.z[i][0] = fsqrt(W.G[i][0]);
-  wsync();
+  for (int i = lane; i < nk1; i += PG::N) W.z[i][0] = fsqrt(W.G[i][0]);
+  PG::sync();
   double p = 0.0;
 #pragma unroll 1
   for (int i = 0; i < nk1; ++i) p += W.z[i][0];
   F.p = fdiv((double)nk1, p);
-  wsync();
+  PG::sync();
   disc_jumps(W, n, k);
   // D^T D, one band entry per lane: (D^T D)[i][i+d] = sum over the jump rows r = i - a of bd[r][a] bd[r][a+d]
   const int n8 = n - nmin;
 #pragma unroll 1
-  for (int e = lane; e < nk1 * BW; e += FSD_LANES) {
+  for (int e = lane; e < nk1 * BW; e += PG::N) {
     const int i = e / BW, d = e % BW;
     double acc = 0.0;
     if (i + d < nk1)
@@ -673,7 +693,7 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
       }
     W.DtD[i][d] = acc;
   }
-  wsync();
+  PG::sync();
   F.p1 = 0.0;
   F.f1 = F.fp0 - F.s;
   F.p3 = -1.0;
@@ -681,23 +701,23 @@ FSD_DEVFN void fit_step_smooth_setup(SplineWork &W, FitState &F) {
   // the least-squares spline of this knot set: its coefficients and residual anchor F(p) below
   F.fp_ls = F.fp;
 #pragma unroll 1
-  for (int e = lane; e < nk1 * 2; e += FSD_LANES) (&W.c0[0][0])[e] = (&W.c[0][0])[e];
+  for (int e = lane; e < nk1 * 2; e += PG::N) (&W.c0[0][0])[e] = (&W.c[0][0])[e];
   F.ich1 = F.ich3 = 0;
   F.iter = 0;
   F.phase = FIT_SMOOTH;
-  wsync();
+  PG::sync();
 }
 
 // smoothing phase, one evaluation of F(p) and the next p (fppara's iteration incl. fprati)
 FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
-  const int lane = fsd_lane();
+  const int lane = PG::lane();
   const int k = F.k, k2 = k + 2, nk1 = F.nk1;
   const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
   ++F.iter;
   const double pinv = frcp(F.p), pinv2 = pinv * pinv;
 #pragma unroll 1
-  for (int i = lane; i < nk1 * BW; i += FSD_LANES) (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
-  wsync();
+  for (int i = lane; i < nk1 * BW; i += PG::N) (&W.G[0][0])[i] = (&W.N[0][0])[i] + (&W.DtD[0][0])[i] * pinv2;
+  PG::sync();
   if (!chol_solve(W.G, nk1, k2, W.rhs, W.z, W.c, W.rpiv)) {
     *status |= FSD_ST_UNSUPPORTED;
     fit_finish(W, F, 10);
