@@ -433,9 +433,10 @@ def run_ours(args):
     h_st = pin(np.empty((B,), dtype=np.int32))
 
     def e2e_step():
-        # the host-to-host entry point: per chunk H2D of the inputs, the planner launches, D2H of paths / sort indices /
-        # status, chunks on streams of their own (copies overlap kernels)
-        planner.plan_pinned(h_xy, h_ty, h_off, h_pos, h_dir, h_path, h_li, h_ri, h_st)
+        # the host-to-host entry point: per chunk H2D of the inputs and the sort + match launches on streams of their own
+        # (copies overlap kernels), the path stage over the whole batch storing the paths straight into the pinned host
+        # buffer (zero copy; N > 1: into a device buffer that is all-gathered, plus a D2H copy), D2H of sort indices / status
+        planner.plan_pinned(h_xy, h_ty, h_off, h_pos, h_dir, h_path, h_li, h_ri, h_st, zero_copy=not distributed)
         if distributed:
             off = 0
             for p, sz in enumerate(main.sizes):

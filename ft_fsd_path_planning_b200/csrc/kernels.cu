@@ -272,7 +272,10 @@ constexpr int PATH_WPC = FSD_PATH_WPC;             // warps per path CTA
 constexpr int PATH_FPW = 32 / PG::N;               // frames per warp
 constexpr int PATH_FPC = PATH_WPC * PATH_FPW;      // frames per CTA and round
 constexpr int PATH_THREADS = 32 * PATH_WPC;
-constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE;
+#ifndef FSD_PATH_SMEM_PAD
+#define FSD_PATH_SMEM_PAD 0 /* measurement builds only: extra dynamic shared memory that lowers the CTAs resident per SM */
+#endif
+constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE + FSD_PATH_SMEM_PAD;
 
 // drop a frame's point-buffer lines from L2 (they are dead; written back they were 5x the algorithmic bytes of the step)
 __device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned) {

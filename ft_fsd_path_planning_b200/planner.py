@@ -307,13 +307,19 @@ class BatchPlanner:
 
     def plan_pinned(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
                     direction: torch.Tensor, out_path: torch.Tensor, out_left_idx: torch.Tensor,
-                    out_right_idx: torch.Tensor, out_status: torch.Tensor, *, chunks: Optional[int] = None) -> None:
+                    out_right_idx: torch.Tensor, out_status: torch.Tensor, *, chunks: Optional[int] = None,
+                    zero_copy: bool = True) -> None:
         """Host-to-host entry point: all arguments are PINNED host tensors (inputs as for `plan`, outputs
         [B, 40, 4] float32 / [B, 12] int16 / [B, 12] int16 / [B] int32).  The batch is cut into `chunks` contiguous
-        chunks (default: one per ~2 500 frames, at most 4); each chunk's host->device copies, its planner launches
-        and its device->host copies are queued on a stream of its own, so the copies of one chunk overlap the
-        kernels of the others.  Asynchronous: the caller's current stream waits for all chunks (synchronize it
-        before reading the outputs)."""
+        chunks (default: one per ~2 500 frames, at most 2).  Each chunk's host->device copies, its sort + match launches
+        (free-running kernels: small chunks cost nothing) and the device->host copy of its sort indices are queued on a
+        stream of its own, so the copies of one chunk overlap the kernels of the others; the path stage then runs ONCE
+        over the whole batch (its CTA-synchronous rounds want a full grid).  With `zero_copy` (default) the path kernel
+        stores every frame's 40 x 4 path STRAIGHT INTO `out_path` -- pinned host memory is mapped into the device's
+        address space (unified addressing), the stores are posted writes over PCIe that overlap the kernel's own work --
+        so no device->host copy of the paths follows the kernel; only the status words (4 B per frame) are copied.
+        Asynchronous: everything is ordered on the caller's current stream (synchronize it before reading the
+        outputs)."""
         B = offsets.numel() - 1
         if B <= 0:
             return
@@ -330,30 +336,34 @@ class BatchPlanner:
             raise ValueError("outputs must be [B,40,4] float32, [B,12] int16, [B,12] int16, [B] int32")
         _check_offsets(offsets.numpy(), int(cones_xy.shape[0]))
         f64 = cones_xy.dtype == torch.float64
-        K = chunks if chunks is not None else max(1, min(4, B // 2500))
+        K = chunks if chunks is not None else max(1, min(2, B // 2500))
         K = max(1, min(int(K), B))
         dev = self.device
         key = ("pinned", B, int(cones_xy.shape[0]), f64, K)
         if self._pinned_key != key:
             e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
             bounds = [B * k // K for k in range(K + 1)]
-            with torch.cuda.device(dev):  # the workspace is sized for the current device
-                ws_bytes = [int(self.lib.fsd_workspace_bytes(bounds[k + 1] - bounds[k], 0)) for k in range(K)]
             self._pinned = {
                 "xy": e((max(int(cones_xy.shape[0]), 1), 2), cones_xy.dtype), "ty": e((max(int(cones_xy.shape[0]), 1),), torch.uint8),
                 "off": e((B + 1,), torch.int32), "pos": e((B, 2), cones_xy.dtype), "dir": e((B, 2), cones_xy.dtype),
-                "path": e((B, HORIZON, 4), torch.float32), "li": e((B, MAX_SORTED), torch.int16),
+                "li": e((B, MAX_SORTED), torch.int16),
                 "ri": e((B, MAX_SORTED), torch.int16), "st": e((B,), torch.int32), "bounds": bounds,
-                "ws": [e((ws_bytes[k],), torch.uint8) for k in range(K)],
+                "n_wv": e((B, 2), torch.int16), "left_wv": e((B, MAX_WV, 2), torch.float64),
+                "right_wv": e((B, MAX_WV, 2), torch.float64), "l2r": e((B, MAX_WV), torch.int16),
+                "r2l": e((B, MAX_WV), torch.int16),
                 "streams": [torch.cuda.Stream(dev) for _ in range(K)],
+                "sorted": [torch.cuda.Event() for _ in range(K)],
             }
             self._pinned_key = key
         P = self._pinned
-        fn = self.lib.fsd_plan_batch_f64 if f64 else self.lib.fsd_plan_batch
+        if not zero_copy and "path" not in P:
+            P["path"] = torch.empty((B, HORIZON, 4), dtype=torch.float32, device=dev)
+        ws = self._workspace(B)
         esz = cones_xy.element_size()
         off_host = offsets.numpy()
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
+            self._order_after_previous_call(cur)
             for k in range(K):
                 lo, hi = P["bounds"][k], P["bounds"][k + 1]
                 c0, c1 = int(off_host[lo]), int(off_host[hi])
@@ -366,20 +376,33 @@ class BatchPlanner:
                     P["off"][lo:hi + 1].copy_(offsets[lo:hi + 1], non_blocking=True)
                     P["pos"][lo:hi].copy_(pos[lo:hi], non_blocking=True)
                     P["dir"][lo:hi].copy_(direction[lo:hi], non_blocking=True)
-                    # the CSR offsets are absolute: a chunk is the same arrays entered at frame `lo`
-                    rc = fn(C.byref(self.params), self.mission, hi - lo, P["xy"].data_ptr(), P["ty"].data_ptr(),
-                            P["off"].data_ptr() + 4 * lo, P["pos"].data_ptr() + 2 * esz * lo,
-                            P["dir"].data_ptr() + 2 * esz * lo, P["path"].data_ptr() + 4 * HORIZON * 4 * lo,
-                            P["li"].data_ptr() + 2 * MAX_SORTED * lo, P["ri"].data_ptr() + 2 * MAX_SORTED * lo, None,
-                            None, None, 0, P["st"].data_ptr() + 4 * lo, P["ws"][k].data_ptr(), P["ws"][k].numel(),
-                            st.cuda_stream)
-                    _lib.check(rc)
-                    out_path[lo:hi].copy_(P["path"][lo:hi], non_blocking=True)
+                    # sort + match of the chunk (the CSR offsets are absolute: a chunk is the same arrays entered at frame lo)
+                    inter = _lib.Intermediate(None, P["n_wv"].data_ptr() + 4 * lo, P["left_wv"].data_ptr() + 16 * MAX_WV * lo,
+                                              P["right_wv"].data_ptr() + 16 * MAX_WV * lo, P["l2r"].data_ptr() + 2 * MAX_WV * lo,
+                                              P["r2l"].data_ptr() + 2 * MAX_WV * lo, None, None)
+                    _lib.check(self.lib.fsd_sort_match_batch(
+                        C.byref(self.params), hi - lo, int(f64), P["xy"].data_ptr(), P["ty"].data_ptr(),
+                        P["off"].data_ptr() + 4 * lo, P["pos"].data_ptr() + 2 * esz * lo, P["dir"].data_ptr() + 2 * esz * lo,
+                        P["li"].data_ptr() + 2 * MAX_SORTED * lo, P["ri"].data_ptr() + 2 * MAX_SORTED * lo, C.byref(inter),
+                        P["st"].data_ptr() + 4 * lo, st.cuda_stream))
+                    P["sorted"][k].record(st)  # the path stage waits for the chunk's kernels, not for its copies
                     out_left_idx[lo:hi].copy_(P["li"][lo:hi], non_blocking=True)
                     out_right_idx[lo:hi].copy_(P["ri"][lo:hi], non_blocking=True)
-                    out_status[lo:hi].copy_(P["st"][lo:hi], non_blocking=True)
             for k in range(K):
+                cur.wait_event(P["sorted"][k])
+            # the path stage over the whole batch, then the paths and the status words back to the host
+            inter = _lib.Intermediate(None, P["n_wv"].data_ptr(), P["left_wv"].data_ptr(), P["right_wv"].data_ptr(),
+                                      P["l2r"].data_ptr(), P["r2l"].data_ptr(), None, None)
+            _lib.check(self.lib.fsd_path_batch(
+                C.byref(self.params), B, int(f64), P["pos"].data_ptr(), P["dir"].data_ptr(), C.byref(inter), None,
+                self._default_prev().data_ptr(), 0, (out_path if zero_copy else P["path"]).data_ptr(), P["st"].data_ptr(),
+                ws.data_ptr(), ws.numel(), cur.cuda_stream))
+            if not zero_copy:
+                out_path.copy_(P["path"], non_blocking=True)
+            out_status.copy_(P["st"], non_blocking=True)
+            for k in range(K):  # the sort-index copies still running on the chunk streams
                 cur.wait_stream(P["streams"][k])
+            self._mark_call(cur)
 
     def initial_path(self) -> torch.Tensor:
         """The constant path of a fresh planner (core_calculate_path.py:103-107), computed on the device."""
