@@ -272,7 +272,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from ft_fsd_path_planning_b200 import synth
-    from ft_fsd_path_planning_b200.distributed import GatherPipeline, shard_parts
+    from ft_fsd_path_planning_b200.distributed import GatherPipeline, PeerGather, shard_parts
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -309,20 +309,43 @@ def run_ours(args):
     pin = (lambda a: torch.from_numpy(np.ascontiguousarray(a))) if REHEARSAL else \
         (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory())
 
+    # N > 1: the all-gather of the paths is fused into the path kernel (stores into every peer's gathered buffer over
+    # NVLink peer memory / NVSwitch multicast, distributed.PeerGather); --gather nccl (or a box without symmetric
+    # memory) keeps the NCCL all-gather pipeline.  All ranks must agree, hence the all-reduce of the outcome.
+    p2p = {"on": False, "why": "--gather nccl" if args.gather == "nccl" else ""}
+    if distributed and not REHEARSAL and args.gather != "nccl":
+        ok = 1
+        try:
+            probe = PeerGather(world, dev, buffers=1, multicast=args.gather != "p2p-unicast")
+            probe.finish()
+            sync()
+            del probe
+        except Exception as exc:  # noqa: BLE001 - any failure means: fall back to NCCL, and say why
+            ok, p2p["why"] = 0, f"symmetric memory unavailable: {type(exc).__name__}: {exc}"[:300]
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        p2p["on"] = bool(flag.item())
+        if not p2p["on"] and not p2p["why"]:
+            p2p["why"] = "symmetric memory unavailable on another rank"
+
     class Workload:
         """One rank's share of a global batch: the frames of this rank's blocks (shard_parts layout: the planner's first
         chunk and the rest, so that the all-gather of the first chunk can start while the rest is planned)."""
 
         def __init__(self, kind, seed, per_gpu):
             na = planner.first_chunk(per_gpu)
-            self.sizes = [na, per_gpu - na] if 0 < na < per_gpu else [per_gpu]
+            self.sizes = [na, per_gpu - na] if 0 < na < per_gpu and not p2p["on"] else [per_gpu]
             self.n_global = per_gpu * world
             gen = synth.gen_mixed if kind == "mixed" else synth.gen_autocross
             blocks = shard_parts(self.sizes, rank, world)
             self.batch = synth.concat_batches([gen(seed, hi - lo, start=lo, workers=min(host_threads, 16)) for lo, hi in blocks])
             b = self.batch
             self.dev_args = tuple(torch.from_numpy(a).to(dev) for a in (b.cones_xy, b.cones_type, b.offsets, b.pos, b.dir))
-            self.pipe = GatherPipeline(self.n_global, (40, 4), torch.float32, dev, part_sizes=self.sizes) if distributed else None
+            self.peer = PeerGather(self.n_global, dev, multicast=args.gather != "p2p-unicast") if p2p["on"] else None
+            self.first_row = rank * per_gpu
+            self.pipe = GatherPipeline(self.n_global, (40, 4), torch.float32, dev, part_sizes=self.sizes) \
+                if distributed and self.peer is None else None
+            self.bar_ev = (new_event(), new_event()) if self.peer is not None else None
             self.ready = None if (REHEARSAL and not distributed) else (new_event() if REHEARSAL else torch.cuda.Event())
             self.res = None
 
@@ -333,6 +356,16 @@ def run_ours(args):
                     return planner.plan(*self.dev_args, kernel_events=True).path
                 self.res = planner.plan(*self.dev_args, out=self.res)
                 return self.res.path
+            if self.peer is not None:
+                if events:  # kernel timing pass: the stage entry points, no peer stores
+                    return planner.plan(*self.dev_args, kernel_events=True).path
+                # the path kernel stores every frame's path into all ranks' gathered buffers; what is left of the
+                # "all-gather" is the cross-GPU barrier in finish()
+                self.res = planner.plan(*self.dev_args, out=self.res, gather=self.peer.descriptor(self.first_row))
+                self.bar_ev[0].record()
+                full = self.peer.finish()
+                self.bar_ev[1].record()
+                return full
             if events:
                 res = planner.plan(*self.dev_args, kernel_events=True)
             elif len(self.sizes) == 1:
@@ -346,6 +379,10 @@ def run_ours(args):
                 self.pipe.gather(p, res.path[off:off + sz], after=self.ready if (p == 0 and not events and len(self.sizes) > 1) else None)
                 off += sz
             return self.pipe.finish()
+
+        def gather_ms(self):
+            """Device time of the last step's collective part: the NCCL gathers, or the symmetric-memory barrier."""
+            return self.bar_ev[0].elapsed_time(self.bar_ev[1]) if self.peer is not None else self.pipe.gather_ms()
 
     main = Workload("autocross", SEED, FRAMES_PER_GPU)
     batch, B, n_global = main.batch, main.batch.n_frames, main.n_global
@@ -364,7 +401,7 @@ def run_ours(args):
             evs.append((e0, e1))
             if distributed and not REHEARSAL and args.comm_detail:
                 sync()
-                gather_ms.append(w.pipe.gather_ms())
+                gather_ms.append(w.gather_ms())
         barrier()
         return [a.elapsed_time(b) for a, b in evs], gather_ms
 
@@ -436,6 +473,11 @@ def run_ours(args):
         # the host-to-host entry point: per chunk H2D of the inputs and the sort + match launches on streams of their own
         # (copies overlap kernels), the path stage over the whole batch storing the paths straight into the pinned host
         # buffer (zero copy; N > 1: into a device buffer that is all-gathered, plus a D2H copy), D2H of sort indices / status
+        if distributed and main.peer is not None:
+            planner.plan_pinned(h_xy, h_ty, h_off, h_pos, h_dir, h_path, h_li, h_ri, h_st,
+                                gather=main.peer.descriptor(main.first_row))
+            main.peer.finish()
+            return
         planner.plan_pinned(h_xy, h_ty, h_off, h_pos, h_dir, h_path, h_li, h_ri, h_st, zero_copy=not distributed)
         if distributed:
             off = 0
@@ -473,6 +515,21 @@ def run_ours(args):
         parity = parity_vs_oracle(planner, batch, main.dev_args, timed_path, host_threads)
         parity5 = parity_vs_oracle(planner, c5.batch, c5.dev_args, c5.res.path if c5.res is not None else
                                    planner.plan(*c5.dev_args).path, host_threads)
+
+    # ---- the gathered buffer of one more step: this rank's rows equal its local output, all ranks hold the same bytes ----
+    gathered_ok = None
+    if distributed and not REHEARSAL:
+        full = main.step()
+        sync()
+        lo = rank * B
+        own = bool(torch.equal(full[lo:lo + B], main.res.path)) if main.peer is not None else True
+        digest = full.view(torch.int32).to(torch.int64).sum().reshape(1)
+        digests = torch.empty((world,), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(digests, digest)
+        same = bool((digests == digests[0]).all().item())
+        flag = torch.tensor([int(own and same)], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gathered_ok = bool(flag.item())
 
     # ---- max over ranks; per-rank numbers for the comm block ----------------------------------------------------------
     mine = [step_ms, e2e_ms, sort_ms, path_ms, c5_ms, comm["gather_ms"] or 0.0 if comm else 0.0,
@@ -536,8 +593,9 @@ def run_ours(args):
         cfg = bench_config(world)
         cfg.update({"cones_per_frame_mean": batch.total_cones / B,
                     "parallelism": (f"frames partitioned over {world} GPU(s), {main.sizes} frames per rank and planner chunk; "
-                                    "the paths are all-gathered on a communication stream (the first chunk's gather "
-                                    "starts at the planner's chunk-ready event when the planner splits the batch)")
+                                    + ("the all-gather of the paths is fused into the path kernel (peer stores)" if distributed and main.peer is not None else
+                                       "the paths are all-gathered on a communication stream (the first chunk's gather "
+                                       "starts at the planner's chunk-ready event when the planner splits the batch)"))
                     if distributed else "single GPU"})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -562,14 +620,23 @@ def run_ours(args):
             names = ["step_ms", "e2e_ms", "sort_kernel_ms", "path_kernel_ms", "config5_step_ms", "gather_ms",
                      "step_ms_with_sync_per_step", "knn_kernel_ms"]
             out["comm"] = {
-                "collective": f"{len(main.sizes)} x all_gather_into_tensor of the fp32 paths per step (NCCL), "
-                              + " + ".join(str(4 * 160 * sz) for sz in main.sizes) + " bytes per rank",
+                "collective": (f"none: the path kernel stores every frame's fp32 path ({4 * 160 * B} bytes per rank and step) "
+                               f"into all {world} ranks' gathered buffers ("
+                               + ("one multimem store per value through the NVSwitch multicast address" if main.peer.multicast
+                                  else "plain stores through peer-mapped pointers over NVLink")
+                               + "; torch symmetric memory), then ONE symmetric-memory barrier per step") if main.peer is not None else
+                              (f"{len(main.sizes)} x all_gather_into_tensor of the fp32 paths per step (NCCL), "
+                               + " + ".join(str(4 * 160 * sz) for sz in main.sizes) + " bytes per rank"
+                               + (f" [{p2p['why']}]" if p2p["why"] else "")),
+                "fused_peer_stores": main.peer is not None,
+                "gathered_buffer_identical_on_all_ranks": gathered_ok,
                 "gather_ms_max_over_ranks": float(per_rank[:, 5].max()),
                 "gather_share_of_step": float(per_rank[:, 5].max() / step_ms),
                 "per_rank": {n: [float(v) for v in per_rank[:, i]] for i, n in enumerate(names)},
                 "step_ms_min_median_max": [float(per_rank[:, 0].min()), float(np.median(per_rank[:, 0])), float(per_rank[:, 0].max())],
-                "note": "gather_ms = device time of the gathers on the communication stream (events), measured in a "
-                        "separate pass with one synchronisation per step",
+                "note": "gather_ms = device time of the collective part of a step (events): the NCCL gathers on the "
+                        "communication stream, or -- with fused peer stores -- the symmetric-memory barrier that waits for "
+                        "the slowest rank; measured in a separate pass with one synchronisation per step",
             }
         else:
             # ---- the CPU beside it (rank 0, N = 1 only): the oracle port on all host threads, and the real reference ---
@@ -590,6 +657,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-unicast", "nccl"],
+                    help="N > 1: p2p = all-gather fused into the path kernel (peer stores, multicast when available), "
+                         "p2p-unicast = the same without multicast, nccl = all_gather_into_tensor on a side stream")
     ap.add_argument("--no-reference-numba", dest="reference_numba", action="store_false",
                     help="skip the live timing of the numba reference in the cpu_baseline block (saves ~1-2 minutes)")
     args = ap.parse_args()

@@ -45,6 +45,15 @@ class Intermediate(C.Structure):
                 ("path_f64", "n_wv", "left_wv", "right_wv", "l2r", "r2l", "grid", "sort_dbg")]
 
 
+MAX_PEERS = 16
+
+
+class Gather(C.Structure):
+    """struct fsd_gather: the all-gather of the output paths fused into the path kernel (peer-mapped device pointers)"""
+    _fields_ = [("n_peers", C.c_int32), ("reserved0", C.c_int32), ("first_row", C.c_int64),
+                ("peer_out_path", C.c_void_p * MAX_PEERS), ("multicast_out_path", C.c_void_p)]
+
+
 def sources():
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h")) or f == "cpu_backend.cpp"]
     return files + [INCLUDE]
@@ -95,6 +104,8 @@ def lib():
         L.fsd_plan_first_chunk.argtypes = [i32]
         L.fsd_plan_batch_ex.argtypes = [C.POINTER(Params), i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                         C.POINTER(Intermediate), vp, vp, i32, vp, vp, sz, vp, vp]
+        L.fsd_plan_batch_gather.argtypes = [C.POINTER(Params), i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                            C.POINTER(Intermediate), vp, vp, i32, vp, vp, sz, vp, vp, C.POINTER(Gather)]
         L.fsd_plan_batch_cpu.argtypes = [C.POINTER(Params), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                          C.POINTER(Intermediate), vp, vp, i32, vp, i32]
         L.fsd_initial_path_cpu.argtypes = [C.POINTER(Params), vp]
@@ -105,6 +116,8 @@ def lib():
                                            C.POINTER(Intermediate), vp, vp]
         L.fsd_path_batch.argtypes = [C.POINTER(Params), i32, i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp, vp,
                                      vp, sz, vp]
+        L.fsd_path_batch_gather.argtypes = [C.POINTER(Params), i32, i32, vp, vp, C.POINTER(Intermediate), vp, vp, i32, vp,
+                                            vp, vp, sz, vp, C.POINTER(Gather)]
         L.fsd_global_path_workspace_bytes.restype = sz
         L.fsd_global_path_workspace_bytes.argtypes = [i32]
         L.fsd_global_path_batch.argtypes = [C.POINTER(Params), i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]

@@ -21,4 +21,20 @@ size_t fsd_big_path_fixup_scratch_bytes();
 int fsd_big_path_fixup(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                        const int16_t *n_wv, const double *left_wv, const double *right_wv, const int16_t *l2r,
                        const int16_t *r2l, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
-                       float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, cudaStream_t stream);
+                       float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, cudaStream_t stream,
+                       const fsd_gather *gather = nullptr);
+
+#ifdef __CUDACC__
+// The all-gather of the output paths fused into the kernels that produce them (fsdplan.h: fsd_gather): value i of frame b
+// goes to row first_row + b of every GPU's gathered buffer -- one multimem.st through the NVSwitch multicast address when
+// the caller has one (the switch replicates the store to all GPUs), else one plain store per peer-mapped pointer (NVLink
+// peer memory).  Posted writes: they overlap the planning of the next frame.
+__device__ __forceinline__ void fsd_store_peers(const fsd_gather &G, int b, int i, float v) {
+  const size_t o = (size_t)(G.first_row + b) * (FSD_HORIZON * 4) + (size_t)i;
+  if (G.multicast_out_path) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(G.multicast_out_path + o), "f"(v) : "memory");
+  } else {
+    for (int r = 0; r < G.n_peers; ++r) G.peer_out_path[r][o] = v;
+  }
+}
+#endif

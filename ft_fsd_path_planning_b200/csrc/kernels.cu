@@ -289,7 +289,7 @@ template <typename T>
 __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
-                unsigned char *scratch, int *counter, int flags) {
+                unsigned char *scratch, int *counter, int flags, fsd_gather G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_state[PATH_FPC];
   __shared__ int s_base;
@@ -361,6 +361,8 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
         const double v = out[i];
         if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
         if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;  // only when the caller asked for the fp64 path
+        // multi-GPU: the all-gather of the paths happens HERE -- the frame's row goes to every peer's gathered buffer
+        if (flags & 4) fsd_store_peers(G, b, i, (float)v);
       }
       if (lane == 0) {
         const unsigned before = O.status[b];
@@ -804,11 +806,20 @@ template <typename T>
 int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
               const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
               unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream,
-              unsigned char *fixup_scratch = nullptr) {
+              unsigned char *fixup_scratch = nullptr, const fsd_gather *gather = nullptr) {
   if (!path_scratch) return FSD_ERR_WORKSPACE;
   if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
   if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
-  if (!inter->path_f64 && !out_path) return FSD_ERR_ARG;  // at least one of the two path outputs
+  fsd_gather G;
+  std::memset(&G, 0, sizeof(G));
+  if (gather) {
+    if (gather->n_peers < 0 || gather->n_peers > FSD_MAX_PEERS || gather->first_row < 0) return FSD_ERR_ARG;
+    for (int r = 0; r < gather->n_peers; ++r)
+      if (!gather->peer_out_path[r]) return FSD_ERR_ARG;
+    G = *gather;
+  }
+  const bool peers = G.n_peers > 0 || G.multicast_out_path;
+  if (!inter->path_f64 && !out_path && !peers) return FSD_ERR_ARG;  // at least one path output
   if (prev_path && prev_path_stride != 0 && prev_path_stride != FSD_HORIZON * 4) return FSD_ERR_ARG;
   if (n_frames == 0) return FSD_OK;
   DeviceInfo *D = nullptr;
@@ -826,16 +837,16 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
                 inter->l2r, inter->r2l, out_status};
   const int grid = grid_for(n_frames, D->sm_count, D->path_ctas, PATH_FPC);
   int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
-  const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0);
+  const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0) | (peers ? 4 : 0);
   path_kernel<T><<<grid, PATH_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
-      round_counter, flags);
+      round_counter, flags, G);
   rc = check_launch();
   if (rc != FSD_OK || !fixup_scratch) return rc;
   // frames on which a static bound of path_kernel overflowed get a second chance with the large bounds (kernels_big.cu)
   return fsd_big_path_fixup(params, n_frames, sizeof(T) == 8, pos, dir, inter->n_wv, inter->left_wv, inter->right_wv,
                             inter->l2r, inter->r2l, force_P, prev, stride, inter->path_f64, out_path, inter->grid,
-                            out_status, fixup_scratch, stream);
+                            out_status, fixup_scratch, stream, peers ? &G : nullptr);
 }
 
 // take / return a side stream of the current device (created on first use)
@@ -880,7 +891,8 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                     const int32_t *offsets, const T *pos, const T *dir, float *out_path, int16_t *out_left_idx,
                     int16_t *out_right_idx, const fsd_intermediate *inter, const int16_t *force_P,
                     const double *prev_path, int prev_path_stride, uint32_t *out_status, void *workspace,
-                    size_t workspace_bytes_given, void *stream_v, void *chunk_ready_v = nullptr) {
+                    size_t workspace_bytes_given, void *stream_v, void *chunk_ready_v = nullptr,
+                    const fsd_gather *gather = nullptr) {
   if (!params || n_frames < 0) return FSD_ERR_ARG;
   if (mission != FSD_MISSION_AUTOCROSS && mission != FSD_MISSION_TRACKDRIVE) return FSD_ERR_MISSION;
   if (n_frames == 0) return FSD_OK;
@@ -911,7 +923,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                             out_status, stream, X.idx);
     if (rc != FSD_OK) return rc;
     rc = path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
-                      out_status, stream, X.fixup[0]);
+                      out_status, stream, X.fixup[0], gather);
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
       cudaGetLastError();
       rc = FSD_ERR_LAUNCH;
@@ -936,17 +948,24 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                               side->stream, X.idx + 2 * h * FSD_MAX_SORTED);
     if (rc == FSD_OK)
       rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
-                        stream, X.fixup[0]);
+                        stream, X.fixup[0], gather);
     // the outputs of frames [0, na) are final here: a caller that passed an event can start consuming them (e.g. an
     // all-gather on a communication stream) while chunk B is still being planned
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
       cudaGetLastError();
       rc = FSD_ERR_LAUNCH;
     }
-    if (rc == FSD_OK)
+    if (rc == FSD_OK) {
+      fsd_gather GB;  // chunk B's rows follow chunk A's in the gathered buffers
+      if (gather) {
+        GB = *gather;
+        GB.first_row += (int64_t)h;
+      }
       rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
                         prev + h * (size_t)stride, stride, init_slot, scratch_b,
-                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.fixup[1]);
+                        out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.fixup[1],
+                        gather ? &GB : nullptr);
+    }
   }
   // always join, so that the caller's stream never runs ahead of work queued on the side stream
   ok = cudaEventRecord(side->join, side->stream) == cudaSuccess && ok;
@@ -1029,6 +1048,23 @@ int fsd_plan_batch_ex(const fsd_params *params, int mission, int n_frames, int c
                                 static_cast<const float *>(pos), static_cast<const float *>(dir), out_path, out_left_idx,
                                 out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status, workspace,
                                 workspace_bytes_given, stream, chunk_ready_event);
+}
+
+int fsd_plan_batch_gather(const fsd_params *params, int mission, int n_frames, int coords_f64, const void *cones_xy,
+                          const uint8_t *cones_type, const int32_t *offsets, const void *pos, const void *dir,
+                          float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                          const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                          void *workspace, size_t workspace_bytes_given, void *stream, void *chunk_ready_event,
+                          const fsd_gather *gather) {
+  if (coords_f64)
+    return plan_batch_impl<double>(params, mission, n_frames, static_cast<const double *>(cones_xy), cones_type, offsets,
+                                   static_cast<const double *>(pos), static_cast<const double *>(dir), out_path,
+                                   out_left_idx, out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status,
+                                   workspace, workspace_bytes_given, stream, chunk_ready_event, gather);
+  return plan_batch_impl<float>(params, mission, n_frames, static_cast<const float *>(cones_xy), cones_type, offsets,
+                                static_cast<const float *>(pos), static_cast<const float *>(dir), out_path, out_left_idx,
+                                out_right_idx, inter, force_P, prev_path, prev_path_stride, out_status, workspace,
+                                workspace_bytes_given, stream, chunk_ready_event, gather);
 }
 
 int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stream) {
@@ -1138,10 +1174,10 @@ int fsd_sort_match_batch(const fsd_params *params, int n_frames, int coords_f64,
                                 out_right_idx, inter, out_status, st);
 }
 
-int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
+int fsd_path_batch_gather(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                    const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
                    int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
-                   size_t workspace_bytes_given, void *stream) {
+                   size_t workspace_bytes_given, void *stream, const fsd_gather *gather) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_frames > 0 && (!workspace || workspace_bytes_given < path_grid_bound(n_frames) * PATH_SCRATCH_BYTES))
     return FSD_ERR_WORKSPACE;
@@ -1153,9 +1189,17 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
   if (n_frames > 0 && workspace_bytes_given >= fix_at + fsd_big_path_fixup_scratch_bytes()) fixup = scratch + fix_at;
   if (coords_f64)
     return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
-                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup);
+                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup, gather);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
-                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup);
+                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup, gather);
+}
+
+int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
+                   const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
+                   size_t workspace_bytes_given, void *stream) {
+  return fsd_path_batch_gather(params, n_frames, coords_f64, pos, dir, inter, force_P, prev_path, prev_path_stride,
+                               out_path, out_status, workspace, workspace_bytes_given, stream, nullptr);
 }
 
 size_t fsd_global_path_workspace_bytes(int n_poses) {

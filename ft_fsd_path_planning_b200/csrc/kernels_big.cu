@@ -6,6 +6,8 @@
 #define FSD_PCAP 2048
 #define FSD_NCAP 64
 #define fsd fsd_big  // the same sources, a second namespace (distinct symbols next to kernels.cu's instantiation)
+#include <cstring>
+
 #include "big_kernels.h"
 #include "path.cuh"
 
@@ -31,11 +33,12 @@ __device__ PathSmem &group_state(unsigned char *smem_raw, unsigned char *scratch
 }
 
 __device__ void store_result(const double *out, unsigned st, const int *grid, int b, double *out_f64, float *out_f32,
-                             int16_t *grid_out) {
+                             int16_t *grid_out, const fsd_gather *G = nullptr) {
   for (int i = PG::lane(); i < FSD_HORIZON * 4; i += PG::N) {
     const double v = out[i];
     if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
     if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;
+    if (G) fsd_store_peers(*G, b, i, (float)v);
   }
   if (PG::lane() == 0 && grid_out) {
     grid_out[2 * (size_t)b] = (int16_t)grid[0];
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(32 * BIG_WPC)
     path_fixup_kernel(DevParams P, int n_frames, int coords_f64, const void *pos_v, const void *dir_v, const int16_t *n_wv,
                       const double *left_wv, const double *right_wv, const int16_t *l2r, const int16_t *r2l,
                       const int16_t *force_P, const double *prev, int prev_stride, double *out_f64, float *out_f32,
-                      int16_t *grid_out, uint32_t *status, unsigned char *scratch) {
+                      int16_t *grid_out, uint32_t *status, unsigned char *scratch, fsd_gather G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PathSmem &S = group_state(smem_raw, scratch);
   const int n_groups = (int)gridDim.x * BIG_FPC, g = (int)blockIdx.x * BIG_FPC + (int)threadIdx.x / PG::N;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(32 * BIG_WPC)
                                      reinterpret_cast<const d2 *>(right_wv + (size_t)b * FSD_MAX_WV * 2), n_wv[2 * (size_t)b + 1],
                                      l2r + (size_t)b * FSD_MAX_WV, r2l + (size_t)b * FSD_MAX_WV, F,
                                      force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out, grid);
-      store_result(out, st, grid, b, out_f64, out_f32, grid_out);
+      store_result(out, st, grid, b, out_f64, out_f32, grid_out, (G.n_peers > 0 || G.multicast_out_path) ? &G : nullptr);
       if (PG::lane() == 0) status[b] = ((status[b] >> 16) & 0x7fffu) | st;  // the sort / match stage's bits + this run's
       PG::sync();
     }
@@ -120,8 +123,12 @@ size_t fsd_big_path_fixup_scratch_bytes() { return (size_t)FIXUP_CTAS * BIG_FPC 
 int fsd_big_path_fixup(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
                        const int16_t *n_wv, const double *left_wv, const double *right_wv, const int16_t *l2r,
                        const int16_t *r2l, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
-                       float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, cudaStream_t stream) {
+                       float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, cudaStream_t stream,
+                       const fsd_gather *gather) {
   const size_t smem = BIG_FPC * BIG_STRIDE;
+  fsd_gather G;
+  memset(&G, 0, sizeof(G));
+  if (gather) G = *gather;
   if (cudaFuncSetAttribute(path_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return FSD_ERR_LAUNCH;
@@ -129,7 +136,7 @@ int fsd_big_path_fixup(const fsd_params *params, int n_frames, int coords_f64, c
   const int need = (n_frames + PG::N * BIG_FPC - 1) / (PG::N * BIG_FPC);
   path_fixup_kernel<<<need < FIXUP_CTAS ? need : FIXUP_CTAS, 32 * BIG_WPC, smem, stream>>>(
       make_dev_params(*params), n_frames, coords_f64, pos, dir, n_wv, left_wv, right_wv, l2r, r2l, force_P, prev,
-      prev_stride, out_f64, out_f32, grid_out, status, scratch);
+      prev_stride, out_f64, out_f32, grid_out, status, scratch, G);
   return cudaGetLastError() == cudaSuccess ? FSD_OK : FSD_ERR_LAUNCH;
 }
 

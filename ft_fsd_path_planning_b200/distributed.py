@@ -9,6 +9,10 @@ Two partitions:
   * `shard_blocks`      `parts` blocks per rank (block p of rank r = frames [p * B/parts + r * h, ... + h)), so that the
                         all-gather of part p fills the contiguous slice p of the result and can run on a side stream
                         while the rank plans part p + 1 (`GatherPipeline`).
+`PeerGather` removes the collective altogether: the path kernel stores every finished frame's path straight into ALL
+GPUs' gathered buffers (peer-mapped symmetric memory over NVLink, or one multimem store through the NVSwitch multicast
+address), so the "all-gather" overlaps the planning frame by frame and only a cross-GPU barrier remains.
+
 Skidpad: steps of one trajectory are sequential, trajectories are independent ->
 `shard_trajectories` gives every rank whole trajectories.
 """
@@ -163,3 +167,69 @@ class GatherPipeline:
         if not self.cuda:
             return 0.0
         return float(sum(a.elapsed_time(b) for a, b in self.events))
+
+
+class PeerGather:
+    """The all-gather of the output paths FUSED into the path kernel (fsdplan.h: fsd_gather, fsd_plan_batch_gather).
+
+        pg = PeerGather(n_global, device)                       # collective: every rank of the group calls it
+        res = planner.plan(..., gather=pg.descriptor(lo))        # lo = global row of this rank's first frame
+        full = pg.finish()                                       # [n_global, 40, 4]; a cross-GPU barrier, no copy
+
+    The gathered buffers live in torch symmetric memory (CUDA VMM allocations exchanged between the ranks' processes and
+    mapped into every GPU's address space): the kernel writes row `lo + b` of every peer's buffer through the peer
+    pointers -- or, where the NVSwitch fabric offers a multicast address for the allocation, with ONE multimem store per
+    value that the switch replicates to all GPUs.  `buffers` gathered buffers are used in turn, so a rank that is already
+    planning step k + 1 never overwrites the step-k result a slower peer is still reading.  CUDA + NCCL group only; the
+    gloo / CPU path keeps `GatherPipeline`."""
+
+    def __init__(self, n_frames: int, device: torch.device, group: Optional[dist.ProcessGroup] = None, buffers: int = 2,
+                 multicast: bool = True, tail: Tuple[int, ...] = (40, 4)):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        g = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(g), dist.get_rank(g)
+        if self.world > 16:
+            raise ValueError("fsd_gather holds at most 16 peers")
+        self.n, self.device = n_frames, torch.device(device)
+        self.bufs, self.hdls = [], []
+        with torch.cuda.device(self.device):
+            for _ in range(buffers):
+                t = symm_mem.empty((n_frames, *tail), dtype=torch.float32, device=self.device)
+                try:
+                    h = symm_mem.rendezvous(t, g)
+                except TypeError:
+                    h = symm_mem.rendezvous(t, g.group_name)
+                self.bufs.append(t)
+                self.hdls.append(h)
+        self.multicast = bool(multicast) and all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.hdls)
+        self.cur = 0
+
+    @staticmethod
+    def make_descriptor(peer_ptrs: List[int], first_row: int, multicast_ptr: int = 0):
+        """fsd_gather from raw device pointers (one per rank, every GPU's [n_global, 40, 4] fp32 buffer)."""
+        from . import _lib
+
+        if len(peer_ptrs) > _lib.MAX_PEERS:
+            raise ValueError("too many peers")
+        d = _lib.Gather()
+        d.n_peers, d.first_row = (0 if multicast_ptr else len(peer_ptrs)), int(first_row)
+        for r, ptr in enumerate(peer_ptrs):
+            d.peer_out_path[r] = int(ptr)
+        d.multicast_out_path = int(multicast_ptr) or None
+        return d
+
+    def descriptor(self, first_row: int):
+        """Descriptor of the buffer of the current step; `first_row`: global row of the caller's frame 0."""
+        h = self.hdls[self.cur]
+        return self.make_descriptor([int(p) for p in h.buffer_ptrs], first_row,
+                                    int(h.multicast_ptr) if self.multicast else 0)
+
+    def finish(self) -> torch.Tensor:
+        """Cross-GPU barrier on the current stream (every rank's kernels, hence its peer stores, have completed when it
+        passes), returns the gathered buffer of this step and moves on to the next buffer."""
+        with torch.cuda.device(self.device):
+            self.hdls[self.cur].barrier()
+        out = self.bufs[self.cur]
+        self.cur = (self.cur + 1) % len(self.bufs)
+        return out

@@ -143,7 +143,7 @@ class BatchPlanner:
              direction: torch.Tensor, *, force_P: Optional[torch.Tensor] = None,
              prev_path: Optional[torch.Tensor] = None, intermediates: bool = False,
              kernel_events: bool = False, out: Optional[PlanResult] = None,
-             chunk_ready: Optional[torch.cuda.Event] = None) -> PlanResult:
+             chunk_ready: Optional[torch.cuda.Event] = None, gather: Optional["_lib.Gather"] = None) -> PlanResult:
         """cones_xy [total, 2] float32|float64, cones_type [total] uint8, offsets [B+1] int32, pos/direction [B, 2]
         (same dtype as cones_xy); all on this planner's device.  Asynchronous on the current stream.  The CSR
         `offsets` must be non-decreasing with offsets[-1] <= total (checked for free by plan_host / plan_pinned, which
@@ -154,6 +154,10 @@ class BatchPlanner:
 
         chunk_ready: a CUDA event recorded as soon as the outputs of the first `first_chunk(B)` frames are final
         (fsd_plan_batch_ex) -- the multi-GPU pipeline starts their all-gather on a side stream at that point.
+
+        gather: a `_lib.Gather` descriptor (distributed.PeerGather.descriptor()) -- the path kernel then stores every
+        frame's path into all peers' gathered buffers as well (fsd_plan_batch_gather: the all-gather fused into the
+        kernel over NVLink peer memory / NVSwitch multicast); call PeerGather.finish() before reading the gathered buffer.
 
         kernel_events=True issues the two launches through the stage entry points (fsd_sort_match_batch,
         fsd_path_batch) with CUDA events around each; the events are kept in `self.kernel_events`
@@ -220,6 +224,16 @@ class BatchPlanner:
                     ws.data_ptr(), ws.numel(), stream)
                 ev[2].record()
                 self.kernel_events.append(ev)
+            elif gather is not None:
+                if chunk_ready is not None:
+                    chunk_ready.record(cur)
+                rc = self.lib.fsd_plan_batch_gather(
+                    C.byref(self.params), self.mission, B, int(f64), cones_xy.data_ptr(), cones_type.data_ptr(),
+                    offsets.data_ptr(), pos.data_ptr(), direction.data_ptr(), bufs["path"].data_ptr(),
+                    bufs["left_idx"].data_ptr(), bufs["right_idx"].data_ptr(),
+                    C.byref(inter) if inter is not None else None, _ptr(force_P), _ptr(prev_path), stride,
+                    bufs["status"].data_ptr(), ws.data_ptr(), ws.numel(), stream,
+                    chunk_ready.cuda_event if chunk_ready is not None else None, C.byref(gather))
             elif chunk_ready is not None:
                 chunk_ready.record(cur)  # creates the lazily-initialised CUDA event; re-recorded by the library
                 rc = self.lib.fsd_plan_batch_ex(
@@ -308,7 +322,7 @@ class BatchPlanner:
     def plan_pinned(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
                     direction: torch.Tensor, out_path: torch.Tensor, out_left_idx: torch.Tensor,
                     out_right_idx: torch.Tensor, out_status: torch.Tensor, *, chunks: Optional[int] = None,
-                    zero_copy: bool = True) -> None:
+                    zero_copy: bool = True, gather: Optional["_lib.Gather"] = None) -> None:
         """Host-to-host entry point: all arguments are PINNED host tensors (inputs as for `plan`, outputs
         [B, 40, 4] float32 / [B, 12] int16 / [B, 12] int16 / [B] int32).  The batch is cut into `chunks` contiguous
         chunks (default: one per ~2 500 frames, at most 2).  Each chunk's host->device copies, its sort + match launches
@@ -318,6 +332,7 @@ class BatchPlanner:
         stores every frame's 40 x 4 path STRAIGHT INTO `out_path` -- pinned host memory is mapped into the device's
         address space (unified addressing), the stores are posted writes over PCIe that overlap the kernel's own work --
         so no device->host copy of the paths follows the kernel; only the status words (4 B per frame) are copied.
+        `gather`: as for `plan` -- the path kernel also stores the paths into every peer GPU's gathered buffer.
         Asynchronous: everything is ordered on the caller's current stream (synchronize it before reading the
         outputs)."""
         B = offsets.numel() - 1
@@ -393,10 +408,10 @@ class BatchPlanner:
             # the path stage over the whole batch, then the paths and the status words back to the host
             inter = _lib.Intermediate(None, P["n_wv"].data_ptr(), P["left_wv"].data_ptr(), P["right_wv"].data_ptr(),
                                       P["l2r"].data_ptr(), P["r2l"].data_ptr(), None, None)
-            _lib.check(self.lib.fsd_path_batch(
+            _lib.check(self.lib.fsd_path_batch_gather(
                 C.byref(self.params), B, int(f64), P["pos"].data_ptr(), P["dir"].data_ptr(), C.byref(inter), None,
                 self._default_prev().data_ptr(), 0, (out_path if zero_copy else P["path"]).data_ptr(), P["st"].data_ptr(),
-                ws.data_ptr(), ws.numel(), cur.cuda_stream))
+                ws.data_ptr(), ws.numel(), cur.cuda_stream, C.byref(gather) if gather is not None else None))
             if not zero_copy:
                 out_path.copy_(P["path"], non_blocking=True)
             out_status.copy_(P["st"], non_blocking=True)

@@ -140,7 +140,9 @@ int fsd_initial_path(const fsd_params *params, double *out_prev_path, void *stre
 /*
  * Full planner: sort -> match -> path for n_frames independent frames.
  *   cones_xy [total][2], pos [B][2], dir [B][2] : fp32 (fsd_plan_batch) or fp64 (fsd_plan_batch_f64)
- *   out_path      [B][40][4] fp32  (u, x, y, curvature)
+ *   out_path      [B][40][4] fp32  (u, x, y, curvature).  Write-only for the library: it may be a device pointer
+ *                 or PINNED (mapped) HOST memory -- the path kernel then stores every finished frame straight
+ *                 into host memory (posted PCIe writes that overlap the planning; no device->host copy afterwards)
  *   out_left_idx  [B][12] int16, -1 padded;  out_right_idx likewise  (the "sort indices")
  *   inter         nullable
  *   force_P       nullable, [B]; > 0 forces the size of the last evaluation grid (parity mode)
@@ -188,6 +190,35 @@ int fsd_plan_batch_ex(const fsd_params *params, int mission, int n_frames, int c
                       const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
                       void *workspace, size_t workspace_bytes, void *stream, void *chunk_ready_event);
 
+/*
+ * Multi-GPU: the all-gather of the output paths FUSED into the path kernel (replaces the
+ * all_gather_into_tensor that follows fsd_plan_batch when a frame batch is sharded over the GPUs of one box).
+ * Every GPU plans its shard and the path kernel stores each finished frame's 40 x 4 fp32 path, besides out_path, into
+ * row (first_row + b) of EVERY peer's gathered [n_global][40][4] buffer: plain stores through peer-mapped pointers
+ * (NVLink / NVSwitch peer memory: CUDA IPC or torch symmetric memory, ft_fsd_path_planning_b200/distributed.py
+ * PeerGather), or -- when multicast_out_path is non-NULL -- ONE multimem.st per value through the NVSwitch multicast
+ * address of the buffer, which the switch replicates to all GPUs.  The transfer overlaps the planning frame by frame;
+ * no collective runs afterwards, only a cross-GPU barrier before the gathered buffer is read (the caller's:
+ * PeerGather.finish).  peer_out_path[r] may equal the local buffer for r = own rank.  Frames re-planned by the
+ * large-bounds second chance are stored to the peers as well.
+ */
+#define FSD_MAX_PEERS 16
+typedef struct fsd_gather {
+  int32_t n_peers;                       /* entries used in peer_out_path (0: no peer stores) */
+  int32_t reserved0;
+  int64_t first_row;                     /* row of this call's frame 0 in the gathered buffers */
+  float *peer_out_path[FSD_MAX_PEERS];   /* device-accessible pointers to every GPU's [n_global][40][4] fp32 buffer */
+  float *multicast_out_path;             /* nullable: multicast (multimem) address of the same buffer */
+} fsd_gather;
+
+/* fsd_plan_batch_ex + gather (nullable: exactly fsd_plan_batch_ex).  out_path may be NULL when gather is given. */
+int fsd_plan_batch_gather(const fsd_params *params, int mission, int n_frames, int coords_f64, const void *cones_xy,
+                          const uint8_t *cones_type, const int32_t *offsets, const void *pos, const void *dir,
+                          float *out_path, int16_t *out_left_idx, int16_t *out_right_idx, const fsd_intermediate *inter,
+                          const int16_t *force_P, const double *prev_path, int prev_path_stride, uint32_t *out_status,
+                          void *workspace, size_t workspace_bytes, void *stream, void *chunk_ready_event,
+                          const fsd_gather *gather);
+
 /* Stage entry points (same conventions).  fsd_sort_batch: ConeSorting only. */
 int fsd_sort_batch(const fsd_params *params, int n_frames, const float *cones_xy, const uint8_t *cones_type,
                    const int32_t *offsets, const float *pos, const float *dir, int16_t *out_left_idx,
@@ -227,6 +258,12 @@ int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const
                    const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
                    int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
                    size_t workspace_bytes, void *stream);
+/* fsd_path_batch with the fused all-gather of fsd_plan_batch_gather (gather nullable). */
+int fsd_path_batch_gather(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
+                   const fsd_intermediate *inter, const int16_t *force_P, const double *prev_path,
+                   int prev_path_stride, float *out_path, uint32_t *out_status, void *workspace,
+                   size_t workspace_bytes, void *stream,
+                          const fsd_gather *gather);
 
 /*
  * fsd_global_path_batch: CalculatePath.run_path_calculation with a GLOBAL PATH

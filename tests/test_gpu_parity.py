@@ -372,15 +372,49 @@ def test_plan_pinned_equals_plan(planner):
     ref = _np(planner.plan_host(batch, intermediates=True))
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h = [pin(a) for a in (batch.cones_xy, batch.cones_type, batch.offsets, batch.pos, batch.dir)]
-    for chunks in (None, 1, 3):
+    for chunks, zero_copy in ((None, True), (1, True), (3, True), (None, False), (3, False)):
+        # zero_copy: the path kernel stores straight into the pinned host buffer (no device->host copy of the paths)
         out = [torch.zeros((B, 40, 4), dtype=torch.float32).pin_memory(), torch.zeros((B, 12), dtype=torch.int16).pin_memory(),
                torch.zeros((B, 12), dtype=torch.int16).pin_memory(), torch.zeros((B,), dtype=torch.int32).pin_memory()]
-        planner.plan_pinned(*h, *out, chunks=chunks)
+        planner.plan_pinned(*h, *out, chunks=chunks, zero_copy=zero_copy)
         torch.cuda.synchronize()
         assert np.array_equal(out[0].numpy(), ref["path"]) and np.array_equal(out[1].numpy(), ref["left_idx"])
         assert np.array_equal(out[2].numpy(), ref["right_idx"]) and np.array_equal(out[3].numpy(), ref["status"])
     with pytest.raises(ValueError):
         planner.plan_pinned(torch.zeros((4, 2)), *h[1:], *out)  # not pinned
+
+
+def test_fused_gather_stores_every_row_into_every_peer_buffer(planner):
+    """fsd_plan_batch_gather / fsd_path_batch_gather: the path kernel stores each frame's path into row first_row + b of
+    every peer's gathered buffer (here: three buffers on the one GPU stand in for the peers' -- the stores are the same
+    instructions whether the pointer maps local or NVLink peer memory; the multi-process run is bench.py --gpus N)."""
+    from ft_fsd_path_planning_b200.distributed import PeerGather
+
+    B, first_row, n_global = 6000, 777, 8000  # large enough for the two-chunk plan: chunk B's rows must follow chunk A's
+    batch = synth.gen_autocross(47, B)
+    dev = planner.device
+    args = tuple(torch.from_numpy(a).to(dev) for a in (batch.cones_xy, batch.cones_type, batch.offsets, batch.pos, batch.dir))
+    ref = planner.plan(*args)
+    ref_path = ref.path.clone()
+    peers = [torch.full((n_global, 40, 4), -7.0, dtype=torch.float32, device=dev) for _ in range(3)]
+    res = planner.plan(*args, gather=PeerGather.make_descriptor([t.data_ptr() for t in peers], first_row))
+    torch.cuda.synchronize()
+    assert torch.equal(res.path, ref_path)
+    for t in peers:
+        assert torch.equal(t[first_row:first_row + B], ref_path)
+        assert bool((t[:first_row] == -7.0).all()) and bool((t[first_row + B:] == -7.0).all())
+    # the host-to-host entry point with the fused gather: paths to pinned host memory AND to the peers
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(a) for a in (batch.cones_xy, batch.cones_type, batch.offsets, batch.pos, batch.dir)]
+    out = [torch.zeros((B, 40, 4), dtype=torch.float32).pin_memory(), torch.zeros((B, 12), dtype=torch.int16).pin_memory(),
+           torch.zeros((B, 12), dtype=torch.int16).pin_memory(), torch.zeros((B,), dtype=torch.int32).pin_memory()]
+    for t in peers:
+        t.fill_(-7.0)
+    planner.plan_pinned(*h, *out, gather=PeerGather.make_descriptor([t.data_ptr() for t in peers], 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(out[0].numpy(), ref_path.cpu().numpy())
+    for t in peers:
+        assert torch.equal(t[:B], ref_path)
 
 
 def test_edge_cases(planner):

@@ -131,3 +131,20 @@ def test_host_planner_is_explicit_and_matches_goldens():
             BatchPlanner("cuda")
         with pytest.raises(RuntimeError):
             PathPlanner(MissionTypes.trackdrive)  # the default device is CUDA: no silent fallback to the host planner
+
+
+def test_peer_gather_descriptor_layout():
+    """struct fsd_gather as the kernels see it: peer pointers, first row, multicast address (no GPU needed)."""
+    import ctypes as C
+
+    from ft_fsd_path_planning_b200 import _lib
+    from ft_fsd_path_planning_b200.distributed import PeerGather
+
+    d = PeerGather.make_descriptor([0x1000, 0x2000, 0x3000], 4096)
+    assert (d.n_peers, d.first_row) == (3, 4096) and [d.peer_out_path[i] for i in range(3)] == [0x1000, 0x2000, 0x3000]
+    assert d.multicast_out_path is None and d.peer_out_path[3] is None
+    m = PeerGather.make_descriptor([0x1000, 0x2000], 0, multicast_ptr=0x9000)
+    assert m.n_peers == 0 and m.multicast_out_path == 0x9000  # one multimem store instead of a store per peer
+    assert C.sizeof(_lib.Gather) == 4 + 4 + 8 + 8 * _lib.MAX_PEERS + 8
+    with pytest.raises(ValueError):
+        PeerGather.make_descriptor(list(range(1, 18)), 0)
