@@ -34,6 +34,8 @@ void plan_range(const DevParams &P, int lo_frame, int hi_frame, const double *xy
   PathSmem *Q = new PathSmem();
   Q->pts = new d2[PCAP];
   Q->u = new double[PCAP];
+  Q->pcap = PCAP;
+  Q->W.cap = NCAP;
   FrameOut F0;
   StageOut O = {F0.li, F0.ri, F0.dbg, F0.n_wv, F0.lw, F0.rw, F0.l2r, F0.r2l, &F0.status};
   for (int b = lo_frame; b < hi_frame; ++b) {
@@ -101,6 +103,8 @@ extern "C" int fsd_plan_batch_cpu(const fsd_params *params, int mission, int n_f
     PathSmem *Q = new PathSmem();
     Q->pts = new d2[PCAP];
     Q->u = new double[PCAP];
+    Q->pcap = PCAP;
+    Q->W.cap = NCAP;
     initial_path_frame(*Q, P, initial);
     delete[] Q->pts;
     delete[] Q->u;
@@ -132,6 +136,8 @@ extern "C" int fsd_initial_path_cpu(const fsd_params *params, double *out) {
   PathSmem *Q = new PathSmem();
   Q->pts = new d2[PCAP];
   Q->u = new double[PCAP];
+  Q->pcap = PCAP;
+  Q->W.cap = NCAP;
   initial_path_frame(*Q, P, out);
   delete[] Q->pts;
   delete[] Q->u;

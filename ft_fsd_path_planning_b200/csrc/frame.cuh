@@ -82,14 +82,14 @@ FSD_DEVFN void store_match(const MatchSmem &M, int b, const StageOut &O) {
 // path stage for frame b, reading the matching tensors written by store_match
 FSD_DEVFN void path_from_tensors(PathSmem &S, int b, const StageOut &O, const FramePose &F, int force_P,
                                  const double *prev, const DevParams &P, double *out_f64, float *out_f32,
-                                 int16_t *grid_out) {
+                                 int16_t *grid_out, int xcap = 0) {
   const int nl = O.n_wv[2 * (size_t)b], nr = O.n_wv[2 * (size_t)b + 1];
   const d2 *left = reinterpret_cast<const d2 *>(O.left_wv + (size_t)b * WV_CAP * 2);
   const d2 *right = reinterpret_cast<const d2 *>(O.right_wv + (size_t)b * WV_CAP * 2);
   int grid[2] = {0, 0};
   double *out = out_f64 + (size_t)b * FSD_HORIZON * 4;
   unsigned st = path_frame(S, left, nl, right, nr, O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP, F, force_P,
-                           prev, P, out, grid);
+                           prev, P, out, grid, xcap);
   wsync();
   if (out_f32)
 #pragma unroll 1

@@ -14,16 +14,33 @@
 
 using namespace fsd;
 
+// Capacities of the working memory handed to the per-frame code: NCAP knot records / PCAP path points as compiled, or
+// more (fsd_hostcheck_set_caps) -- the records then continue BEHIND the PathSmem image, exactly as in path_kernel's
+// second chance, where frame slot 0's arena is extended over the shared memory of the whole CTA.
+// g_resume: the extra records are held in reserve -- fits start with NCAP records, suspend when they outgrow them and
+// are resumed with all g_cap records (path_kernel's in-kernel second chance, spline.cuh FIT_SUSPENDED / fit_resume).
+// start_cap: the records a fit starts with in that mode (NCAP, or fewer to make ordinary frames suspend in a test).
+static int g_cap = NCAP, g_pcap = PCAP, g_resume = 0, g_start = NCAP;
+extern "C" void fsd_hostcheck_set_caps(int cap, int pcap, int resume, int start_cap) {
+  g_cap = cap > NCAP ? cap : NCAP;
+  g_pcap = pcap > 0 ? pcap : PCAP;
+  g_start = start_cap >= 8 && start_cap <= NCAP ? start_cap : NCAP;
+  g_resume = resume && g_cap > g_start;
+}
 static PathSmem *new_path_smem() {
-  PathSmem *S = new PathSmem();
-  S->pts = new d2[PCAP];
-  S->u = new double[PCAP];
+  void *raw = std::calloc(1, sizeof(PathSmem) + (size_t)(g_cap - NCAP) * sizeof(KnotRec));
+  PathSmem *S = new (raw) PathSmem();
+  S->pts = new d2[g_pcap];
+  S->u = new double[g_pcap];
+  S->pcap = g_pcap;
+  S->W.cap = g_resume ? g_start : g_cap;
+  S->W.suspendable = g_resume;
   return S;
 }
 static void free_path_smem(PathSmem *S) {
   delete[] S->pts;
   delete[] S->u;
-  delete S;
+  std::free(S);
 }
 
 extern "C" int fsd_hostcheck_initial_path(const fsd_params *params, double *out) {
@@ -63,7 +80,7 @@ extern "C" int fsd_hostcheck_plan(const fsd_params *params, int n_frames, const 
     st |= match_from_sort(*S, *MS, F, P);
     store_match(*MS, b, O);
     status[b] = st;
-    path_from_tensors(*Q, b, O, F, force_P ? force_P[b] : 0, prev, P, out_path, nullptr, grid);
+    path_from_tensors(*Q, b, O, F, force_P ? force_P[b] : 0, prev, P, out_path, nullptr, grid, g_resume ? g_cap : 0);
   }
   delete S;
   delete MS;
@@ -154,10 +171,10 @@ extern "C" int fsd_hostcheck_fit(const double *pts, int m, double s, double *t, 
   if (ier != 10) {
     *n = Q->W.n;
     *k = Q->W.k;
-    for (int i = 0; i < Q->W.n; ++i) t[i] = Q->W.t[i];
+    for (int i = 0; i < Q->W.n; ++i) t[i] = Q->W.r[i].t;
     for (int i = 0; i < Q->W.n - Q->W.k - 1; ++i) {
-      c[2 * i] = Q->W.c[i][0];
-      c[2 * i + 1] = Q->W.c[i][1];
+      c[2 * i] = Q->W.r[i].c[0];
+      c[2 * i + 1] = Q->W.r[i].c[1];
     }
   }
   free_path_smem(Q);

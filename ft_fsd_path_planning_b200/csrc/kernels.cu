@@ -276,6 +276,9 @@ constexpr int PATH_THREADS = 32 * PATH_WPC;
 #define FSD_PATH_SMEM_PAD 0 /* measurement builds only: extra dynamic shared memory that lowers the CTAs resident per SM */
 #endif
 constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE + FSD_PATH_SMEM_PAD;
+// knot records behind frame slot 0 when its arena is extended over the shared memory of all the CTA's slots
+constexpr int PATH_XCAP_RAW = (int)((PATH_FPC * PATH_CTA_STRIDE - (sizeof(PathSmem) - sizeof(SplineWork::r))) / sizeof(KnotRec));
+constexpr int PATH_XCAP = PATH_XCAP_RAW < 192 ? PATH_XCAP_RAW : 192;
 
 // drop a frame's point-buffer lines from L2 (they are dead; written back they were 5x the algorithmic bytes of the step)
 __device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned) {
@@ -285,11 +288,39 @@ __device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned
       asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
 }
 
+// a finished frame: the 40 x 4 result from shared memory to the caller's buffers (and, multi-GPU, to every peer's gathered
+// buffer: the all-gather of the paths happens HERE), the status word, the grid sizes
+__device__ __noinline__ void store_path_frame(const double *out, unsigned st, const int *gr, int b, uint32_t *status,
+                                                 double *out_f64, float *out_f32, int16_t *grid_out, int flags,
+                                                 const fsd_gather &G) {
+  const int lane = PG::lane();
+  PG::sync();
+  for (int i = lane; i < FSD_HORIZON * 4; i += PG::N) {
+    const double v = out[i];
+    if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
+    if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;  // only when the caller asked for the fp64 path
+    if (flags & 4) fsd_store_peers(G, b, i, (float)v);
+  }
+  if (lane == 0) {
+    const unsigned before = status[b];
+    unsigned after = before | st;
+    // a static bound overflowed even with the CTA's whole memory: marked for the large-bounds kernel (kernels_big.cu), the
+    // earlier stages' bits parked in bits 16-30 meanwhile
+    if ((flags & 2) && (st & FSD_ST_OVERFLOW)) after |= 0x80000000u | ((before & 0x7fffu) << 16);
+    status[b] = after;
+    if (grid_out) {
+      grid_out[2 * (size_t)b] = (int16_t)gr[0];
+      grid_out[2 * (size_t)b + 1] = (int16_t)gr[1];
+    }
+  }
+  PG::sync();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
-                unsigned char *scratch, int *counter, int flags, fsd_gather G) {
+                unsigned char *scratch, int *counter, int flags, int cap0, const __grid_constant__ fsd_gather G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_state[PATH_FPC];
   __shared__ int s_base;
@@ -297,11 +328,7 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)grp * PATH_CTA_STRIDE);
   unsigned char *mine = scratch + ((size_t)blockIdx.x * PATH_FPC + grp) * PATH_SCRATCH_BYTES;
   const bool aligned = (reinterpret_cast<uintptr_t>(scratch) & 127u) == 0;  // never touch a line shared with a neighbour
-  if (lane == 0) {
-    S.pts = reinterpret_cast<d2 *>(mine);
-    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
-  }
-  PG::sync();
+  path_smem_bind(S, mine, PCAP, cap0, (flags & 8) ? 1 : 0);  // cap0 = NCAP (less only in tests of the suspend / resume path)
   for (int base = (int)blockIdx.x * PATH_FPC;; base += (int)gridDim.x * PATH_FPC) {
     if (counter) {
       // rounds handed out from a counter (zeroed before the launch): a CTA whose frames were cheap takes more rounds, so
@@ -323,8 +350,8 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     M.status = 0;
     M.P_grid = M.n_trim = 0;
     // the frame's 40 x 4 result is assembled in shared memory (the fits' factor storage is dead by the time it is written)
-    static_assert(sizeof(S.W.G) >= FSD_HORIZON * 4 * sizeof(double), "the result aliases SplineWork::G");
-    double *out = &S.W.G[0][0];
+    static_assert(sizeof(S.W.r) >= FSD_HORIZON * 4 * sizeof(double), "the result aliases the spline arena");
+    double *out = reinterpret_cast<double *>(S.W.r);
     if (active) {
       const FramePose F =
           make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
@@ -335,7 +362,7 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
                      force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P, out);
     }
 #if defined(FSD_NO_LOCKSTEP)
-    while (M.state != PS_DONE) pm_step(S, M, P);  // A/B and measurement builds only: free-running groups
+    while (M.state != PS_DONE && !pm_suspended(M)) pm_step(S, M, P);  // A/B and measurement builds only: free-running groups
 #ifdef FSD_FRAME_CYCLES
     fsd_t1 = clock64();
 #endif
@@ -344,42 +371,74 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     for (;;) {
       // free-run to the next alignment point (the end of a spline fit): the groups of the CTA are then inside the same
       // fit at the same time without waiting for each other after every pass
-      while (M.state != PS_DONE && !pm_is_alignment_state(M.state)) pm_step(S, M, P);
-      if (lane == 0) s_state[grp] = M.state;
+      while (M.state != PS_DONE && !pm_is_alignment_state(M.state) && !pm_suspended(M)) pm_step(S, M, P);
+      if (lane == 0) s_state[grp] = pm_suspended(M) ? (int)PS_DONE : M.state;  // nobody waits for a suspended frame
       __syncthreads();
       int behind = PS_DONE;
 #pragma unroll
       for (int g = 0; g < PATH_FPC; ++g) behind = min(behind, s_state[g]);
       __syncthreads();
       if (behind == PS_DONE) break;
-      if (M.state != PS_DONE && !(pm_is_alignment_state(M.state) && behind < M.state)) pm_step(S, M, P);
+      if (M.state != PS_DONE && !pm_suspended(M) && !(pm_is_alignment_state(M.state) && behind < M.state)) pm_step(S, M, P);
     }
 #endif
-    if (active) {
-      PG::sync();
-      for (int i = lane; i < FSD_HORIZON * 4; i += PG::N) {
-        const double v = out[i];
-        if (out_f32) out_f32[(size_t)b * FSD_HORIZON * 4 + i] = (float)v;
-        if (out_f64) out_f64[(size_t)b * FSD_HORIZON * 4 + i] = v;  // only when the caller asked for the fp64 path
-        // multi-GPU: the all-gather of the paths happens HERE -- the frame's row goes to every peer's gathered buffer
-        if (flags & 4) fsd_store_peers(G, b, i, (float)v);
-      }
-      if (lane == 0) {
-        const unsigned before = O.status[b];
-        unsigned after = before | M.status;
-        // a static bound overflowed in this stage: marked for the large-bounds second chance (kernels_big.cu), the earlier
-        // stages' bits parked in bits 16-30 meanwhile
-        if ((flags & 2) && (M.status & FSD_ST_OVERFLOW)) after |= 0x80000000u | ((before & 0x7fffu) << 16);
-        O.status[b] = after;
-        if (grid_out) {
-          grid_out[2 * (size_t)b] = (int16_t)M.P_grid;
-          grid_out[2 * (size_t)b + 1] = (int16_t)M.n_trim;
+    // A frame whose fit wants more knots than its arena holds is SUSPENDED, not truncated (spline.cuh: FIT_SUSPENDED); the
+    // others of its round do not wait for it.  When the round is over -- every other frame stored, their shared memory
+    // dead -- the frame's own warp moves its state to frame slot 0, whose arena now extends over the shared memory of ALL
+    // the CTA's slots (PATH_XCAP knot records), and carries on from where it stopped: same code, warm instruction caches,
+    // nothing recomputed, while the other CTAs keep taking rounds from the counter.  Rare (about one frame in 10^5), but a
+    // frame that is planned again from scratch by a kernel of its own after this one costs a whole single-warp path
+    // calculation of latency at the end of the step.
+    const bool resume = active && pm_suspended(M);
+    if (active && !resume) {
+      int gr[2] = {M.P_grid, M.n_trim};
 #ifdef FSD_FRAME_CYCLES
-          // measurement build only: this frame's own path-machine time in units of 256 cycles instead of n_trim
-          grid_out[2 * (size_t)b + 1] = (int16_t)min((fsd_t1 - fsd_t0) >> 8, 32767ll);
+      gr[1] = (int)min((fsd_t1 - fsd_t0) >> 8, 32767ll);  // measurement build only: the frame's path-machine time / 256 cycles
 #endif
+      store_path_frame(out, M.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
+    }
+    if (flags & 8) {
+      if (lane == 0) s_state[grp] = resume ? 1 : 0;
+      __syncthreads();
+      int any = 0;
+#pragma unroll
+      for (int g = 0; g < PATH_FPC; ++g) any |= s_state[g] << g;
+      if (any) {
+        PathSmem &X = *reinterpret_cast<PathSmem *>(smem_raw);  // frame slot 0
+        const int first = __ffs(any) - 1;
+        for (int g = 0; g < PATH_FPC; ++g) {
+          if (!((any >> g) & 1)) continue;
+          if (grp == g && g != first) {
+            // a second suspended frame in the same round (its image would not survive the first one's resume): flagged
+            // like a truncated fit; with fixup scratch (flags & 2) the large-bounds kernel plans it again
+            pm_give_up_suspended(M);
+            int gr[2] = {0, 0};
+            store_path_frame(out, M.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
+          } else if (grp == g) {
+            if (g != 0) {
+              // the frame's image (pointers to ITS point buffers, spline header, knot records) moves to slot 0
+              const double *src = reinterpret_cast<const double *>(&S);
+              double *dst = reinterpret_cast<double *>(&X);
+              for (int i = lane; i < (int)(sizeof(PathSmem) / sizeof(double)); i += PG::N) dst[i] = src[i];
+              PG::sync();
+            }
+            if (lane == 0) {
+              X.W.cap = PATH_XCAP;
+              X.W.suspendable = 0;  // whatever does not fit now is flagged (FSD_ST_OVERFLOW) as ever
+            }
+            PG::sync();
+            M.out = reinterpret_cast<double *>(X.W.r);
+            fit_resume(X.W, M.fit);
+            pm_run(X, M, P);
+            int gr[2] = {M.P_grid, M.n_trim};
+            store_path_frame(M.out, M.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
+          }
+          __syncthreads();
         }
+        // slot 0 belongs to warp 0 again
+        if (grp == 0) path_smem_bind(S, mine, PCAP, cap0, 1);
       }
+      if (!counter) __syncthreads();  // (static stride: no barrier at the top of the next round before s_state is rewritten)
     }
     if (flags & 1) {
       // the frame's points are dead: drop the buffer's lines from L2 now, before the cache gets round to writing the
@@ -397,12 +456,7 @@ __global__ void __launch_bounds__(32) initial_path_kernel(DevParams P, double *o
   // PathSmem image
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
-  if (PG::lane() == 0) {
-    unsigned char *mine = smem_raw + ((sizeof(PathSmem) + 15) / 16) * 16;
-    S.pts = reinterpret_cast<d2 *>(mine);
-    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
-  }
-  PG::sync();
+  path_smem_bind(S, smem_raw + ((sizeof(PathSmem) + 15) / 16) * 16, PCAP, NCAP);
   initial_path_frame(S, P, out);
 }
 
@@ -450,12 +504,7 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int grp = (int)threadIdx.x / PG::N;
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)grp * PATH_CTA_STRIDE);
-  if (PG::lane() == 0) {
-    unsigned char *mine = scratch + ((size_t)blockIdx.x * PATH_FPC + grp) * PATH_SCRATCH_BYTES;
-    S.pts = reinterpret_cast<d2 *>(mine);
-    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
-  }
-  PG::sync();
+  path_smem_bind(S, scratch + ((size_t)blockIdx.x * PATH_FPC + grp) * PATH_SCRATCH_BYTES, PCAP, NCAP);
   for (int s = (int)blockIdx.x * PATH_FPC + grp; s < n_steps; s += (int)gridDim.x * PATH_FPC) {
     const SkidReloc R = *reinterpret_cast<const SkidReloc *>(reloc + 8 * (size_t)traj_of_step[s]);
     int grid[2] = {0, 0};
@@ -487,12 +536,7 @@ __global__ void __launch_bounds__(32) skid_fixup_kernel(DevParams P, int n_traj,
                                                         unsigned char *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw);
-  if (PG::lane() == 0) {
-    unsigned char *mine = scratch + (size_t)blockIdx.x * PATH_SCRATCH_BYTES;
-    S.pts = reinterpret_cast<d2 *>(mine);
-    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
-  }
-  PG::sync();
+  path_smem_bind(S, scratch + (size_t)blockIdx.x * PATH_SCRATCH_BYTES, PCAP, NCAP);
   const unsigned uses_prev = FSD_ST_FEW_CONES | FSD_ST_FEW_MATCHES | FSD_ST_FIT1_FAILED | FSD_ST_PATH_TOO_FAR |
                              FSD_ST_MPC_FAILED | FSD_ST_REF_RAISES | FSD_ST_UNSUPPORTED;
   for (int t = blockIdx.x; t < n_traj; t += gridDim.x) {
@@ -559,12 +603,25 @@ void set_smem(K kernel, size_t bytes) {
 //   bit 3: fsd_plan_batch never splits a batch into two chunks on two streams
 //   bit 4: the path kernel discards a frame's point-buffer lines from L2 when the frame ends
 //   (bit 5, the point buffers as a persisting L2 access-policy window, was measured and removed: 4x MORE write-back)
+//   bit 6: fits that outgrow their arena are truncated and flagged (kernels_big.cu plans the frame again afterwards) instead
+//          of being suspended and resumed inside the path kernel with the CTA's whole shared memory
 int plan_mode() {
   static const int mode = [] {
     const char *e = std::getenv("FSD_PLAN_MODE");
     return e ? std::atoi(e) : FSD_DEFAULT_PLAN_MODE;
   }();
   return mode;
+}
+
+// Knot records a frame's fits start with in path_kernel: NCAP.  FSD_TEST_CAP (8 .. NCAP, read once) lowers it so that
+// ordinary frames outgrow their arena and exercise the suspend / resume path in the GPU tests; results do not change.
+int start_cap() {
+  static const int cap = [] {
+    const char *e = std::getenv("FSD_TEST_CAP");
+    const int v = e ? std::atoi(e) : NCAP;
+    return v >= 8 && v <= NCAP ? v : NCAP;
+  }();
+  return cap;
 }
 
 int device_info(DeviceInfo **out) {
@@ -837,10 +894,11 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
                 inter->l2r, inter->r2l, out_status};
   const int grid = grid_for(n_frames, D->sm_count, D->path_ctas, PATH_FPC);
   int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
-  const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0) | (peers ? 4 : 0);
+  const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0) | (peers ? 4 : 0) |
+                    (((plan_mode() & 64) || PATH_FPW != 1) ? 0 : 8);
   path_kernel<T><<<grid, PATH_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
-      round_counter, flags, G);
+      round_counter, flags, start_cap(), G);
   rc = check_launch();
   if (rc != FSD_OK || !fixup_scratch) return rc;
   // frames on which a static bound of path_kernel overflowed get a second chance with the large bounds (kernels_big.cu)

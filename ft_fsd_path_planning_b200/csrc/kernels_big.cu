@@ -23,12 +23,7 @@ constexpr size_t BIG_STRIDE = (sizeof(PathSmem) + 15) / 16 * 16;
 __device__ PathSmem &group_state(unsigned char *smem_raw, unsigned char *scratch) {
   const int grp = (int)threadIdx.x / PG::N;
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)grp * BIG_STRIDE);
-  if (PG::lane() == 0) {
-    unsigned char *mine = scratch + ((size_t)blockIdx.x * BIG_FPC + grp) * PATH_SCRATCH_BYTES;
-    S.pts = reinterpret_cast<d2 *>(mine);
-    S.u = reinterpret_cast<double *>(mine + (size_t)PCAP * sizeof(d2));
-  }
-  PG::sync();
+  path_smem_bind(S, scratch + ((size_t)blockIdx.x * BIG_FPC + grp) * PATH_SCRATCH_BYTES, PCAP, NCAP);
   return S;
 }
 
@@ -60,7 +55,7 @@ __global__ void __launch_bounds__(32 * BIG_WPC)
     if (b >= n_poses) break;
     const FramePose F = make_pose(pos[2 * b], pos[2 * b + 1], dir[2 * b], dir[2 * b + 1]);
     int grid[2] = {0, 0};
-    double *out = &S.W.G[0][0];  // the 40 x 4 result is assembled in shared memory (the fits' factor storage is dead)
+    double *out = reinterpret_cast<double *>(S.W.r);  // the 40 x 4 result is assembled in shared memory (the fits' factor storage is dead)
     const unsigned st = path_global(S, gpath, n_points, F, force_P ? (int)force_P[b] : 0, prev + (size_t)b * prev_stride, P,
                                     out, grid);
     store_result(out, st, grid, b, out_f64, out_f32, grid_out);
@@ -97,7 +92,7 @@ __global__ void __launch_bounds__(32 * BIG_WPC)
       }
       const FramePose F = make_pose(px, py, dx, dy);
       int grid[2] = {0, 0};
-      double *out = &S.W.G[0][0];
+      double *out = reinterpret_cast<double *>(S.W.r);
       const unsigned st = path_frame(S, reinterpret_cast<const d2 *>(left_wv + (size_t)b * FSD_MAX_WV * 2), n_wv[2 * (size_t)b],
                                      reinterpret_cast<const d2 *>(right_wv + (size_t)b * FSD_MAX_WV * 2), n_wv[2 * (size_t)b + 1],
                                      l2r + (size_t)b * FSD_MAX_WV, r2l + (size_t)b * FSD_MAX_WV, F,
@@ -148,7 +143,7 @@ int fsd_big_global_path(const fsd_params *params, int n_poses, const double *pos
                         int n_points, const int16_t *force_P, const double *prev, int prev_stride, double *out_f64,
                         float *out_f32, int16_t *grid_out, uint32_t *status, unsigned char *scratch, int *counter,
                         int sm_count, cudaStream_t stream) {
-  static_assert(sizeof(SplineWork::G) >= FSD_HORIZON * 4 * sizeof(double), "the result aliases SplineWork::G");
+  static_assert(sizeof(SplineWork::r) >= FSD_HORIZON * 4 * sizeof(double), "the result aliases the spline arena");
   const size_t smem = BIG_FPC * BIG_STRIDE;
   if (cudaFuncSetAttribute(global_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();

@@ -27,11 +27,25 @@ enum { RC_OK = 0, RC_VALUE_ERROR = 1, RC_RAISES = 2, RC_UNSUPPORTED = 3 };
 constexpr size_t PATH_SCRATCH_BYTES = (size_t)PCAP * (sizeof(d2) + sizeof(double));
 
 struct PathSmem {
-  d2 *pts;    // [PCAP]
-  double *u;  // [PCAP]
-  SplineWork W;
-  int32_t si[4];
+  d2 *pts;       // [pcap]
+  double *u;     // [pcap]
+  int32_t pcap;  // path points behind pts / u (PCAP unless the caller provides larger buffers)
+  int32_t pad_[3];
+  SplineWork W;  // LAST member (its arena may extend past the struct, see SplineWork::cap)
 };
+
+// a frame's working memory: the point buffers (`pcap` points in one block: pts, then u) and the spline arena (`cap`
+// records, at least NCAP of them inside S itself)
+FSD_DEV void path_smem_bind(PathSmem &S, unsigned char *points, int pcap, int cap, int suspendable = 0) {
+  if (PG::lane() == 0) {
+    S.pts = reinterpret_cast<d2 *>(points);
+    S.u = reinterpret_cast<double *>(points + (size_t)pcap * sizeof(d2));
+    S.pcap = pcap;
+    S.W.cap = cap;
+    S.W.suspendable = suspendable;  // a fit that outgrows `cap` stops as FIT_SUSPENDED instead of being truncated
+  }
+  PG::sync();
+}
 
 // ---- hyper circle fit -----------------------------------------------------------------------------
 
@@ -377,7 +391,7 @@ FSD_DEVFN void pm_stage_tail(PathSmem &S, PathMachine &M, const DevParams &P) {
       circle_fit_warp(rel, nr, cx, cy, radius);
       const double r_use = fmin(fmax(radius, 10.0), 100.0);
       const double lastx = path[n - 1].x, lasty = path[n - 1].y;
-      const int room = PCAP - (int)(path - S.pts) - n;
+      const int room = S.pcap - (int)(path - S.pts) - n;
       if (room < 49) {
         M.tail_status |= FSD_ST_OVERFLOW;
         pm_tail_failed(S, M, RC_UNSUPPORTED);
@@ -445,7 +459,7 @@ FSD_DEVFN void pm_stage_after_fit2(PathSmem &S, PathMachine &M, const DevParams 
     pm_tail_failed(S, M, (M.tail_status & FSD_ST_UNSUPPORTED) ? RC_UNSUPPORTED : RC_VALUE_ERROR);
     return;
   }
-  const int nfix = pm_evaluate(S, P.mpc_len * 1.5, P.predict_every, S.pts, PCAP);
+  const int nfix = pm_evaluate(S, P.mpc_len * 1.5, P.predict_every, S.pts, S.pcap);
   if (nfix < 0 || nfix - 1 <= 1) {
     if (nfix < 0) M.tail_status |= FSD_ST_OVERFLOW;
     pm_tail_failed(S, M, RC_UNSUPPORTED);
@@ -509,9 +523,9 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   }
   PG::sync();
   // _calculate_path_curvature :163-193 / calculate_path_curvature :49-93 (open path).  The curvature samples live in the
-  // fit's normal-equation storage: the fits are over, only knots and coefficients of the last one are still needed.
-  static_assert(sizeof(S.W.N) >= GRID_CAP * sizeof(double), "curvature samples alias SplineWork::N");
-  double *curv = &S.W.N[0][0];
+  // chord-parameter buffer: the fits are over and their data abscissae dead.
+  static_assert(PCAP >= GRID_CAP, "curvature samples alias the chord-parameter buffer");
+  double *curv = S.u;
   int window = Pn / 5 < 30 ? Pn / 5 : 30;
   if (window % 2 == 0) window += 1;
   const int hw = window / 2;
@@ -560,7 +574,7 @@ FSD_DEVFN void pm_stage_after_fit1(PathSmem &S, PathMachine &M, const DevParams 
     return;
   }
   if (M.mode == 1) {
-    const int nd = pm_evaluate(S, S.W.max_u, P.predict_every, S.pts, PCAP);
+    const int nd = pm_evaluate(S, S.W.max_u, P.predict_every, S.pts, S.pcap);
     if (nd < 0) {
       M.status |= FSD_ST_UNSUPPORTED | FSD_ST_OVERFLOW;
       M.state = PS_DONE;
@@ -571,7 +585,7 @@ FSD_DEVFN void pm_stage_after_fit1(PathSmem &S, PathMachine &M, const DevParams 
     return;
   }
   // the path update lives in S.pts[1..], slot 0 is kept for connect_path_to_car
-  const int nu = pm_evaluate(S, S.W.max_u, P.predict_every, S.pts + 1, PCAP - 1);
+  const int nu = pm_evaluate(S, S.W.max_u, P.predict_every, S.pts + 1, S.pcap - 1);
   if (nu < 1) {
     pm_finish_with_prev(M, nu < 0 ? (FSD_ST_UNSUPPORTED | FSD_ST_OVERFLOW) : FSD_ST_REF_RAISES);
     return;
@@ -726,7 +740,7 @@ FSD_DEVFN void pm_begin_global(PathSmem &S, PathMachine &M, const double *gpath,
     const unsigned mask = PG::ballot(keep);
     const int slot = ncl + FSD_POPC(mask & ((1u << lane) - 1u));
     if (keep) {
-      if (slot < PCAP) {
+      if (slot < S.pcap) {
         S.pts[slot].x = x;
         S.pts[slot].y = y;
       } else {
@@ -770,19 +784,48 @@ FSD_DEVFN void pm_begin_initial(PathSmem &S, PathMachine &M, const DevParams &P,
   pm_start_fit1(S, M, S.pts, FSD_HORIZON, P);
 }
 
+// a fit of the machine is waiting for a larger arena (only when the caller set SplineWork::suspendable)
+FSD_DEV bool pm_suspended(const PathMachine &M) { return M.state != PS_DONE && M.fit.phase == FIT_SUSPENDED; }
+
 FSD_DEVFN void pm_run(PathSmem &S, PathMachine &M, const DevParams &P) {
 #pragma unroll 1
-  while (M.state != PS_DONE) pm_step(S, M, P);
+  while (M.state != PS_DONE && !pm_suspended(M)) pm_step(S, M, P);
 }
 
 // ---- blocking wrappers -------------------------------------------------------------------------------------------
 
+// a suspended fit (SplineWork::suspendable) that nobody resumes: flagged like a truncated one, output = previous path
+FSD_DEVFN void pm_give_up_suspended(PathMachine &M) {
+  if (pm_suspended(M)) pm_finish_with_prev(M, FSD_ST_OVERFLOW | FSD_ST_UNSUPPORTED);
+}
+
+// xcap: knot records really available behind S.W.r when the caller set S.W.suspendable and holds a larger arena in
+// reserve than S.W.cap says (the host-check build does, to exercise the suspend / resume path of path_kernel): a
+// suspended fit is resumed with them.
 FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *right, int nr, const int16_t *l2r,
                               const int16_t *r2l, const FramePose &F, int force_P, const double *prev,
-                              const DevParams &P, double *out, int *grid) {
+                              const DevParams &P, double *out, int *grid, int xcap = 0) {
   PathMachine M;
   pm_begin_frame(S, M, left, nl, right, nr, l2r, r2l, F, force_P, prev, P, out);
   pm_run(S, M, P);
+  if (pm_suspended(M) && xcap > S.W.cap) {
+    const int cap0 = S.W.cap;
+    PG::sync();
+    if (PG::lane() == 0) {
+      S.W.cap = xcap;
+      S.W.suspendable = 0;
+    }
+    PG::sync();
+    fit_resume(S.W, M.fit);
+    pm_run(S, M, P);
+    PG::sync();
+    if (PG::lane() == 0) {
+      S.W.cap = cap0;
+      S.W.suspendable = 1;
+    }
+    PG::sync();
+  }
+  pm_give_up_suspended(M);
   if (grid && PG::lane() == 0) {
     grid[0] = M.P_grid;
     grid[1] = M.n_trim;

@@ -333,7 +333,7 @@ FSD_DEVFN unsigned skidpad_step(PathSmem &S, const SkidReloc &R, const double *t
     int fin = index + (int)fdiv(25.0, mean);
     if (fin > n_table) fin = n_table;
     nu = fin - index;
-    if (nu > PCAP - 64) nu = PCAP - 64;
+    if (nu > S.pcap - 64) nu = S.pcap - 64;
 #pragma unroll 1
     for (int i = lane; i < nu; i += PG::N) {
       S.pts[1 + i].x = table[2 * (index + i)];

@@ -69,6 +69,15 @@ def lib():
     return _lib
 
 
+def set_caps(cap: int = 0, pcap: int = 0, resume: bool = False, start_cap: int = 0) -> None:
+    """Knot records / path points of the working memory of later calls (0, 0: the compiled NCAP / PCAP).  With cap > NCAP
+    the records continue behind the PathSmem image -- the memory layout of path_kernel's in-kernel second chance.
+    resume=True holds the extra records in reserve: a fit starts with NCAP records, is SUSPENDED when it outgrows them and
+    resumed with all `cap` (what path_kernel does); resume=False gives every fit all `cap` records from the start.
+    start_cap (8 .. NCAP): the records a fit starts with when resume=True -- small values make ordinary frames suspend."""
+    lib().fsd_hostcheck_set_caps(int(cap), int(pcap), int(bool(resume)), int(start_cap))
+
+
 def default_params() -> Params:
     p = Params()
     lib().fsd_hostcheck_params_default(C.byref(p))

@@ -417,6 +417,46 @@ def test_fused_gather_stores_every_row_into_every_peer_buffer(planner):
         assert torch.equal(t[:B], ref_path)
 
 
+def test_frame_that_outgrows_its_knot_records_is_resumed_inside_the_path_kernel(planner):
+    """Frame 59 383 of the bench stream needs 33 knots in one fit (a frame slot holds 34 records).  A fit that outgrows
+    its slot is suspended and resumed at the end of its round with the arena extended over the CTA's shared memory: no
+    OVERFLOW flag, result equal to the oracle's, the neighbours in its round untouched."""
+    batch = synth.gen_autocross(2, 64, start=59352)
+    ref = oracle.plan_batch(batch.astype(np.float64), threads=4)
+    r = _np(planner.plan_host(batch, intermediates=True))
+    assert not (r["status"].astype(np.uint32) & 0x80000100).any()
+    assert np.array_equal(r["left_idx"], ref["left_idx"]) and np.array_equal(r["right_idx"], ref["right_idx"])
+    assert np.array_equal(r["status"].astype(np.uint32) & 0xFFFFFF7F, ref["status"].astype(np.uint32) & 0xFFFFFF7F)
+    same_P = r["grid"][:, 0] == ref["P"]
+    assert same_P[31]
+    assert np.abs(r["path_f64"] - ref["path"])[same_P].max() <= 1e-7
+    assert np.abs(r["path"].astype(np.float64) - ref["path"])[same_P].max() <= 1e-4
+
+
+def test_suspend_and_resume_is_invisible_in_the_results():
+    """FSD_TEST_CAP=14 makes the fits of ordinary frames outgrow their (artificially small) arena: about every second
+    frame is suspended and resumed with the CTA's shared memory, or -- a second one in the same round -- handed to the
+    large-bounds kernel.  A child process (the library reads the variable once) must produce the very bytes of the
+    default run."""
+    import subprocess
+    import sys
+    import tempfile
+
+    B = 3000
+    batch = synth.gen_mixed(31, B)
+    ref = _np(BatchPlanner("cuda:0").plan_host(batch, intermediates=True))
+    with tempfile.TemporaryDirectory() as tmp:
+        code = (f"import sys, numpy as np, torch; sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r});"
+                "from ft_fsd_path_planning_b200 import BatchPlanner, synth;"
+                f"r = BatchPlanner('cuda:0').plan_host(synth.gen_mixed(31, {B}), intermediates=True); torch.cuda.synchronize();"
+                f"np.savez({os.path.join(tmp, 'o.npz')!r}, path=r.path_f64.cpu().numpy(), status=r.status.cpu().numpy(), grid=r.grid.cpu().numpy())")
+        env = dict(os.environ, FSD_TEST_CAP="14")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+        z = np.load(os.path.join(tmp, "o.npz"))
+        assert np.array_equal(z["status"], ref["status"]) and np.array_equal(z["grid"], ref["grid"])
+        assert np.array_equal(z["path"], ref["path_f64"])
+
+
 def test_edge_cases(planner):
     """Empty batch, frames without cones, ragged frames, more than FSD_MAX_CONES cones."""
     z = np.zeros((0, 2))

@@ -83,3 +83,34 @@ def test_knn_graph_sources_match_oracle_adjacency(golden):
     nbr, deg = hostcheck.knn(batch)
     ref_nbr, ref_deg = oracle.adjacency(batch)
     assert adjacency_equal(nbr, deg, ref_nbr, ref_deg), name
+
+
+def test_suspended_fit_resumed_with_an_extended_arena():
+    """A fit that wants more knots than its arena holds is SUSPENDED (not truncated) and resumed -- nothing recomputed --
+    once the arena is larger: path_kernel does this for the rare frame that outgrows its NCAP knot records, with the
+    CTA's whole shared memory as the larger arena.  Same sources, one lane: frames that start with 12 / 16 / 24 records
+    and are resumed with 192 give the same bytes as fits that had the large arena all along; frame 59 383 of the bench
+    stream (33 knots in one fit, in rank 5's shard of the 8-GPU bench) equals the oracle, which has no static bounds."""
+    import oracle
+    from ft_fsd_path_planning_b200 import synth
+
+    batch = synth.concat_batches([synth.gen_autocross(2, 4, start=59382), synth.gen_autocross(7, 60),
+                                  synth.remove_color_info(synth.gen_autocross(8, 32))]).astype(np.float64)
+    try:
+        hostcheck.set_caps(192, 8 * 704)
+        ext = hostcheck.plan_batch(batch)
+        outs = {}
+        for start in (12, 16, 24, 0):
+            hostcheck.set_caps(192, 0, resume=True, start_cap=start)
+            outs[start] = hostcheck.plan_batch(batch)
+    finally:
+        hostcheck.set_caps(0, 0)
+    assert not (ext["status"] & 0x100).any()
+    for start, res in outs.items():
+        for k in ("path", "grid", "status", "left_idx", "right_idx"):
+            assert np.array_equal(res[k], ext[k]), (start, k)
+    ref = oracle.plan_batch(batch, threads=2)
+    assert np.array_equal(ext["left_idx"], ref["left_idx"]) and np.array_equal(ext["right_idx"], ref["right_idx"])
+    same_P = ext["grid"][:, 0] == ref["P"]
+    assert same_P[1] and same_P.mean() > 0.5
+    assert np.abs(ext["path"] - ref["path"])[same_P].max() <= 1e-8
