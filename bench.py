@@ -249,6 +249,21 @@ def parity_vs_oracle(planner, batch, dev_args, timed_path, threads):
     path = g(res.path)
     same_P = grid[:, 0] == ref["P"]
     err = np.abs(path.astype(np.float64) - ref["path"]).reshape(B, -1).max(1)
+    # Frames above the tolerance: is the frame ill-posed for the ORACLE itself?  Some frames sit on a decision boundary of
+    # the smoothing-spline fit (SURVEY Q13 is one family): perturbing the input coordinates by one unit in the last place
+    # flips the oracle's own path by millimetres.  Such a frame is counted as a tie when the CUDA path is within the
+    # tolerance of one of the oracle's answers on the perturbed inputs; anything else is a real mismatch.
+    above = np.nonzero(same_P & (err > 1e-4))[0]
+    ties, rng = [], np.random.default_rng(0)
+    for b in above[:16]:
+        one = batch.slice(int(b), int(b) + 1).astype(np.float64)
+        for _ in range(64):
+            jit = type(one)(one.cones_xy * (1.0 + rng.normal(0.0, 2e-16, one.cones_xy.shape)), one.cones_type, one.offsets,
+                            one.pos, one.dir)
+            alt = oracle.plan_batch(jit, threads=1)
+            if alt["P"][0] == grid[b, 0] and np.abs(path[b].astype(np.float64) - alt["path"][0]).max() <= 1e-4:
+                ties.append(int(b))
+                break
     return {
         "frames": B,
         "sort_idx_mismatch": int(((li != ref["left_idx"]).any(1) | (ri != ref["right_idx"]).any(1)).sum()),
@@ -260,7 +275,9 @@ def parity_vs_oracle(planner, batch, dev_args, timed_path, threads):
         "status_mismatch": int(((st & 0xFFFFFF7F) != (ref["status"] & 0xFFFFFF7F)).sum()),
         "grid_P_mismatch": int((~same_P).sum()),
         "path_max_err": float(err[same_P].max()) if same_P.any() else None,
-        "path_frames_above_1e-4": int((err[same_P] > 1e-4).sum()),
+        "path_frames_above_1e-4": int(len(above)),
+        "of_which_oracle_ties": len(ties),  # the oracle itself gives the CUDA answer when its inputs move by 1 ulp
+        "path_frames_mismatching": int(len(above) - len(ties)),
         "timed_output_identical": bool(torch.equal(res.path, timed_path)),
         "frames_with_2plus_configs": int((ref["n_configs"] >= 2).any(1).sum()),
         "flagged": int(((ref["status"] & 0x700) != 0).sum()),

@@ -9,6 +9,7 @@ frame" semantics).  `PathPlanner` mirrors the reference's facade
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Any, List, Optional, Sequence, Tuple, Union
 
@@ -321,11 +322,11 @@ class BatchPlanner:
 
     def plan_pinned(self, cones_xy: torch.Tensor, cones_type: torch.Tensor, offsets: torch.Tensor, pos: torch.Tensor,
                     direction: torch.Tensor, out_path: torch.Tensor, out_left_idx: torch.Tensor,
-                    out_right_idx: torch.Tensor, out_status: torch.Tensor, *, chunks: Optional[int] = None,
+                    out_right_idx: torch.Tensor, out_status: torch.Tensor, *, chunks=None,
                     zero_copy: bool = True, gather: Optional["_lib.Gather"] = None) -> None:
         """Host-to-host entry point: all arguments are PINNED host tensors (inputs as for `plan`, outputs
         [B, 40, 4] float32 / [B, 12] int16 / [B, 12] int16 / [B] int32).  The batch is cut into `chunks` contiguous
-        chunks (default: one per ~2 500 frames, at most 2).  Each chunk's host->device copies, its sort + match launches
+        chunks (default: two equal chunks from 5 000 frames on).  Each chunk's host->device copies, its sort + match launches
         (free-running kernels: small chunks cost nothing) and the device->host copy of its sort indices are queued on a
         stream of its own, so the copies of one chunk overlap the kernels of the others; the path stage then runs ONCE
         over the whole batch (its CTA-synchronous rounds want a full grid).  With `zero_copy` (default) the path kernel
@@ -351,13 +352,21 @@ class BatchPlanner:
             raise ValueError("outputs must be [B,40,4] float32, [B,12] int16, [B,12] int16, [B] int32")
         _check_offsets(offsets.numpy(), int(cones_xy.shape[0]))
         f64 = cones_xy.dtype == torch.float64
-        K = chunks if chunks is not None else max(1, min(2, B // 2500))
-        K = max(1, min(int(K), B))
+        # chunks: None = two equal chunks (one below 5 000 frames; measured best, tools/pinned_probe.py: a short first chunk
+        # whose copy is exposed for less loses more in kernel launches than it gains); an int = that many equal chunks; a
+        # sequence of fractions = the upper bounds of the chunks (ending in 1.0)
+        if chunks is None:
+            fr = [0.5, 1.0] if B >= 5000 else [1.0]
+        elif isinstance(chunks, int):
+            fr = [(k + 1) / max(1, min(chunks, B)) for k in range(max(1, min(chunks, B)))]
+        else:
+            fr = [float(f) for f in chunks]
+        bounds = sorted({0, B, *(min(B, max(0, int(round(f * B)))) for f in fr)})
+        K = len(bounds) - 1
         dev = self.device
-        key = ("pinned", B, int(cones_xy.shape[0]), f64, K)
+        key = ("pinned", B, int(cones_xy.shape[0]), f64, tuple(bounds))
         if self._pinned_key != key:
             e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
-            bounds = [B * k // K for k in range(K + 1)]
             self._pinned = {
                 "xy": e((max(int(cones_xy.shape[0]), 1), 2), cones_xy.dtype), "ty": e((max(int(cones_xy.shape[0]), 1),), torch.uint8),
                 "off": e((B + 1,), torch.int32), "pos": e((B, 2), cones_xy.dtype), "dir": e((B, 2), cones_xy.dtype),

@@ -17,7 +17,7 @@ out = [torch.zeros((n, 40, 4), dtype=torch.float32).pin_memory(), torch.zeros((n
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
 ref = None
 for zc in (False, True):
-    for K in (1, 2, 3, 4):
+    for K in (2, None, (0.0625, 0.25, 0.5, 1.0), (0.25, 1.0), (0.125, 0.375, 0.6875, 1.0)):
         for o in out:
             o.zero_()
         for _ in range(3):

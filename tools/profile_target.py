@@ -18,5 +18,7 @@ pos, dr = torch.from_numpy(batch.pos).to(dev), torch.from_numpy(batch.dir).to(de
 stage = len(sys.argv) > 3 and sys.argv[3] == "stage"  # the two stage entry points over the whole batch (no chunking)
 for _ in range(iters):
     bp.plan(xy, ty, off, pos, dr, kernel_events=stage)
+if stage:
+    bp.knn(xy, ty, off)  # the cost-matrix step in isolation (fsd_knn_batch)
 torch.cuda.synchronize()
 print("done", n, iters)
