@@ -288,6 +288,69 @@ __device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned
       asm volatile("discard.global.L2 [%0], 128;" ::"l"(mine + o) : "memory");
 }
 
+// ---- work-ordered scheduling of the path stage --------------------------------------------------------------------------
+// The frames of a round run their fits in lockstep, so a round costs what its slowest frame costs, and a heavy frame taken
+// late is what the whole kernel ends up waiting for.  How heavy a frame is follows from how much its centre line turns
+// (spearman 0.5 with the measured per-frame time; tools/dump_cycles.py, profiles/r2_session2_ab.txt): frames are taken
+// in descending order of that turning -- rounds become homogeneous (less waiting at the fit boundaries, more shared
+// instruction-cache fills) and the heavy frames come first (short tail).  10 240 frames: path kernel 1.37 -> 1.23 ms with
+// this key, 1.08 ms with a perfect one.  The order changes WHEN a frame is planned, never its result.
+constexpr int ORDER_BINS = 64;
+
+// one warp per frame: total absolute turning angle of the centre line of the matches (the points fit #1 will get,
+// path.cuh pm_begin_frame), quantised to ORDER_BINS bins of 1/16 rad; histogram of the bins
+__global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O, uint8_t *key, int *hist) {
+  __shared__ d2 s_c[8][WV_CAP];
+  const int lane = (int)(threadIdx.x & 31u), w = (int)(threadIdx.x >> 5);
+  const int b = (int)blockIdx.x * 8 + w;
+  if (b >= n_frames) return;
+  const int nl = O.n_wv[2 * (size_t)b], nr = O.n_wv[2 * (size_t)b + 1];
+  const int ml = lane < nl ? (int)O.l2r[(size_t)b * WV_CAP + lane] : -1;
+  const int mr = lane < nr ? (int)O.r2l[(size_t)b * WV_CAP + lane] : -1;
+  const int nml = __popc(__ballot_sync(FULL, ml >= 0)), nmr = __popc(__ballot_sync(FULL, mr >= 0));
+  const int sl = __reduce_add_sync(FULL, ml >= 0 ? ml : 0), sr = __reduce_add_sync(FULL, mr >= 0 ? mr : 0);
+  const bool use_left = !(nmr > nml || (nmr == nml && sr > sl));  // select_side_to_use (core_calculate_path.py:165-183)
+  const double *a = (use_left ? O.left_wv : O.right_wv) + (size_t)b * WV_CAP * 2;
+  const double *o = (use_left ? O.right_wv : O.left_wv) + (size_t)b * WV_CAP * 2;
+  const int m = use_left ? ml : mr;
+  const unsigned have = __ballot_sync(FULL, m >= 0);
+  const int nc = __popc(have);
+  if (m >= 0) {
+    const int slot = __popc(have & ((1u << lane) - 1u));
+    s_c[w][slot].x = 0.5 * (a[2 * lane] + o[2 * m]);
+    s_c[w][slot].y = 0.5 * (a[2 * lane + 1] + o[2 * m + 1]);
+  }
+  __syncwarp();
+  double turn = 0.0;
+  if (lane >= 1 && lane + 1 < nc) {
+    const double ax = s_c[w][lane].x - s_c[w][lane - 1].x, ay = s_c[w][lane].y - s_c[w][lane - 1].y;
+    const double bx = s_c[w][lane + 1].x - s_c[w][lane].x, by = s_c[w][lane + 1].y - s_c[w][lane].y;
+    turn = fabs(atan2(ax * by - ay * bx, ax * bx + ay * by));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) turn += __shfl_xor_sync(FULL, turn, off);
+  if (lane == 0) {
+    int bin = turn < 64.0 ? (int)(turn * 16.0) : ORDER_BINS - 1;
+    bin = bin < 0 ? 0 : (bin > ORDER_BINS - 1 ? ORDER_BINS - 1 : bin);
+    key[b] = (uint8_t)bin;
+    atomicAdd(&hist[bin], 1);
+  }
+}
+
+// one CTA: counting sort of the frames by bin, heaviest bin first (the order inside a bin is whatever the atomics give)
+__global__ void __launch_bounds__(1024) path_order_kernel(int n_frames, const uint8_t *key, const int *hist, int *order) {
+  __shared__ int s_cursor[ORDER_BINS];
+  if (threadIdx.x == 0) {
+    int at = 0;
+    for (int bin = ORDER_BINS - 1; bin >= 0; --bin) {
+      s_cursor[bin] = at;
+      at += hist[bin];
+    }
+  }
+  __syncthreads();
+  for (int b = (int)threadIdx.x; b < n_frames; b += (int)blockDim.x) order[atomicAdd(&s_cursor[key[b]], 1)] = b;
+}
+
 // a finished frame: the 40 x 4 result from shared memory to the caller's buffers (and, multi-GPU, to every peer's gathered
 // buffer: the all-gather of the paths happens HERE), the status word, the grid sizes
 __device__ __noinline__ void store_path_frame(const double *out, unsigned st, const int *gr, int b, uint32_t *status,
@@ -320,7 +383,8 @@ template <typename T>
 __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
-                unsigned char *scratch, int *counter, int flags, int cap0, const __grid_constant__ fsd_gather G) {
+                unsigned char *scratch, int *counter, int flags, int cap0, const int *order,
+                const __grid_constant__ fsd_gather G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_state[PATH_FPC];
   __shared__ int s_base;
@@ -339,8 +403,8 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
       base = s_base;
     }
     if (base >= n_frames) break;
-    const int b = base + grp;
-    const bool active = b < n_frames;
+    const bool active = base + grp < n_frames;
+    const int b = active && order ? order[base + grp] : base + grp;  // (work-ordered: see path_key_kernel)
 #ifdef FSD_FRAME_CYCLES
     const long long fsd_t0 = clock64();
     long long fsd_t1 = fsd_t0;
@@ -603,6 +667,7 @@ void set_smem(K kernel, size_t bytes) {
 //   bit 3: fsd_plan_batch never splits a batch into two chunks on two streams
 //   bit 4: the path kernel discards a frame's point-buffer lines from L2 when the frame ends
 //   (bit 5, the point buffers as a persisting L2 access-policy window, was measured and removed: 4x MORE write-back)
+//   bit 7: NO work-ordered scheduling of the path stage (frames in batch order)
 //   bit 6: fits that outgrow their arena are truncated and flagged (kernels_big.cu plans the frame again afterwards) instead
 //          of being suspended and resumed inside the path kernel with the CTA's whole shared memory
 int plan_mode() {
@@ -748,6 +813,12 @@ size_t path_scratch_bytes(int n_frames) {
   return align_up(path_grid_bound(a) * PATH_SCRATCH_BYTES, 256) + align_up(path_grid_bound(n_frames - a) * PATH_SCRATCH_BYTES, 256);
 }
 
+// memory of the work-ordered scheduling of n frames: order [n] int32, key [n] uint8, histogram [ORDER_BINS] int32
+size_t order_ws_bytes(int n_frames) {
+  const size_t n = (size_t)(n_frames > 0 ? n_frames : 0);
+  return align_up(n * sizeof(int), 256) + align_up(n, 256) + align_up(ORDER_BINS * sizeof(int), 256);
+}
+
 size_t workspace_bytes(int n_frames) {
   const size_t B = (size_t)(n_frames > 0 ? n_frames : 0);
   size_t total = align_up(path_scratch_bytes(n_frames), 256);
@@ -758,6 +829,7 @@ size_t workspace_bytes(int n_frames) {
   total += align_up(FSD_HORIZON * 4 * sizeof(double), 256);             // initial path (non-default params)
   total += align_up(B * 2 * FSD_MAX_SORTED * sizeof(int16_t), 256);     // sort indices when the caller wants none
   total += 2 * align_up(fsd_big_path_fixup_scratch_bytes(), 256);       // point buffers of the large-bounds second chance
+  total += 2 * align_up(order_ws_bytes(n_frames), 256);                 // work-ordered scheduling (one block per chunk)
   return total;
 }
 
@@ -765,6 +837,7 @@ size_t workspace_bytes(int n_frames) {
 struct Extra {
   int16_t *idx = nullptr;
   unsigned char *fixup[2] = {nullptr, nullptr};
+  unsigned char *order[2] = {nullptr, nullptr};
 };
 
 int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t workspace_bytes_given,
@@ -786,10 +859,14 @@ int resolve(const fsd_intermediate *inter, int n_frames, void *workspace, size_t
   int16_t *w_idx = cv.take<int16_t>(B * 2 * FSD_MAX_SORTED);
   unsigned char *w_fix0 = cv.take<unsigned char>(fsd_big_path_fixup_scratch_bytes());
   unsigned char *w_fix1 = cv.take<unsigned char>(fsd_big_path_fixup_scratch_bytes());
+  unsigned char *w_ord0 = cv.take<unsigned char>(order_ws_bytes(n_frames));
+  unsigned char *w_ord1 = cv.take<unsigned char>(order_ws_bytes(n_frames));
   if (extra) {
     extra->idx = w_idx;
     extra->fixup[0] = w_fix0;
     extra->fixup[1] = w_fix1;
+    extra->order[0] = w_ord0;
+    extra->order[1] = w_ord1;
   }
   if (!r.n_wv) r.n_wv = w_nwv;
   if (!r.left_wv) r.left_wv = w_lwv;
@@ -863,7 +940,8 @@ template <typename T>
 int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir, const fsd_intermediate *inter,
               const int16_t *force_P, const double *prev_path, int prev_path_stride, double *init_scratch,
               unsigned char *path_scratch, float *out_path, uint32_t *out_status, cudaStream_t stream,
-              unsigned char *fixup_scratch = nullptr, const fsd_gather *gather = nullptr) {
+              unsigned char *fixup_scratch = nullptr, const fsd_gather *gather = nullptr,
+              unsigned char *order_ws = nullptr) {
   if (!path_scratch) return FSD_ERR_WORKSPACE;
   if (!params || n_frames < 0 || !pos || !dir || !out_status || !inter) return FSD_ERR_ARG;
   if (!inter->n_wv || !inter->left_wv || !inter->right_wv || !inter->l2r || !inter->r2l) return FSD_ERR_ARG;
@@ -893,12 +971,28 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r, inter->r2l, out_status};
   const int grid = grid_for(n_frames, D->sm_count, D->path_ctas, PATH_FPC);
+  // work-ordered scheduling (path_key_kernel): worth it from two full waves of resident frames on; FSD_PLAN_MODE bit 7 = off
+  const int *order = nullptr;
+  if (order_ws && !(plan_mode() & 128) && (long)n_frames >= 2L * D->sm_count * D->path_ctas * PATH_FPC) {
+    int *ord = reinterpret_cast<int *>(order_ws);
+    uint8_t *key = order_ws + align_up((size_t)n_frames * sizeof(int), 256);
+    int *hist = reinterpret_cast<int *>(order_ws + align_up((size_t)n_frames * sizeof(int), 256) + align_up((size_t)n_frames, 256));
+    if (cudaMemsetAsync(hist, 0, ORDER_BINS * sizeof(int), stream) != cudaSuccess) {
+      cudaGetLastError();
+      return FSD_ERR_LAUNCH;
+    }
+    path_key_kernel<<<(n_frames + 7) / 8, 256, 0, stream>>>(n_frames, O, key, hist);
+    path_order_kernel<<<1, 1024, 0, stream>>>(n_frames, key, hist, ord);
+    rc = check_launch();
+    if (rc != FSD_OK) return rc;
+    order = ord;
+  }
   int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
   const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0) | (peers ? 4 : 0) |
                     (((plan_mode() & 64) || PATH_FPW != 1) ? 0 : 8);
   path_kernel<T><<<grid, PATH_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
-      round_counter, flags, start_cap(), G);
+      round_counter, flags, start_cap(), order, G);
   rc = check_launch();
   if (rc != FSD_OK || !fixup_scratch) return rc;
   // frames on which a static bound of path_kernel overflowed get a second chance with the large bounds (kernels_big.cu)
@@ -981,7 +1075,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                             out_status, stream, X.idx);
     if (rc != FSD_OK) return rc;
     rc = path_impl<T>(params, n_frames, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path,
-                      out_status, stream, X.fixup[0], gather);
+                      out_status, stream, X.fixup[0], gather, X.order[0]);
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
       cudaGetLastError();
       rc = FSD_ERR_LAUNCH;
@@ -1006,7 +1100,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
                               side->stream, X.idx + 2 * h * FSD_MAX_SORTED);
     if (rc == FSD_OK)
       rc = path_impl<T>(params, na, pos, dir, &R, force_P, prev, stride, init_slot, path_scratch, out_path, out_status,
-                        stream, X.fixup[0], gather);
+                        stream, X.fixup[0], gather, X.order[0]);
     // the outputs of frames [0, na) are final here: a caller that passed an event can start consuming them (e.g. an
     // all-gather on a communication stream) while chunk B is still being planned
     if (rc == FSD_OK && chunk_ready_v && cudaEventRecord(static_cast<cudaEvent_t>(chunk_ready_v), stream) != cudaSuccess) {
@@ -1022,7 +1116,7 @@ int plan_batch_impl(const fsd_params *params, int mission, int n_frames, const T
       rc = path_impl<T>(params, nb, pos + 2 * h, dir + 2 * h, &RB, force_P ? force_P + h : nullptr,
                         prev + h * (size_t)stride, stride, init_slot, scratch_b,
                         out_path ? out_path + h * FSD_HORIZON * 4 : nullptr, out_status + h, side->stream, X.fixup[1],
-                        gather ? &GB : nullptr);
+                        gather ? &GB : nullptr, X.order[1]);
     }
   }
   // always join, so that the caller's stream never runs ahead of work queued on the side stream
@@ -1245,11 +1339,17 @@ int fsd_path_batch_gather(const fsd_params *params, int n_frames, int coords_f64
   unsigned char *fixup = nullptr;
   const size_t fix_at = align_up(path_grid_bound(n_frames) * PATH_SCRATCH_BYTES, 256);
   if (n_frames > 0 && workspace_bytes_given >= fix_at + fsd_big_path_fixup_scratch_bytes()) fixup = scratch + fix_at;
+  // ... and the memory of the work-ordered scheduling behind those
+  unsigned char *order_ws = nullptr;
+  const size_t ord_at = fix_at + align_up(fsd_big_path_fixup_scratch_bytes(), 256);
+  if (fixup && workspace_bytes_given >= ord_at + order_ws_bytes(n_frames)) order_ws = scratch + ord_at;
   if (coords_f64)
     return path_impl<double>(params, n_frames, static_cast<const double *>(pos), static_cast<const double *>(dir), inter,
-                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup, gather);
+                             force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup, gather,
+                             order_ws);
   return path_impl<float>(params, n_frames, static_cast<const float *>(pos), static_cast<const float *>(dir), inter,
-                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup, gather);
+                          force_P, prev_path, prev_path_stride, nullptr, scratch, out_path, out_status, st, fixup, gather,
+                          order_ws);
 }
 
 int fsd_path_batch(const fsd_params *params, int n_frames, int coords_f64, const void *pos, const void *dir,
