@@ -290,17 +290,18 @@ __device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned
 
 // ---- work-ordered scheduling of the path stage --------------------------------------------------------------------------
 // The frames of a round run their fits in lockstep, so a round costs what its slowest frame costs, and a heavy frame taken
-// late is what the whole kernel ends up waiting for.  How heavy a frame is follows from how much its centre line turns
-// (spearman 0.5 with the measured per-frame time; tools/dump_cycles.py, profiles/r2_session2_ab.txt): frames are taken
-// in descending order of that turning -- rounds become homogeneous (less waiting at the fit boundaries, more shared
-// instruction-cache fills) and the heavy frames come first (short tail).  10 240 frames: path kernel 1.37 -> 1.23 ms with
-// this key, 1.08 ms with a perfect one.  The order changes WHEN a frame is planned, never its result.
+// late is what the whole kernel ends up waiting for.  How heavy a frame is can be guessed from its centre line before any
+// spline is fitted (path_key_kernel; tools/dump_cycles.py, profiles/r2_session2_ab.txt): frames are taken in descending
+// order of that guess -- rounds become homogeneous (less waiting at the fit boundaries, more shared instruction-cache
+// fills) and the heavy frames come first (short tail).  10 240 frames: path kernel 1.37 -> 1.19 ms, 1.08 ms with a perfect
+// predictor.  The order changes WHEN a frame is planned, never its result.
 constexpr int ORDER_BINS = 64;
 
-// one warp per frame: total absolute turning angle of the centre line of the matches (the points fit #1 will get,
-// path.cuh pm_begin_frame), quantised to ORDER_BINS bins of 1/16 rad; histogram of the bins
+// one warp per frame: how far the centre line of the matches (the points fit #1 will get, path.cuh pm_begin_frame) is from
+// a cubic polynomial in its chord length -- the squared residual of the least-squares cubic, which is what the first knot
+// pass of the spline fits sees -- on a logarithmic scale of ORDER_BINS bins; histogram of the bins.  (Spearman correlation
+// with the measured per-frame time: 0.66; the total turning angle of the centre line: 0.51.)
 __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O, uint8_t *key, int *hist) {
-  __shared__ d2 s_c[8][WV_CAP];
   const int lane = (int)(threadIdx.x & 31u), w = (int)(threadIdx.x >> 5);
   const int b = (int)blockIdx.x * 8 + w;
   if (b >= n_frames) return;
@@ -315,22 +316,97 @@ __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O,
   const int m = use_left ? ml : mr;
   const unsigned have = __ballot_sync(FULL, m >= 0);
   const int nc = __popc(have);
+  // the matched points in order, one per lane (lane j = j-th centre point), relative to the first one
+  const int slot = __popc(have & ((1u << lane) - 1u));
+  double cx = 0.0, cy = 0.0;
   if (m >= 0) {
-    const int slot = __popc(have & ((1u << lane) - 1u));
-    s_c[w][slot].x = 0.5 * (a[2 * lane] + o[2 * m]);
-    s_c[w][slot].y = 0.5 * (a[2 * lane + 1] + o[2 * m + 1]);
+    cx = 0.5 * (a[2 * lane] + o[2 * m]);
+    cy = 0.5 * (a[2 * lane + 1] + o[2 * m + 1]);
   }
-  __syncwarp();
-  double turn = 0.0;
-  if (lane >= 1 && lane + 1 < nc) {
-    const double ax = s_c[w][lane].x - s_c[w][lane - 1].x, ay = s_c[w][lane].y - s_c[w][lane - 1].y;
-    const double bx = s_c[w][lane + 1].x - s_c[w][lane].x, by = s_c[w][lane + 1].y - s_c[w][lane].y;
-    turn = fabs(atan2(ax * by - ay * bx, ax * bx + ay * by));
-  }
+  // compaction: lane j fetches the point of the lane that holds slot j
+  const int src = __fns(have, 0, lane + 1);  // lane of the (lane+1)-th set bit, or -1
+  double px = __shfl_sync(FULL, cx, src < 0 ? 0 : src), py = __shfl_sync(FULL, cy, src < 0 ? 0 : src);
+  (void)slot;
+  const bool on = lane < nc;
+  const double x0 = __shfl_sync(FULL, px, 0), y0 = __shfl_sync(FULL, py, 0);
+  px = on ? px - x0 : 0.0;
+  py = on ? py - y0 : 0.0;
+  // chord-length parameter, scaled to [0, 1]
+  const double qx = __shfl_up_sync(FULL, px, 1), qy = __shfl_up_sync(FULL, py, 1);
+  double u = (on && lane > 0) ? sqrt((px - qx) * (px - qx) + (py - qy) * (py - qy)) : 0.0;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) turn += __shfl_xor_sync(FULL, turn, off);
+  for (int off = 1; off < 32; off <<= 1) {
+    const double v = __shfl_up_sync(FULL, u, off);
+    if (lane >= off) u += v;
+  }
+  const double total = __shfl_sync(FULL, u, nc > 0 ? nc - 1 : 0);
+  double res = 0.0;
+  if (nc >= 5 && total > 0.0) {
+    const double t = on ? u / total : 0.0, wgt = on ? 1.0 : 0.0;
+    // normal equations of the cubic: moments s[k] = sum t^k (k = 0..6), bx[k] = sum t^k x, by[k] = sum t^k y (k = 0..3)
+    double v[15];
+    double tk = wgt;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      v[k] = tk;
+      if (k < 4) {
+        v[7 + k] = tk * px;
+        v[11 + k] = tk * py;
+      }
+      tk *= t;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 15; ++e) v[e] += __shfl_xor_sync(FULL, v[e], off);
+    }
+    // every lane solves the same 4 x 4 system with two right-hand sides (Gaussian elimination; SPD, no pivoting)
+    double A[4][4], rx[4], ry[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) A[i][j] = v[i + j];
+      rx[i] = v[7 + i];
+      ry[i] = v[11 + i];
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ok = ok && A[i][i] > 1e-300;
+      const double inv = 1.0 / (ok ? A[i][i] : 1.0);
+#pragma unroll
+      for (int r = i + 1; r < 4; ++r) {
+        const double f = A[r][i] * inv;
+#pragma unroll
+        for (int c = i; c < 4; ++c) A[r][c] -= f * A[i][c];
+        rx[r] -= f * rx[i];
+        ry[r] -= f * ry[i];
+      }
+    }
+    double kx[4], ky[4];
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      double sx = rx[i], sy = ry[i];
+#pragma unroll
+      for (int c = i + 1; c < 4; ++c) {
+        sx -= A[i][c] * kx[c];
+        sy -= A[i][c] * ky[c];
+      }
+      const double inv = 1.0 / (ok ? A[i][i] : 1.0);
+      kx[i] = sx * inv;
+      ky[i] = sy * inv;
+    }
+    if (ok && on) {
+      const double ex = ((kx[3] * t + kx[2]) * t + kx[1]) * t + kx[0] - px;
+      const double ey = ((ky[3] * t + ky[2]) * t + ky[1]) * t + ky[0] - py;
+      res = ex * ex + ey * ey;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) res += __shfl_xor_sync(FULL, res, off);
+  }
   if (lane == 0) {
-    int bin = turn < 64.0 ? (int)(turn * 16.0) : ORDER_BINS - 1;
+    int bin = 0;
+    if (res > 0.0 && res == res) bin = (int)(log1p(100.0 * res) * 8.0);
     bin = bin < 0 ? 0 : (bin > ORDER_BINS - 1 ? ORDER_BINS - 1 : bin);
     key[b] = (uint8_t)bin;
     atomicAdd(&hist[bin], 1);
