@@ -299,8 +299,9 @@ constexpr int ORDER_BINS = 64;
 
 // one warp per frame: how far the centre line of the matches (the points fit #1 will get, path.cuh pm_begin_frame) is from
 // a cubic polynomial in its chord length -- the squared residual of the least-squares cubic, which is what the first knot
-// pass of the spline fits sees -- on a logarithmic scale of ORDER_BINS bins; histogram of the bins.  (Spearman correlation
-// with the measured per-frame time: 0.66; the total turning angle of the centre line: 0.51.)
+// pass of the spline fits sees --, on a logarithmic scale, combined with how the centre line turns and how many points it
+// has; ORDER_BINS bins; histogram of the bins.  (Spearman correlation with the measured per-frame time: residual alone 0.66,
+// total turning angle alone 0.51, the combination 0.73.)
 __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O, uint8_t *key, int *hist) {
   const int lane = (int)(threadIdx.x & 31u), w = (int)(threadIdx.x >> 5);
   const int b = (int)blockIdx.x * 8 + w;
@@ -404,9 +405,27 @@ __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O,
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) res += __shfl_xor_sync(FULL, res, off);
   }
+  // turning of the centre line: total absolute turning angle minus its largest single term (many moderate bends cost more
+  // knots than one sharp corner)
+  double ang = 0.0;
+  {
+    const double nx = __shfl_down_sync(FULL, px, 1), ny = __shfl_down_sync(FULL, py, 1);
+    if (lane >= 1 && lane + 1 < nc) {
+      const double ax = px - qx, ay = py - qy, bx = nx - px, by = ny - py;
+      ang = fabs(atan2(ax * by - ay * bx, ax * bx + ay * by));
+    }
+  }
+  double turn = ang, mx = ang;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    turn += __shfl_xor_sync(FULL, turn, off);
+    mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+  }
   if (lane == 0) {
-    int bin = 0;
-    if (res > 0.0 && res == res) bin = (int)(log1p(100.0 * res) * 8.0);
+    // least-squares combination of the features against the measured per-frame times of 10 240 bench frames (spearman 0.73,
+    // the same on the mixed stream it was not fitted on); only the ORDER of the keys matters
+    double k = (res > 0.0 && res == res ? log1p(100.0 * res) : 0.0) + (turn - mx) - 0.43 * (double)nc;
+    int bin = (int)((k + 5.5) * 4.0);
     bin = bin < 0 ? 0 : (bin > ORDER_BINS - 1 ? ORDER_BINS - 1 : bin);
     key[b] = (uint8_t)bin;
     atomicAdd(&hist[bin], 1);
