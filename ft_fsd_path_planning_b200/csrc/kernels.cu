@@ -174,6 +174,9 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     if (n < 0) n = 0;
     const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
     int16_t *dbg = O.sort_dbg ? O.sort_dbg + 8 * (size_t)b : nullptr;
+#ifdef FSD_FRAME_CYCLES
+    const long long fsd_t0 = clock64();
+#endif
     stage_frame<T>(C, cones_xy + 2 * (size_t)lo, cones_type + lo, n, phase);
     if (n >= 3) build_knn(C.S, n, P);
     int nl = 0, nr = 0;
@@ -181,6 +184,10 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     st |= sort_finish(C.S, nl, nr);
     store_sort(C.S, b, O);
     if (fsd_lane() == 0) O.status[b] = st;
+#ifdef FSD_FRAME_CYCLES
+    // measurement build only: the frame's sort time in units of 64 cycles instead of the right side's DFS pop count
+    if (dbg && fsd_lane() == 0) dbg[7] = (int16_t)min((clock64() - fsd_t0) >> 6, 32767ll);
+#endif
     __syncwarp();
   }
 }

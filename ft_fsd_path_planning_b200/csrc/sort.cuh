@@ -669,13 +669,29 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, SideScratch &Q, int n, int C, i
     if (lo < nall) Q.flag2[Q.close[lo]] = 1;  // removed
   }
   SG::sync();
+  // One configuration per round, ONE CONE OF THE CONFIGURATION PER LANE (<= 12 of the group's lanes); every lane walks the
+  // candidate lists itself -- all lanes read the same entries, i.e. broadcasts.  (The first version ran the (configuration,
+  // cone) pairs one after the other with the candidates lane-strided: 84 short passes with a reduction-sized tail each for
+  // 7 configurations; frames with >= 2 configurations, 10 % of the stream, cost 4 x the others and make the kernel's tail.)
   FSD_ROLLED
   for (int r = 0; r < C; ++r) {
     const int16_t *c = Q.leaves[r];
-    int len = row_len(c);
+    const int len = row_len(c);
     int good = 0, bad = 0;
+    // the configuration's own cones as a bit mask (cone indices < 256)
+    unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;
     FSD_ROLLED
-    for (int j = 0; j < len; ++j) {
+    for (int w = 0; w < len; ++w) {
+      const int v = c[w];
+      const unsigned long long bit = 1ull << (v & 63);
+      const int k = v >> 6;
+      m0 |= k == 0 ? bit : 0ull;
+      m1 |= k == 1 ? bit : 0ull;
+      m2 |= k == 2 ? bit : 0ull;
+      m3 |= k == 3 ? bit : 0ull;
+    }
+#pragma unroll 1
+    for (int j = lane; j < len; j += SG::N) {
       double sx, sy;
       if (j == 0)
         search_dir(S, c[0], c[1], side, sx, sy);
@@ -684,26 +700,25 @@ FSD_DEVFN void cones_on_either_side(SortSmem &S, SideScratch &Q, int n, int C, i
       else
         search_dir(S, c[j - 1], c[j + 1], side, sx, sy);
       const int cj = c[j];
-      const double x0 = S.xy[cj].x, y0 = S.xy[cj].y;
+      const double x0 = S.xy[cj].x, y0 = S.xy[cj].y, s2 = sx * sx + sy * sy;
       // other = close (minus removed) ++ configuration cones of OTHER configurations
-#pragma unroll 1
-      for (int q = lane; q < nall + nidx; q += SG::N) {
+      FSD_ROLLED
+      for (int q = 0; q < nall + nidx; ++q) {
         int o;
         if (q < nall) {
           o = Q.close[q];
           if (Q.flag2[o]) continue;
         } else {
           o = Q.idxs[q - nall];
-          bool member = false;
-          FSD_ROLLED
-          for (int w = 0; w < len; ++w) member |= c[w] == o;
-          if (member) continue;
+          const int k = o >> 6;
+          const unsigned long long mk = k == 0 ? m0 : (k == 1 ? m1 : (k == 2 ? m2 : m3));
+          if ((mk >> (o & 63)) & 1ull) continue;
         }
         if (o == cj) continue;
-        double vx = S.xy[o].x - x0, vy = S.xy[o].y - y0;
+        const double vx = S.xy[o].x - x0, vy = S.xy[o].y - y0;
         const double v2 = vx * vx + vy * vy;
         if (!(v2 < range2)) continue;
-        const double dot = vx * sx + vy * sy, w2 = v2 * (sx * sx + sy * sy);
+        const double dot = vx * sx + vy * sy, w2 = v2 * s2;
         good += gt_scaled(dot, 0.5, w2);   // angle to the search direction < 60 deg
         bad += lt_scaled(dot, -0.5, w2);   // angle to the opposite direction < 60 deg
       }
