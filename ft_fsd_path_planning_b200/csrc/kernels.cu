@@ -226,6 +226,37 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
 // matching on given sort indices (stage entry point fsd_match_batch; second kernel of the split sort stage): free-running
 // warps, dynamic frame fetch, the <= 24 sorted cones gathered straight from global memory
 constexpr size_t MATCH_CTA_STRIDE = (sizeof(MatchSmem) + 15) / 16 * 16;
+// one frame's matching by one warp
+template <typename T>
+__device__ __forceinline__ void match_one(MatchSmem &M, const DevParams &P, int b, const T *cones_xy, const int32_t *offsets,
+                                          const T *pos, const T *dir, const int16_t *left_idx, const int16_t *right_idx,
+                                          const StageOut &O, int or_status) {
+  const T *xy = cones_xy + 2 * (size_t)offsets[b];
+  const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
+  int nl = 0, nr = 0;
+  {
+    const int q = fsd_lane();
+    const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
+    const int idx = q < 2 * FSD_MAX_SORTED ? (int)(s == 0 ? left_idx : right_idx)[(size_t)b * FSD_MAX_SORTED + j] : -1;
+    if (idx >= 0) {
+      M.side[s][j].x = (double)xy[2 * idx];
+      M.side[s][j].y = (double)xy[2 * idx + 1];
+    }
+    const unsigned have = __ballot_sync(FULL, idx >= 0);
+    nl = __popc(have & ((1u << FSD_MAX_SORTED) - 1u));
+    nr = __popc(have >> FSD_MAX_SORTED);
+  }
+  if (fsd_lane() == 0) {
+    M.nside[0] = nl;
+    M.nside[1] = nr;
+  }
+  __syncwarp();
+  unsigned st = match_frame(M, F, P);
+  store_match(M, b, O);
+  if (fsd_lane() == 0) O.status[b] = or_status ? (O.status[b] | st) : st;
+  __syncwarp();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
     match_kernel(DevParams P, int n_frames, const T *cones_xy, const int32_t *offsets, const T *pos, const T *dir,
@@ -235,30 +266,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
   for (;;) {
     const int b = next_frame(counter);
     if (b >= n_frames) break;
-    const T *xy = cones_xy + 2 * (size_t)offsets[b];
-    const FramePose F = make_pose((double)pos[2 * b], (double)pos[2 * b + 1], (double)dir[2 * b], (double)dir[2 * b + 1]);
-    int nl = 0, nr = 0;
-    {
-      const int q = fsd_lane();
-      const int s = q / FSD_MAX_SORTED, j = q % FSD_MAX_SORTED;
-      const int idx = q < 2 * FSD_MAX_SORTED ? (int)(s == 0 ? left_idx : right_idx)[(size_t)b * FSD_MAX_SORTED + j] : -1;
-      if (idx >= 0) {
-        M.side[s][j].x = (double)xy[2 * idx];
-        M.side[s][j].y = (double)xy[2 * idx + 1];
-      }
-      const unsigned have = __ballot_sync(FULL, idx >= 0);
-      nl = __popc(have & ((1u << FSD_MAX_SORTED) - 1u));
-      nr = __popc(have >> FSD_MAX_SORTED);
-    }
-    if (fsd_lane() == 0) {
-      M.nside[0] = nl;
-      M.nside[1] = nr;
-    }
-    __syncwarp();
-    unsigned st = match_frame(M, F, P);
-    store_match(M, b, O);
-    if (fsd_lane() == 0) O.status[b] = or_status ? (O.status[b] | st) : st;
-    __syncwarp();
+    match_one<T>(M, P, b, cones_xy, offsets, pos, dir, left_idx, right_idx, O, or_status);
   }
 }
 
@@ -302,58 +310,56 @@ __device__ __forceinline__ void discard_points(unsigned char *mine, bool aligned
 // order of that guess -- rounds become homogeneous (less waiting at the fit boundaries, more shared instruction-cache
 // fills) and the heavy frames come first (short tail).  10 240 frames: path kernel 1.37 -> 1.19 ms, 1.08 ms with a perfect
 // predictor.  The order changes WHEN a frame is planned, never its result.
-constexpr int ORDER_BINS = 64;
+constexpr int ORDER_BINS = 64;  // (= COUNTER_STRIDE - 8: the histogram lives in the counter ring)
 
 // one warp per frame: how far the centre line of the matches (the points fit #1 will get, path.cuh pm_begin_frame) is from
 // a cubic polynomial in its chord length -- the squared residual of the least-squares cubic, which is what the first knot
 // pass of the spline fits sees --, on a logarithmic scale, combined with how the centre line turns and how many points it
 // has; ORDER_BINS bins; histogram of the bins.  (Spearman correlation with the measured per-frame time: residual alone 0.66,
 // total turning angle alone 0.51, the combination 0.73.)
-__global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O, uint8_t *key, int *hist) {
-  const int lane = (int)(threadIdx.x & 31u), w = (int)(threadIdx.x >> 5);
-  const int b = (int)blockIdx.x * 8 + w;
-  if (b >= n_frames) return;
-  const int nl = O.n_wv[2 * (size_t)b], nr = O.n_wv[2 * (size_t)b + 1];
-  const int ml = lane < nl ? (int)O.l2r[(size_t)b * WV_CAP + lane] : -1;
-  const int mr = lane < nr ? (int)O.r2l[(size_t)b * WV_CAP + lane] : -1;
+// (fp32 arithmetic: only the ORDER of the keys matters -- with the parameter centred on [-1, 1] the cubic's normal equations
+// are well conditioned, and the fp32 keys fall into the same bins as fp64 ones on all 28 432 frames of the three bench
+// streams; in fp64 -- divisions, log1p, atan2 -- this function cost the matching kernel 0.05 ms per 10 240 frames.)
+// left / right / l2r / r2l: the frame's with-virtual cones and matches, in global OR shared memory.
+__device__ __noinline__ int path_key_bin(const d2 *left, int nl, const d2 *right, int nr, const int16_t *l2r,
+                                         const int16_t *r2l) {
+  const int lane = (int)(threadIdx.x & 31u);
+  const int ml = lane < nl ? (int)l2r[lane] : -1;
+  const int mr = lane < nr ? (int)r2l[lane] : -1;
   const int nml = __popc(__ballot_sync(FULL, ml >= 0)), nmr = __popc(__ballot_sync(FULL, mr >= 0));
   const int sl = __reduce_add_sync(FULL, ml >= 0 ? ml : 0), sr = __reduce_add_sync(FULL, mr >= 0 ? mr : 0);
   const bool use_left = !(nmr > nml || (nmr == nml && sr > sl));  // select_side_to_use (core_calculate_path.py:165-183)
-  const double *a = (use_left ? O.left_wv : O.right_wv) + (size_t)b * WV_CAP * 2;
-  const double *o = (use_left ? O.right_wv : O.left_wv) + (size_t)b * WV_CAP * 2;
+  const d2 *a = use_left ? left : right, *o = use_left ? right : left;
   const int m = use_left ? ml : mr;
   const unsigned have = __ballot_sync(FULL, m >= 0);
   const int nc = __popc(have);
-  // the matched points in order, one per lane (lane j = j-th centre point), relative to the first one
-  const int slot = __popc(have & ((1u << lane) - 1u));
   double cx = 0.0, cy = 0.0;
   if (m >= 0) {
-    cx = 0.5 * (a[2 * lane] + o[2 * m]);
-    cy = 0.5 * (a[2 * lane + 1] + o[2 * m + 1]);
+    cx = 0.5 * (a[lane].x + o[m].x);
+    cy = 0.5 * (a[lane].y + o[m].y);
   }
-  // compaction: lane j fetches the point of the lane that holds slot j
+  // compaction: lane j fetches the point of the lane that holds the j-th match; relative to the first point (the
+  // subtraction in fp64: SLAM coordinates are large), then fp32
   const int src = __fns(have, 0, lane + 1);  // lane of the (lane+1)-th set bit, or -1
-  double px = __shfl_sync(FULL, cx, src < 0 ? 0 : src), py = __shfl_sync(FULL, cy, src < 0 ? 0 : src);
-  (void)slot;
+  const double gx = __shfl_sync(FULL, cx, src < 0 ? 0 : src), gy = __shfl_sync(FULL, cy, src < 0 ? 0 : src);
   const bool on = lane < nc;
-  const double x0 = __shfl_sync(FULL, px, 0), y0 = __shfl_sync(FULL, py, 0);
-  px = on ? px - x0 : 0.0;
-  py = on ? py - y0 : 0.0;
-  // chord-length parameter, scaled to [0, 1]
-  const double qx = __shfl_up_sync(FULL, px, 1), qy = __shfl_up_sync(FULL, py, 1);
-  double u = (on && lane > 0) ? sqrt((px - qx) * (px - qx) + (py - qy) * (py - qy)) : 0.0;
+  const double x0 = __shfl_sync(FULL, gx, 0), y0 = __shfl_sync(FULL, gy, 0);
+  const float px = on ? (float)(gx - x0) : 0.0f, py = on ? (float)(gy - y0) : 0.0f;
+  // chord-length parameter, scaled to [-1, 1]
+  const float qx = __shfl_up_sync(FULL, px, 1), qy = __shfl_up_sync(FULL, py, 1);
+  float u = (on && lane > 0) ? sqrtf((px - qx) * (px - qx) + (py - qy) * (py - qy)) : 0.0f;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const double v = __shfl_up_sync(FULL, u, off);
+    const float v = __shfl_up_sync(FULL, u, off);
     if (lane >= off) u += v;
   }
-  const double total = __shfl_sync(FULL, u, nc > 0 ? nc - 1 : 0);
-  double res = 0.0;
-  if (nc >= 5 && total > 0.0) {
-    const double t = on ? u / total : 0.0, wgt = on ? 1.0 : 0.0;
+  const float total = __shfl_sync(FULL, u, nc > 0 ? nc - 1 : 0);
+  float res = 0.0f;
+  if (nc >= 5 && total > 0.0f) {
+    const float t = on ? 2.0f * __fdividef(u, total) - 1.0f : 0.0f, wgt = on ? 1.0f : 0.0f;
     // normal equations of the cubic: moments s[k] = sum t^k (k = 0..6), bx[k] = sum t^k x, by[k] = sum t^k y (k = 0..3)
-    double v[15];
-    double tk = wgt;
+    float v[15];
+    float tk = wgt;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       v[k] = tk;
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O,
       for (int e = 0; e < 15; ++e) v[e] += __shfl_xor_sync(FULL, v[e], off);
     }
     // every lane solves the same 4 x 4 system with two right-hand sides (Gaussian elimination; SPD, no pivoting)
-    double A[4][4], rx[4], ry[4];
+    float A[4][4], rx[4], ry[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -378,35 +384,35 @@ __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O,
       ry[i] = v[11 + i];
     }
     bool ok = true;
+    float inv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ok = ok && A[i][i] > 1e-300;
-      const double inv = 1.0 / (ok ? A[i][i] : 1.0);
+      ok = ok && A[i][i] > 1e-30f;
+      inv[i] = __frcp_rn(ok ? A[i][i] : 1.0f);
 #pragma unroll
       for (int r = i + 1; r < 4; ++r) {
-        const double f = A[r][i] * inv;
+        const float f = A[r][i] * inv[i];
 #pragma unroll
         for (int c = i; c < 4; ++c) A[r][c] -= f * A[i][c];
         rx[r] -= f * rx[i];
         ry[r] -= f * ry[i];
       }
     }
-    double kx[4], ky[4];
+    float kx[4], ky[4];
 #pragma unroll
     for (int i = 3; i >= 0; --i) {
-      double sx = rx[i], sy = ry[i];
+      float sx = rx[i], sy = ry[i];
 #pragma unroll
       for (int c = i + 1; c < 4; ++c) {
         sx -= A[i][c] * kx[c];
         sy -= A[i][c] * ky[c];
       }
-      const double inv = 1.0 / (ok ? A[i][i] : 1.0);
-      kx[i] = sx * inv;
-      ky[i] = sy * inv;
+      kx[i] = sx * inv[i];
+      ky[i] = sy * inv[i];
     }
     if (ok && on) {
-      const double ex = ((kx[3] * t + kx[2]) * t + kx[1]) * t + kx[0] - px;
-      const double ey = ((ky[3] * t + ky[2]) * t + ky[1]) * t + ky[0] - py;
+      const float ex = ((kx[3] * t + kx[2]) * t + kx[1]) * t + kx[0] - px;
+      const float ey = ((ky[3] * t + ky[2]) * t + ky[1]) * t + ky[0] - py;
       res = ex * ex + ey * ey;
     }
 #pragma unroll
@@ -414,28 +420,49 @@ __global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O,
   }
   // turning of the centre line: total absolute turning angle minus its largest single term (many moderate bends cost more
   // knots than one sharp corner)
-  double ang = 0.0;
+  float ang = 0.0f;
   {
-    const double nx = __shfl_down_sync(FULL, px, 1), ny = __shfl_down_sync(FULL, py, 1);
+    const float nx = __shfl_down_sync(FULL, px, 1), ny = __shfl_down_sync(FULL, py, 1);
     if (lane >= 1 && lane + 1 < nc) {
-      const double ax = px - qx, ay = py - qy, bx = nx - px, by = ny - py;
-      ang = fabs(atan2(ax * by - ay * bx, ax * bx + ay * by));
+      const float ax = px - qx, ay = py - qy, bx = nx - px, by = ny - py;
+      ang = fabsf(atan2f(ax * by - ay * bx, ax * bx + ay * by));
     }
   }
-  double turn = ang, mx = ang;
+  float turn = ang, mx = ang;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     turn += __shfl_xor_sync(FULL, turn, off);
-    mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, off));
   }
-  if (lane == 0) {
-    // least-squares combination of the features against the measured per-frame times of 10 240 bench frames (spearman 0.73,
-    // the same on the mixed stream it was not fitted on); only the ORDER of the keys matters
-    double k = (res > 0.0 && res == res ? log1p(100.0 * res) : 0.0) + (turn - mx) - 0.43 * (double)nc;
-    int bin = (int)((k + 5.5) * 4.0);
-    bin = bin < 0 ? 0 : (bin > ORDER_BINS - 1 ? ORDER_BINS - 1 : bin);
-    key[b] = (uint8_t)bin;
-    atomicAdd(&hist[bin], 1);
+  // least-squares combination of the features against the measured per-frame times of 10 240 bench frames (spearman 0.73,
+  // the same on the mixed stream it was not fitted on); only the ORDER of the keys matters
+  const float k = (res > 0.0f && res == res ? log1pf(100.0f * res) : 0.0f) + (turn - mx) - 0.43f * (float)nc;
+  int bin = (int)((k + 5.5f) * 4.0f);
+  bin = bin < 0 ? 0 : (bin > ORDER_BINS - 1 ? ORDER_BINS - 1 : bin);
+  return __shfl_sync(FULL, bin, 0);
+}
+
+// one warp per frame: the frame's bin; the frame is appended to its bin's list bin_items [ORDER_BINS][n_frames] (the path
+// kernel looks its rounds up in the lists: no counting-sort launch), or -- key != nullptr, FSD_PLAN_MODE bit 8 -- the bin goes
+// to key[b] for path_order_kernel.  hist [ORDER_BINS] zero at launch.
+// (Measured and rejected, profiles/r2_session4_ab.txt: the keys computed by the matching kernel's warps right after a frame's
+// matching -- no key launch at all, but the persistent 16-warps-per-SM kernel pays 0.026 ms for what this kernel's 10 240
+// independent warps do in 0.01 ms; and sorting + matching as ONE kernel whose warps match the sorted frames when there is
+// nothing left to sort, to fill the idle tail of the sort kernel: 0.19 ms SLOWER, the matching code evicts the sorting code
+// from the SM's instruction cache exactly while the last heavy frames, the kernel's critical path, are being sorted.)
+__global__ void __launch_bounds__(256) path_key_kernel(int n_frames, StageOut O, uint8_t *key, int *hist, int *bin_items) {
+  const int b = (int)blockIdx.x * 8 + (int)(threadIdx.x >> 5);
+  if (b >= n_frames) return;
+  const int bin = path_key_bin(reinterpret_cast<const d2 *>(O.left_wv + (size_t)b * WV_CAP * 2), O.n_wv[2 * (size_t)b],
+                               reinterpret_cast<const d2 *>(O.right_wv + (size_t)b * WV_CAP * 2), O.n_wv[2 * (size_t)b + 1],
+                               O.l2r + (size_t)b * WV_CAP, O.r2l + (size_t)b * WV_CAP);
+  if ((threadIdx.x & 31u) == 0) {
+    if (key) {
+      key[b] = (uint8_t)bin;
+      atomicAdd(&hist[bin], 1);
+    } else {
+      bin_items[(size_t)bin * n_frames + atomicAdd(&hist[bin], 1)] = b;
+    }
   }
 }
 
@@ -485,11 +512,32 @@ template <typename T>
 __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     path_kernel(DevParams P, int n_frames, const T *pos, const T *dir, StageOut O, const int16_t *force_P,
                 const double *prev, int prev_stride, double *out_f64, float *out_f32, int16_t *grid_out,
-                unsigned char *scratch, int *counter, int flags, int cap0, const int *order,
-                const __grid_constant__ fsd_gather G) {
+                unsigned char *scratch, int *counter, int flags, int cap0, const int *order, const int *bin_hist,
+                const int *bin_items, const __grid_constant__ fsd_gather G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_state[PATH_FPC];
   __shared__ int s_base;
+  __shared__ int s_bin_end[ORDER_BINS];  // frames in the bins up to and including q, heaviest bin (ORDER_BINS - 1) = q 0
+  if (bin_hist) {
+    if (threadIdx.x < 32) {
+      // inclusive scan of the 64 bin counts in processing order, two per lane
+      const int l = (int)threadIdx.x;
+      const int c0 = bin_hist[ORDER_BINS - 1 - l], c1 = bin_hist[ORDER_BINS - 1 - (l + 32)];
+      int a = c0, bsum = c1;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int va = __shfl_up_sync(FULL, a, off), vb = __shfl_up_sync(FULL, bsum, off);
+        if (l >= off) {
+          a += va;
+          bsum += vb;
+        }
+      }
+      const int first_half = __shfl_sync(FULL, a, 31);
+      s_bin_end[l] = a;
+      s_bin_end[l + 32] = first_half + bsum;
+    }
+    __syncthreads();
+  }
   const int grp = (int)threadIdx.x / PG::N, lane = PG::lane();  // this frame's slot in the CTA, lane within the frame
   PathSmem &S = *reinterpret_cast<PathSmem *>(smem_raw + (size_t)grp * PATH_CTA_STRIDE);
   unsigned char *mine = scratch + ((size_t)blockIdx.x * PATH_FPC + grp) * PATH_SCRATCH_BYTES;
@@ -506,7 +554,18 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     }
     if (base >= n_frames) break;
     const bool active = base + grp < n_frames;
-    const int b = active && order ? order[base + grp] : base + grp;  // (work-ordered: see path_key_kernel)
+    int b = base + grp;
+    if (active && order) b = order[b];  // (work-ordered: see path_key_kernel)
+    if (bin_hist) {
+      // the (base + grp)-th frame of the heaviest-first order: the first bin whose running count exceeds it
+      // (binary search; j < n_frames = s_bin_end[ORDER_BINS - 1])
+      const int j = active ? base + grp : 0;
+      int q = 0;
+#pragma unroll
+      for (int step = ORDER_BINS / 2; step > 0; step >>= 1)
+        if (s_bin_end[q + step - 1] <= j) q += step;
+      if (active) b = bin_items[(size_t)(ORDER_BINS - 1 - q) * n_frames + (j - (q ? s_bin_end[q - 1] : 0))];
+    }
 #ifdef FSD_FRAME_CYCLES
     const long long fsd_t0 = clock64();
     long long fsd_t1 = fsd_t0;
@@ -748,10 +807,12 @@ struct DeviceInfo {
   bool initial_ready = false;
   double key[3] = {0, 0, 0};
   SideStream side[SIDE_STREAMS];
-  int *counter_ring = nullptr;  // COUNTER_SLOTS x 8 ints of device memory: frame counters of the free-running kernels
+  int *counter_ring = nullptr;  // COUNTER_SLOTS x COUNTER_STRIDE ints of device memory: frame counters of the free-running kernels
   unsigned counter_next = 0;
 };
 constexpr int COUNTER_SLOTS = 128;
+constexpr int COUNTER_STRIDE = 8 + 64;  // eight counters + the histogram of the path keys (ORDER_BINS), zeroed by ONE memset
+static_assert(COUNTER_STRIDE == 8 + ORDER_BINS, "the histogram of the path keys lives behind the eight counters");
 DeviceInfo g_dev[MAX_DEVICES];
 std::mutex g_mutex;
 
@@ -845,7 +906,7 @@ int device_info(DeviceInfo **out) {
       D.key[2] = dp.refit_smoothing;
       D.initial_ready = true;
     }
-    if (cudaMalloc(reinterpret_cast<void **>(&D.counter_ring), COUNTER_SLOTS * 8 * sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(reinterpret_cast<void **>(&D.counter_ring), COUNTER_SLOTS * COUNTER_STRIDE * sizeof(int)) != cudaSuccess) {
       cudaGetLastError();
       D.counter_ring = nullptr;  // the free-running kernels are not used without it
     }
@@ -855,7 +916,7 @@ int device_info(DeviceInfo **out) {
   return FSD_OK;
 }
 
-// Eight zeroed frame counters for one sequence of free-running kernels on `stream` (a slot of the per-device ring; a slot
+// Eight zeroed frame counters (+ a zeroed histogram of ORDER_BINS ints behind them) for one sequence of free-running kernels on `stream` (a slot of the per-device ring; a slot
 // comes round again after COUNTER_SLOTS sequences, far more than can be in flight).  nullptr: not available.
 int *take_counters(DeviceInfo &D, cudaStream_t stream) {
   if (!D.counter_ring) return nullptr;
@@ -864,8 +925,8 @@ int *take_counters(DeviceInfo &D, cudaStream_t stream) {
     std::lock_guard<std::mutex> lock(g_mutex);
     slot = D.counter_next++ % COUNTER_SLOTS;
   }
-  int *p = D.counter_ring + 8 * slot;
-  if (cudaMemsetAsync(p, 0, 8 * sizeof(int), stream) != cudaSuccess) {
+  int *p = D.counter_ring + COUNTER_STRIDE * slot;
+  if (cudaMemsetAsync(p, 0, COUNTER_STRIDE * sizeof(int), stream) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -910,15 +971,41 @@ int first_chunk(int n_frames) {
   return (n_frames / 2 + PATH_FPC - 1) / PATH_FPC * PATH_FPC;
 }
 
+// work-ordered scheduling of the path stage: worth it from two full waves of resident frames on; FSD_PLAN_MODE bit 7 = off
+bool order_wanted(int n_frames, const DeviceInfo &D) {
+  return !(plan_mode() & 128) && (long)n_frames >= 2L * D.sm_count * D.path_ctas * PATH_FPC;
+}
+
 size_t path_scratch_bytes(int n_frames) {
   const int a = first_chunk(n_frames);
   return align_up(path_grid_bound(a) * PATH_SCRATCH_BYTES, 256) + align_up(path_grid_bound(n_frames - a) * PATH_SCRATCH_BYTES, 256);
 }
 
 // memory of the work-ordered scheduling of n frames: order [n] int32, key [n] uint8, histogram [ORDER_BINS] int32
+// + the bins' frame lists [ORDER_BINS][n] int32 (path_key_kernel appends, path_kernel looks its rounds up in them)
 size_t order_ws_bytes(int n_frames) {
   const size_t n = (size_t)(n_frames > 0 ? n_frames : 0);
-  return align_up(n * sizeof(int), 256) + align_up(n, 256) + align_up(ORDER_BINS * sizeof(int), 256);
+  return align_up(n * sizeof(int), 256) + align_up(n, 256) + align_up(ORDER_BINS * sizeof(int), 256) +
+         align_up((size_t)ORDER_BINS * n * sizeof(int), 256);
+}
+
+struct OrderWs {
+  int *ord;       // [n] order of the frames (path_order_kernel; stage entry points only)
+  uint8_t *key;   // [n]
+  int *hist;      // [ORDER_BINS]
+  int *items;     // [ORDER_BINS][n]
+  size_t head_bytes;  // ord .. hist
+};
+
+OrderWs order_ws_view(unsigned char *ws, int n_frames) {
+  const size_t n = (size_t)n_frames;
+  OrderWs v;
+  v.ord = reinterpret_cast<int *>(ws);
+  v.key = ws + align_up(n * sizeof(int), 256);
+  v.hist = reinterpret_cast<int *>(ws + align_up(n * sizeof(int), 256) + align_up(n, 256));
+  v.head_bytes = align_up(n * sizeof(int), 256) + align_up(n, 256) + align_up(ORDER_BINS * sizeof(int), 256);
+  v.items = reinterpret_cast<int *>(ws + v.head_bytes);
+  return v;
 }
 
 size_t workspace_bytes(int n_frames) {
@@ -1073,28 +1160,33 @@ int path_impl(const fsd_params *params, int n_frames, const T *pos, const T *dir
   StageOut O = {nullptr,    nullptr,    nullptr,   inter->n_wv, inter->left_wv, inter->right_wv,
                 inter->l2r, inter->r2l, out_status};
   const int grid = grid_for(n_frames, D->sm_count, D->path_ctas, PATH_FPC);
-  // work-ordered scheduling (path_key_kernel): worth it from two full waves of resident frames on; FSD_PLAN_MODE bit 7 = off
-  const int *order = nullptr;
-  if (order_ws && !(plan_mode() & 128) && (long)n_frames >= 2L * D->sm_count * D->path_ctas * PATH_FPC) {
-    int *ord = reinterpret_cast<int *>(order_ws);
-    uint8_t *key = order_ws + align_up((size_t)n_frames * sizeof(int), 256);
-    int *hist = reinterpret_cast<int *>(order_ws + align_up((size_t)n_frames * sizeof(int), 256) + align_up((size_t)n_frames, 256));
-    if (cudaMemsetAsync(hist, 0, ORDER_BINS * sizeof(int), stream) != cudaSuccess) {
-      cudaGetLastError();
-      return FSD_ERR_LAUNCH;
+  // work-ordered scheduling: path_key_kernel files every frame in the list of its bin, the path kernel takes its rounds from
+  // the lists, heaviest bin first (FSD_PLAN_MODE bit 8: key array + counting sort into an order array, as before r2_zb).
+  // The histogram lives behind the round counter in the counter ring: one memset for both.
+  const int *order = nullptr, *bin_hist = nullptr, *bin_items = nullptr;
+  const bool ordered = order_ws && order_wanted(n_frames, *D);
+  int *slot = ((plan_mode() & 4) || ordered) ? take_counters(*D, stream) : nullptr;
+  if (ordered && slot) {
+    const OrderWs W = order_ws_view(order_ws, n_frames);
+    const bool lists = !(plan_mode() & 256);
+    int *hist = slot + 8;
+    path_key_kernel<<<(n_frames + 7) / 8, 256, 0, stream>>>(n_frames, O, lists ? nullptr : W.key, hist, W.items);
+    if (lists) {
+      bin_hist = hist;
+      bin_items = W.items;
+    } else {
+      path_order_kernel<<<1, 1024, 0, stream>>>(n_frames, W.key, hist, W.ord);
+      order = W.ord;
     }
-    path_key_kernel<<<(n_frames + 7) / 8, 256, 0, stream>>>(n_frames, O, key, hist);
-    path_order_kernel<<<1, 1024, 0, stream>>>(n_frames, key, hist, ord);
     rc = check_launch();
     if (rc != FSD_OK) return rc;
-    order = ord;
   }
-  int *round_counter = (plan_mode() & 4) ? take_counters(*D, stream) : nullptr;
+  int *round_counter = (plan_mode() & 4) ? slot : nullptr;
   const int flags = ((plan_mode() & 16) ? 1 : 0) | (fixup_scratch ? 2 : 0) | (peers ? 4 : 0) |
                     (((plan_mode() & 64) || PATH_FPW != 1) ? 0 : 8);
   path_kernel<T><<<grid, PATH_THREADS, PATH_KERNEL_SMEM, stream>>>(
       P, n_frames, pos, dir, O, force_P, prev, stride, inter->path_f64, out_path, inter->grid, path_scratch,
-      round_counter, flags, start_cap(), order, G);
+      round_counter, flags, start_cap(), order, bin_hist, bin_items, G);
   rc = check_launch();
   if (rc != FSD_OK || !fixup_scratch) return rc;
   // frames on which a static bound of path_kernel overflowed get a second chance with the large bounds (kernels_big.cu)
@@ -1281,9 +1373,13 @@ size_t fsd_workspace_bytes(int n_frames, int total_cones) {
 
 int fsd_plan_launches(int n_frames) {
   if (n_frames <= 0) return 0;
-  // sort (+ match as a kernel of its own), path (or its three phases), the large-bounds second chance of the path stage
-  const int per_chunk = 4;
-  return first_chunk(n_frames) < n_frames ? 2 * per_chunk : per_chunk;
+  // kernels of this library per chunk: sort, match, path, the large-bounds second chance of the path stage, and -- batches
+  // large enough for the work-ordered path stage -- the path keys (FSD_PLAN_MODE bit 8: + the counting sort of the keys)
+  DeviceInfo *D = nullptr;
+  const bool dev = device_info(&D) == FSD_OK;
+  auto chunk = [&](int n) { return n <= 0 ? 0 : 4 + (dev && order_wanted(n, *D) ? ((plan_mode() & 256) ? 2 : 1) : 0); };
+  const int na = first_chunk(n_frames);
+  return chunk(na) + chunk(n_frames - na);
 }
 
 int fsd_plan_first_chunk(int n_frames) { return n_frames <= 0 ? 0 : first_chunk(n_frames); }

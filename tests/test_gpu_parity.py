@@ -331,7 +331,8 @@ def test_two_chunk_plan_equals_stage_entry_points(planner):
     B = 6000
     batch = synth.gen_mixed(42, B)
     dev = planner.device
-    assert planner.lib.fsd_plan_launches(B) in (planner.lib.fsd_plan_launches(256), 2 * planner.lib.fsd_plan_launches(256))
+    assert planner.lib.fsd_plan_launches(256) == 4  # sort, match, path, second chance
+    assert planner.lib.fsd_plan_launches(B) in (4, 5, 8, 10)  # + the path keys of a work-ordered path stage; one or two chunks
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     args = (t(batch.cones_xy), t(batch.cones_type), t(batch.offsets), t(batch.pos), t(batch.dir))
     side = torch.cuda.Stream(dev)
@@ -455,6 +456,33 @@ def test_suspend_and_resume_is_invisible_in_the_results():
         z = np.load(os.path.join(tmp, "o.npz"))
         assert np.array_equal(z["status"], ref["status"]) and np.array_equal(z["grid"], ref["grid"])
         assert np.array_equal(z["path"], ref["path_f64"])
+
+
+def test_filing_frames_under_their_path_keys_in_the_match_kernel_changes_nothing():
+    """fsd_plan_batch's matching kernel also computes the path keys and files the frames in their bins' lists, where the
+    path kernel looks its rounds up.  FSD_PLAN_MODE bit 8 brings back the separate key / counting-sort kernels and the order
+    array: a child process with it must produce the very bytes of the default run, on a batch large enough for the
+    work-ordered path stage and on a small one (no ordering)."""
+    import subprocess
+    import sys
+    import tempfile
+
+    for B in (6000, 300):
+        batch = synth.gen_mixed(37, B)
+        ref = _np(BatchPlanner("cuda:0").plan_host(batch, intermediates=True))
+        with tempfile.TemporaryDirectory() as tmp:
+            code = (f"import sys, numpy as np, torch; sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r});"
+                    "from ft_fsd_path_planning_b200 import BatchPlanner, synth;"
+                    f"r = BatchPlanner('cuda:0').plan_host(synth.gen_mixed(37, {B}), intermediates=True); torch.cuda.synchronize();"
+                    f"np.savez({os.path.join(tmp, 'o.npz')!r}, path=r.path_f64.cpu().numpy(), status=r.status.cpu().numpy(), "
+                    "grid=r.grid.cpu().numpy(), li=r.left_idx.cpu().numpy(), ri=r.right_idx.cpu().numpy(), l2r=r.l2r.cpu().numpy(), "
+                    "r2l=r.r2l.cpu().numpy())")
+            env = dict(os.environ, FSD_PLAN_MODE=str(29 + 256))
+            subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+            z = np.load(os.path.join(tmp, "o.npz"))
+            for k, kr in (("status", "status"), ("grid", "grid"), ("li", "left_idx"), ("ri", "right_idx"), ("l2r", "l2r"),
+                          ("r2l", "r2l"), ("path", "path_f64")):
+                assert np.array_equal(z[k], ref[kr]), (B, k)
 
 
 def test_edge_cases(planner):
