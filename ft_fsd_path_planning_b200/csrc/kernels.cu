@@ -290,7 +290,15 @@ constexpr int PATH_THREADS = 32 * PATH_WPC;
 #ifndef FSD_PATH_SMEM_PAD
 #define FSD_PATH_SMEM_PAD 0 /* measurement builds only: extra dynamic shared memory that lowers the CTAs resident per SM */
 #endif
-constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE + FSD_PATH_SMEM_PAD;
+// The frames' path machines (PathMachine: fit bookkeeping, pose, flags -- every lane holds the same values) live in shared
+// memory behind the frame slots, not on the stack: passed by reference to the out-of-line stages they were local memory,
+// 32 identical copies per warp, 9.6 M local loads / stores per launch whose write-through traffic (~0.9 GB into L2) and dirty
+// lines were most of what the kernel wrote back to HBM.  Every lane stores the same value to the same address.
+#ifndef FSD_PM_SHARED
+#define FSD_PM_SHARED 1
+#endif
+constexpr size_t PATH_PM_STRIDE = FSD_PM_SHARED ? (sizeof(PathMachine) + 15) / 16 * 16 : 0;
+constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * (PATH_CTA_STRIDE + PATH_PM_STRIDE) + FSD_PATH_SMEM_PAD;
 // knot records behind frame slot 0 when its arena is extended over the shared memory of all the CTA's slots
 constexpr int PATH_XCAP_RAW = (int)((PATH_FPC * PATH_CTA_STRIDE - (sizeof(PathSmem) - sizeof(SplineWork::r))) / sizeof(KnotRec));
 constexpr int PATH_XCAP = PATH_XCAP_RAW < 192 ? PATH_XCAP_RAW : 192;
@@ -570,7 +578,11 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     const long long fsd_t0 = clock64();
     long long fsd_t1 = fsd_t0;
 #endif
+#if FSD_PM_SHARED
+    PathMachine &M = *reinterpret_cast<PathMachine *>(smem_raw + PATH_FPC * PATH_CTA_STRIDE + (size_t)grp * PATH_PM_STRIDE);
+#else
     PathMachine M;
+#endif
     M.state = PS_DONE;
     M.status = 0;
     M.P_grid = M.n_trim = 0;

@@ -606,7 +606,12 @@ FSD_DEVFN void pm_step(PathSmem &S, PathMachine &M, const DevParams &P) {
       // the whole fit in one machine step (the kernel aligns its warps at the fit boundaries only)
       if (M.fit.phase != FIT_DONE) fit_run(S.W, M.fit, M.state == PS_FIT1 ? &M.status : &M.tail_status);
 #endif
-      if (M.fit.phase == FIT_DONE) M.state += 1;
+      if (M.fit.phase == FIT_DONE) {
+        // (the machine may live in shared memory, one copy for all lanes: every lane reads before any lane writes)
+        const int next = M.state + 1;
+        PG::sync();
+        M.state = next;
+      }
       break;
     case PS_FIT1_DONE:
       pm_stage_after_fit1(S, M, P);

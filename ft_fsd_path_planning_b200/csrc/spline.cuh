@@ -645,7 +645,11 @@ FSD_DEV void fit_add_knots(SplineWork &W, FitState &F, int count) {
     }
   }
   F.n = n;
-  if (++F.iter >= m) fit_finish(W, F, F.ier);  // fppara's outer loop bound (never reached in practice)
+  // (FitState may live in shared memory, one copy for all lanes: every lane reads the counter before any lane writes it)
+  const int iter = F.iter + 1;
+  PG::sync();
+  F.iter = iter;
+  if (iter >= m) fit_finish(W, F, F.ier);  // fppara's outer loop bound (never reached in practice)
   PG::sync();
 }
 
@@ -687,6 +691,7 @@ FSD_DEVFN void fit_resume(SplineWork &W, FitState &F) {
 // one least-squares pass for the current knots + FITPACK's decision what to do next
 FSD_DEVFN void fit_step_knots(SplineWork &W, FitState &F, unsigned *status) {
   const int lane = PG::lane();
+  PG::sync();  // (lanes aligned where a step starts: see fit_step_smooth)
   const int k = F.k, k1 = k + 1, k2 = k + 2, nmin = 2 * k1, m = F.m;
   const double *u = F.u;
   int n = F.n;
@@ -804,7 +809,12 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
   const int lane = PG::lane();
   const int k = F.k, k2 = k + 2, nk1 = F.nk1;
   const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
-  ++F.iter;
+  // FitState may live in shared memory, ONE copy for all lanes (path_kernel): the lanes are aligned where a step starts, and
+  // where a field is updated from its own value every lane reads before any lane writes
+  PG::sync();
+  const int iter = F.iter + 1;
+  PG::sync();
+  F.iter = iter;
   const double pinv = frcp(F.p), pinv2 = pinv * pinv;
 #pragma unroll 1
   for (int i = lane; i < nk1; i += PG::N) {
@@ -828,11 +838,12 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
     return;
   }
   const double p2 = F.p, f2 = F.fpms;
+  PG::sync();
   if (F.ich3 == 0) {
     if (!((f2 - F.f3) > F.acc)) {
       F.p3 = p2;
       F.f3 = f2;
-      F.p = F.p * con4;
+      F.p = p2 * con4;
       if (F.p <= F.p1) F.p = F.p1 * con9 + p2 * con1;
       return;
     }
@@ -842,7 +853,7 @@ FSD_DEVFN void fit_step_smooth(SplineWork &W, FitState &F, unsigned *status) {
     if (!((F.f1 - f2) > F.acc)) {
       F.p1 = p2;
       F.f1 = f2;
-      F.p = fdiv(F.p, con4);
+      F.p = fdiv(p2, con4);
       if (F.p3 < 0.0) return;
       if (F.p >= F.p3) F.p = p2 * con1 + F.p3 * con9;
       return;
