@@ -49,8 +49,10 @@ FSD_DEV void path_smem_bind(PathSmem &S, unsigned char *points, int pcap, int ca
 
 // ---- hyper circle fit -----------------------------------------------------------------------------
 
-FSD_DEVFN void hyper_from_moments(double mx, double my, double Mxx, double Myy, double Mxy, double Mxz, double Myz,
-                                double Mzz, double &cx, double &cy, double &r) {
+// Returns the radius BY VALUE and writes the centre through `centre` only when asked to: reference outputs of an out-of-line
+// function are local memory, and the 120 curvature windows of every frame need nothing but the radius.
+FSD_DEVFN double hyper_from_moments(double mx, double my, double Mxx, double Myy, double Mxy, double Mxz, double Myz,
+                                  double Mzz, d2 *centre) {
   const double Mz = Mxx + Myy, Cov_xy = Mxx * Myy - Mxy * Mxy, Var_z = Mzz - Mz * Mz;
   const double A2 = 4.0 * Cov_xy - 3.0 * Mz * Mz - Mzz;
   const double A1 = Var_z * Mz + 4.0 * Cov_xy * Mz - Mxz * Mxz - Myz * Myz;
@@ -70,9 +72,11 @@ FSD_DEVFN void hyper_from_moments(double mx, double my, double Mxx, double Myy, 
   const double det = x * x - x * Mz + Cov_xy;
   const double Xc = fdiv(Mxz * (Myy - x) - Myz * Mxy, det) / 2.0;
   const double Yc = fdiv(Myz * (Mxx - x) - Mxz * Mxy, det) / 2.0;
-  cx = Xc + mx;
-  cy = Yc + my;
-  r = fsqrt(fabs(Xc * Xc + Yc * Yc + Mz));
+  if (centre) {
+    centre->x = Xc + mx;
+    centre->y = Yc + my;
+  }
+  return fsqrt(fabs(Xc * Xc + Yc * Yc + Mz));
 }
 
 FSD_DEV double orient(const d2 &p0, const d2 &p1, const d2 &p2) {
@@ -129,8 +133,7 @@ FSD_DEVFN void curvature_windows(const d2 *p, int Pn, int hw, double *curv) {
     const double sl2 = mx * mx * sxx + 2.0 * mx * my * sxy + my * my * syy;
     const double szl = mx * (sxxx + sxyy) + my * (sxxy + syyy);
     const double Mzz = (sz2 + 4.0 * sl2 - 4.0 * szl + 2.0 * q2 * (sxx + syy) - 3.0 * n * q2 * q2) * inv;
-    double cx, cy, r;
-    hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, cx, cy, r);
+    double r = hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, nullptr);
     r = fmin(fmax(r, 1.0), 3000.0);
     const int cnt = nhi - nlo + 1;
     curv[i] = frcp(r) * sgn(orient(p[nlo], p[nlo + cnt / 2], p[nhi]));
@@ -164,7 +167,10 @@ FSD_DEVFN void circle_fit_warp(const d2 *p, int n, double &cx, double &cy, doubl
   Mxz = PG::sum(Mxz) * inv_n;
   Myz = PG::sum(Myz) * inv_n;
   Mzz = PG::sum(Mzz) * inv_n;
-  hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, cx, cy, r);
+  d2 c;
+  r = hyper_from_moments(mx, my, Mxx, Myy, Mxy, Mxz, Myz, Mzz, &c);
+  cx = c.x;
+  cy = c.y;
 }
 
 // ---- chord-length parameters: u[0] = 0, u[i] = u[i-1] + |p_i - p_{i-1}| (np.cumsum) -------------------
@@ -241,10 +247,9 @@ FSD_DEVFN int pm_evaluate(PathSmem &S, double max_u, double step, d2 *dst, int d
   PG::sync();
 #pragma unroll 1
   for (int i = PG::lane(); i < n; i += PG::N) {
-    double x, y;
-    spline_point(S.W, (double)i * step, x, y);
-    dst[i].x = x;
-    dst[i].y = y;
+    const d2 p = spline_point(S.W, (double)i * step);
+    dst[i].x = p.x;
+    dst[i].y = p.y;
   }
   PG::sync();
   return n;
@@ -516,10 +521,9 @@ FSD_DEVFN void pm_stage_after_fit3(PathSmem &S, PathMachine &M, const DevParams 
   PG::sync();
 #pragma unroll 1
   for (int i = lane; i < Pn; i += PG::N) {
-    double x, y;
-    spline_point(S.W, (double)i * predict_every, x, y);
-    S.pts[i].x = x;
-    S.pts[i].y = y;
+    const d2 p = spline_point(S.W, (double)i * predict_every);
+    S.pts[i].x = p.x;
+    S.pts[i].y = p.y;
   }
   PG::sync();
   // _calculate_path_curvature :163-193 / calculate_path_curvature :49-93 (open path).  The curvature samples live in the

@@ -146,9 +146,11 @@ FSD_DEVFN void skidpad_relocalize(SkidSmem &S, const double *cones, int n, doubl
         Myz += yi * zi;
         Mzz += zi * zi;
       }
-      double r;
-      hyper_from_moments(mx, my, Mxx * (1.0 / 3.0), Myy * (1.0 / 3.0), Mxy * (1.0 / 3.0), Mxz * (1.0 / 3.0),
-                         Myz * (1.0 / 3.0), Mzz * (1.0 / 3.0), cx, cy, r);
+      d2 ctr;
+      const double r = hyper_from_moments(mx, my, Mxx * (1.0 / 3.0), Myy * (1.0 / 3.0), Mxy * (1.0 / 3.0),
+                                          Mxz * (1.0 / 3.0), Myz * (1.0 / 3.0), Mzz * (1.0 / 3.0), &ctr);
+      cx = ctr.x;
+      cy = ctr.y;
       double resid = 0.0;
       for (int q = 0; q < 3; ++q) resid += fabs(fnorm(cx - p[q].x, cy - p[q].y) - r);
       resid *= (1.0 / 3.0);

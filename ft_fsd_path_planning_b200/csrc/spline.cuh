@@ -145,7 +145,8 @@ FSD_DEV void bspl(const SplineWork &W, int k, double x, int ii, double (&h)[4]) 
   }
 }
 
-FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &oy) {
+// (the point BY VALUE: reference outputs of an out-of-line function are local memory)
+FSD_DEVFN d2 spline_point(const SplineWork &W, double x) {
   // splev with ext=0: the end polynomial pieces extrapolate
   const int k = W.k, nk1 = W.n - k - 1;
   int l = k;
@@ -160,8 +161,10 @@ FSD_DEVFN void spline_point(const SplineWork &W, double x, double &ox, double &o
       sx += W.r[l - k + j].c[0] * h[j];
       sy += W.r[l - k + j].c[1] * h[j];
     }
-  ox = sx;
-  oy = sy;
+  d2 out;
+  out.x = sx;
+  out.y = sy;
+  return out;
 }
 
 // Task (a, b) of lane/task index e in the elimination step of chol_solve: e < npairs -> band update (a, b), 1 <= a <= b <=
