@@ -26,8 +26,8 @@
  *     is still ONE asynchronous operation ordered on `stream` (see fsd_plan_launches);
  *   - no CPU fallback exists: without a CUDA device every CUDA entry point returns FSD_ERR_NO_DEVICE (the host planner
  *     fsd_plan_batch_cpu is a separate, explicit entry point);
- *   - besides its internal streams / events the library owns 4 KB of device memory per device (frame counters of its
- *     free-running kernels, allocated on first use).
+ *   - besides its internal streams / events the library owns 36 KB of device memory per device (frame counters of its
+ *     free-running kernels and the histograms of the path keys, allocated on first use).
  */
 #ifndef FSDPLAN_H
 #define FSDPLAN_H
@@ -125,8 +125,9 @@ int fsd_params_default(fsd_params *params);
 /* bytes of scratch needed by the batch entry points below for B frames */
 size_t fsd_workspace_bytes(int n_frames, int total_cones);
 
-/* Kernel launches one fsd_plan_batch call makes for n_frames frames on the current device: 2 (sort+match, path), or 4
- * when the batch is large enough to be planned as two chunks -- the second one on an internal side stream that is
+/* Kernel launches one fsd_plan_batch call makes for n_frames frames on the current device: 4 (sort, match, path, the
+ * large-bounds second chance of the path stage), 5 for batches large enough for the work-ordered path stage (+ the path
+ * keys), twice that when the plan mode splits the batch into two chunks -- the second one on an internal side stream that is
  * forked from and joined back into the caller's stream with events, so the call stays asynchronous and ordered on
  * the caller's stream (and capturable in a CUDA graph -- after one warm-up call: the FIRST call on a device initialises
  * per-device constants, among them the initial path of a fresh planner, on a private stream with its own
