@@ -672,8 +672,13 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
           }
           __syncthreads();
         }
-        // slot 0 belongs to warp 0 again
-        if (grp == 0) path_smem_bind(S, mine, PCAP, cap0, 1);
+        // The slots belong to their warps again.  EVERY slot is bound afresh: the extended arena of the resumed fit runs over
+        // the neighbours' slots, and a fit that ends up with >= 39 knots writes band rows (record 34 and up) on top of slot
+        // 1's header -- its point-buffer pointers and arena capacity (fewer knots only touch the neighbours' dead records).
+#ifdef FSD_REBIND_SLOT0_ONLY /* the behaviour before r2_zc, kept for tools/resume_probe.py */
+        if (grp == 0)
+#endif
+        path_smem_bind(S, mine, PCAP, cap0, 1);
       }
       if (!counter) __syncthreads();  // (static stride: no barrier at the top of the next round before s_state is rewritten)
     }

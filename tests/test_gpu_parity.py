@@ -485,6 +485,26 @@ def test_filing_frames_under_their_path_keys_in_the_match_kernel_changes_nothing
                 assert np.array_equal(z[k], ref[kr]), (B, k)
 
 
+def test_fits_that_outgrow_their_slot_by_many_knots():
+    """With tiny smoothing parameters the spline fits want far more knots than a frame slot's 34 records: most rounds hold
+    suspended frames, the resumed fits run with the arena extended over the CTA's shared memory, and fits that end up with
+    >= 39 knots write band rows on top of the NEIGHBOURING slots' headers (point-buffer pointers, arena capacity) -- which
+    must be bound afresh before the next round (they were not before r2_zc: illegal memory access on this very input,
+    tools/resume_probe.py).  The CUDA path, round after round, must give what the host build of the same sources gives
+    (large static bounds, one lane): identical decisions; paths equal up to the summation order of a 32-lane warp, which a
+    near-interpolating fit amplifies on a handful of frames.  A child process: an illegal address would poison this one."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "resume_probe.py"), "4096", "1e-5", "1e-6", "json"],
+                         check=True, cwd=root, capture_output=True, text=True, timeout=600).stdout
+    r = __import__("json").loads(out.strip().splitlines()[-1])
+    assert r["status_differs"] == 0 and r["sort_idx_differ"] == 0
+    assert r["compared"] >= 0.99 * r["frames"]
+    assert r["frames_above_1e-6"] <= 0.005 * r["frames"] and r["path_max_err"] < 5e-3, r
+
+
 def test_edge_cases(planner):
     """Empty batch, frames without cones, ragged frames, more than FSD_MAX_CONES cones."""
     z = np.zeros((0, 2))
