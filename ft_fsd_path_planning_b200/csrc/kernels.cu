@@ -290,15 +290,8 @@ constexpr int PATH_THREADS = 32 * PATH_WPC;
 #ifndef FSD_PATH_SMEM_PAD
 #define FSD_PATH_SMEM_PAD 0 /* measurement builds only: extra dynamic shared memory that lowers the CTAs resident per SM */
 #endif
-// The frames' path machines (PathMachine: fit bookkeeping, pose, flags -- every lane holds the same values) live in shared
-// memory behind the frame slots, not on the stack: passed by reference to the out-of-line stages they were local memory,
-// 32 identical copies per warp, 9.6 M local loads / stores per launch whose write-through traffic (~0.9 GB into L2) and dirty
-// lines were most of what the kernel wrote back to HBM.  Every lane stores the same value to the same address.
-#ifndef FSD_PM_SHARED
-#define FSD_PM_SHARED 1
-#endif
-constexpr size_t PATH_PM_STRIDE = FSD_PM_SHARED ? (sizeof(PathMachine) + 15) / 16 * 16 : 0;
-constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * (PATH_CTA_STRIDE + PATH_PM_STRIDE) + FSD_PATH_SMEM_PAD;
+// (the frames' path machines live in their slots, PathSmem::M: shared memory, not the stack)
+constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE + FSD_PATH_SMEM_PAD;
 // knot records behind frame slot 0 when its arena is extended over the shared memory of all the CTA's slots
 constexpr int PATH_XCAP_RAW = (int)((PATH_FPC * PATH_CTA_STRIDE - (sizeof(PathSmem) - sizeof(SplineWork::r))) / sizeof(KnotRec));
 constexpr int PATH_XCAP = PATH_XCAP_RAW < 192 ? PATH_XCAP_RAW : 192;
@@ -578,11 +571,7 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
     const long long fsd_t0 = clock64();
     long long fsd_t1 = fsd_t0;
 #endif
-#if FSD_PM_SHARED
-    PathMachine &M = *reinterpret_cast<PathMachine *>(smem_raw + PATH_FPC * PATH_CTA_STRIDE + (size_t)grp * PATH_PM_STRIDE);
-#else
-    PathMachine M;
-#endif
+    PathMachine &M = S.M;
     M.state = PS_DONE;
     M.status = 0;
     M.P_grid = M.n_trim = 0;
@@ -643,35 +632,36 @@ __global__ void __launch_bounds__(PATH_THREADS, FSD_PATH_CTAS_PER_SM)
       if (any) {
         PathSmem &X = *reinterpret_cast<PathSmem *>(smem_raw);  // frame slot 0
         const int first = __ffs(any) - 1;
-        for (int g = 0; g < PATH_FPC; ++g) {
-          if (!((any >> g) & 1)) continue;
-          if (grp == g && g != first) {
-            // a second suspended frame in the same round (its image would not survive the first one's resume): flagged
-            // like a truncated fit; with fixup scratch (flags & 2) the large-bounds kernel plans it again
-            pm_give_up_suspended(M);
-            int gr[2] = {0, 0};
-            store_path_frame(out, M.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
-          } else if (grp == g) {
-            if (g != 0) {
-              // the frame's image (pointers to ITS point buffers, spline header, knot records) moves to slot 0
-              const double *src = reinterpret_cast<const double *>(&S);
-              double *dst = reinterpret_cast<double *>(&X);
-              for (int i = lane; i < (int)(sizeof(PathSmem) / sizeof(double)); i += PG::N) dst[i] = src[i];
-              PG::sync();
-            }
-            if (lane == 0) {
-              X.W.cap = PATH_XCAP;
-              X.W.suspendable = 0;  // whatever does not fit now is flagged (FSD_ST_OVERFLOW) as ever
-            }
-            PG::sync();
-            M.out = reinterpret_cast<double *>(X.W.r);
-            fit_resume(X.W, M.fit);
-            pm_run(X, M, P);
-            int gr[2] = {M.P_grid, M.n_trim};
-            store_path_frame(M.out, M.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
-          }
-          __syncthreads();
+        // Further suspended frames of the same round (their images would not survive the first one's resume) are flagged
+        // like a truncated fit -- with fixup scratch (flags & 2) the large-bounds kernel plans them again --, and they are
+        // dealt with FIRST: their slots, path machines included, are intact now, not after the resume.
+        if (resume && grp != first) {
+          pm_give_up_suspended(M);
+          int gr[2] = {0, 0};
+          store_path_frame(out, M.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
         }
+        __syncthreads();
+        if (grp == first) {
+          if (first != 0) {
+            // the frame's image (pointers to ITS point buffers, path machine, spline header, knot records) moves to slot 0
+            const double *src = reinterpret_cast<const double *>(&S);
+            double *dst = reinterpret_cast<double *>(&X);
+            for (int i = lane; i < (int)(sizeof(PathSmem) / sizeof(double)); i += PG::N) dst[i] = src[i];
+            PG::sync();
+          }
+          if (lane == 0) {
+            X.W.cap = PATH_XCAP;
+            X.W.suspendable = 0;  // whatever does not fit now is flagged (FSD_ST_OVERFLOW) as ever
+          }
+          PG::sync();
+          PathMachine &MX = X.M;  // (the machine moved with the image; this frame's own slot is about to be run over)
+          MX.out = reinterpret_cast<double *>(X.W.r);
+          fit_resume(X.W, MX.fit);
+          pm_run(X, MX, P);
+          int gr[2] = {MX.P_grid, MX.n_trim};
+          store_path_frame(MX.out, MX.status, gr, b, O.status, out_f64, out_f32, grid_out, flags, G);
+        }
+        __syncthreads();
         // The slots belong to their warps again.  EVERY slot is bound afresh: the extended arena of the resumed fit runs over
         // the neighbours' slots, and a fit that ends up with >= 39 knots writes band rows (record 34 and up) on top of slot
         // 1's header -- its point-buffer pointers and arena capacity (fewer knots only touch the neighbours' dead records).

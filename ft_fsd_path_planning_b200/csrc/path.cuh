@@ -26,11 +26,39 @@ enum { RC_OK = 0, RC_VALUE_ERROR = 1, RC_RAISES = 2, RC_UNSUPPORTED = 3 };
 // per-frame point buffers live in per-CTA global scratch (L2 resident): PCAP x (16 + 8) bytes
 constexpr size_t PATH_SCRATCH_BYTES = (size_t)PCAP * (sizeof(d2) + sizeof(double));
 
+// states and state of the path machine (the pipeline itself: further down)
+enum {
+  PS_FIT1 = 1,
+  PS_FIT1_DONE = 2,  // alignment point
+  PS_TAIL = 3,
+  PS_FIT2 = 4,
+  PS_FIT2_DONE = 5,  // alignment point
+  PS_FIT3 = 6,
+  PS_FIT3_DONE = 7,  // alignment point
+  PS_DONE = 100
+};
+
+struct PathMachine {
+  int state, mode;  // mode 0: planner frame, 1: initial path (fit #1 on the chord, then the parameterisation only)
+  FitState fit;
+  FramePose F;
+  const double *prev;  // previous path, 40 x 4
+  double *out;         // 40 x 4
+  int force_P, nu, P_grid, n_trim;
+  unsigned status, tail_status;
+  bool fit1_retry, tail_retry;
+  double predict_every;
+};
+
 struct PathSmem {
   d2 *pts;       // [pcap]
   double *u;     // [pcap]
   int32_t pcap;  // path points behind pts / u (PCAP unless the caller provides larger buffers)
   int32_t pad_[3];
+  // The frame's path machine lives HERE, in the frame's shared-memory slot, not on the stack: passed by reference to the
+  // out-of-line stages a stack object is local memory -- 32 identical copies per warp whose stores are written through to
+  // L2 (most of the path kernel's HBM write-back before r2_zb).  One copy per lane group: every lane stores the same value.
+  PathMachine M;
   SplineWork W;  // LAST member (its arena may extend past the struct, see SplineWork::cap)
 };
 
@@ -201,29 +229,6 @@ FSD_DEVFN void chord_params(const d2 *p, int m, double *u) {
 // fits.  The path kernel keeps the warps of a CTA in lockstep at this granularity (they wait for each other at the
 // *_DONE states), the blocking wrappers below (path_frame, path_from_update, initial_path_frame) simply run the
 // machine to completion.  Every lane holds an identical copy of the machine state.
-
-enum {
-  PS_FIT1 = 1,
-  PS_FIT1_DONE = 2,  // alignment point
-  PS_TAIL = 3,
-  PS_FIT2 = 4,
-  PS_FIT2_DONE = 5,  // alignment point
-  PS_FIT3 = 6,
-  PS_FIT3_DONE = 7,  // alignment point
-  PS_DONE = 100
-};
-
-struct PathMachine {
-  int state, mode;  // mode 0: planner frame, 1: initial path (fit #1 on the chord, then the parameterisation only)
-  FitState fit;
-  FramePose F;
-  const double *prev;  // previous path, 40 x 4
-  double *out;         // 40 x 4
-  int force_P, nu, P_grid, n_trim;
-  unsigned status, tail_status;
-  bool fit1_retry, tail_retry;
-  double predict_every;
-};
 
 FSD_DEV bool pm_is_alignment_state(int st) { return st == PS_FIT1_DONE || st == PS_FIT2_DONE || st == PS_FIT3_DONE; }
 
@@ -814,7 +819,7 @@ FSD_DEVFN void pm_give_up_suspended(PathMachine &M) {
 FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *right, int nr, const int16_t *l2r,
                               const int16_t *r2l, const FramePose &F, int force_P, const double *prev,
                               const DevParams &P, double *out, int *grid, int xcap = 0) {
-  PathMachine M;
+  PathMachine &M = S.M;
   pm_begin_frame(S, M, left, nl, right, nr, l2r, r2l, F, force_P, prev, P, out);
   pm_run(S, M, P);
   if (pm_suspended(M) && xcap > S.W.cap) {
@@ -845,7 +850,7 @@ FSD_DEVFN unsigned path_frame(PathSmem &S, const d2 *left, int nl, const d2 *rig
 
 FSD_DEVFN unsigned path_global(PathSmem &S, const double *gpath, int Mn, const FramePose &F, int force_P,
                                const double *prev, const DevParams &P, double *out, int *grid) {
-  PathMachine M;
+  PathMachine &M = S.M;
   pm_begin_global(S, M, gpath, Mn, F, force_P, prev, P, out);
   pm_run(S, M, P);
   if (grid && PG::lane() == 0) {
@@ -858,7 +863,7 @@ FSD_DEVFN unsigned path_global(PathSmem &S, const double *gpath, int Mn, const F
 
 FSD_DEVFN unsigned path_from_update(PathSmem &S, int nu, const FramePose &F, int force_P, const double *prev,
                                     const DevParams &P, double *out, int *grid) {
-  PathMachine M;
+  PathMachine &M = S.M;
   pm_begin_update(S, M, nu, F, force_P, prev, P, out);
   pm_run(S, M, P);
   if (grid && PG::lane() == 0) {
@@ -870,7 +875,7 @@ FSD_DEVFN unsigned path_from_update(PathSmem &S, int nu, const FramePose &F, int
 }
 
 FSD_DEVFN unsigned initial_path_frame(PathSmem &S, const DevParams &P, double *out) {
-  PathMachine M;
+  PathMachine &M = S.M;
   pm_begin_initial(S, M, P, out);
   pm_run(S, M, P);
   return M.status;
