@@ -595,7 +595,8 @@ def run_ours(args):
                     ipc = t["warp_inst"] / (dom_ms * 1e-3 * sm_clock * n_sm)
                     issue = {"warp_inst_per_launch": t["warp_inst"], "warp_inst_per_frame": t["warp_inst"] / B,
                              "achieved_ipc_per_sm": ipc, "peak_ipc_per_sm": 4.0, "frac": ipc / 4.0,
-                             "source": "profiles/ncu_traffic.json (ncu inst_executed) / live kernel time"}
+                             "source": "profiles/ncu_traffic.json (ncu inst_executed) / live kernel time",
+                             "capture_build": json.load(open(tpath)).get("build")}
         # the cost-matrix step: SURVEY 8d's B_cm = 19.25 N + 16 bytes per frame (9 N + 16 read, 10 N of k-NN lists + two
         # N/8-byte masks written); the kernel actually writes 12 N (adjacency lists + degrees)
         cm_bytes = 19.25 * batch.total_cones + 16 * B
