@@ -292,6 +292,11 @@ constexpr int PATH_THREADS = 32 * PATH_WPC;
 #endif
 // (the frames' path machines live in their slots, PathSmem::M: shared memory, not the stack)
 constexpr size_t PATH_KERNEL_SMEM = PATH_FPC * PATH_CTA_STRIDE + FSD_PATH_SMEM_PAD;
+#if FSD_PATH_SMEM_PAD == 0 && FSD_PATH_WPC == 8 && FSD_PATH_CTAS_PER_SM == 2
+// two CTAs (+ 1 KB each that the driver reserves) under the 132 KB shared-memory carve-out: what is left of the SM's 256 KB is
+// the L1 that serves the point buffers -- a slot that grows past this costs 32 KB of it (section 3 of DESIGN.md)
+static_assert(2 * (PATH_KERNEL_SMEM + 1024) <= 132 * 1024, "the path kernel's frame slots outgrew the 132 KB carve-out");
+#endif
 // knot records behind frame slot 0 when its arena is extended over the shared memory of all the CTA's slots
 constexpr int PATH_XCAP_RAW = (int)((PATH_FPC * PATH_CTA_STRIDE - (sizeof(PathSmem) - sizeof(SplineWork::r))) / sizeof(KnotRec));
 constexpr int PATH_XCAP = PATH_XCAP_RAW < 192 ? PATH_XCAP_RAW : 192;

@@ -1,4 +1,5 @@
 # session-4 A/B (GPU box): PathMachine in shared memory (default build) vs on the stack (ab_pmstack.so)
+# (as run at build r2_zb, where -DFSD_PM_SHARED=0 put the machine back on the stack; since r2_zd it is a member of the frame slot)
 set -x
 C=$PWD/ft_fsd_path_planning_b200/csrc
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r5e_tests.txt 2>&1; tail -3 gpurun_out/r5e_tests.txt
